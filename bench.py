@@ -1,0 +1,375 @@
+"""Benchmark of the NLP-evaluation hot path (contract in the task statement).
+
+    python bench.py --gpus N --steps K --warmup W                 # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W # the CPU reference arm
+
+Workload (BASELINE.json configs[3], the config the metric is quoted on): benchmark_6_ackermann_wave
+with 65,536 multi-start problems resident per GPU (weak scaling: every rank owns its own 65,536
+starts, global indices rank*65536 ...).  One step = one pass of the hot path over the batch:
+g(w), all structural non-zeros of dg/dw, f(w), grad f(w) -> 324 learned-SDF value+Jacobian points per
+problem.  The SDF network is the YAML's model (mlp, ReLU, 2->128->128->1) with seeded synthetic weights.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+
+METRIC = "learned-SDF value+Jacobian points/s"
+UNIT = "points/s"
+YAML = "benchmark_6_ackermann_wave.yaml"
+
+
+def load_peaks():
+    p = REPO / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ln in self.lines:
+            f = [c.strip() for c in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def synthetic_net():
+    """The YAML's model: l4c.naive.MultiLayerPerceptron(2, 128, 1, 2, 'ReLU') -> 2->128->128->1, seeded weights
+    (W ~ N(0, 1/fan_in))."""
+    rng = np.random.default_rng(0)
+    H = 128
+    W0 = rng.standard_normal((H, 2)) / np.sqrt(2.0)
+    b0 = 0.1 * rng.standard_normal(H)
+    W1 = rng.standard_normal((H, H)) / np.sqrt(H)
+    b1 = 0.1 * rng.standard_normal(H)
+    w_out = rng.standard_normal(H) / np.sqrt(H)
+    return dict(W0=W0.astype(np.float32), b0=b0.astype(np.float32), W1=W1.astype(np.float32), b1=b1.astype(np.float32),
+                w_out=w_out.astype(np.float32), b_out=np.float32(0.05))
+
+
+FLOP_PER_POINT = 4 * (3 * 128 + 128 * 128)      # value + Jacobian, 2->128->128->1 = 67,072
+BYTES_PER_EVAL = (727 + 1057 + 3225) * 4        # read w, write g and nnz(J) = 20,036 B / problem-eval
+POINTS_PER_PROBLEM = 324
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU baseline: strong batched CPU port (baseline B + C) on a bounded sample
+# ---------------------------------------------------------------------------------------------------------
+def cpu_step_factory(n_problems: int):
+    """One step of the same workload on the host cores: numpy assembly (oracle.nlp_oracle, fp64) with the SDF
+    evaluated by batched torch-CPU fp32 forward + hand-written reverse pass over all host threads."""
+    import torch
+    import yaml
+    from oracle import nlp_oracle as no
+    net = synthetic_net()
+    t = {k: torch.from_numpy(np.asarray(v)) for k, v in net.items()}
+    W0t, W1t = t["W0"].T.contiguous(), t["W1"].T.contiguous()
+
+    def sdf(P):
+        with torch.no_grad():
+            p = torch.from_numpy(np.ascontiguousarray(P, np.float32))
+            a0 = torch.addmm(t["b0"], p, W0t)
+            h0 = torch.relu(a0)
+            a1 = torch.addmm(t["b1"], h0, W1t)
+            s = torch.relu(a1) @ t["w_out"] + t["b_out"]
+            g1 = (a1 > 0).float() * t["w_out"]
+            g0 = (g1 @ t["W1"]) * (a0 > 0).float()
+            J = g0 @ t["W0"]
+        return s.numpy(), J.numpy()
+
+    spec = no.NlpSpec.from_yaml_dict(yaml.safe_load(open(REPO / "nlotrajectories_b200" / "benchmarks" / YAML)))
+    w = no.multistart_guess(spec, n_problems)
+
+    def step():
+        no.eval_g_jac(spec, w, sdf)
+        no.eval_f_grad(spec, w)
+    return step, torch.get_num_threads()
+
+
+def time_cpu(n_problems: int, steps: int, warmup: int):
+    step, threads = cpu_step_factory(n_problems)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return n_problems * POINTS_PER_PROBLEM / dt, dt, threads
+
+
+def reference_call_pattern_rate(max_calls: int = 300):
+    """Baseline A: the reference's real call pattern - the shipped TorchScript
+    modules nn_sdf.pt + jac_nn_sdf.pt called one 1x2 point at a time on one thread."""
+    ref = REPO / "oracle" / "_ref"
+    if not (ref / "nn_sdf.pt").exists():
+        return None
+    import torch
+    torch.set_num_threads(1)
+    f = torch.jit.load(str(ref / "nn_sdf.pt")); j = torch.jit.load(str(ref / "jac_nn_sdf.pt"))
+    p = torch.rand(1, 2)
+    for _ in range(30):
+        f(p); j(p)
+    t0 = time.perf_counter()
+    for _ in range(max_calls):
+        f(p); j(p)
+    return max_calls / (time.perf_counter() - t0)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    n_problems = args.cpu_problems
+    rate, dt, threads = time_cpu(n_problems, args.steps, args.warmup)
+    cores = os.cpu_count()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{YAML} NLP eval (g, nnz(dg/dw), f, grad f); CPU sample of {n_problems} multi-start problems per step "
+                               f"({n_problems * POINTS_PER_PROBLEM} SDF points), mlp ReLU 2-128-128-1 synthetic weights"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "host_cpus": cores, "kind": "port",
+                         "sample": f"{n_problems} problems/step x {args.steps} steps; numpy fp64 assembly (oracle.nlp_oracle) + torch-CPU fp32 "
+                                   "batched SDF forward + analytic reverse on all host threads"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CUDA arm
+# ---------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from nlotrajectories_b200 import lib
+    from nlotrajectories_b200.config import Config
+    from nlotrajectories_b200.distributed import init_process_group, merit, select_best
+    from nlotrajectories_b200.problem import NlpProblem
+    from nlotrajectories_b200.sdf import LearnedSDF, SdfWeights
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    rank, local_rank, world = init_process_group("nccl")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    L = lib.load()
+    peaks, peak_src = load_peaks()
+    net = synthetic_net()
+    weights = SdfWeights.pack("mlp", net["W0"], net["b0"], [(net["W1"], net["b1"])], net["w_out"], float(net["b_out"]), 0, 0)
+    model = LearnedSDF(weights, device=local_rank, precision=args.precision)
+    prob = NlpProblem.from_config(Config.load(REPO / "nlotrajectories_b200" / "benchmarks" / YAML), model, device=local_rank)
+    P = args.problems
+    first = rank * P
+    w_host = prob.multistart_guess(P, first=first)                       # (P, n_w) problem-major, seeded
+    w_pin = torch.empty((P, prob.n_w), dtype=torch.float32).pin_memory()
+    w_pin.copy_(torch.from_numpy(w_host))
+    w = w_pin.to(dev).T.contiguous()                                      # SoA (n_w, P), resident in HBM
+    g, jac, f, grad = prob.alloc_outputs(P, dev)
+    n_pts = P * prob.n_sdf_points
+
+    def step():
+        prob.eval_device(w, g, jac, f, grad)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = L.nlo_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    launches = int(L.nlo_launch_count() - l0)
+    ms = e0.elapsed_time(e1)
+    # dominant kernel alone (the fused learned-SDF value+Jacobian kernel on this step's footprint points)
+    xs = torch.rand(n_pts, device=dev) * 2 - 0.5
+    ys = torch.rand(n_pts, device=dev) * 2 - 0.5
+    so_, jx_, jy_ = torch.empty_like(xs), torch.empty_like(xs), torch.empty_like(xs)
+    for _ in range(3):
+        model.eval(xs, ys, out=(so_, jx_, jy_))
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(args.steps):
+        model.eval(xs, ys, out=(so_, jx_, jy_))
+    k1.record()
+    torch.cuda.synchronize()
+    k_ms = k0.elapsed_time(k1) / args.steps
+    clocks = sampler.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * n_pts / (ms_per_step * 1e-3)
+
+    # ---- end to end: host buffers in, host buffers out, through the C-ABI host entry point --------------------
+    out_pin = {"g": torch.empty((P, prob.n_g), dtype=torch.float32).pin_memory().numpy(),
+               "jac": torch.empty((P, prob.nnz), dtype=torch.float32).pin_memory().numpy(),
+               "f": torch.empty((P,), dtype=torch.float32).pin_memory().numpy(),
+               "grad_f": torch.empty((P, prob.n_w), dtype=torch.float32).pin_memory().numpy()}
+    w_np = w_pin.numpy()
+    e2e_steps = max(2, min(args.steps, 5))
+    prob.eval_host(w_np, out=out_pin)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        prob.eval_host(w_np, out=out_pin)                                  # synchronous: results are in host memory on return
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    h2d = int(w_np.nbytes)
+    d2h = int(sum(v.nbytes for v in out_pin.values()))
+
+    # ---- best-of-batch selection (the only collective on the path; outside the timed region) ------------------
+    lb, ub = prob.bounds()
+    big = 3.0e38
+    lbd = torch.from_numpy(np.clip(lb, -big, big).astype(np.float32)).to(dev)
+    ubd = torch.from_numpy(np.clip(ub, -big, big).astype(np.float32)).to(dev)
+    viol = prob.violation(g, lbd, ubd)
+    best_val, best_idx, _ = select_best(merit(f, viol), w, first, prob.n_w)
+
+    if rank != 0:
+        return
+    prec = model.precision
+    if prec == "tc3xtf32":
+        peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+        bound = "tensor"
+        peak_note = f"{peak_src} cuBLAS bf16 sustained; the kernel runs 3 TF32 passes at half the bf16 rate, so its algorithmic ceiling is peak/6"
+    else:
+        sm_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+        peak = model_sm_count(L, local_rank) * 128 * 2 * sm_mhz * 1e6 / 1e12
+        bound = "fp32_simt"
+        peak_note = f"FP32 FMA pipe = SMs x 128 lanes x 2 x {sm_mhz:.0f} MHz (median SM clock sampled during the run)"
+    achieved = FLOP_PER_POINT * n_pts / (k_ms * 1e-3) / 1e12
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if prec == "fp32" else "f32 (3xTF32 tensor tiles, fp32 accumulate)", "data": "synthetic",
+        "config": {"workload": f"{YAML} x {P} multi-starts per GPU: NLP eval g + nnz(dg/dw) + f + grad f, SoA fp32 resident in HBM",
+                   "problems_per_gpu": P, "sdf_points_per_step_per_gpu": n_pts, "n_w": prob.n_w, "n_g": prob.n_g, "nnz_jac": prob.nnz,
+                   "sdf_model": "mlp ReLU 2-128-128-1 (synthetic seeded weights)", "sdf_precision": prec,
+                   "l2": f"inputs {w.numel() * 4 / 1e6:.0f} MB + outputs {(g.numel() + jac.numel() + grad.numel()) * 4 / 1e6:.0f} MB per step exceed the 126 MB L2",
+                   "parallelism": f"problem-sharded x{world}, no data-path collective"},
+        "nlp_evals_per_s": world * P / (ms_per_step * 1e-3),
+        "clocks": clocks,
+        "e2e": {"value": world * n_pts / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_s * 1e3, "api": "nlo_nlp_eval_host (pinned host buffers, problem-major)"},
+        "gpu_launches": launches,
+        "roofline": {"kernel": "sdf_tc_kernel" if prec == "tc3xtf32" else "sdf_simt_kernel", "bound": bound, "achieved": achieved,
+                     "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                     "flop_per_point": FLOP_PER_POINT, "points_per_launch": n_pts, "kernel_ms": k_ms, "peak_source": peak_note,
+                     "kernel_share_of_step": k_ms / ms_per_step,
+                     "step_hbm": {"algorithmic_bytes_per_step": BYTES_PER_EVAL * P, "achieved_gbs": BYTES_PER_EVAL * P / (ms_per_step * 1e-3) / 1e9,
+                                  "peak_gbs": peaks["hbm_gbs"]}},
+        "best_of_batch": {"merit": best_val, "global_index": best_idx},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        rate, dt, threads = time_cpu(args.cpu_problems, 3, 1)
+        cb = {"value": rate, "unit": UNIT, "cores": threads, "host_cpus": os.cpu_count(), "kind": "port",
+              "sample": f"{args.cpu_problems} problems/step x 3 steps ({dt * 3:.1f} s); numpy fp64 assembly + torch-CPU fp32 batched SDF on all host threads"}
+        a = reference_call_pattern_rate()
+        if a is not None:
+            cb["reference_call_pattern_points_per_s_1thread"] = a
+        line["cpu_baseline"] = cb
+    print(json.dumps(line), flush=True)
+
+
+def model_sm_count(L, device):
+    return int(L.nlo_device_sm_count(device))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--problems", type=int, default=65536, help="multi-start problems per GPU")
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tc3xtf32"])
+    ap.add_argument("--cpu-problems", type=int, default=2048, help="problems per CPU-baseline step (bounded sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,558 @@
+// C ABI of libnlo_b200.so (declared in include/nlo_b200.h): handles, batched entry points,
+// host-buffer entry points and the CasADi external ABI that replaces _l4c_generated/nn_sdf.cpp.
+#include "nlo_common.cuh"
+#include "nlp_internal.cuh"
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+// ---- errors / counters ---------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+static thread_local unsigned long long g_launches = 0;
+
+int nlo_fail(const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  if (getenv("NLO_B200_VERBOSE")) fprintf(stderr, "[nlo_b200] error: %s\n", g_err);
+  return 1;
+}
+void nlo_count_launch(unsigned n) { g_launches += n; }
+
+extern "C" {
+
+int nlo_version(void) { return 100; }
+const char* nlo_last_error(void) { return g_err; }
+unsigned long long nlo_launch_count(void) { return g_launches; }
+
+int nlo_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { nlo_fail("cudaGetDeviceCount failed: no usable CUDA device"); return -1; }
+  return n;
+}
+int nlo_device_sm_count(int device) {
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) { nlo_fail("cannot query device %d", device); return -1; }
+  return n;
+}
+
+// ---- SDF model --------------------------------------------------------------------------------------
+size_t nlo_sdf_weight_count(const nlo_sdf_desc* d) {
+  const size_t H = d->hidden, M = d->n_hidden_mats;
+  return 3 * H + M * (H * H + H) + H + 1;
+}
+
+static int validate_desc(const nlo_sdf_desc* d) {
+  if (!d) return nlo_fail("null descriptor");
+  if (d->hidden < 4 || d->hidden > 1024 || d->hidden % 4) return nlo_fail("hidden width %u unsupported (multiple of 4 in [4,1024])", d->hidden);
+  if (d->n_hidden_mats > 16) return nlo_fail("too many hidden layers (%u)", d->n_hidden_mats);
+  if (d->act0 > NLO_ACT_IDENTITY || d->act > NLO_ACT_IDENTITY) return nlo_fail("unknown activation id");
+  return 0;
+}
+
+int nlo_sdf_create(const nlo_sdf_desc* desc, const float* weights, size_t n_weights, int device, nlo_sdf_model** out) {
+  if (!out) return nlo_fail("null out");
+  *out = nullptr;
+  if (validate_desc(desc)) return 1;
+  if (!weights) return nlo_fail("null weights");
+  if (n_weights != nlo_sdf_weight_count(desc))
+    return nlo_fail("weight count %zu does not match descriptor (%zu expected)", n_weights, nlo_sdf_weight_count(desc));
+  int ndev = nlo_device_count();
+  if (ndev <= 0) return nlo_fail("no CUDA device available: libnlo_b200 has no CPU fallback");
+  if (device < 0 || device >= ndev) return nlo_fail("device %d out of range (have %d)", device, ndev);
+  NLO_CUDA(cudaSetDevice(device));
+  nlo_sdf_model* m = new (std::nothrow) nlo_sdf_model();
+  if (!m) return nlo_fail("out of host memory");
+  memset(m, 0, sizeof(*m));
+  m->desc = *desc; m->device = device; m->n_w = n_weights;
+  NLO_CUDA(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device));
+  NLO_CUDA(cudaMalloc(&m->d_w, n_weights * sizeof(float)));
+  NLO_CUDA(cudaMemcpy(m->d_w, weights, n_weights * sizeof(float), cudaMemcpyHostToDevice));
+  NLO_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  m->prec = NLO_PREC_FP32_SIMT;
+  if (nlo_sdf_tc_supported(desc)) {
+    if (nlo_sdf_tc_prepare(m, weights)) { nlo_sdf_destroy(m); return 1; }
+    m->prec = NLO_PREC_TC_3XTF32;     // AUTO default: tensor tiles when the shape supports them
+  }
+  const char* env = getenv("NLO_B200_PRECISION");
+  if (env && !strcmp(env, "fp32")) m->prec = NLO_PREC_FP32_SIMT;
+  *out = m;
+  return 0;
+}
+
+struct NlowHeader { char magic[4]; uint32_t version; nlo_sdf_desc desc; uint32_t pad0; uint64_t n_weights; uint8_t pad[16]; };
+static_assert(sizeof(nlo_sdf_desc) == 28, "descriptor layout is part of the file format");
+static_assert(sizeof(NlowHeader) == 64, "header must be 64 bytes");
+
+int nlo_sdf_save(const char* path, const nlo_sdf_desc* desc, const float* weights, size_t n_weights) {
+  if (validate_desc(desc)) return 1;
+  if (n_weights != nlo_sdf_weight_count(desc)) return nlo_fail("weight count mismatch");
+  FILE* fp = fopen(path, "wb");
+  if (!fp) return nlo_fail("cannot open %s for writing", path);
+  NlowHeader h; memset(&h, 0, sizeof(h));
+  memcpy(h.magic, "NLOW", 4); h.version = 1; h.desc = *desc; h.n_weights = n_weights;
+  bool ok = fwrite(&h, sizeof(h), 1, fp) == 1 && fwrite(weights, sizeof(float), n_weights, fp) == n_weights;
+  fclose(fp);
+  return ok ? 0 : nlo_fail("short write to %s", path);
+}
+
+int nlo_sdf_load(const char* path, int device, nlo_sdf_model** out) {
+  if (!path) return nlo_fail("null path");
+  FILE* fp = fopen(path, "rb");
+  if (!fp) return nlo_fail("cannot open weight file %s", path);
+  NlowHeader h;
+  if (fread(&h, sizeof(h), 1, fp) != 1 || memcmp(h.magic, "NLOW", 4) || h.version != 1) { fclose(fp); return nlo_fail("%s is not a .nlow v1 file", path); }
+  if (validate_desc(&h.desc) || h.n_weights != nlo_sdf_weight_count(&h.desc)) { fclose(fp); return nlo_fail("%s: inconsistent header", path); }
+  std::vector<float> w(h.n_weights);
+  bool ok = fread(w.data(), sizeof(float), w.size(), fp) == w.size();
+  fclose(fp);
+  if (!ok) return nlo_fail("%s: truncated", path);
+  return nlo_sdf_create(&h.desc, w.data(), w.size(), device, out);
+}
+
+void nlo_sdf_destroy(nlo_sdf_model* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  if (m->d_w) cudaFree(m->d_w);
+  if (m->d_tc) cudaFree(m->d_tc);
+  if (m->d_io) cudaFree(m->d_io);
+  if (m->d_ws) cudaFree(m->d_ws);
+  if (m->h_io) cudaFreeHost(m->h_io);
+  if (m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+}
+
+int nlo_sdf_set_precision(nlo_sdf_model* m, int prec) {
+  if (!m) return nlo_fail("null model");
+  if (prec == NLO_PREC_AUTO) prec = nlo_sdf_tc_supported(&m->desc) ? NLO_PREC_TC_3XTF32 : NLO_PREC_FP32_SIMT;
+  if (prec == NLO_PREC_TC_3XTF32 && !nlo_sdf_tc_supported(&m->desc))
+    return nlo_fail("tensor-tile path supports H in {64,128} with one hidden matrix; this model has H=%u M=%u", m->desc.hidden, m->desc.n_hidden_mats);
+  if (prec != NLO_PREC_TC_3XTF32 && prec != NLO_PREC_FP32_SIMT) return nlo_fail("unknown precision %d", prec);
+  m->prec = prec;
+  return 0;
+}
+int nlo_sdf_get_precision(const nlo_sdf_model* m) { return m ? m->prec : -1; }
+int nlo_sdf_describe(const nlo_sdf_model* m, nlo_sdf_desc* out) { if (!m || !out) return nlo_fail("null argument"); *out = m->desc; return 0; }
+
+int nlo_sdf_eval(nlo_sdf_model* m, const float* x, const float* y, const float* sbar, size_t n,
+                 float* s, float* jx, float* jy, void* stream) {
+  if (!m) return nlo_fail("null model");
+  if (n == 0) return 0;
+  if (!x || !y) return nlo_fail("null coordinate array");
+  NLO_CUDA(cudaSetDevice(m->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (m->prec == NLO_PREC_TC_3XTF32) return nlo_sdf_tc_launch(m, x, y, sbar, n, s, jx, jy, st);
+  return nlo_sdf_simt_launch(m, x, y, sbar, n, s, jx, jy, st);
+}
+
+int nlo_sdf_hess(nlo_sdf_model* m, const float* x, const float* y, const float* sbar, size_t n,
+                 float* hxx, float* hxy, float* hyy, void* stream) {
+  if (!m) return nlo_fail("null model");
+  if (n == 0) return 0;
+  if (!x || !y) return nlo_fail("null coordinate array");
+  NLO_CUDA(cudaSetDevice(m->device));
+  return nlo_sdf_simt_hess_launch(m, x, y, sbar, n, hxx, hxy, hyy, (cudaStream_t)stream);
+}
+
+static int ensure_io(nlo_sdf_model* m, size_t floats) {
+  if (m->io_cap < floats) {
+    if (m->d_io) cudaFree(m->d_io);
+    m->d_io = nullptr; m->io_cap = 0;
+    NLO_CUDA(cudaMalloc(&m->d_io, floats * sizeof(float)));
+    m->io_cap = floats;
+  }
+  return 0;
+}
+
+// Host-buffer evaluation on the model's private stream.  Pinned caller buffers move at full PCIe
+// speed; pageable ones are staged by the driver.
+int nlo_sdf_eval_host(nlo_sdf_model* m, const float* x, const float* y, const float* sbar, size_t n,
+                      float* s, float* jx, float* jy) {
+  if (!m) return nlo_fail("null model");
+  if (n == 0) return 0;
+  if (!x || !y) return nlo_fail("null coordinate array");
+  NLO_CUDA(cudaSetDevice(m->device));
+  const size_t n_in = sbar ? 3 : 2;
+  if (ensure_io(m, (n_in + 3) * n)) return 1;
+  float* d = m->d_io;
+  cudaStream_t st = m->stream;
+  NLO_CUDA(cudaMemcpyAsync(d, x, n * sizeof(float), cudaMemcpyHostToDevice, st));
+  NLO_CUDA(cudaMemcpyAsync(d + n, y, n * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (sbar) NLO_CUDA(cudaMemcpyAsync(d + 2 * n, sbar, n * sizeof(float), cudaMemcpyHostToDevice, st));
+  float* ds = d + n_in * n; float* djx = ds + n; float* djy = djx + n;
+  int rc = (m->prec == NLO_PREC_TC_3XTF32)
+               ? nlo_sdf_tc_launch(m, d, d + n, sbar ? d + 2 * n : nullptr, n, s ? ds : nullptr, jx ? djx : nullptr, jy ? djy : nullptr, st)
+               : nlo_sdf_simt_launch(m, d, d + n, sbar ? d + 2 * n : nullptr, n, s ? ds : nullptr, jx ? djx : nullptr, jy ? djy : nullptr, st);
+  if (rc) return rc;
+  if (s) NLO_CUDA(cudaMemcpyAsync(s, ds, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (jx) NLO_CUDA(cudaMemcpyAsync(jx, djx, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (jy) NLO_CUDA(cudaMemcpyAsync(jy, djy, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  NLO_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int nlo_sdf_hess_host(nlo_sdf_model* m, const float* x, const float* y, const float* sbar, size_t n,
+                      float* hxx, float* hxy, float* hyy) {
+  if (!m) return nlo_fail("null model");
+  if (n == 0) return 0;
+  NLO_CUDA(cudaSetDevice(m->device));
+  if (ensure_io(m, 6 * n)) return 1;
+  float* d = m->d_io; cudaStream_t st = m->stream;
+  NLO_CUDA(cudaMemcpyAsync(d, x, n * sizeof(float), cudaMemcpyHostToDevice, st));
+  NLO_CUDA(cudaMemcpyAsync(d + n, y, n * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (sbar) NLO_CUDA(cudaMemcpyAsync(d + 2 * n, sbar, n * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (nlo_sdf_simt_hess_launch(m, d, d + n, sbar ? d + 2 * n : nullptr, n, d + 3 * n, d + 4 * n, d + 5 * n, st)) return 1;
+  if (hxx) NLO_CUDA(cudaMemcpyAsync(hxx, d + 3 * n, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (hxy) NLO_CUDA(cudaMemcpyAsync(hxy, d + 4 * n, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (hyy) NLO_CUDA(cudaMemcpyAsync(hyy, d + 5 * n, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  NLO_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ---- CasADi external ABI (replaces _l4c_generated/nn_sdf.cpp) ----------------------------------------
+static std::mutex g_mu;
+static nlo_sdf_model* g_model = nullptr;
+static bool g_model_owned = false;
+static long long g_batch = 0;
+static std::vector<long long> g_sp[8];
+static std::vector<float> g_hbuf;
+
+int nlo_casadi_bind(nlo_sdf_model* m) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_model_owned && g_model) nlo_sdf_destroy(g_model);
+  g_model = m; g_model_owned = false;
+  return 0;
+}
+
+static long long batch_size() {
+  if (g_batch <= 0) { const char* e = getenv("NLO_B200_BATCH"); g_batch = e ? atoll(e) : 1; if (g_batch <= 0) g_batch = 1; }
+  return g_batch;
+}
+int nlo_casadi_set_batch(long long n) {
+  if (n <= 0) return nlo_fail("batch must be positive");
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_batch = n;
+  for (auto& v : g_sp) v.clear();
+  return 0;
+}
+
+static nlo_sdf_model* casadi_model() {
+  if (g_model) return g_model;
+  const char* path = getenv("NLO_B200_WEIGHTS");
+  if (!path) { nlo_fail("no model bound: call nlo_casadi_bind() or set NLO_B200_WEIGHTS=<file.nlow>"); return nullptr; }
+  const char* dev = getenv("NLO_B200_DEVICE");
+  nlo_sdf_model* m = nullptr;
+  if (nlo_sdf_load(path, dev ? atoi(dev) : 0, &m)) return nullptr;
+  g_model = m; g_model_owned = true;
+  return m;
+}
+
+// mode 0: value, 1: jac, 2: adj1, 3: jac_adj1.  in: x[P], y[P] doubles (column-major P x 2).
+static int casadi_eval(int mode, long long P, const double* p, const double* seed, double* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  nlo_sdf_model* m = casadi_model();
+  if (!m) { fprintf(stderr, "[nlo_b200] %s\n", g_err); return 1; }
+  const size_t n = (size_t)P;
+  g_hbuf.resize(6 * n);
+  float* hx = g_hbuf.data(); float* hy = hx + n; float* hs = hy + n; float* o0 = hs + n; float* o1 = o0 + n; float* o2 = o1 + n;
+  for (size_t i = 0; i < n; ++i) { hx[i] = p ? (float)p[i] : 0.f; hy[i] = p ? (float)p[n + i] : 0.f; hs[i] = seed ? (float)seed[i] : 0.f; }
+  const bool use_seed = (mode == 2 || mode == 3);   // NULL seed == zeros (CasADi convention)
+  int rc;
+  if (mode == 0) rc = nlo_sdf_eval_host(m, hx, hy, nullptr, n, o0, nullptr, nullptr);
+  else if (mode == 1 || mode == 2) rc = nlo_sdf_eval_host(m, hx, hy, use_seed ? hs : nullptr, n, nullptr, o0, o1);
+  else rc = nlo_sdf_hess_host(m, hx, hy, hs, n, o0, o1, o2);
+  if (rc) { fprintf(stderr, "[nlo_b200] %s\n", g_err); return 1; }
+  if (mode == 0) for (size_t i = 0; i < n; ++i) out[i] = o0[i];
+  else if (mode == 1 || mode == 2) for (size_t i = 0; i < n; ++i) { out[i] = o0[i]; out[n + i] = o1[i]; }
+  else for (size_t i = 0; i < n; ++i) {                  // column-major over the 4-per-point pattern
+    out[2 * i] = o0[i]; out[2 * i + 1] = o1[i]; out[2 * n + 2 * i] = o1[i]; out[2 * n + 2 * i + 1] = o2[i];
+  }
+  return 0;
+}
+
+static const long long s_in0[3] = {1, 2, 1};
+static const long long s_out0[3] = {1, 1, 1};
+long long nn_sdf_n_in(void) { return 1; }
+long long nn_sdf_n_out(void) { return 1; }
+const long long* nn_sdf_sparsity_in(long long i) { return i == 0 ? s_in0 : nullptr; }
+const long long* nn_sdf_sparsity_out(long long i) { return i == 0 ? s_out0 : nullptr; }
+void nn_sdf_incref(void) {}
+void nn_sdf_decref(void) {}
+int nn_sdf(const double** arg, double** res, long long*, double*, int) {
+  if (!res || !res[0]) return 0;
+  return casadi_eval(0, 1, arg ? arg[0] : nullptr, nullptr, res[0]);
+}
+long long jac_nn_sdf_n_in(void) { return 2; }
+long long jac_nn_sdf_n_out(void) { return 1; }
+int jac_nn_sdf(const double** arg, double** res, long long*, double*, int) {
+  if (!res || !res[0]) return 0;
+  return casadi_eval(1, 1, arg ? arg[0] : nullptr, nullptr, res[0]);
+}
+long long adj1_nn_sdf_n_in(void) { return 3; }
+long long adj1_nn_sdf_n_out(void) { return 1; }
+int adj1_nn_sdf(const double** arg, double** res, long long*, double*, int) {
+  // adj1 [i0, out_o0, adj_o0] -> [out_adj_i0]   (nn_sdf.cpp:80)
+  if (!res || !res[0]) return 0;
+  return casadi_eval(2, 1, arg ? arg[0] : nullptr, arg ? arg[2] : nullptr, res[0]);
+}
+long long jac_adj1_nn_sdf_n_in(void) { return 4; }
+long long jac_adj1_nn_sdf_n_out(void) { return 3; }
+static int jac_adj1_common(long long P, const double** arg, double** res) {
+  // jac_adj1 [i0, out_o0, adj_o0, out_adj_i0] -> [jac_adj_i0_i0, jac_adj_i0_out_o0, jac_adj_i0_adj_o0]  (nn_sdf.cpp:92)
+  if (!res) return 0;
+  if (res[1] != nullptr) { nlo_fail("jac_adj_i0_out_o0 is not provided"); fprintf(stderr, "[nlo_b200] %s\n", g_err); return 1; }
+  if (res[2] != nullptr) { nlo_fail("jac_adj_i0_adj_o0 is not provided"); fprintf(stderr, "[nlo_b200] %s\n", g_err); return 1; }
+  if (res[0] == nullptr) { nlo_fail("only jac_adj_i0_i0 can be provided"); fprintf(stderr, "[nlo_b200] %s\n", g_err); return 1; }
+  return casadi_eval(3, P, arg ? arg[0] : nullptr, arg ? arg[2] : nullptr, res[0]);
+}
+int jac_adj1_nn_sdf(const double** arg, double** res, long long*, double*, int) {
+  if (!res || !res[0]) return jac_adj1_common(1, arg, res);
+  // single point: dense 2x2 column-major {hxx, hxy, hxy, hyy}
+  double tmp[4];
+  double* r2[3] = {tmp, res[1], res[2]};
+  int rc = jac_adj1_common(1, arg, r2);
+  if (!rc) { res[0][0] = tmp[0]; res[0][1] = tmp[1]; res[0][2] = tmp[2]; res[0][3] = tmp[3]; }
+  return rc;
+}
+
+// batched forms ------------------------------------------------------------------------------------------
+static const long long* dense_sp(int slot, long long r, long long c) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto& v = g_sp[slot];
+  if (v.empty()) { v = {r, c, 1}; }
+  return v.data();
+}
+long long nn_sdf_batch_n_in(void) { return 1; }
+long long nn_sdf_batch_n_out(void) { return 1; }
+const long long* nn_sdf_batch_sparsity_in(long long i) { return i == 0 ? dense_sp(0, batch_size(), 2) : nullptr; }
+const long long* nn_sdf_batch_sparsity_out(long long i) { return i == 0 ? dense_sp(1, batch_size(), 1) : nullptr; }
+int nn_sdf_batch(const double** arg, double** res, long long*, double*, int) {
+  if (!res || !res[0]) return 0;
+  return casadi_eval(0, batch_size(), arg ? arg[0] : nullptr, nullptr, res[0]);
+}
+long long jac_nn_sdf_batch_n_in(void) { return 2; }
+long long jac_nn_sdf_batch_n_out(void) { return 1; }
+const long long* jac_nn_sdf_batch_sparsity_in(long long i) {
+  return i == 0 ? dense_sp(0, batch_size(), 2) : i == 1 ? dense_sp(1, batch_size(), 1) : nullptr;
+}
+const long long* jac_nn_sdf_batch_sparsity_out(long long i) {
+  if (i != 0) return nullptr;
+  const long long P = batch_size();
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto& v = g_sp[2];
+  if (v.empty()) {           // P x 2P, column c holds row c % P
+    v.reserve(2 + 2 * P + 1 + 2 * P);
+    v.push_back(P); v.push_back(2 * P);
+    for (long long c = 0; c <= 2 * P; ++c) v.push_back(c);
+    for (long long c = 0; c < 2 * P; ++c) v.push_back(c % P);
+  }
+  return v.data();
+}
+int jac_nn_sdf_batch(const double** arg, double** res, long long*, double*, int) {
+  if (!res || !res[0]) return 0;
+  return casadi_eval(1, batch_size(), arg ? arg[0] : nullptr, nullptr, res[0]);
+}
+long long adj1_nn_sdf_batch_n_in(void) { return 3; }
+long long adj1_nn_sdf_batch_n_out(void) { return 1; }
+const long long* adj1_nn_sdf_batch_sparsity_in(long long i) {
+  return i == 0 ? dense_sp(0, batch_size(), 2) : (i == 1 || i == 2) ? dense_sp(1, batch_size(), 1) : nullptr;
+}
+const long long* adj1_nn_sdf_batch_sparsity_out(long long i) { return i == 0 ? dense_sp(0, batch_size(), 2) : nullptr; }
+int adj1_nn_sdf_batch(const double** arg, double** res, long long*, double*, int) {
+  if (!res || !res[0]) return 0;
+  return casadi_eval(2, batch_size(), arg ? arg[0] : nullptr, arg ? arg[2] : nullptr, res[0]);
+}
+long long jac_adj1_nn_sdf_batch_n_in(void) { return 4; }
+long long jac_adj1_nn_sdf_batch_n_out(void) { return 3; }
+const long long* jac_adj1_nn_sdf_batch_sparsity_in(long long i) {
+  return (i == 0 || i == 3) ? dense_sp(0, batch_size(), 2) : (i == 1 || i == 2) ? dense_sp(1, batch_size(), 1) : nullptr;
+}
+const long long* jac_adj1_nn_sdf_batch_sparsity_out(long long i) {
+  const long long P = batch_size();
+  if (i == 0) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto& v = g_sp[3];
+    if (v.empty()) {         // 2P x 2P, column c holds rows {c % P, c % P + P}
+      v.push_back(2 * P); v.push_back(2 * P);
+      for (long long c = 0; c <= 2 * P; ++c) v.push_back(2 * c);
+      for (long long c = 0; c < 2 * P; ++c) { v.push_back(c % P); v.push_back(c % P + P); }
+    }
+    return v.data();
+  }
+  if (i == 1 || i == 2) {    // structurally empty 2P x P blocks
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto& v = g_sp[4];
+    if (v.empty()) { v.push_back(2 * P); v.push_back(P); for (long long c = 0; c <= P; ++c) v.push_back(0); }
+    return v.data();
+  }
+  return nullptr;
+}
+int jac_adj1_nn_sdf_batch(const double** arg, double** res, long long*, double*, int) {
+  if (!res) return 0;
+  // outputs 1 and 2 are structurally empty here, so CasADi may pass non-NULL zero-length buffers: ignore them
+  if (!res[0]) return 0;
+  return casadi_eval(3, batch_size(), arg ? arg[0] : nullptr, arg ? arg[2] : nullptr, res[0]);
+}
+
+// ---- NLP -------------------------------------------------------------------------------------------------
+int nlo_nlp_create(const nlo_nlp_desc* desc, nlo_sdf_model* model, int device, nlo_nlp** out) {
+  if (!out) return nlo_fail("null out");
+  *out = nullptr;
+  if (!desc) return nlo_fail("null descriptor");
+  if (desc->sdf_mode == NLO_SDF_LEARNED && !model) return nlo_fail("learned-SDF mode needs a model");
+  if (desc->sdf_mode > NLO_SDF_CIRCLES) return nlo_fail("unknown sdf_mode");
+  int ndev = nlo_device_count();
+  if (ndev <= 0) return nlo_fail("no CUDA device available: libnlo_b200 has no CPU fallback");
+  if (device < 0 || device >= ndev) return nlo_fail("device %d out of range", device);
+  if (model && model->device != device) return nlo_fail("model lives on device %d, nlp requested on %d", model->device, device);
+  NLO_CUDA(cudaSetDevice(device));
+  nlo_nlp* p = new (std::nothrow) nlo_nlp();
+  if (!p) return nlo_fail("out of host memory");
+  p->desc = *desc; p->model = model; p->device = device;
+  p->d_tables = nullptr; p->cap_P = 0; p->d_px = p->d_py = p->d_s = p->d_jx = p->d_jy = nullptr;
+  p->host_cap_P = 0; p->d_aos = p->d_w = p->d_g = p->d_jac = p->d_f = p->d_grad = nullptr;
+  p->h_pinned = nullptr; p->h_pinned_cap = 0; p->stream = nullptr;
+  std::vector<int> nzmap, copy_row, copy_var, copy_emit;
+  if (nlo_nlp_build_layout(desc, &p->L, &p->rows_ccs, &p->cols_ccs, &nzmap, &copy_row, &copy_var, &copy_emit)) { delete p; return 1; }
+  if (cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) { delete p; return nlo_fail("cannot query device"); }
+  const int nc = (int)copy_row.size();
+  std::vector<int> tables(nzmap);
+  tables.insert(tables.end(), copy_row.begin(), copy_row.end());
+  tables.insert(tables.end(), copy_var.begin(), copy_var.end());
+  for (int i = 0; i < nc; ++i) tables.push_back(nzmap[copy_emit[i]]);
+  if (cudaMalloc(&p->d_tables, tables.size() * sizeof(int)) != cudaSuccess ||
+      cudaMemcpy(p->d_tables, tables.data(), tables.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
+    nlo_nlp_destroy(p); return nlo_fail("device allocation failed");
+  }
+  p->L.nzmap = p->d_tables; p->L.copy_row = p->d_tables + nzmap.size();
+  p->L.copy_var = p->L.copy_row + nc; p->L.copy_nz = p->L.copy_var + nc; p->L.n_copy = nc;
+  if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess) { nlo_nlp_destroy(p); return nlo_fail("stream creation failed"); }
+  *out = p;
+  return 0;
+}
+
+void nlo_nlp_destroy(nlo_nlp* p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  float* bufs[] = {p->d_px, p->d_py, p->d_s, p->d_jx, p->d_jy, p->d_aos, p->d_w, p->d_g, p->d_jac, p->d_f, p->d_grad};
+  for (float* b : bufs) if (b) cudaFree(b);
+  if (p->d_tables) cudaFree(p->d_tables);
+  if (p->h_pinned) cudaFreeHost(p->h_pinned);
+  if (p->stream) cudaStreamDestroy(p->stream);
+  delete p;
+}
+
+long long nlo_nlp_n_w(const nlo_nlp* p) { return p ? p->L.n_w : -1; }
+long long nlo_nlp_n_g(const nlo_nlp* p) { return p ? p->L.n_g : -1; }
+long long nlo_nlp_nnz_jac(const nlo_nlp* p) { return p ? p->L.nnz : -1; }
+long long nlo_nlp_n_sdf_points(const nlo_nlp* p) { return p ? (long long)(p->L.N + 1) * p->L.nb : -1; }
+
+int nlo_nlp_jac_sparsity(const nlo_nlp* p, int32_t* colind, int32_t* row) {
+  if (!p || !colind || !row) return nlo_fail("null argument");
+  const int n_w = p->L.n_w, nnz = p->L.nnz;
+  for (int c = 0; c <= n_w; ++c) colind[c] = 0;
+  for (int i = 0; i < nnz; ++i) { colind[p->cols_ccs[i] + 1]++; row[i] = p->rows_ccs[i]; }
+  for (int c = 0; c < n_w; ++c) colind[c + 1] += colind[c];
+  return 0;
+}
+
+static int ensure_work(nlo_nlp* p, size_t P) {
+  if (p->cap_P >= P) return 0;
+  float** bufs[] = {&p->d_px, &p->d_py, &p->d_s, &p->d_jx, &p->d_jy};
+  for (float** b : bufs) { if (*b) cudaFree(*b); *b = nullptr; }
+  p->cap_P = 0;
+  const size_t n = (size_t)(p->L.N + 1) * p->L.nb * P;
+  for (float** b : bufs) NLO_CUDA(cudaMalloc(b, n * sizeof(float)));
+  p->cap_P = P;
+  return 0;
+}
+
+int nlo_nlp_eval(nlo_nlp* p, const float* w, size_t P, size_t ld, float* g, float* jac, float* f, float* grad_f, void* stream) {
+  if (!p) return nlo_fail("null nlp");
+  if (P == 0) return 0;
+  if (!w) return nlo_fail("null w");
+  if (ld < P) return nlo_fail("ld (%zu) < P (%zu)", ld, P);
+  NLO_CUDA(cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((g || jac) && ensure_work(p, P)) return 1;
+  if (nlo_nlp_launch_assembly(p, w, P, ld, g, jac, f, grad_f, st, 0)) return 1;
+  if (g || jac) {
+    if (p->L.sdf_mode == NLO_SDF_LEARNED) {
+      const size_t n = (size_t)(p->L.N + 1) * p->L.nb * P;
+      if (nlo_sdf_eval(p->model, p->d_px, p->d_py, nullptr, n, p->d_s, jac ? p->d_jx : nullptr, jac ? p->d_jy : nullptr, st)) return 1;
+    }
+    if (nlo_nlp_launch_assembly(p, w, P, ld, g, jac, f, grad_f, st, 1)) return 1;
+  }
+  return 0;
+}
+
+int nlo_nlp_violation(nlo_nlp* p, const float* g, const float* lbg, const float* ubg, size_t P, size_t ld, float* viol, void* stream) {
+  if (!p || !g || !lbg || !ubg || !viol) return nlo_fail("null argument");
+  NLO_CUDA(cudaSetDevice(p->device));
+  return nlo_launch_violation(p->L.n_g, g, lbg, ubg, P, ld, viol, p->sm_count, (cudaStream_t)stream);
+}
+
+int nlo_transpose_to_soa(const float* aos, float* soa, size_t P, size_t rows, size_t ld, void* stream) {
+  int dev = 0, sm = 148;
+  cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+  return nlo_launch_transpose(aos, soa, P, rows, rows, ld, sm, (cudaStream_t)stream);
+}
+int nlo_transpose_to_aos(const float* soa, float* aos, size_t P, size_t rows, size_t ld, void* stream) {
+  int dev = 0, sm = 148;
+  cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+  return nlo_launch_transpose(soa, aos, rows, P, ld, rows, sm, (cudaStream_t)stream);
+}
+
+static int ensure_host_bufs(nlo_nlp* p, size_t P) {
+  if (p->host_cap_P >= P) return 0;
+  float** bufs[] = {&p->d_aos, &p->d_w, &p->d_g, &p->d_jac, &p->d_f, &p->d_grad};
+  for (float** b : bufs) { if (*b) cudaFree(*b); *b = nullptr; }
+  p->host_cap_P = 0;
+  const NlpDev& L = p->L;
+  const size_t big = (size_t)std::max(std::max(L.n_w, L.n_g), L.nnz);
+  NLO_CUDA(cudaMalloc(&p->d_aos, big * P * sizeof(float)));
+  NLO_CUDA(cudaMalloc(&p->d_w, (size_t)L.n_w * P * sizeof(float)));
+  NLO_CUDA(cudaMalloc(&p->d_g, (size_t)L.n_g * P * sizeof(float)));
+  NLO_CUDA(cudaMalloc(&p->d_jac, (size_t)L.nnz * P * sizeof(float)));
+  NLO_CUDA(cudaMalloc(&p->d_f, P * sizeof(float)));
+  NLO_CUDA(cudaMalloc(&p->d_grad, (size_t)L.n_w * P * sizeof(float)));
+  p->host_cap_P = P;
+  return 0;
+}
+
+int nlo_nlp_eval_host(nlo_nlp* p, const float* w_host, size_t P, float* g_host, float* jac_host, float* f_host, float* grad_host) {
+  if (!p) return nlo_fail("null nlp");
+  if (P == 0) return 0;
+  if (!w_host) return nlo_fail("null w");
+  NLO_CUDA(cudaSetDevice(p->device));
+  if (ensure_host_bufs(p, P)) return 1;
+  const NlpDev& L = p->L;
+  cudaStream_t st = p->stream;
+  NLO_CUDA(cudaMemcpyAsync(p->d_aos, w_host, (size_t)L.n_w * P * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (nlo_launch_transpose(p->d_aos, p->d_w, P, L.n_w, L.n_w, P, p->sm_count, st)) return 1;
+  if (nlo_nlp_eval(p, p->d_w, P, P, g_host ? p->d_g : nullptr, jac_host ? p->d_jac : nullptr, f_host ? p->d_f : nullptr,
+                   grad_host ? p->d_grad : nullptr, st)) return 1;
+  if (g_host) {
+    if (nlo_launch_transpose(p->d_g, p->d_aos, L.n_g, P, P, L.n_g, p->sm_count, st)) return 1;
+    NLO_CUDA(cudaMemcpyAsync(g_host, p->d_aos, (size_t)L.n_g * P * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  if (jac_host) {
+    if (nlo_launch_transpose(p->d_jac, p->d_aos, L.nnz, P, P, L.nnz, p->sm_count, st)) return 1;
+    NLO_CUDA(cudaMemcpyAsync(jac_host, p->d_aos, (size_t)L.nnz * P * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  if (grad_host) {
+    if (nlo_launch_transpose(p->d_grad, p->d_aos, L.n_w, P, P, L.n_w, p->sm_count, st)) return 1;
+    NLO_CUDA(cudaMemcpyAsync(grad_host, p->d_aos, (size_t)L.n_w * P * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  if (f_host) NLO_CUDA(cudaMemcpyAsync(f_host, p->d_f, P * sizeof(float), cudaMemcpyDeviceToHost, st));
+  NLO_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+}  // extern "C"

