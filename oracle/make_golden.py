@@ -167,7 +167,7 @@ def make_nlp_golden(ref: Path, net: so.SdfNet, names, P: int = 3):
         raw, opti = record_reference_nlp(ref, yaml_path)
         spec = no.NlpSpec.from_yaml_dict(raw)
         rows, cols, f_g, f_j, f_f = lambdify_reference(opti, net64)
-        w = golden_w(spec, P, seed=7)
+        w = golden_w(spec, P, seed=7).astype(np.float32).astype(np.float64)   # fp32-representable: identical inputs on both sides
         assert len(opti.w_symbols()) == spec.n_w, (len(opti.w_symbols()), spec.n_w)
         g = np.array([np.asarray(f_g(*wi), float) for wi in w])
         jv = np.array([np.asarray(f_j(*wi), float) for wi in w])
