@@ -301,10 +301,10 @@ def run_ours(args):
     if rank != 0:
         return
     prec = model.precision
-    if prec == "tc3xtf32":
+    if prec == "tc3xf16":
         peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
         bound = "tensor"
-        peak_note = f"{peak_src} cuBLAS bf16 sustained; the kernel runs 3 TF32 passes at half the bf16 rate, so its algorithmic ceiling is peak/6"
+        peak_note = f"{peak_src} cuBLAS bf16 sustained; the kernel runs 3 fp16 passes (hi.hi, hi.lo, lo.hi) per contraction, so its algorithmic ceiling is peak/3"
     else:
         sm_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
         peak = model_sm_count(L, local_rank) * 128 * 2 * sm_mhz * 1e6 / 1e12
@@ -314,7 +314,7 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32" if prec == "fp32" else "f32 (3xTF32 tensor tiles, fp32 accumulate)", "data": "synthetic",
+        "dtype": "f32" if prec == "fp32" else "f32 (tcgen05 split-fp16 x3 tiles, fp32 accumulate)", "data": "synthetic",
         "config": {"workload": f"{YAML} x {P} multi-starts per GPU: NLP eval g + nnz(dg/dw) + f + grad f, SoA fp32 resident in HBM",
                    "problems_per_gpu": P, "sdf_points_per_step_per_gpu": n_pts, "n_w": prob.n_w, "n_g": prob.n_g, "nnz_jac": prob.nnz,
                    "sdf_model": "mlp ReLU 2-128-128-1 (synthetic seeded weights)", "sdf_precision": prec,
@@ -325,7 +325,7 @@ def run_ours(args):
         "e2e": {"value": world * n_pts / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s * 1e3, "api": "nlo_nlp_eval_host (pinned host buffers, problem-major)"},
         "gpu_launches": launches,
-        "roofline": {"kernel": "sdf_tc_kernel" if prec == "tc3xtf32" else "sdf_simt_kernel", "bound": bound, "achieved": achieved,
+        "roofline": {"kernel": "sdf_tc_kernel" if prec == "tc3xf16" else "sdf_simt_kernel", "bound": bound, "achieved": achieved,
                      "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                      "flop_per_point": FLOP_PER_POINT, "points_per_launch": n_pts, "kernel_ms": k_ms, "peak_source": peak_note,
                      "kernel_share_of_step": k_ms / ms_per_step,
@@ -355,7 +355,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--problems", type=int, default=65536, help="multi-start problems per GPU")
-    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tc3xtf32"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tc3xf16"])
     ap.add_argument("--cpu-problems", type=int, default=2048, help="problems per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

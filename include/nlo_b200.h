@@ -62,7 +62,7 @@ enum { NLO_KIND_MLP = 0, NLO_KIND_FOURIER = 1, NLO_KIND_SIREN = 2 };
 /* arithmetic of the H x H layers                                                              */
 enum {
   NLO_PREC_FP32_SIMT = 0,   /* FP32 FMA pipe                                                   */
-  NLO_PREC_TC_3XTF32 = 1,   /* tcgen05 tensor tiles, error-compensated 3xTF32, FP32 accumulate */
+  NLO_PREC_TC_3XF16 = 1,    /* tcgen05 tensor tiles, error-compensated split-fp16 (3 products), FP32 accumulate */
   NLO_PREC_AUTO      = 2    /* tensor tiles when the shape supports them (H in {64,128})       */
 };
 

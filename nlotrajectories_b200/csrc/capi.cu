@@ -78,7 +78,7 @@ int nlo_sdf_create(const nlo_sdf_desc* desc, const float* weights, size_t n_weig
   m->prec = NLO_PREC_FP32_SIMT;
   if (nlo_sdf_tc_supported(desc)) {
     if (nlo_sdf_tc_prepare(m, weights)) { nlo_sdf_destroy(m); return 1; }
-    m->prec = NLO_PREC_TC_3XTF32;     // AUTO default: tensor tiles when the shape supports them
+    m->prec = NLO_PREC_TC_3XF16;     // AUTO default: tensor tiles when the shape supports them
   }
   const char* env = getenv("NLO_B200_PRECISION");
   if (env && !strcmp(env, "fp32")) m->prec = NLO_PREC_FP32_SIMT;
@@ -130,10 +130,10 @@ void nlo_sdf_destroy(nlo_sdf_model* m) {
 
 int nlo_sdf_set_precision(nlo_sdf_model* m, int prec) {
   if (!m) return nlo_fail("null model");
-  if (prec == NLO_PREC_AUTO) prec = nlo_sdf_tc_supported(&m->desc) ? NLO_PREC_TC_3XTF32 : NLO_PREC_FP32_SIMT;
-  if (prec == NLO_PREC_TC_3XTF32 && !nlo_sdf_tc_supported(&m->desc))
+  if (prec == NLO_PREC_AUTO) prec = nlo_sdf_tc_supported(&m->desc) ? NLO_PREC_TC_3XF16 : NLO_PREC_FP32_SIMT;
+  if (prec == NLO_PREC_TC_3XF16 && !nlo_sdf_tc_supported(&m->desc))
     return nlo_fail("tensor-tile path supports H in {64,128} with one hidden matrix; this model has H=%u M=%u", m->desc.hidden, m->desc.n_hidden_mats);
-  if (prec != NLO_PREC_TC_3XTF32 && prec != NLO_PREC_FP32_SIMT) return nlo_fail("unknown precision %d", prec);
+  if (prec != NLO_PREC_TC_3XF16 && prec != NLO_PREC_FP32_SIMT) return nlo_fail("unknown precision %d", prec);
   m->prec = prec;
   return 0;
 }
@@ -147,7 +147,7 @@ int nlo_sdf_eval(nlo_sdf_model* m, const float* x, const float* y, const float* 
   if (!x || !y) return nlo_fail("null coordinate array");
   NLO_CUDA(cudaSetDevice(m->device));
   cudaStream_t st = (cudaStream_t)stream;
-  if (m->prec == NLO_PREC_TC_3XTF32) return nlo_sdf_tc_launch(m, x, y, sbar, n, s, jx, jy, st);
+  if (m->prec == NLO_PREC_TC_3XF16) return nlo_sdf_tc_launch(m, x, y, sbar, n, s, jx, jy, st);
   return nlo_sdf_simt_launch(m, x, y, sbar, n, s, jx, jy, st);
 }
 
@@ -186,7 +186,7 @@ int nlo_sdf_eval_host(nlo_sdf_model* m, const float* x, const float* y, const fl
   NLO_CUDA(cudaMemcpyAsync(d + n, y, n * sizeof(float), cudaMemcpyHostToDevice, st));
   if (sbar) NLO_CUDA(cudaMemcpyAsync(d + 2 * n, sbar, n * sizeof(float), cudaMemcpyHostToDevice, st));
   float* ds = d + n_in * n; float* djx = ds + n; float* djy = djx + n;
-  int rc = (m->prec == NLO_PREC_TC_3XTF32)
+  int rc = (m->prec == NLO_PREC_TC_3XF16)
                ? nlo_sdf_tc_launch(m, d, d + n, sbar ? d + 2 * n : nullptr, n, s ? ds : nullptr, jx ? djx : nullptr, jy ? djy : nullptr, st)
                : nlo_sdf_simt_launch(m, d, d + n, sbar ? d + 2 * n : nullptr, n, s ? ds : nullptr, jx ? djx : nullptr, jy ? djy : nullptr, st);
   if (rc) return rc;

@@ -50,8 +50,9 @@ struct nlo_sdf_model {
   float* d_w;                // fp32 blob
   size_t n_w;
   // tensor-path operand images (built on demand by sdf_tc.cu)
-  float* d_tc;               // W1 split hi/lo in UMMA core-matrix order + small vectors
+  void* d_tc;                // W1 split into fp16 hi | lo images in UMMA core-matrix order
   size_t tc_bytes;
+  float tc_params[8];        // TcParams of sdf_tc.cu (scales and bounds)
   // scratch for the host-buffer entry points
   float* d_io; size_t io_cap;        // device staging
   float* h_io; size_t h_cap;         // pinned staging

@@ -1,24 +1,32 @@
 // K1 (tcgen05 form): fused learned-SDF value + Jacobian / adjoint with the two H x H contractions on
-// 5th-generation tensor cores, error-compensated 3xTF32 with FP32 accumulation in tensor memory.
+// 5th-generation tensor cores: error-compensated split-fp16 (hi + lo, three products) with FP32
+// accumulation in tensor memory, i.e. FP32-grade results at three kind::f16 MMA passes.
 //
 // Replaces the per-point TorchScript calls behind _l4c_generated/nn_sdf.cpp:57-83 (nn_sdf, jac_nn_sdf,
 // adj1_nn_sdf) for networks 2 -> H -> H -> 1 with H in {64, 128}: the benchmark model
 // (scripts/run_benchmark.py:65 with benchmarks/*.yaml model: hidden_dim 128, num_hidden_layers 2) and
 // the shipped FourierMLP-128 (_l4c_generated/nn_sdf.pt).
 //
-// One persistent CTA per SM, 128 threads, tile = 128 points; thread t owns point t == TMEM lane t, so
-// there is no cross-thread traffic at all:
-//   layer 0 (SIMT)   h0 = phi0(W0 p + b0)                       -> split hi/lo -> tcgen05.st -> A (TMEM)
+// Persistent CTAs of 128 threads (512/TMEM_COLS of them share an SM, so one CTA's SIMT phases overlap the
+// other's MMAs); tile = 128 points; thread t owns point t == TMEM lane t, so there is no cross-thread
+// traffic at all:
+//   layer 0 (SIMT)   h0 = phi0(W0 p + b0)  -> row-scaled, split into fp16 hi/lo -> tcgen05.st -> A (TMEM)
 //   GEMM 1 (tcgen05) Z1[128 x H] = H0 . W1^T   3 passes (lo.hi, hi.lo, hi.hi), B = W1 K-major in smem
 //   epilogue 1       tcgen05.ld Z1; s = w2.phi(z1+b1)+b2; g1 = sbar*w2*phi'(z1+b1) -> hi/lo -> A (TMEM)
-//   GEMM 2 (tcgen05) G0[128 x H] = G1 . W1     same smem bytes read through an MN-major descriptor
+//   GEMM 2 (tcgen05) G0[128 x H] = G1 . W1     the same smem bytes read through an MN-major descriptor
 //   epilogue 2       tcgen05.ld G0; g0 = G0 * phi0'(a0); J = g0 . W0
-// W1 is split once on the host into tf32 hi + tf32 lo and stored in UMMA core-matrix order (no swizzle):
-// element (n,k) at ((k/4)*(H/8) + n/8)*128 + (n%8)*16 + (k%4)*4 bytes, which is simultaneously the
+// fp16 has tf32's 11 significant bits at twice the MMA rate and half the bytes; its narrow exponent is
+// handled by exact power-of-two scaling: W1 by one global factor (host), every A row (= point) by its own
+// factor from a cheap bound on the row, both undone in the epilogue.
+// W1*S is split once on the host into fp16 hi + fp16 lo, each stored in UMMA core-matrix order (no swizzle):
+// element (n,k) at ((k/8)*(H/8) + n/8)*128 + (n%8)*16 + (k%8)*2 bytes, which is simultaneously the
 // canonical K-major layout of B(n,k) = W1[n][k] (LBO = 16H, SBO = 128) and the canonical MN-major layout
-// of B'(i,j) = W1[j][i] (LBO = 128, SBO = 16H).
+// of B'(i,j) = W1[j][i] (LBO = 128, SBO = 16H).  (tf32 cannot do this: its MN-major form exists only in the
+// 128B_BASE32B swizzle, which has no K-major twin, and two tf32 images of W1 do not fit in shared memory.)
 #include "nlo_common.cuh"
+#include <cuda_fp16.h>
 #include <vector>
+#include <cmath>
 #include <cstring>
 
 namespace {
@@ -54,9 +62,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// D[tmem] (+)= A[tmem] . B[smem descriptor], kind::tf32, issued by one thread
-__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+// D[tmem] (+)= A[tmem] . B[smem descriptor], kind::f16, issued by one thread
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
                ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -67,9 +75,9 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
   return d;                                     // base_offset 0, lbo_mode 0, layout_type 0 = no swizzle
 }
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, int b_mn_major) {
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, int b_mn_major) {
   return (1u << 4)                              // D format: F32
-         | (2u << 7) | (2u << 10)               // A, B format: TF32
+         | (0u << 7) | (0u << 10)               // A, B format: F16
          | ((uint32_t)b_mn_major << 16)         // B major: 0 = K, 1 = MN
          | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
@@ -97,81 +105,118 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
       ::TM_W32(v), "r"(taddr) : "memory");
 }
 
-// tf32 split of a runtime value: hi = top 19 bits (truncation), lo = exact remainder, truncated the same way
-__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
-  hi = __float_as_uint(v) & 0xffffe000u;
-  lo = __float_as_uint(v - __uint_as_float(hi)) & 0xffffe000u;
+// Split two row-scaled values into fp16 hi + fp16 lo and pack the pair the way a 16-bit A operand sits in
+// tensor memory (element 2c in the low half of column c, element 2c+1 in the high half).
+// hi = value truncated to 11 significant bits (exact in fp16 inside the normal range), lo = exact remainder.
+__device__ __forceinline__ void split_pack_f16(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  const float h0 = __uint_as_float(__float_as_uint(v0) & 0xffffe000u);
+  const float h1 = __uint_as_float(__float_as_uint(v1) & 0xffffe000u);
+  const __half2 ph = __floats2half2_rn(h0, h1);
+  const __half2 pl = __floats2half2_rn(v0 - h0, v1 - h1);
+  hi = *reinterpret_cast<const uint32_t*>(&ph);
+  lo = *reinterpret_cast<const uint32_t*>(&pl);
+}
+// 2^e such that bound * 2^e lies in [2^13, 2^15): exact scaling into fp16's comfortable range
+__device__ __forceinline__ void row_scale(float bound, float& sc, float& inv) {
+  const int ex = (int)((__float_as_uint(bound) >> 23) & 0xffu) - 127;      // floor(log2(bound)) for normal bound
+  int e = 13 - ex;
+  e = e < -60 ? -60 : (e > 60 ? 60 : e);
+  sc = __uint_as_float((uint32_t)(127 + e) << 23);
+  inv = __uint_as_float((uint32_t)(127 - e) << 23);
 }
 
 template <int A>
 __device__ __forceinline__ void act_vd(float a, int rt, float prm, float& v, float& d) {
   if (A >= 0) nlo_phi_d(a, A, prm, v, d); else nlo_phi_d(a, rt, prm, v, d);
 }
+// upper bound of |phi(a)| given |a| <= ba, and of |phi'|
+__device__ __forceinline__ float act_bound(int act, float prm, float ba) {
+  switch (act) {
+    case NLO_ACT_TANH: case NLO_ACT_SIGMOID: case NLO_ACT_SIN: return 1.f;
+    case NLO_ACT_COS_SCALE: return fabsf(prm);
+    default: return ba;
+  }
+}
+__device__ __forceinline__ float act_dbound(int act, float prm) {
+  switch (act) {
+    case NLO_ACT_SIGMOID: return 0.25f;
+    case NLO_ACT_SIN: case NLO_ACT_COS_SCALE: return fabsf(prm);
+    default: return 1.f;
+  }
+}
 
 constexpr int TILE = 128;
 
+struct TcParams {          // built by nlo_sdf_tc_prepare
+  float inv_sw;            // 1 / (power-of-two scale applied to W1 in the fp16 images)
+  float max_w0x, max_w0y, max_b0, max_w2;
+};
+
 template <int H>
-struct TcSmem {
-  static constexpr int B_FLOATS = 2 * H * H;                        // hi | lo images
+struct TcCfg {
+  static constexpr int IMG_HALFS = H * H;                           // one fp16 image
   static constexpr int VEC_FLOATS = 2 * H + 3 * H + 4;              // W0 | b0 | b1 | w2 | b_out,pad
-  static constexpr size_t BYTES = (size_t)(B_FLOATS + VEC_FLOATS) * 4 + 16;
-  static constexpr uint32_t TMEM_COLS = (3 * H <= 256) ? 256 : 512;
+  static constexpr size_t BYTES = (size_t)2 * IMG_HALFS * 2 + (size_t)VEC_FLOATS * 4 + 16;
+  static constexpr uint32_t TMEM_COLS = 2 * H;                      // A hi H/2 | A lo H/2 | D H   (power of two)
+  static constexpr int CTAS_PER_SM = 512 / TMEM_COLS;
 };
 
 template <int H, int ACT0, int ACT>
-__global__ void __launch_bounds__(TILE, 1) sdf_tc_kernel(SdfNetDev net, const float* __restrict__ bimg, const float* __restrict__ x,
-                                                         const float* __restrict__ y, const float* __restrict__ sbar, size_t n,
-                                                         float* __restrict__ s_out, float* __restrict__ jx_out, float* __restrict__ jy_out) {
+__global__ void __launch_bounds__(TILE) sdf_tc_kernel(SdfNetDev net, TcParams prm_tc, const __half* __restrict__ bimg,
+                                                      const float* __restrict__ x, const float* __restrict__ y,
+                                                      const float* __restrict__ sbar, size_t n, float* __restrict__ s_out,
+                                                      float* __restrict__ jx_out, float* __restrict__ jy_out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  float* sB = reinterpret_cast<float*>(smem_raw);
-  float* sW0 = sB + TcSmem<H>::B_FLOATS;
+  __half* sB = reinterpret_cast<__half*>(smem_raw);                  // hi image | lo image
+  float* sW0 = reinterpret_cast<float*>(smem_raw + (size_t)2 * TcCfg<H>::IMG_HALFS * 2);
   float* sb0 = sW0 + 2 * H;
   float* sb1 = sb0 + H;
   float* sw2 = sb1 + H;
   uint64_t* mbar = reinterpret_cast<uint64_t*>(sw2 + H + 4);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
   const int t = threadIdx.x, warp = t >> 5;
-  constexpr int NCH = H / 32;
 
   // ---- one-time setup: operand images to smem, barrier, tensor memory ---------------------------------------
   {
-    const float4* src = reinterpret_cast<const float4*>(bimg);
-    float4* dst = reinterpret_cast<float4*>(sB);
-    for (int i = t; i < TcSmem<H>::B_FLOATS / 4; i += TILE) dst[i] = src[i];
+    const uint4* src = reinterpret_cast<const uint4*>(bimg);
+    uint4* dst = reinterpret_cast<uint4*>(sB);
+    for (int i = t; i < 2 * TcCfg<H>::IMG_HALFS / 8; i += TILE) dst[i] = src[i];
     for (int i = t; i < 2 * H; i += TILE) sW0[i] = net.w[net.off_W0() + i];
     for (int i = t; i < H; i += TILE) { sb0[i] = net.w[net.off_b0() + i]; sb1[i] = net.w[net.off_b(1) + i]; sw2[i] = net.w[net.off_wout() + i]; }
     if (t == 0) { sw2[H] = net.w[net.off_bout()]; mbar_init(mbar, 1); }
     fence_async_smem();                          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
   }
-  if (warp == 0) tmem_alloc(tmem_slot, TcSmem<H>::TMEM_COLS);
+  if (warp == 0) tmem_alloc(tmem_slot, TcCfg<H>::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-  const uint32_t COL_AHI = 0, COL_ALO = H, COL_D = 2 * H;
+  constexpr uint32_t COL_AHI = 0, COL_ALO = H / 2, COL_D = H;
   const float bout = sw2[H];
   const bool want_jac = (jx_out != nullptr) || (jy_out != nullptr);
+  const int act0 = ACT0 >= 0 ? ACT0 : net.act0, act = ACT >= 0 ? ACT : net.act;
   const float prm0 = net.p0, prm = net.p;
-  const uint32_t sB_hi = smem_u32(sB), sB_lo = smem_u32(sB + H * H);
-  constexpr uint32_t IDESC_FWD = umma_idesc_tf32(TILE, H, 0), IDESC_BWD = umma_idesc_tf32(TILE, H, 1);
+  const uint32_t sB_hi = smem_u32(sB), sB_lo = smem_u32(sB + TcCfg<H>::IMG_HALFS);
+  constexpr uint32_t IDESC_FWD = umma_idesc_f16(TILE, H, 0), IDESC_BWD = umma_idesc_f16(TILE, H, 1);
+  const float g1_bound = prm_tc.max_w2 * act_dbound(act, prm);
   uint32_t phase = 0;
 
-  // one thread issues the 3 x (H/8) MMAs of a GEMM and commits them to the mbarrier
+  // one thread issues the 3 x (H/16) MMAs of a GEMM and commits them to the mbarrier
   auto issue_gemm = [&](bool fwd) {
     if (t == 0) {
       tc_fence_after();
       const uint32_t lbo = fwd ? 16u * H : 128u, sbo = fwd ? 128u : 16u * H;
-      const uint32_t kstep_bytes = fwd ? 32u * H : 128u;
+      const uint32_t kstep_bytes = fwd ? 32u * H : 256u;     // 16 k: two K-adjacent core matrices
       const uint32_t idesc = fwd ? IDESC_FWD : IDESC_BWD;
 #pragma unroll
       for (int pass = 0; pass < 3; ++pass) {               // smallest terms first: lo.hi, hi.lo, hi.hi
         const uint32_t a_col = (pass == 0) ? COL_ALO : COL_AHI;
         const uint32_t b_base = (pass == 1) ? sB_lo : sB_hi;
-#pragma unroll 4
-        for (int ks = 0; ks < H / 8; ++ks) {
-          tc_mma_tf32_ts(tmem_base + COL_D, tmem_base + a_col + ks * 8, umma_desc(b_base + ks * kstep_bytes, lbo, sbo), idesc,
-                         (pass | ks) != 0);
+#pragma unroll
+        for (int ks = 0; ks < H / 16; ++ks) {
+          tc_mma_f16_ts(tmem_base + COL_D, tmem_base + a_col + ks * 8, umma_desc(b_base + ks * kstep_bytes, lbo, sbo), idesc,
+                        (pass | ks) != 0);
         }
       }
       tc_commit(mbar);
@@ -186,18 +231,23 @@ __global__ void __launch_bounds__(TILE, 1) sdf_tc_kernel(SdfNetDev net, const fl
     const float px = x[ic], py = y[ic];
     const float seed = sbar ? sbar[ic] : 1.f;
 
-    // ---- layer 0 -> A operand ----------------------------------------------------------------------------------
+    // ---- layer 0 -> A operand (row-scaled fp16 hi/lo) ------------------------------------------------------------
+    float sc0, inv0;
+    row_scale(act_bound(act0, prm0, fmaf(fabsf(px), prm_tc.max_w0x, fmaf(fabsf(py), prm_tc.max_w0y, prm_tc.max_b0))) + 1e-30f, sc0, inv0);
 #pragma unroll 1
-    for (int c = 0; c < NCH; ++c) {
+    for (int c = 0; c < H / 64; ++c) {
       uint32_t hi[32], lo[32];
 #pragma unroll
       for (int q = 0; q < 32; ++q) {
-        const int k = c * 32 + q;
-        const float2 w0 = *reinterpret_cast<const float2*>(sW0 + 2 * k);
-        const float a = fmaf(w0.x, px, fmaf(w0.y, py, sb0[k]));
-        float v;
-        if (ACT0 >= 0) v = nlo_phi(a, ACT0, prm0); else v = nlo_phi(a, net.act0, prm0);
-        split_tf32(v, hi[q], lo[q]);
+        float v[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int k = c * 64 + 2 * q + e;
+          const float2 w0 = *reinterpret_cast<const float2*>(sW0 + 2 * k);
+          const float a = fmaf(w0.x, px, fmaf(w0.y, py, sb0[k]));
+          v[e] = nlo_phi(a, act0, prm0) * sc0;
+        }
+        split_pack_f16(v[0], v[1], hi[q], lo[q]);
       }
       tmem_st32(lane_base + COL_AHI + c * 32, hi);
       tmem_st32(lane_base + COL_ALO + c * 32, lo);
@@ -211,20 +261,30 @@ __global__ void __launch_bounds__(TILE, 1) sdf_tc_kernel(SdfNetDev net, const fl
 
     // ---- epilogue 1: value, and g1 -> A operand ------------------------------------------------------------------
     float s = bout;
+    const float unscale1 = inv0 * prm_tc.inv_sw;
+    float sc1, inv1;
+    row_scale(fabsf(seed) * g1_bound + 1e-30f, sc1, inv1);
+    const float seed_sc = seed * sc1;
 #pragma unroll 1
-    for (int c = 0; c < NCH; ++c) {
-      uint32_t z[32];
-      tmem_ld32(lane_base + COL_D + c * 32, z);
+    for (int c = 0; c < H / 64; ++c) {
+      uint32_t z[64];
+      tmem_ld32(lane_base + COL_D + c * 64, *reinterpret_cast<uint32_t(*)[32]>(&z[0]));
+      tmem_ld32(lane_base + COL_D + c * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&z[32]));
       tc_wait_ld();
       uint32_t hi[32], lo[32];
 #pragma unroll
       for (int q = 0; q < 32; ++q) {
-        const int j = c * 32 + q;
-        float v, d;
-        act_vd<ACT>(__uint_as_float(z[q]) + sb1[j], net.act, prm, v, d);
-        const float w2 = sw2[j];
-        s = fmaf(w2, v, s);
-        split_tf32(seed * w2 * d, hi[q], lo[q]);
+        float g[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = c * 64 + 2 * q + e;
+          float v, d;
+          act_vd<ACT>(fmaf(__uint_as_float(z[2 * q + e]), unscale1, sb1[j]), net.act, prm, v, d);
+          const float w2 = sw2[j];
+          s = fmaf(w2, v, s);
+          g[e] = seed_sc * w2 * d;
+        }
+        split_pack_f16(g[0], g[1], hi[q], lo[q]);
       }
       if (want_jac) {
         tmem_st32(lane_base + COL_AHI + c * 32, hi);
@@ -241,8 +301,9 @@ __global__ void __launch_bounds__(TILE, 1) sdf_tc_kernel(SdfNetDev net, const fl
       tc_fence_after();
       // ---- epilogue 2: through layer 0 to the Jacobian ---------------------------------------------------------------
       float jx = 0.f, jy = 0.f;
+      const float unscale2 = inv1 * prm_tc.inv_sw;
 #pragma unroll 1
-      for (int c = 0; c < NCH; ++c) {
+      for (int c = 0; c < H / 32; ++c) {
         uint32_t gz[32];
         tmem_ld32(lane_base + COL_D + c * 32, gz);
         tc_wait_ld();
@@ -258,7 +319,7 @@ __global__ void __launch_bounds__(TILE, 1) sdf_tc_kernel(SdfNetDev net, const fl
           jy = fmaf(g0, w0.y, jy);
         }
       }
-      if (valid) { if (jx_out) jx_out[i] = jx; if (jy_out) jy_out[i] = jy; }
+      if (valid) { if (jx_out) jx_out[i] = jx * unscale2; if (jy_out) jy_out[i] = jy * unscale2; }
     }
     // the next tile's tcgen05.st / MMA must not overtake this tile's TMEM reads
     tc_fence_before();
@@ -266,27 +327,23 @@ __global__ void __launch_bounds__(TILE, 1) sdf_tc_kernel(SdfNetDev net, const fl
     tc_fence_after();
   }
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, TcSmem<H>::TMEM_COLS);
-}
-
-inline uint32_t rn_tf32_bits(float v) {
-  uint32_t b; memcpy(&b, &v, 4);
-  if ((b & 0x7f800000u) == 0x7f800000u) return b & 0xffffe000u;
-  b += 0x00000fffu + ((b >> 13) & 1u);
-  return b & 0xffffe000u;
+  if (warp == 0) tmem_dealloc(tmem_base, TcCfg<H>::TMEM_COLS);
 }
 
 template <int H, int ACT0, int ACT>
 int launch_tc(nlo_sdf_model* m, const float* x, const float* y, const float* sbar, size_t n, float* s, float* jx, float* jy, cudaStream_t st) {
   auto kfn = sdf_tc_kernel<H, ACT0, ACT>;
-  // H = 64 allocates 256 TMEM columns: at most two CTAs may share an SM, so pad the request past a third of the SM
-  size_t smem = TcSmem<H>::BYTES;
-  if (H == 64 && smem < 80 * 1024) smem = 80 * 1024;
+  // exactly 512 / TMEM_COLS CTAs may share an SM (tensor memory is 512 columns): pad the smem request so that no more fit
+  size_t smem = TcCfg<H>::BYTES;
+  const size_t floor_smem = (size_t)(227 * 1024) / (TcCfg<H>::CTAS_PER_SM + 1) + 1024;
+  if (smem < floor_smem) smem = floor_smem;
   NLO_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const size_t tiles = (n + TILE - 1) / TILE;
-  const size_t cap = (size_t)m->sm_count * (H == 64 ? 2 : 1);
+  const size_t cap = (size_t)m->sm_count * TcCfg<H>::CTAS_PER_SM;
   const int grid = (int)(tiles < cap ? tiles : cap);
-  kfn<<<grid, TILE, smem, st>>>(m->net(), m->d_tc, x, y, sbar, n, s, jx, jy);
+  TcParams prm;
+  memcpy(&prm, m->tc_params, sizeof(prm));
+  kfn<<<grid, TILE, smem, st>>>(m->net(), prm, reinterpret_cast<const __half*>(m->d_tc), x, y, sbar, n, s, jx, jy);
   NLO_CHECK_LAUNCH();
   return 0;
 }
@@ -297,27 +354,42 @@ bool nlo_sdf_tc_supported(const nlo_sdf_desc* d) {
   return d->n_hidden_mats == 1 && (d->hidden == 64 || d->hidden == 128);
 }
 
-// Split W1 into tf32 hi + lo (round-to-nearest) and store both in UMMA core-matrix order.
+// Scale W1 by a power of two into fp16's range, split into fp16 hi + lo, store both in UMMA core-matrix order.
 int nlo_sdf_tc_prepare(nlo_sdf_model* m, const float* w) {
   const int H = (int)m->desc.hidden;
-  const float* W1 = w + 3 * H;                          // blob order: W0[H][2], b0[H], W1[H][H], ...
-  std::vector<float> img((size_t)2 * H * H);
+  const float* W0 = w;
+  const float* b0 = w + 2 * H;
+  const float* W1 = w + 3 * H;                          // blob order: W0[H][2], b0[H], W1[H][H], b1[H], w_out[H], b_out
+  const float* w2 = W1 + (size_t)H * H + H;
+  float mx = 0.f;
+  for (size_t i = 0; i < (size_t)H * H; ++i) mx = fmaxf(mx, fabsf(W1[i]));
+  int ex = 0;
+  if (mx > 0.f) frexpf(mx, &ex);                        // mx = f * 2^ex, f in [0.5, 1)
+  const float sw = ldexpf(1.f, 14 - ex);                // max |W1| * sw in [2^13, 2^14)
+  TcParams prm;
+  prm.inv_sw = 1.f / sw;
+  prm.max_w0x = prm.max_w0y = prm.max_b0 = prm.max_w2 = 0.f;
+  for (int k = 0; k < H; ++k) {
+    prm.max_w0x = fmaxf(prm.max_w0x, fabsf(W0[2 * k])); prm.max_w0y = fmaxf(prm.max_w0y, fabsf(W0[2 * k + 1]));
+    prm.max_b0 = fmaxf(prm.max_b0, fabsf(b0[k])); prm.max_w2 = fmaxf(prm.max_w2, fabsf(w2[k]));
+  }
+  static_assert(sizeof(TcParams) <= sizeof(m->tc_params), "tc_params too small");
+  memcpy(m->tc_params, &prm, sizeof(prm));
+  std::vector<__half> img((size_t)2 * H * H);
   for (int nn = 0; nn < H; ++nn)
     for (int k = 0; k < H; ++k) {
-      const float v = W1[(size_t)nn * H + k];
-      const uint32_t hb = rn_tf32_bits(v);
-      float hi; memcpy(&hi, &hb, 4);
-      const uint32_t lb = rn_tf32_bits(v - hi);
-      float lo; memcpy(&lo, &lb, 4);
-      const size_t off = ((size_t)(k / 4) * (H / 8) + nn / 8) * 32 + (nn % 8) * 4 + (k % 4);   // in floats
+      const float v = W1[(size_t)nn * H + k] * sw;
+      const __half hi = __float2half_rn(v);
+      const __half lo = __float2half_rn(v - __half2float(hi));
+      const size_t off = ((size_t)(k / 8) * (H / 8) + nn / 8) * 64 + (nn % 8) * 8 + (k % 8);   // in halfs
       img[off] = hi;
       img[(size_t)H * H + off] = lo;
     }
   if (m->d_tc) cudaFree(m->d_tc);
   m->d_tc = nullptr;
-  NLO_CUDA(cudaMalloc(&m->d_tc, img.size() * sizeof(float)));
-  NLO_CUDA(cudaMemcpy(m->d_tc, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice));
-  m->tc_bytes = img.size() * sizeof(float);
+  NLO_CUDA(cudaMalloc(&m->d_tc, img.size() * sizeof(__half)));
+  NLO_CUDA(cudaMemcpy(m->d_tc, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  m->tc_bytes = img.size() * sizeof(__half);
   return 0;
 }
 

@@ -9,7 +9,7 @@ PKG = Path(__file__).resolve().parent
 LIB_PATH = PKG / "libnlo_b200.so"
 
 NLO_MAX_CIRCLES = 8
-PREC_FP32_SIMT, PREC_TC_3XTF32, PREC_AUTO = 0, 1, 2
+PREC_FP32_SIMT, PREC_TC_3XF16, PREC_AUTO = 0, 1, 2
 
 
 class NloError(RuntimeError):

@@ -157,12 +157,12 @@ class LearnedSDF:
             self.set_precision(precision)
 
     def set_precision(self, precision: str) -> None:
-        code = {"fp32": _lib.PREC_FP32_SIMT, "tc3xtf32": _lib.PREC_TC_3XTF32, "auto": _lib.PREC_AUTO}[precision]
+        code = {"fp32": _lib.PREC_FP32_SIMT, "tc3xf16": _lib.PREC_TC_3XF16, "auto": _lib.PREC_AUTO}[precision]
         _lib.check(self._L.nlo_sdf_set_precision(self._h, code))
 
     @property
     def precision(self) -> str:
-        return {0: "fp32", 1: "tc3xtf32"}[self._L.nlo_sdf_get_precision(self._h)]
+        return {0: "fp32", 1: "tc3xf16"}[self._L.nlo_sdf_get_precision(self._h)]
 
     @property
     def handle(self):

@@ -31,11 +31,11 @@ nets = {"relu128": so.synthetic_mlp(128, 1, seed=0), "relu64": so.synthetic_mlp(
         "tanh64": so.synthetic_mlp(64, 1, seed=4, act=so.ACT_TANH)}
 for name, net in nets.items():
     for n in (128, 1000, 100003):
-        for prec in ("tc3xtf32", "fp32"):
+        for prec in ("tc3xf16", "fp32"):
             run(net, n, prec, name)
 # timing
 net = nets["relu128"]
-for prec in ("tc3xtf32", "fp32"):
+for prec in ("tc3xf16", "fp32"):
     model = LearnedSDF(to_weights(net), precision=prec)
     n = 1 << 22
     x = torch.rand(n, device="cuda") * 2 - 0.5; y = torch.rand(n, device="cuda") * 2 - 0.5
