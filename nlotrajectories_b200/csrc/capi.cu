@@ -71,6 +71,7 @@ int nlo_sdf_create(const nlo_sdf_desc* desc, const float* weights, size_t n_weig
   if (!m) return nlo_fail("out of host memory");
   memset(m, 0, sizeof(*m));
   m->desc = *desc; m->device = device; m->n_w = n_weights;
+  { static std::mutex mu; static unsigned long long next_uid = 1; std::lock_guard<std::mutex> lk(mu); m->uid = next_uid++; }
   NLO_CUDA(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device));
   NLO_CUDA(cudaMalloc(&m->d_w, n_weights * sizeof(float)));
   NLO_CUDA(cudaMemcpy(m->d_w, weights, n_weights * sizeof(float), cudaMemcpyHostToDevice));
@@ -147,6 +148,7 @@ int nlo_sdf_eval(nlo_sdf_model* m, const float* x, const float* y, const float* 
   if (!x || !y) return nlo_fail("null coordinate array");
   NLO_CUDA(cudaSetDevice(m->device));
   cudaStream_t st = (cudaStream_t)stream;
+  if ((jx == nullptr) != (jy == nullptr)) return nlo_fail("jx and jy must be requested together");
   if (m->prec == NLO_PREC_TC_3XF16) return nlo_sdf_tc_launch(m, x, y, sbar, n, s, jx, jy, st);
   return nlo_sdf_simt_launch(m, x, y, sbar, n, s, jx, jy, st);
 }

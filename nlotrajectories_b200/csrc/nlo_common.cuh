@@ -47,12 +47,14 @@ struct nlo_sdf_model {
   int device;
   int sm_count;
   int prec;                  // resolved NLO_PREC_*
+  unsigned long long uid;    // process-unique id (owner tag of per-device constant memory)
   float* d_w;                // fp32 blob
   size_t n_w;
   // tensor-path operand images (built on demand by sdf_tc.cu)
   void* d_tc;                // W1 split into fp16 hi | lo images in UMMA core-matrix order
   size_t tc_bytes;
   float tc_params[8];        // TcParams of sdf_tc.cu (scales and bounds)
+  float tc_const[648];       // TcConst of sdf_tc.cu (small vectors handed to the kernel as a __grid_constant__ parameter)
   // scratch for the host-buffer entry points
   float* d_io; size_t io_cap;        // device staging
   float* h_io; size_t h_cap;         // pinned staging

@@ -7,9 +7,11 @@
 // (scripts/run_benchmark.py:65 with benchmarks/*.yaml model: hidden_dim 128, num_hidden_layers 2) and
 // the shipped FourierMLP-128 (_l4c_generated/nn_sdf.pt).
 //
-// Persistent CTAs of 128 threads (512/TMEM_COLS of them share an SM, so one CTA's SIMT phases overlap the
-// other's MMAs); tile = 128 points; thread t owns point t == TMEM lane t, so there is no cross-thread
-// traffic at all:
+// Persistent CTAs of 256 threads, two per SM (so one CTA's SIMT phases overlap the other's MMAs);
+// tile = 128 points == the 128 TMEM lanes; a point is owned by two threads (one per half of the columns)
+// that meet only to add three partial sums per point through shared memory.  The small vectors (W0, b0, b1, w2) sit in __constant__ memory and every loop is
+// fully unrolled, so they enter the arithmetic as constant-bank operands and shared memory is left to
+// the tensor core's B-operand fetches:
 //   layer 0 (SIMT)   h0 = phi0(W0 p + b0)  -> row-scaled, split into fp16 hi/lo -> tcgen05.st -> A (TMEM)
 //   GEMM 1 (tcgen05) Z1[128 x H] = H0 . W1^T   3 passes (lo.hi, hi.lo, hi.hi), B = W1 K-major in smem
 //   epilogue 1       tcgen05.ld Z1; s = w2.phi(z1+b1)+b2; g1 = sbar*w2*phi'(z1+b1) -> hi/lo -> A (TMEM)
@@ -27,6 +29,8 @@
 #include <cuda_fp16.h>
 #include <vector>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace {
@@ -107,12 +111,12 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
 
 // Split two row-scaled values into fp16 hi + fp16 lo and pack the pair the way a 16-bit A operand sits in
 // tensor memory (element 2c in the low half of column c, element 2c+1 in the high half).
-// hi = value truncated to 11 significant bits (exact in fp16 inside the normal range), lo = exact remainder.
+// hi = round-to-nearest fp16 of the value, lo = round-to-nearest fp16 of the exact remainder (22 significant bits
+// together).  One packed conversion each way; the unpack + subtract run on the FMA pipe, keeping the ALU pipe free.
 __device__ __forceinline__ void split_pack_f16(float v0, float v1, uint32_t& hi, uint32_t& lo) {
-  const float h0 = __uint_as_float(__float_as_uint(v0) & 0xffffe000u);
-  const float h1 = __uint_as_float(__float_as_uint(v1) & 0xffffe000u);
-  const __half2 ph = __floats2half2_rn(h0, h1);
-  const __half2 pl = __floats2half2_rn(v0 - h0, v1 - h1);
+  const __half2 ph = __floats2half2_rn(v0, v1);
+  const float2 hf = __half22float2(ph);
+  const __half2 pl = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
   hi = *reinterpret_cast<const uint32_t*>(&ph);
   lo = *reinterpret_cast<const uint32_t*>(&pl);
 }
@@ -145,195 +149,312 @@ __device__ __forceinline__ float act_dbound(int act, float prm) {
   }
 }
 
-constexpr int TILE = 128;
+constexpr int TILE = 128;          // points per tile == TMEM lanes
 
 struct TcParams {          // built by nlo_sdf_tc_prepare
   float inv_sw;            // 1 / (power-of-two scale applied to W1 in the fp16 images)
   float max_w0x, max_w0y, max_b0, max_w2;
 };
+// Small vectors of the network live in __constant__ memory: with fully unrolled loops every use is an FFMA/FMUL
+// with a constant-bank operand (c[3][imm]) - no load instruction and no shared-memory bandwidth (which the tensor
+// core needs for its B-operand fetches).  One copy per device context; nlo_sdf_tc_launch re-uploads it, ordered on
+// the launch stream, whenever a different model is evaluated.
+struct TcConst {
+  float w0x[128], w0y[128], b0[128], b1[128], w2[128];
+  float bout;
+};
+__constant__ TcConst cst;
 
 template <int H>
 struct TcCfg {
   static constexpr int IMG_HALFS = H * H;                           // one fp16 image
-  static constexpr int VEC_FLOATS = 2 * H + 3 * H + 4;              // W0 | b0 | b1 | w2 | b_out,pad
-  static constexpr size_t BYTES = (size_t)2 * IMG_HALFS * 2 + (size_t)VEC_FLOATS * 4 + 16;
+  static constexpr size_t BYTES = (size_t)2 * IMG_HALFS * 2 + 2 * 128 * 2 * 4 + 16;
   static constexpr uint32_t TMEM_COLS = 2 * H;                      // A hi H/2 | A lo H/2 | D H   (power of two)
-  static constexpr int CTAS_PER_SM = 512 / TMEM_COLS;
+  // H = 128: TMEM allows two tiles per SM, so two threads share a point (256-thread CTAs) to have 16 warps per SM;
+  // H = 64: four tiles per SM fit, one thread per point (128-thread CTAs).
+  static constexpr int SPLIT = (H >= 128) ? 2 : 1;
+  static constexpr int THREADS = TILE * SPLIT;
+  static constexpr int CTAS_PER_SM = (512 / TMEM_COLS) > 4 ? 4 : (512 / TMEM_COLS);
 };
 
+template <int N> struct TmemIO;
+template <> struct TmemIO<32> {
+  __device__ static __forceinline__ void ld(uint32_t a, uint32_t (&v)[32]) { tmem_ld32(a, v); }
+  __device__ static __forceinline__ void st(uint32_t a, const uint32_t (&v)[32]) { tmem_st32(a, v); }
+};
+template <> struct TmemIO<16> {
+  __device__ static __forceinline__ void ld(uint32_t a, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(a) : "memory");
+  }
+  __device__ static __forceinline__ void st(uint32_t a, const uint32_t (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};"
+                 ::"r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+                   "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(a) : "memory");
+  }
+};
+
+struct TileCtx {
+  uint32_t tmem_base, lane_base, sB_hi, sB_lo, mbar_addr;
+  int act0, act;
+  float prm0, prm, inv_sw, max_w0x, max_w0y, max_b0, g1_bound;
+  long long* dbg;          // optional phase timeline (NLO_B200_TC_TIMELINE): 8 clock stamps per tile of CTA 0 / 1
+};
+
+// one thread issues the 3 x (H/16) MMAs of a GEMM and commits them to the mbarrier
+template <int H>
+__device__ __forceinline__ void issue_gemm(const TileCtx& c, bool fwd) {
+  constexpr uint32_t COL_AHI = 0, COL_ALO = H / 2, COL_D = H;
+  constexpr uint32_t IDESC_FWD = umma_idesc_f16(TILE, H, 0), IDESC_BWD = umma_idesc_f16(TILE, H, 1);
+  tc_fence_after();
+  const uint32_t lbo = fwd ? 16u * H : 128u, sbo = fwd ? 128u : 16u * H;
+  const uint32_t kstep_bytes = fwd ? 32u * H : 256u;     // 16 k: two K-adjacent core matrices
+  const uint32_t idesc = fwd ? IDESC_FWD : IDESC_BWD;
+#pragma unroll
+  for (int pass = 0; pass < 3; ++pass) {               // smallest terms first: lo.hi, hi.lo, hi.hi
+    const uint32_t a_col = (pass == 0) ? COL_ALO : COL_AHI;
+    const uint32_t b_base = (pass == 1) ? c.sB_lo : c.sB_hi;
+#pragma unroll
+    for (int ks = 0; ks < H / 16; ++ks) {
+      tc_mma_f16_ts(c.tmem_base + COL_D, c.tmem_base + a_col + ks * 8, umma_desc(b_base + ks * kstep_bytes, lbo, sbo), idesc,
+                    (pass | ks) != 0);
+    }
+  }
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(c.mbar_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_addr(uint32_t a, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+  } while (!ok);
+}
+
+// One tile (128 points).  Two threads own a point: HALF 0 (warps 0-3) the low half of the neurons / D columns,
+// HALF 1 (warps 4-7) the high half; they meet only to add three partial sums per point through shared memory.
+// Deliberately NOT inlined into the persistent loop: the constants are loop-invariant, and an inlined body makes
+// the compiler hoist hundreds of them into registers (and spill) instead of feeding them to the arithmetic from
+// the constant bank.
+template <int H, int ACT0, int ACT, bool FULL, int SPLIT, int HALF>
+__device__ __noinline__ uint32_t sdf_tc_tile(TileCtx c, uint32_t phase, float px, float py, float seed, bool want_jac,
+                                             float* __restrict__ part, float* __restrict__ s_ptr, float* __restrict__ j_ptr,
+                                             ptrdiff_t jy_off) {
+  constexpr int HH = H / SPLIT;                    // neurons per thread
+  constexpr int C0 = HALF * HH;                    // first neuron / D column of this thread
+  constexpr int NCH = HH / 32;                     // 32-neuron chunks per thread
+  constexpr uint32_t COL_AHI = HALF * (HH / 2), COL_ALO = H / 2 + HALF * (HH / 2), COL_D = H + C0;
+  const int pt = threadIdx.x & (TILE - 1);
+  long long* dbg = (c.dbg && (threadIdx.x & 127) == 0) ? c.dbg + HALF * 8 : nullptr;
+#define TC_STAMP(i) do { if (dbg) dbg[i] = clock64(); } while (0)
+  TC_STAMP(0);
+  // ---- layer 0 -> A operand (row-scaled fp16 hi/lo) ------------------------------------------------------------
+  float sc0, inv0;
+  row_scale(act_bound(c.act0, c.prm0, fmaf(fabsf(px), c.max_w0x, fmaf(fabsf(py), c.max_w0y, c.max_b0))) + 1e-30f, sc0, inv0);
+  auto layer0 = [&](int cc) {
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      float v[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int k = C0 + cc * 32 + 2 * q + e;
+        const float a = fmaf(cst.w0x[k], px, fmaf(cst.w0y[k], py, cst.b0[k]));
+        if (ACT0 >= 0) v[e] = nlo_phi(a, ACT0, c.prm0) * sc0; else v[e] = nlo_phi(a, c.act0, c.prm0) * sc0;
+      }
+      split_pack_f16(v[0], v[1], hi[q], lo[q]);
+    }
+    TmemIO<16>::st(c.lane_base + COL_AHI + cc * 16, hi);
+    TmemIO<16>::st(c.lane_base + COL_ALO + cc * 16, lo);
+  };
+  if (FULL) {
+#pragma unroll
+    for (int cc = 0; cc < NCH; ++cc) layer0(cc);
+  } else {
+#pragma unroll 1
+    for (int cc = 0; cc < NCH; ++cc) layer0(cc);
+  }
+  TC_STAMP(1);
+  tc_wait_st();
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) issue_gemm<H>(c, true);
+  TC_STAMP(2);
+  mbar_wait_addr(c.mbar_addr, phase); phase ^= 1;
+  tc_fence_after();
+  TC_STAMP(3);
+
+  // ---- epilogue 1: value, and g1 -> A operand ------------------------------------------------------------------
+  float s = HALF == 0 ? cst.bout : 0.f;
+  const float unscale1 = inv0 * c.inv_sw;
+  float sc1, inv1;
+  row_scale(fabsf(seed) * c.g1_bound + 1e-30f, sc1, inv1);
+  const float seed_sc = seed * sc1;
+  auto epi1 = [&](int cc) {
+    uint32_t z[32];
+    tmem_ld32(c.lane_base + COL_D + cc * 32, z);
+    tc_wait_ld();
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      float g[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = C0 + cc * 32 + 2 * q + e;
+        float v, d;
+        act_vd<ACT>(fmaf(__uint_as_float(z[2 * q + e]), unscale1, cst.b1[j]), c.act, c.prm, v, d);
+        s = fmaf(cst.w2[j], v, s);
+        g[e] = seed_sc * cst.w2[j] * d;
+      }
+      split_pack_f16(g[0], g[1], hi[q], lo[q]);
+    }
+    if (want_jac) {
+      TmemIO<16>::st(c.lane_base + COL_AHI + cc * 16, hi);
+      TmemIO<16>::st(c.lane_base + COL_ALO + cc * 16, lo);
+    }
+  };
+  if (FULL) {
+#pragma unroll
+    for (int cc = 0; cc < NCH; ++cc) epi1(cc);
+  } else {
+#pragma unroll 1
+    for (int cc = 0; cc < NCH; ++cc) epi1(cc);
+  }
+  float jx = 0.f, jy = 0.f;
+  if (want_jac) {
+    TC_STAMP(4);
+    tc_wait_st();
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) issue_gemm<H>(c, false);
+    TC_STAMP(5);
+    mbar_wait_addr(c.mbar_addr, phase); phase ^= 1;
+    tc_fence_after();
+    TC_STAMP(6);
+    // ---- epilogue 2: through layer 0 to the Jacobian ---------------------------------------------------------------
+    auto epi2 = [&](int cc) {
+      uint32_t gz[32];
+      tmem_ld32(c.lane_base + COL_D + cc * 32, gz);
+      tc_wait_ld();
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const int k = C0 + cc * 32 + q;
+        const float a = fmaf(cst.w0x[k], px, fmaf(cst.w0y[k], py, cst.b0[k]));
+        float v, d;
+        act_vd<ACT0>(a, c.act0, c.prm0, v, d);
+        const float g0 = __uint_as_float(gz[q]) * d;
+        jx = fmaf(g0, cst.w0x[k], jx);
+        jy = fmaf(g0, cst.w0y[k], jy);
+      }
+    };
+    if (FULL) {
+#pragma unroll
+      for (int cc = 0; cc < NCH; ++cc) epi2(cc);
+    } else {
+#pragma unroll 1
+      for (int cc = 0; cc < NCH; ++cc) epi2(cc);
+    }
+    const float unscale2 = inv1 * c.inv_sw;
+    jx *= unscale2; jy *= unscale2;
+  }
+  TC_STAMP(7);
+  if (SPLIT == 1) {
+    if (s_ptr) *s_ptr = s;
+    if (j_ptr) { j_ptr[0] = jx; j_ptr[jy_off] = jy; }
+    // the next tile's tcgen05.st / MMA must not overtake this tile's TMEM reads
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    return phase;
+  }
+  // ---- hand the other half what it stores: HALF 0 writes s and jx, HALF 1 writes jy ------------------------------
+  float* mine = part + (HALF * TILE + pt) * 2;
+  if (HALF == 0) { mine[0] = jy; } else { mine[0] = s; mine[1] = jx; }
+  // (this barrier also keeps the next tile's tcgen05.st / MMA from overtaking this tile's TMEM reads)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const float* other = part + ((1 - HALF) * TILE + pt) * 2;
+  if (HALF == 0) {
+    if (s_ptr) *s_ptr = s + other[0];
+    if (j_ptr) *j_ptr = jx + other[1];
+  } else {
+    if (j_ptr) *j_ptr = jy + other[0];
+  }
+  return phase;
+}
+
 template <int H, int ACT0, int ACT>
-__global__ void __launch_bounds__(TILE) sdf_tc_kernel(SdfNetDev net, TcParams prm_tc, const __half* __restrict__ bimg,
-                                                      const float* __restrict__ x, const float* __restrict__ y,
-                                                      const float* __restrict__ sbar, size_t n, float* __restrict__ s_out,
-                                                      float* __restrict__ jx_out, float* __restrict__ jy_out) {
+__global__ void __launch_bounds__(TcCfg<H>::THREADS, TcCfg<H>::CTAS_PER_SM)
+sdf_tc_kernel(SdfNetDev net, TcParams prm_tc, const __half* __restrict__ bimg, const float* __restrict__ x,
+              const float* __restrict__ y, const float* __restrict__ sbar, size_t n, float* __restrict__ s_out,
+              float* __restrict__ jx_out, float* __restrict__ jy_out, long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __half* sB = reinterpret_cast<__half*>(smem_raw);                  // hi image | lo image
-  float* sW0 = reinterpret_cast<float*>(smem_raw + (size_t)2 * TcCfg<H>::IMG_HALFS * 2);
-  float* sb0 = sW0 + 2 * H;
-  float* sb1 = sb0 + H;
-  float* sw2 = sb1 + H;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(sw2 + H + 4);
+  float* sPart = reinterpret_cast<float*>(smem_raw + (size_t)2 * TcCfg<H>::IMG_HALFS * 2);   // [2][TILE][2]
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(sPart + 2 * TILE * 2);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
   const int t = threadIdx.x, warp = t >> 5;
+  const int half = warp >> 2;
+  const int pt = t & (TILE - 1);
 
   // ---- one-time setup: operand images to smem, barrier, tensor memory ---------------------------------------
   {
     const uint4* src = reinterpret_cast<const uint4*>(bimg);
     uint4* dst = reinterpret_cast<uint4*>(sB);
-    for (int i = t; i < 2 * TcCfg<H>::IMG_HALFS / 8; i += TILE) dst[i] = src[i];
-    for (int i = t; i < 2 * H; i += TILE) sW0[i] = net.w[net.off_W0() + i];
-    for (int i = t; i < H; i += TILE) { sb0[i] = net.w[net.off_b0() + i]; sb1[i] = net.w[net.off_b(1) + i]; sw2[i] = net.w[net.off_wout() + i]; }
-    if (t == 0) { sw2[H] = net.w[net.off_bout()]; mbar_init(mbar, 1); }
+    for (int i = t; i < 2 * TcCfg<H>::IMG_HALFS / 8; i += TcCfg<H>::THREADS) dst[i] = src[i];
+    if (t == 0) mbar_init(mbar, 1);
     fence_async_smem();                          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
   }
   if (warp == 0) tmem_alloc(tmem_slot, TcCfg<H>::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-  constexpr uint32_t COL_AHI = 0, COL_ALO = H / 2, COL_D = H;
-  const float bout = sw2[H];
+  TileCtx c;
+  c.tmem_base = *tmem_slot;
+  c.lane_base = c.tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+  c.sB_hi = smem_u32(sB); c.sB_lo = smem_u32(sB + TcCfg<H>::IMG_HALFS);
+  c.mbar_addr = smem_u32(mbar);
+  c.act0 = ACT0 >= 0 ? ACT0 : net.act0; c.act = ACT >= 0 ? ACT : net.act;
+  c.prm0 = net.p0; c.prm = net.p; c.inv_sw = prm_tc.inv_sw;
+  c.max_w0x = prm_tc.max_w0x; c.max_w0y = prm_tc.max_w0y; c.max_b0 = prm_tc.max_b0;
+  c.g1_bound = prm_tc.max_w2 * act_dbound(c.act, c.prm);
   const bool want_jac = (jx_out != nullptr) || (jy_out != nullptr);
-  const int act0 = ACT0 >= 0 ? ACT0 : net.act0, act = ACT >= 0 ? ACT : net.act;
-  const float prm0 = net.p0, prm = net.p;
-  const uint32_t sB_hi = smem_u32(sB), sB_lo = smem_u32(sB + TcCfg<H>::IMG_HALFS);
-  constexpr uint32_t IDESC_FWD = umma_idesc_f16(TILE, H, 0), IDESC_BWD = umma_idesc_f16(TILE, H, 1);
-  const float g1_bound = prm_tc.max_w2 * act_dbound(act, prm);
+  constexpr bool FULL = (ACT0 == NLO_ACT_RELU && ACT == NLO_ACT_RELU);
   uint32_t phase = 0;
-
-  // one thread issues the 3 x (H/16) MMAs of a GEMM and commits them to the mbarrier
-  auto issue_gemm = [&](bool fwd) {
-    if (t == 0) {
-      tc_fence_after();
-      const uint32_t lbo = fwd ? 16u * H : 128u, sbo = fwd ? 128u : 16u * H;
-      const uint32_t kstep_bytes = fwd ? 32u * H : 256u;     // 16 k: two K-adjacent core matrices
-      const uint32_t idesc = fwd ? IDESC_FWD : IDESC_BWD;
-#pragma unroll
-      for (int pass = 0; pass < 3; ++pass) {               // smallest terms first: lo.hi, hi.lo, hi.hi
-        const uint32_t a_col = (pass == 0) ? COL_ALO : COL_AHI;
-        const uint32_t b_base = (pass == 1) ? sB_lo : sB_hi;
-#pragma unroll
-        for (int ks = 0; ks < H / 16; ++ks) {
-          tc_mma_f16_ts(tmem_base + COL_D, tmem_base + a_col + ks * 8, umma_desc(b_base + ks * kstep_bytes, lbo, sbo), idesc,
-                        (pass | ks) != 0);
-        }
-      }
-      tc_commit(mbar);
-    }
-  };
-
   const size_t n_tiles = (n + TILE - 1) / TILE;
-  for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const size_t i = tile * TILE + t;
+  int it = 0;
+  for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    // timeline: CTAs 0 and gridDim/2 (same SM on a 2-CTA/SM launch is not guaranteed; smid is recorded), first 64 tiles
+    c.dbg = (dbg && it < 64 && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2)) ? dbg + ((blockIdx.x ? 1 : 0) * 64 + it) * 16 : nullptr;
+    const size_t i = tile * TILE + pt;
     const bool valid = i < n;
     const size_t ic = valid ? i : n - 1;
-    const float px = x[ic], py = y[ic];
-    const float seed = sbar ? sbar[ic] : 1.f;
-
-    // ---- layer 0 -> A operand (row-scaled fp16 hi/lo) ------------------------------------------------------------
-    float sc0, inv0;
-    row_scale(act_bound(act0, prm0, fmaf(fabsf(px), prm_tc.max_w0x, fmaf(fabsf(py), prm_tc.max_w0y, prm_tc.max_b0))) + 1e-30f, sc0, inv0);
-#pragma unroll 1
-    for (int c = 0; c < H / 64; ++c) {
-      uint32_t hi[32], lo[32];
-#pragma unroll
-      for (int q = 0; q < 32; ++q) {
-        float v[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int k = c * 64 + 2 * q + e;
-          const float2 w0 = *reinterpret_cast<const float2*>(sW0 + 2 * k);
-          const float a = fmaf(w0.x, px, fmaf(w0.y, py, sb0[k]));
-          v[e] = nlo_phi(a, act0, prm0) * sc0;
-        }
-        split_pack_f16(v[0], v[1], hi[q], lo[q]);
-      }
-      tmem_st32(lane_base + COL_AHI + c * 32, hi);
-      tmem_st32(lane_base + COL_ALO + c * 32, lo);
+    const float px = x[ic], py = y[ic], seed = sbar ? sbar[ic] : 1.f;
+    if (TcCfg<H>::SPLIT == 1) {
+      // jx and jy are both written by the one owner of the point (both non-null whenever a Jacobian is requested through this path)
+      phase = sdf_tc_tile<H, ACT0, ACT, FULL, 1, 0>(c, phase, px, py, seed, want_jac, sPart, (valid && s_out) ? s_out + i : nullptr,
+                                                    (valid && jx_out) ? jx_out + i : nullptr, jy_out - jx_out);
+    } else if (half == 0) {
+      phase = sdf_tc_tile<H, ACT0, ACT, FULL, TcCfg<H>::SPLIT, 0>(c, phase, px, py, seed, want_jac, sPart,
+                                                                  (valid && s_out) ? s_out + i : nullptr,
+                                                                  (valid && jx_out) ? jx_out + i : nullptr, 0);
+    } else {
+      phase = sdf_tc_tile<H, ACT0, ACT, FULL, TcCfg<H>::SPLIT, TcCfg<H>::SPLIT - 1>(c, phase, px, py, seed, want_jac, sPart, nullptr,
+                                                                                   (valid && jy_out) ? jy_out + i : nullptr, 0);
     }
-    tc_wait_st();
-    tc_fence_before();
-    __syncthreads();
-    issue_gemm(true);
-    mbar_wait(mbar, phase); phase ^= 1;
-    tc_fence_after();
-
-    // ---- epilogue 1: value, and g1 -> A operand ------------------------------------------------------------------
-    float s = bout;
-    const float unscale1 = inv0 * prm_tc.inv_sw;
-    float sc1, inv1;
-    row_scale(fabsf(seed) * g1_bound + 1e-30f, sc1, inv1);
-    const float seed_sc = seed * sc1;
-#pragma unroll 1
-    for (int c = 0; c < H / 64; ++c) {
-      uint32_t z[64];
-      tmem_ld32(lane_base + COL_D + c * 64, *reinterpret_cast<uint32_t(*)[32]>(&z[0]));
-      tmem_ld32(lane_base + COL_D + c * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&z[32]));
-      tc_wait_ld();
-      uint32_t hi[32], lo[32];
-#pragma unroll
-      for (int q = 0; q < 32; ++q) {
-        float g[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int j = c * 64 + 2 * q + e;
-          float v, d;
-          act_vd<ACT>(fmaf(__uint_as_float(z[2 * q + e]), unscale1, sb1[j]), net.act, prm, v, d);
-          const float w2 = sw2[j];
-          s = fmaf(w2, v, s);
-          g[e] = seed_sc * w2 * d;
-        }
-        split_pack_f16(g[0], g[1], hi[q], lo[q]);
-      }
-      if (want_jac) {
-        tmem_st32(lane_base + COL_AHI + c * 32, hi);
-        tmem_st32(lane_base + COL_ALO + c * 32, lo);
-      }
-    }
-    if (valid && s_out) s_out[i] = s;
-    if (want_jac) {
-      tc_wait_st();
-      tc_fence_before();
-      __syncthreads();
-      issue_gemm(false);
-      mbar_wait(mbar, phase); phase ^= 1;
-      tc_fence_after();
-      // ---- epilogue 2: through layer 0 to the Jacobian ---------------------------------------------------------------
-      float jx = 0.f, jy = 0.f;
-      const float unscale2 = inv1 * prm_tc.inv_sw;
-#pragma unroll 1
-      for (int c = 0; c < H / 32; ++c) {
-        uint32_t gz[32];
-        tmem_ld32(lane_base + COL_D + c * 32, gz);
-        tc_wait_ld();
-#pragma unroll
-        for (int q = 0; q < 32; ++q) {
-          const int k = c * 32 + q;
-          const float2 w0 = *reinterpret_cast<const float2*>(sW0 + 2 * k);
-          const float a = fmaf(w0.x, px, fmaf(w0.y, py, sb0[k]));
-          float v, d;
-          act_vd<ACT0>(a, net.act0, prm0, v, d);
-          const float g0 = __uint_as_float(gz[q]) * d;
-          jx = fmaf(g0, w0.x, jx);
-          jy = fmaf(g0, w0.y, jy);
-        }
-      }
-      if (valid) { if (jx_out) jx_out[i] = jx * unscale2; if (jy_out) jy_out[i] = jy * unscale2; }
-    }
-    // the next tile's tcgen05.st / MMA must not overtake this tile's TMEM reads
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
   }
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, TcCfg<H>::TMEM_COLS);
+  if (warp == 0) tmem_dealloc(c.tmem_base, TcCfg<H>::TMEM_COLS);
 }
+
+unsigned long long g_const_owner[64] = {0};   // per device: uid of the model whose vectors sit in `cst`
 
 template <int H, int ACT0, int ACT>
 int launch_tc(nlo_sdf_model* m, const float* x, const float* y, const float* sbar, size_t n, float* s, float* jx, float* jy, cudaStream_t st) {
   auto kfn = sdf_tc_kernel<H, ACT0, ACT>;
-  // exactly 512 / TMEM_COLS CTAs may share an SM (tensor memory is 512 columns): pad the smem request so that no more fit
+  // CTAS_PER_SM CTAs share an SM (tensor memory: 512 columns): pad the smem request so that no more fit
   size_t smem = TcCfg<H>::BYTES;
   const size_t floor_smem = (size_t)(227 * 1024) / (TcCfg<H>::CTAS_PER_SM + 1) + 1024;
   if (smem < floor_smem) smem = floor_smem;
@@ -343,7 +464,29 @@ int launch_tc(nlo_sdf_model* m, const float* x, const float* y, const float* sba
   const int grid = (int)(tiles < cap ? tiles : cap);
   TcParams prm;
   memcpy(&prm, m->tc_params, sizeof(prm));
-  kfn<<<grid, TILE, smem, st>>>(m->net(), prm, reinterpret_cast<const __half*>(m->d_tc), x, y, sbar, n, s, jx, jy);
+  if (g_const_owner[m->device] != m->uid) {        // stream-ordered upload of this model's small vectors
+    NLO_CUDA(cudaMemcpyToSymbolAsync(cst, m->tc_const, sizeof(TcConst), 0, cudaMemcpyHostToDevice, st));
+    g_const_owner[m->device] = m->uid;
+  }
+  long long* dbg = nullptr;
+  if (getenv("NLO_B200_TC_TIMELINE")) {             // debugging aid: dump phase clocks of two CTAs after the launch
+    NLO_CUDA(cudaMalloc(&dbg, 2 * 64 * 16 * sizeof(long long)));
+    NLO_CUDA(cudaMemsetAsync(dbg, 0, 2 * 64 * 16 * sizeof(long long), st));
+  }
+  kfn<<<grid, TcCfg<H>::THREADS, smem, st>>>(m->net(), prm, reinterpret_cast<const __half*>(m->d_tc), x, y, sbar, n, s, jx, jy, dbg);
+  if (dbg) {
+    std::vector<long long> h(2 * 64 * 16);
+    NLO_CUDA(cudaMemcpyAsync(h.data(), dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    NLO_CUDA(cudaStreamSynchronize(st));
+    cudaFree(dbg);
+    for (int cta = 0; cta < 2; ++cta)
+      for (int it = 8; it < 14; ++it) {
+        const long long* r = h.data() + (cta * 64 + it) * 16;
+        fprintf(stderr, "[tc timeline] cta%d tile%2d half0: L0 %5lld sync+issue %5lld mma1 %5lld E1 %5lld sync+issue %5lld mma2 %5lld E2 %5lld | start-to-start %6lld | half1 L0 %5lld E1 %5lld E2 %5lld\n",
+                cta, it, r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[5] - r[4], r[6] - r[5], r[7] - r[6],
+                (h.data() + (cta * 64 + it + 1) * 16)[0] - r[0], r[9] - r[8], r[12] - r[11], r[15] - r[14]);
+      }
+  }
   NLO_CHECK_LAUNCH();
   return 0;
 }
@@ -375,6 +518,12 @@ int nlo_sdf_tc_prepare(nlo_sdf_model* m, const float* w) {
   }
   static_assert(sizeof(TcParams) <= sizeof(m->tc_params), "tc_params too small");
   memcpy(m->tc_params, &prm, sizeof(prm));
+  static_assert(sizeof(TcConst) <= sizeof(m->tc_const), "tc_const too small");
+  TcConst* cst = reinterpret_cast<TcConst*>(m->tc_const);
+  memset(cst, 0, sizeof(TcConst));
+  const float* b1 = W1 + (size_t)H * H;
+  for (int k = 0; k < H; ++k) { cst->w0x[k] = W0[2 * k]; cst->w0y[k] = W0[2 * k + 1]; cst->b0[k] = b0[k]; cst->b1[k] = b1[k]; cst->w2[k] = w2[k]; }
+  cst->bout = w2[H];
   std::vector<__half> img((size_t)2 * H * H);
   for (int nn = 0; nn < H; ++nn)
     for (int k = 0; k < H; ++k) {
