@@ -1,0 +1,96 @@
+"""``run-benchmark --config <yaml>`` for the batched GPU path (reference: scripts/run_benchmark.py:49-234).
+
+Parses the reference's YAML unchanged.  Where the reference trains an SDF, builds one Opti instance and calls
+IPOPT, this runner loads SDF weights, builds ``--batch`` multi-start problems, evaluates the NLP functions for the
+whole batch on the GPU (sharded by problem index under torchrun) and reports the best start by merit
+(objective + penalty on constraint violation).  New knobs are additive flags; the YAML schema is the reference's.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+from .config import Config
+from .distributed import init_process_group, merit, select_best, shard_range
+from .problem import NlpProblem
+from .sdf import LearnedSDF, SdfWeights
+
+
+def synthetic_weights(cfg: Config, seed: int = 0) -> SdfWeights:
+    """Seeded stand-in for the network the reference would train (scripts/run_benchmark.py:64-96): same
+    architecture as the YAML's ``model`` section, W ~ N(0, 1/fan_in)."""
+    from .sdf import ACT_COS_SCALE, ACT_SIN, activation_id
+    m = cfg.model
+    H, M = m.hidden_dim, m.n_hidden_mats()
+    rng = np.random.default_rng(seed)
+    W0 = rng.standard_normal((H, 2)) / np.sqrt(2.0)
+    b0 = 0.1 * rng.standard_normal(H)
+    hidden = [(rng.standard_normal((H, H)) / np.sqrt(H), 0.1 * rng.standard_normal(H)) for _ in range(M)]
+    w_out = rng.standard_normal(H) / np.sqrt(H)
+    if m.type == "mlp":
+        a = activation_id(m.activation_function)
+        return SdfWeights.pack("mlp", W0, b0, hidden, w_out, 0.05, a, a)
+    if m.type == "fourier":
+        return SdfWeights.pack("fourier", W0, b0, hidden, w_out, 0.05, ACT_COS_SCALE, activation_id(m.activation_function), 1.0)
+    return SdfWeights.pack("siren", W0 / 30.0, b0, [(W / m.omega_0, b) for W, b in hidden], w_out, 0.0, ACT_SIN, ACT_SIN,
+                           m.omega_0, m.omega_0)
+
+
+def run_benchmark(config_path: Path, batch: int = 4096, weights: str | None = None, precision: str = "auto",
+                  repeats: int = 3, verbose: bool = True):
+    import torch
+    rank, local_rank, world = init_process_group("nccl")
+    torch.cuda.set_device(local_rank)
+    cfg = Config.load(config_path)
+    sdf = None
+    if cfg.solver.mode == "l4casadi":
+        if verbose and rank == 0:
+            print(f"Using model type: {cfg.model.type}")                   # scripts/run_benchmark.py:56
+        w = SdfWeights.load(weights) if weights else synthetic_weights(cfg)
+        if weights is None and rank == 0:
+            print("[run-benchmark] no --weights given: using seeded synthetic SDF weights of the YAML's architecture", file=sys.stderr)
+        sdf = LearnedSDF(w, device=local_rank, precision=precision)
+    prob = NlpProblem.from_config(cfg, sdf, device=local_rank)
+    lo, hi = shard_range(batch, rank, world)
+    P = hi - lo
+    dev = torch.device("cuda", local_rank)
+    w_soa = torch.from_numpy(prob.multistart_guess(P, first=lo)).to(dev).T.contiguous()
+    g, jac, f, grad = prob.alloc_outputs(P, dev)
+    prob.eval_device(w_soa, g, jac, f, grad)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    for _ in range(repeats):
+        prob.eval_device(w_soa, g, jac, f, grad)
+    torch.cuda.synchronize()
+    dt = (time.time() - t0) / repeats
+    lb, ub = prob.bounds()
+    big = 3.0e38
+    lbd = torch.from_numpy(np.clip(lb, -big, big).astype(np.float32)).to(dev)
+    ubd = torch.from_numpy(np.clip(ub, -big, big).astype(np.float32)).to(dev)
+    viol = prob.violation(g, lbd, ubd)
+    best_val, best_idx, w_best = select_best(merit(f, viol), w_soa, lo, prob.n_w)
+    out = {"config": str(config_path), "batch": batch, "world": world, "n_w": prob.n_w, "n_g": prob.n_g, "nnz_jac": prob.nnz,
+           "sdf_points_per_eval": prob.n_sdf_points if sdf is not None else 0, "precision": sdf.precision if sdf else None,
+           "eval_ms_rank0": dt * 1e3, "problem_evals_per_s_rank0": P / dt, "best_merit": best_val, "best_start": best_idx}
+    if rank == 0 and verbose:
+        print(json.dumps(out))
+    return out, w_best.cpu().numpy()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", type=str, required=True, help="Path to benchmark YAML config")
+    ap.add_argument("--batch", type=int, default=4096, help="number of multi-start problems (whole job)")
+    ap.add_argument("--weights", type=str, default=None, help="SDF weights (.nlow, .npz, TorchScript .pt or state_dict .pt)")
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tc3xf16"])
+    a = ap.parse_args()
+    run_benchmark(Path(a.config), a.batch, a.weights, a.precision)
+
+
+if __name__ == "__main__":
+    main()
