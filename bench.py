@@ -51,7 +51,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -103,6 +103,9 @@ def synthetic_net():
 
 
 FLOP_PER_POINT = 4 * (3 * 128 + 128 * 128)      # value + Jacobian, 2->128->128->1 = 67,072
+# dram__bytes_read.sum + dram__bytes_write.sum of sdf_tc_kernel per point, from the ncu --set full capture committed
+# under profiles/ (profiles/r1_sdf_tc_kernel.md): 376 MB for 21,233,664 points (algorithmic: 20 B/point)
+NCU_DRAM_BYTES_PER_POINT = 17.7
 BYTES_PER_EVAL = (727 + 1057 + 3225) * 4        # read w, write g and nnz(J) = 20,036 B / problem-eval
 POINTS_PER_PROBLEM = 324
 
@@ -232,11 +235,11 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)          # samples SM clocks / throttle reasons across every timed region below
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     l0 = L.nlo_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -261,7 +264,6 @@ def run_ours(args):
     k1.record()
     torch.cuda.synchronize()
     k_ms = k0.elapsed_time(k1) / args.steps
-    clocks = sampler.stop()
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -287,6 +289,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
+    clocks = sampler.stop()
     h2d = int(w_np.nbytes)
     d2h = int(sum(v.nbytes for v in out_pin.values()))
 
@@ -326,7 +329,9 @@ def run_ours(args):
                 "ms_per_step": e2e_s * 1e3, "api": "nlo_nlp_eval_host (pinned host buffers, problem-major)"},
         "gpu_launches": launches,
         "roofline": {"kernel": "sdf_tc_kernel" if prec == "tc3xf16" else "sdf_simt_kernel", "bound": bound, "achieved": achieved,
-                     "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                     "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                     "traffic": (NCU_DRAM_BYTES_PER_POINT * n_pts if prec == "tc3xf16" else None), "traffic_unit": "bytes per launch (ncu dram read+write)",
+                     "algorithmic_bytes_per_launch": 20 * n_pts,
                      "flop_per_point": FLOP_PER_POINT, "points_per_launch": n_pts, "kernel_ms": k_ms, "peak_source": peak_note,
                      "kernel_share_of_step": k_ms / ms_per_step,
                      "step_hbm": {"algorithmic_bytes_per_step": BYTES_PER_EVAL * P, "achieved_gbs": BYTES_PER_EVAL * P / (ms_per_step * 1e-3) / 1e9,
@@ -351,7 +356,7 @@ def model_sm_count(L, device):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--problems", type=int, default=65536, help="multi-start problems per GPU")

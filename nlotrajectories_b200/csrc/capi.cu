@@ -417,9 +417,9 @@ int nlo_nlp_create(const nlo_nlp_desc* desc, nlo_sdf_model* model, int device, n
   nlo_nlp* p = new (std::nothrow) nlo_nlp();
   if (!p) return nlo_fail("out of host memory");
   p->desc = *desc; p->model = model; p->device = device;
-  p->d_tables = nullptr; p->cap_P = 0; p->d_px = p->d_py = p->d_s = p->d_jx = p->d_jy = nullptr;
-  p->host_cap_P = 0; p->d_aos = p->d_w = p->d_g = p->d_jac = p->d_f = p->d_grad = nullptr;
-  p->h_pinned = nullptr; p->h_pinned_cap = 0; p->stream = nullptr;
+  p->d_tables = nullptr;
+  memset(&p->scratch, 0, sizeof(p->scratch));
+  memset(p->lane, 0, sizeof(p->lane));
   std::vector<int> nzmap, copy_row, copy_var, copy_emit;
   if (nlo_nlp_build_layout(desc, &p->L, &p->rows_ccs, &p->cols_ccs, &nzmap, &copy_row, &copy_var, &copy_emit)) { delete p; return 1; }
   if (cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) { delete p; return nlo_fail("cannot query device"); }
@@ -434,19 +434,30 @@ int nlo_nlp_create(const nlo_nlp_desc* desc, nlo_sdf_model* model, int device, n
   }
   p->L.nzmap = p->d_tables; p->L.copy_row = p->d_tables + nzmap.size();
   p->L.copy_var = p->L.copy_row + nc; p->L.copy_nz = p->L.copy_var + nc; p->L.n_copy = nc;
-  if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess) { nlo_nlp_destroy(p); return nlo_fail("stream creation failed"); }
+  for (auto& ln : p->lane)
+    if (cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking) != cudaSuccess) { nlo_nlp_destroy(p); return nlo_fail("stream creation failed"); }
   *out = p;
   return 0;
+}
+
+static void free_scratch(NlpScratch& sc) {
+  float** bufs[] = {&sc.px, &sc.py, &sc.s, &sc.jx, &sc.jy};
+  for (float** b : bufs) { if (*b) cudaFree(*b); *b = nullptr; }
+  sc.cap_P = 0;
+}
+static void free_lane_bufs(NlpLane& ln) {
+  float** bufs[] = {&ln.d_in, &ln.d_w, &ln.d_g, &ln.d_jac, &ln.d_f, &ln.d_grad, &ln.d_og, &ln.d_ojac, &ln.d_ograd};
+  for (float** b : bufs) { if (*b) cudaFree(*b); *b = nullptr; }
+  free_scratch(ln.scratch);
+  ln.cap_P = 0;
 }
 
 void nlo_nlp_destroy(nlo_nlp* p) {
   if (!p) return;
   cudaSetDevice(p->device);
-  float* bufs[] = {p->d_px, p->d_py, p->d_s, p->d_jx, p->d_jy, p->d_aos, p->d_w, p->d_g, p->d_jac, p->d_f, p->d_grad};
-  for (float* b : bufs) if (b) cudaFree(b);
+  free_scratch(p->scratch);
+  for (auto& ln : p->lane) { free_lane_bufs(ln); if (ln.stream) cudaStreamDestroy(ln.stream); }
   if (p->d_tables) cudaFree(p->d_tables);
-  if (p->h_pinned) cudaFreeHost(p->h_pinned);
-  if (p->stream) cudaStreamDestroy(p->stream);
   delete p;
 }
 
@@ -464,14 +475,27 @@ int nlo_nlp_jac_sparsity(const nlo_nlp* p, int32_t* colind, int32_t* row) {
   return 0;
 }
 
-static int ensure_work(nlo_nlp* p, size_t P) {
-  if (p->cap_P >= P) return 0;
-  float** bufs[] = {&p->d_px, &p->d_py, &p->d_s, &p->d_jx, &p->d_jy};
-  for (float** b : bufs) { if (*b) cudaFree(*b); *b = nullptr; }
-  p->cap_P = 0;
+static int ensure_scratch(const nlo_nlp* p, NlpScratch& sc, size_t P) {
+  if (sc.cap_P >= P) return 0;
+  free_scratch(sc);
   const size_t n = (size_t)(p->L.N + 1) * p->L.nb * P;
+  float** bufs[] = {&sc.px, &sc.py, &sc.s, &sc.jx, &sc.jy};
   for (float** b : bufs) NLO_CUDA(cudaMalloc(b, n * sizeof(float)));
-  p->cap_P = P;
+  sc.cap_P = P;
+  return 0;
+}
+
+static int nlp_eval_on(nlo_nlp* p, NlpScratch& sc, const float* w, size_t P, size_t ld, float* g, float* jac, float* f, float* grad_f,
+                       cudaStream_t st) {
+  if ((g || jac) && ensure_scratch(p, sc, P)) return 1;
+  if (nlo_nlp_launch_assembly(p, sc, w, P, ld, g, jac, f, grad_f, st, 0)) return 1;
+  if (g || jac) {
+    if (p->L.sdf_mode == NLO_SDF_LEARNED) {
+      const size_t n = (size_t)(p->L.N + 1) * p->L.nb * P;
+      if (nlo_sdf_eval(p->model, sc.px, sc.py, nullptr, n, sc.s, jac ? sc.jx : nullptr, jac ? sc.jy : nullptr, st)) return 1;
+    }
+    if (nlo_nlp_launch_assembly(p, sc, w, P, ld, g, jac, f, grad_f, st, 1)) return 1;
+  }
   return 0;
 }
 
@@ -481,17 +505,7 @@ int nlo_nlp_eval(nlo_nlp* p, const float* w, size_t P, size_t ld, float* g, floa
   if (!w) return nlo_fail("null w");
   if (ld < P) return nlo_fail("ld (%zu) < P (%zu)", ld, P);
   NLO_CUDA(cudaSetDevice(p->device));
-  cudaStream_t st = (cudaStream_t)stream;
-  if ((g || jac) && ensure_work(p, P)) return 1;
-  if (nlo_nlp_launch_assembly(p, w, P, ld, g, jac, f, grad_f, st, 0)) return 1;
-  if (g || jac) {
-    if (p->L.sdf_mode == NLO_SDF_LEARNED) {
-      const size_t n = (size_t)(p->L.N + 1) * p->L.nb * P;
-      if (nlo_sdf_eval(p->model, p->d_px, p->d_py, nullptr, n, p->d_s, jac ? p->d_jx : nullptr, jac ? p->d_jy : nullptr, st)) return 1;
-    }
-    if (nlo_nlp_launch_assembly(p, w, P, ld, g, jac, f, grad_f, st, 1)) return 1;
-  }
-  return 0;
+  return nlp_eval_on(p, p->scratch, w, P, ld, g, jac, f, grad_f, (cudaStream_t)stream);
 }
 
 int nlo_nlp_violation(nlo_nlp* p, const float* g, const float* lbg, const float* ubg, size_t P, size_t ld, float* viol, void* stream) {
@@ -511,49 +525,63 @@ int nlo_transpose_to_aos(const float* soa, float* aos, size_t P, size_t rows, si
   return nlo_launch_transpose(soa, aos, rows, P, ld, rows, sm, (cudaStream_t)stream);
 }
 
-static int ensure_host_bufs(nlo_nlp* p, size_t P) {
-  if (p->host_cap_P >= P) return 0;
-  float** bufs[] = {&p->d_aos, &p->d_w, &p->d_g, &p->d_jac, &p->d_f, &p->d_grad};
-  for (float** b : bufs) { if (*b) cudaFree(*b); *b = nullptr; }
-  p->host_cap_P = 0;
+static int ensure_lane(nlo_nlp* p, NlpLane& ln, size_t P) {
+  if (ln.cap_P >= P) return 0;
+  cudaStream_t st = ln.stream;
+  free_lane_bufs(ln);
+  ln.stream = st;
   const NlpDev& L = p->L;
-  const size_t big = (size_t)std::max(std::max(L.n_w, L.n_g), L.nnz);
-  NLO_CUDA(cudaMalloc(&p->d_aos, big * P * sizeof(float)));
-  NLO_CUDA(cudaMalloc(&p->d_w, (size_t)L.n_w * P * sizeof(float)));
-  NLO_CUDA(cudaMalloc(&p->d_g, (size_t)L.n_g * P * sizeof(float)));
-  NLO_CUDA(cudaMalloc(&p->d_jac, (size_t)L.nnz * P * sizeof(float)));
-  NLO_CUDA(cudaMalloc(&p->d_f, P * sizeof(float)));
-  NLO_CUDA(cudaMalloc(&p->d_grad, (size_t)L.n_w * P * sizeof(float)));
-  p->host_cap_P = P;
+  NLO_CUDA(cudaMalloc(&ln.d_in, (size_t)L.n_w * P * sizeof(float)));
+  NLO_CUDA(cudaMalloc(&ln.d_w, (size_t)L.n_w * P * sizeof(float)));
+  NLO_CUDA(cudaMalloc(&ln.d_g, (size_t)L.n_g * P * sizeof(float)));
+  NLO_CUDA(cudaMalloc(&ln.d_jac, (size_t)L.nnz * P * sizeof(float)));
+  NLO_CUDA(cudaMalloc(&ln.d_f, P * sizeof(float)));
+  NLO_CUDA(cudaMalloc(&ln.d_grad, (size_t)L.n_w * P * sizeof(float)));
+  NLO_CUDA(cudaMalloc(&ln.d_og, (size_t)L.n_g * P * sizeof(float)));
+  NLO_CUDA(cudaMalloc(&ln.d_ojac, (size_t)L.nnz * P * sizeof(float)));
+  NLO_CUDA(cudaMalloc(&ln.d_ograd, (size_t)L.n_w * P * sizeof(float)));
+  ln.cap_P = P;
   return 0;
 }
 
+// Host-buffer evaluation, problem-major rows.  The batch is cut into chunks that alternate between two lanes
+// (streams): while one lane's results travel device->host, the other lane's inputs travel host->device and its
+// kernels run, so PCIe is busy in both directions and the GPU work hides behind the copies.
 int nlo_nlp_eval_host(nlo_nlp* p, const float* w_host, size_t P, float* g_host, float* jac_host, float* f_host, float* grad_host) {
   if (!p) return nlo_fail("null nlp");
   if (P == 0) return 0;
   if (!w_host) return nlo_fail("null w");
   NLO_CUDA(cudaSetDevice(p->device));
-  if (ensure_host_bufs(p, P)) return 1;
   const NlpDev& L = p->L;
-  cudaStream_t st = p->stream;
-  NLO_CUDA(cudaMemcpyAsync(p->d_aos, w_host, (size_t)L.n_w * P * sizeof(float), cudaMemcpyHostToDevice, st));
-  if (nlo_launch_transpose(p->d_aos, p->d_w, P, L.n_w, L.n_w, P, p->sm_count, st)) return 1;
-  if (nlo_nlp_eval(p, p->d_w, P, P, g_host ? p->d_g : nullptr, jac_host ? p->d_jac : nullptr, f_host ? p->d_f : nullptr,
-                   grad_host ? p->d_grad : nullptr, st)) return 1;
-  if (g_host) {
-    if (nlo_launch_transpose(p->d_g, p->d_aos, L.n_g, P, P, L.n_g, p->sm_count, st)) return 1;
-    NLO_CUDA(cudaMemcpyAsync(g_host, p->d_aos, (size_t)L.n_g * P * sizeof(float), cudaMemcpyDeviceToHost, st));
+  size_t chunk = (P + 7) / 8;
+  if (chunk < 2048) chunk = 2048;
+  if (chunk > P) chunk = P;
+  const size_t n_chunks = (P + chunk - 1) / chunk;
+  const int n_lanes = n_chunks > 1 ? 2 : 1;
+  for (int l = 0; l < n_lanes; ++l) if (ensure_lane(p, p->lane[l], chunk)) return 1;
+  for (size_t c = 0; c < n_chunks; ++c) {
+    NlpLane& ln = p->lane[c % n_lanes];
+    cudaStream_t st = ln.stream;
+    const size_t p0 = c * chunk, Pc = (p0 + chunk <= P) ? chunk : P - p0;
+    NLO_CUDA(cudaMemcpyAsync(ln.d_in, w_host + p0 * L.n_w, (size_t)L.n_w * Pc * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (nlo_launch_transpose(ln.d_in, ln.d_w, Pc, L.n_w, L.n_w, Pc, p->sm_count, st)) return 1;
+    if (nlp_eval_on(p, ln.scratch, ln.d_w, Pc, Pc, g_host ? ln.d_g : nullptr, jac_host ? ln.d_jac : nullptr, f_host ? ln.d_f : nullptr,
+                    grad_host ? ln.d_grad : nullptr, st)) return 1;
+    if (jac_host) {
+      if (nlo_launch_transpose(ln.d_jac, ln.d_ojac, L.nnz, Pc, Pc, L.nnz, p->sm_count, st)) return 1;
+      NLO_CUDA(cudaMemcpyAsync(jac_host + p0 * L.nnz, ln.d_ojac, (size_t)L.nnz * Pc * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    if (g_host) {
+      if (nlo_launch_transpose(ln.d_g, ln.d_og, L.n_g, Pc, Pc, L.n_g, p->sm_count, st)) return 1;
+      NLO_CUDA(cudaMemcpyAsync(g_host + p0 * L.n_g, ln.d_og, (size_t)L.n_g * Pc * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    if (grad_host) {
+      if (nlo_launch_transpose(ln.d_grad, ln.d_ograd, L.n_w, Pc, Pc, L.n_w, p->sm_count, st)) return 1;
+      NLO_CUDA(cudaMemcpyAsync(grad_host + p0 * L.n_w, ln.d_ograd, (size_t)L.n_w * Pc * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    if (f_host) NLO_CUDA(cudaMemcpyAsync(f_host + p0, ln.d_f, Pc * sizeof(float), cudaMemcpyDeviceToHost, st));
   }
-  if (jac_host) {
-    if (nlo_launch_transpose(p->d_jac, p->d_aos, L.nnz, P, P, L.nnz, p->sm_count, st)) return 1;
-    NLO_CUDA(cudaMemcpyAsync(jac_host, p->d_aos, (size_t)L.nnz * P * sizeof(float), cudaMemcpyDeviceToHost, st));
-  }
-  if (grad_host) {
-    if (nlo_launch_transpose(p->d_grad, p->d_aos, L.n_w, P, P, L.n_w, p->sm_count, st)) return 1;
-    NLO_CUDA(cudaMemcpyAsync(grad_host, p->d_aos, (size_t)L.n_w * P * sizeof(float), cudaMemcpyDeviceToHost, st));
-  }
-  if (f_host) NLO_CUDA(cudaMemcpyAsync(f_host, p->d_f, P * sizeof(float), cudaMemcpyDeviceToHost, st));
-  NLO_CUDA(cudaStreamSynchronize(st));
+  for (int l = 0; l < n_lanes; ++l) NLO_CUDA(cudaStreamSynchronize(p->lane[l].stream));
   return 0;
 }
 

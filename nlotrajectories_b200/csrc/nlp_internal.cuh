@@ -20,6 +20,19 @@ struct NlpDev {                 // passed by value to kernels
   const int* copy_nz;
 };
 
+struct NlpScratch {             // footprint points and SDF outputs for cap_P problems: (N+1)*nb*cap_P floats each
+  size_t cap_P;
+  float *px, *py, *s, *jx, *jy;
+};
+struct NlpLane {                // one pipeline lane of nlo_nlp_eval_host
+  cudaStream_t stream;
+  size_t cap_P;                 // problems per chunk the buffers below hold
+  float *d_in, *d_w;            // problem-major staging of w, and its SoA transpose
+  float *d_g, *d_jac, *d_f, *d_grad;          // SoA outputs
+  float *d_og, *d_ojac, *d_ograd;             // problem-major staging of the outputs
+  NlpScratch scratch;
+};
+
 struct nlo_nlp {
   nlo_nlp_desc desc;
   NlpDev L;
@@ -27,14 +40,8 @@ struct nlo_nlp {
   int device, sm_count;
   std::vector<int> rows_ccs, cols_ccs;
   int* d_tables;                // nzmap | copy_row | copy_var | copy_nz
-  // work buffers sized for cap_P problems
-  size_t cap_P;
-  float *d_px, *d_py, *d_s, *d_jx, *d_jy;
-  // host-buffer entry point staging
-  size_t host_cap_P;
-  float *d_aos, *d_w, *d_g, *d_jac, *d_f, *d_grad;
-  float* h_pinned; size_t h_pinned_cap;
-  cudaStream_t stream;
+  NlpScratch scratch;           // SDF point / value scratch of the device entry point
+  NlpLane lane[2];              // host entry point: two lanes (streams) process alternating chunks of problems
 };
 
 // structural A pairs per model, usable in device code after unrolling
@@ -58,7 +65,7 @@ int nlo_nlp_build_layout(const nlo_nlp_desc* d, NlpDev* L, std::vector<int>* row
                          std::vector<int>* copy_emit);
 // phase 0: everything before the SDF evaluation (defects, copy rows, footprint points / circles, f, grad f)
 // phase 1: SDF rows (needs p->d_s/d_jx/d_jy)
-int nlo_nlp_launch_assembly(nlo_nlp* p, const float* w, size_t P, size_t ld, float* g, float* jac, float* f, float* grad_f,
-                            cudaStream_t st, int phase);
+int nlo_nlp_launch_assembly(nlo_nlp* p, const NlpScratch& sc, const float* w, size_t P, size_t ld, float* g, float* jac, float* f,
+                            float* grad_f, cudaStream_t st, int phase);
 int nlo_launch_violation(int n_g, const float* g, const float* lb, const float* ub, size_t P, size_t ld, float* viol, int sm, cudaStream_t st);
 int nlo_launch_transpose(const float* in, float* out, size_t n_in_rows, size_t n_in_cols, size_t ld_in, size_t ld_out, int sm, cudaStream_t st);

@@ -376,8 +376,8 @@ inline int grid_for(size_t total, int threads, int sm_count) {
 
 }  // namespace
 
-int nlo_nlp_launch_assembly(nlo_nlp* p, const float* w, size_t P, size_t ld, float* g, float* jac, float* f, float* grad_f,
-                            cudaStream_t st, int phase) {
+int nlo_nlp_launch_assembly(nlo_nlp* p, const NlpScratch& sc, const float* w, size_t P, size_t ld, float* g, float* jac, float* f,
+                            float* grad_f, cudaStream_t st, int phase) {
   const NlpDev& L = p->L;
   const int sm = p->sm_count;
   if (phase == 0) {
@@ -392,11 +392,11 @@ int nlo_nlp_launch_assembly(nlo_nlp* p, const float* w, size_t P, size_t ld, flo
       NLO_CHECK_LAUNCH();
       nlp_copy_rows_kernel<<<grid_for((size_t)L.n_copy * P, 256, sm), 256, 0, st>>>(L, w, P, ld, g, jac);
       NLO_CHECK_LAUNCH();
-      nlp_points_kernel<<<grid_for((size_t)(L.N + 1) * P, 256, sm), 256, 0, st>>>(L, w, P, ld, p->d_px, p->d_py);
+      nlp_points_kernel<<<grid_for((size_t)(L.N + 1) * P, 256, sm), 256, 0, st>>>(L, w, P, ld, sc.px, sc.py);
       NLO_CHECK_LAUNCH();
       if (L.sdf_mode == NLO_SDF_CIRCLES) {
         const size_t n = (size_t)(L.N + 1) * L.nb * P;
-        nlp_circles_kernel<<<grid_for(n, 256, sm), 256, 0, st>>>(L, p->d_px, p->d_py, n, p->d_s, p->d_jx, p->d_jy);
+        nlp_circles_kernel<<<grid_for(n, 256, sm), 256, 0, st>>>(L, sc.px, sc.py, n, sc.s, sc.jx, sc.jy);
         NLO_CHECK_LAUNCH();
       }
     }
@@ -404,7 +404,7 @@ int nlo_nlp_launch_assembly(nlo_nlp* p, const float* w, size_t P, size_t ld, flo
     if (grad_f) { nlp_grad_kernel<<<grid_for((size_t)L.n_w * P, 256, sm), 256, 0, st>>>(L, w, P, ld, grad_f); NLO_CHECK_LAUNCH(); }
   } else {
     if (g || jac) {
-      nlp_sdf_rows_kernel<<<grid_for((size_t)(L.N + 1) * P, 256, sm), 256, 0, st>>>(L, w, P, ld, p->d_s, p->d_jx, p->d_jy, g, jac);
+      nlp_sdf_rows_kernel<<<grid_for((size_t)(L.N + 1) * P, 256, sm), 256, 0, st>>>(L, w, P, ld, sc.s, sc.jx, sc.jy, g, jac);
       NLO_CHECK_LAUNCH();
     }
   }

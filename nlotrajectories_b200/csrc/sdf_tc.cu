@@ -157,8 +157,8 @@ struct TcParams {          // built by nlo_sdf_tc_prepare
 };
 // Small vectors of the network live in __constant__ memory: with fully unrolled loops every use is an FFMA/FMUL
 // with a constant-bank operand (c[3][imm]) - no load instruction and no shared-memory bandwidth (which the tensor
-// core needs for its B-operand fetches).  One copy per device context; nlo_sdf_tc_launch re-uploads it, ordered on
-// the launch stream, whenever a different model is evaluated.
+// core needs for its B-operand fetches).  One copy per device context; nlo_sdf_tc_launch re-uploads it (after a
+// device-wide sync) whenever a different model is evaluated.
 struct TcConst {
   float w0x[128], w0y[128], b0[128], b1[128], w2[128];
   float bout;
@@ -464,8 +464,11 @@ int launch_tc(nlo_sdf_model* m, const float* x, const float* y, const float* sba
   const int grid = (int)(tiles < cap ? tiles : cap);
   TcParams prm;
   memcpy(&prm, m->tc_params, sizeof(prm));
-  if (g_const_owner[m->device] != m->uid) {        // stream-ordered upload of this model's small vectors
-    NLO_CUDA(cudaMemcpyToSymbolAsync(cst, m->tc_const, sizeof(TcConst), 0, cudaMemcpyHostToDevice, st));
+  if (g_const_owner[m->device] != m->uid) {
+    // A different model's vectors sit in constant memory: drain whatever may still read them, then upload ours
+    // synchronously so that launches on any stream see them.  Rare (model switch), so the device-wide sync is fine.
+    NLO_CUDA(cudaDeviceSynchronize());
+    NLO_CUDA(cudaMemcpyToSymbol(cst, m->tc_const, sizeof(TcConst), 0, cudaMemcpyHostToDevice));
     g_const_owner[m->device] = m->uid;
   }
   long long* dbg = nullptr;

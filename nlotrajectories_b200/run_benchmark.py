@@ -90,6 +90,9 @@ def main():
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tc3xf16"])
     a = ap.parse_args()
     run_benchmark(Path(a.config), a.batch, a.weights, a.precision)
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
