@@ -200,3 +200,29 @@ def test_casadi_external_abi_calls(shipped_net, library, torch_cuda):
     assert np.abs(o4[2 * Pn::2] - Hs[:, 1, 0]).max() <= scale and np.abs(o4[2 * Pn + 1::2] - Hs[:, 1, 1]).max() <= scale
     L.nlo_casadi_bind(None)
     model.close()
+
+
+def test_two_tensor_path_models_alternating_and_streams(torch_cuda):
+    """The tensor path keeps one model's small vectors in __constant__ memory: alternating between two models
+    (and launching on side streams) must re-upload them correctly."""
+    torch = torch_cuda
+    from nlotrajectories_b200.sdf import LearnedSDF
+    nets = [so.synthetic_mlp(128, 1, seed=21), so.synthetic_mlp(128, 1, seed=22), so.synthetic_mlp(64, 1, seed=23)]
+    models = [LearnedSDF(to_weights(n)) for n in nets]
+    assert all(m.precision == "tc3xf16" for m in models)
+    P = sample_points(5000, seed=3)
+    refs = [so.value_jac(n.astype(np.float64), P.astype(np.float64)) for n in nets]
+    ties = [kink_mask(n, P) for n in nets]
+    x = torch.from_numpy(P[:, 0].copy()).cuda(); y = torch.from_numpy(P[:, 1].copy()).cuda()
+    side = torch.cuda.Stream()
+    for rep in range(3):
+        for i in (0, 1, 2, 1, 0):
+            stream = side if (rep + i) % 2 else torch.cuda.current_stream()
+            with torch.cuda.stream(stream):
+                s, jx, jy = models[i].eval(x, y)
+            stream.synchronize()
+            J = np.stack([jx.cpu().numpy(), jy.cpu().numpy()], 1)
+            assert not close(s.cpu().numpy(), refs[i][0], TOL).any()
+            assert not (close(J, refs[i][1], TOL).any(axis=1) & ~ties[i]).any()
+    for m in models:
+        m.close()
