@@ -75,6 +75,16 @@ int nlo_sdf_create(const nlo_sdf_desc* desc, const float* weights, size_t n_weig
   NLO_CUDA(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device));
   NLO_CUDA(cudaMalloc(&m->d_w, n_weights * sizeof(float)));
   NLO_CUDA(cudaMemcpy(m->d_w, weights, n_weights * sizeof(float), cudaMemcpyHostToDevice));
+  if (desc->n_hidden_mats > 0) {
+    const size_t H = desc->hidden, M = desc->n_hidden_mats;
+    std::vector<float> wt(M * H * H);
+    for (size_t l = 0; l < M; ++l) {
+      const float* W = weights + 3 * H + l * (H * H + H);
+      for (size_t j = 0; j < H; ++j) for (size_t k = 0; k < H; ++k) wt[l * H * H + k * H + j] = W[j * H + k];
+    }
+    NLO_CUDA(cudaMalloc(&m->d_wt, wt.size() * sizeof(float)));
+    NLO_CUDA(cudaMemcpy(m->d_wt, wt.data(), wt.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
   NLO_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
   m->prec = NLO_PREC_FP32_SIMT;
   if (nlo_sdf_tc_supported(desc)) {
@@ -121,6 +131,7 @@ void nlo_sdf_destroy(nlo_sdf_model* m) {
   if (!m) return;
   cudaSetDevice(m->device);
   if (m->d_w) cudaFree(m->d_w);
+  if (m->d_wt) cudaFree(m->d_wt);
   if (m->d_tc) cudaFree(m->d_tc);
   if (m->d_io) cudaFree(m->d_io);
   if (m->d_ws) cudaFree(m->d_ws);

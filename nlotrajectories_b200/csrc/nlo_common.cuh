@@ -49,6 +49,7 @@ struct nlo_sdf_model {
   int prec;                  // resolved NLO_PREC_*
   unsigned long long uid;    // process-unique id (owner tag of per-device constant memory)
   float* d_w;                // fp32 blob
+  float* d_wt;               // transposed copies of the hidden matrices: wt[l][k][j] = W_{l+1}[j][k]
   size_t n_w;
   // tensor-path operand images (built on demand by sdf_tc.cu)
   void* d_tc;                // W1 split into fp16 hi | lo images in UMMA core-matrix order
