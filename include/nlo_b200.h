@@ -211,6 +211,10 @@ NLO_API int  nlo_nlp_jac_sparsity(const nlo_nlp* p, int32_t* colind, int32_t* ro
  * Any output may be NULL.  ld >= P.  Asynchronous on `stream`.                                 */
 NLO_API int nlo_nlp_eval(nlo_nlp* p, const float* w, size_t P, size_t ld,
                          float* g, float* jac, float* f, float* grad_f, void* stream);
+/* out = add + (dg/dw)^T y for every problem: jac [nnz][ld] (CCS values from nlo_nlp_eval), y [n_g][ld], add [n_w][ld] or NULL,
+ * out [n_w][ld].  The product a constrained solver needs for the gradient of its (augmented) Lagrangian.        */
+NLO_API int nlo_nlp_jac_tvec(nlo_nlp* p, const float* jac, const float* y, const float* add, size_t P, size_t ld,
+                             float* out, void* stream);
 /* max constraint violation per problem given bounds lbg/ubg (fp32[n_g], device), for best-of selection */
 NLO_API int nlo_nlp_violation(nlo_nlp* p, const float* g, const float* lbg, const float* ubg, size_t P, size_t ld,
                               float* viol, void* stream);

@@ -439,12 +439,21 @@ int nlo_nlp_create(const nlo_nlp_desc* desc, nlo_sdf_model* model, int device, n
   tables.insert(tables.end(), copy_row.begin(), copy_row.end());
   tables.insert(tables.end(), copy_var.begin(), copy_var.end());
   for (int i = 0; i < nc; ++i) tables.push_back(nzmap[copy_emit[i]]);
+  const size_t off_colind = tables.size();
+  {
+    std::vector<int> colind(p->L.n_w + 1, 0);
+    for (int i = 0; i < p->L.nnz; ++i) colind[p->cols_ccs[i] + 1]++;
+    for (int cidx = 0; cidx < p->L.n_w; ++cidx) colind[cidx + 1] += colind[cidx];
+    tables.insert(tables.end(), colind.begin(), colind.end());
+    tables.insert(tables.end(), p->rows_ccs.begin(), p->rows_ccs.end());
+  }
   if (cudaMalloc(&p->d_tables, tables.size() * sizeof(int)) != cudaSuccess ||
       cudaMemcpy(p->d_tables, tables.data(), tables.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
     nlo_nlp_destroy(p); return nlo_fail("device allocation failed");
   }
   p->L.nzmap = p->d_tables; p->L.copy_row = p->d_tables + nzmap.size();
   p->L.copy_var = p->L.copy_row + nc; p->L.copy_nz = p->L.copy_var + nc; p->L.n_copy = nc;
+  p->d_colind = p->d_tables + off_colind; p->d_row = p->d_colind + p->L.n_w + 1;
   for (auto& ln : p->lane)
     if (cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking) != cudaSuccess) { nlo_nlp_destroy(p); return nlo_fail("stream creation failed"); }
   *out = p;
@@ -523,6 +532,13 @@ int nlo_nlp_violation(nlo_nlp* p, const float* g, const float* lbg, const float*
   if (!p || !g || !lbg || !ubg || !viol) return nlo_fail("null argument");
   NLO_CUDA(cudaSetDevice(p->device));
   return nlo_launch_violation(p->L.n_g, g, lbg, ubg, P, ld, viol, p->sm_count, (cudaStream_t)stream);
+}
+
+int nlo_nlp_jac_tvec(nlo_nlp* p, const float* jac, const float* y, const float* add, size_t P, size_t ld, float* out, void* stream) {
+  if (!p || !jac || !y || !out) return nlo_fail("null argument");
+  if (P == 0) return 0;
+  NLO_CUDA(cudaSetDevice(p->device));
+  return nlo_launch_jtv(p->L.n_w, p->d_colind, p->d_row, jac, y, P, ld, add, out, p->sm_count, (cudaStream_t)stream);
 }
 
 int nlo_transpose_to_soa(const float* aos, float* soa, size_t P, size_t rows, size_t ld, void* stream) {

@@ -39,7 +39,8 @@ struct nlo_nlp {
   nlo_sdf_model* model;
   int device, sm_count;
   std::vector<int> rows_ccs, cols_ccs;
-  int* d_tables;                // nzmap | copy_row | copy_var | copy_nz
+  int* d_tables;                // nzmap | copy_row | copy_var | copy_nz | colind (n_w+1) | row (nnz)
+  const int* d_colind; const int* d_row;
   NlpScratch scratch;           // SDF point / value scratch of the device entry point
   NlpLane lane[2];              // host entry point: two lanes (streams) process alternating chunks of problems
 };
@@ -68,4 +69,6 @@ int nlo_nlp_build_layout(const nlo_nlp_desc* d, NlpDev* L, std::vector<int>* row
 int nlo_nlp_launch_assembly(nlo_nlp* p, const NlpScratch& sc, const float* w, size_t P, size_t ld, float* g, float* jac, float* f,
                             float* grad_f, cudaStream_t st, int phase);
 int nlo_launch_violation(int n_g, const float* g, const float* lb, const float* ub, size_t P, size_t ld, float* viol, int sm, cudaStream_t st);
+int nlo_launch_jtv(int n_w, const int* colind, const int* row, const float* jac, const float* y, size_t P, size_t ld, const float* add,
+                   float* out, int sm, cudaStream_t st);
 int nlo_launch_transpose(const float* in, float* out, size_t n_in_rows, size_t n_in_cols, size_t ld_in, size_t ld_out, int sm, cudaStream_t st);

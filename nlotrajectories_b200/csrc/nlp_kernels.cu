@@ -346,6 +346,20 @@ __global__ void __launch_bounds__(256) nlp_violation_kernel(int n_g, const float
   }
 }
 
+// ---- out = J^T y  (one thread per (problem, column); the column's non-zeros are contiguous in CCS order) ------------
+__global__ void __launch_bounds__(256) nlp_jtv_kernel(int n_w, const int* __restrict__ colind, const int* __restrict__ row,
+                                                      const float* __restrict__ jac, const float* __restrict__ y, size_t P, size_t ld,
+                                                      const float* __restrict__ add, float* __restrict__ out) {
+  const size_t total = (size_t)n_w * P;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx / P);
+    const size_t p = idx - (size_t)c * P;
+    float acc = add ? add[(size_t)c * ld + p] : 0.f;
+    for (int z = colind[c]; z < colind[c + 1]; ++z) acc = fmaf(jac[(size_t)z * ld + p], y[(size_t)row[z] * ld + p], acc);
+    out[(size_t)c * ld + p] = acc;
+  }
+}
+
 // ---- [P][rows] <-> [rows][ld] ----------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, float* __restrict__ out, size_t n_in_rows,
                                                         size_t n_in_cols, size_t ld_in, size_t ld_out) {
@@ -413,6 +427,13 @@ int nlo_nlp_launch_assembly(nlo_nlp* p, const NlpScratch& sc, const float* w, si
 
 int nlo_launch_violation(int n_g, const float* g, const float* lb, const float* ub, size_t P, size_t ld, float* viol, int sm, cudaStream_t st) {
   nlp_violation_kernel<<<grid_for(P, 128, sm), 128, 0, st>>>(n_g, g, lb, ub, P, ld, viol);
+  NLO_CHECK_LAUNCH();
+  return 0;
+}
+
+int nlo_launch_jtv(int n_w, const int* colind, const int* row, const float* jac, const float* y, size_t P, size_t ld, const float* add,
+                   float* out, int sm, cudaStream_t st) {
+  nlp_jtv_kernel<<<grid_for((size_t)n_w * P, 256, sm), 256, 0, st>>>(n_w, colind, row, jac, y, P, ld, add, out);
   NLO_CHECK_LAUNCH();
   return 0;
 }

@@ -172,6 +172,17 @@ class NlpProblem:
                                              _lib.ptr(res.get("f")), _lib.ptr(res.get("grad_f"))))
         return res
 
+    def jac_tvec(self, jac, y, add=None, out=None, P: Optional[int] = None):
+        """out = add + J^T y per problem (SoA tensors: jac (nnz, ld), y (n_g, ld), add/out (n_w, ld))."""
+        import torch
+        ld = jac.shape[1]
+        P = ld if P is None else P
+        if out is None:
+            out = torch.empty((self.n_w, ld), dtype=torch.float32, device=jac.device)
+        _lib.check(self._L.nlo_nlp_jac_tvec(self._h, jac.data_ptr(), y.data_ptr(), _lib.ptr(add), P, ld, out.data_ptr(),
+                                            torch.cuda.current_stream(jac.device).cuda_stream))
+        return out
+
     def violation(self, g, lbg, ubg, P: Optional[int] = None):
         import torch
         ld = g.shape[1]
