@@ -307,7 +307,8 @@ def run_ours(args):
     if prec == "tc3xf16":
         peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
         bound = "tensor"
-        peak_note = f"{peak_src} cuBLAS bf16 sustained; the kernel runs 3 fp16 passes (hi.hi, hi.lo, lo.hi) per contraction, so its algorithmic ceiling is peak/3"
+        peak_note = (f"{peak_src} cuBLAS bf16 sustained; per point the kernel executes 5 fp16 MMA passes for 2 algorithmic contractions "
+                     "(forward: hi.hi, hi.lo, lo.hi; reverse of the ReLU layer: exact 0/1 mask x hi/lo of diag(w2)W1), so its algorithmic ceiling is peak x 2/5")
     else:
         sm_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
         peak = model_sm_count(L, local_rank) * 128 * 2 * sm_mhz * 1e6 / 1e12
@@ -317,7 +318,7 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32" if prec == "fp32" else "f32 (tcgen05 split-fp16 x3 tiles, fp32 accumulate)", "data": "synthetic",
+        "dtype": "f32" if prec == "fp32" else "f32 (tcgen05 split-fp16 hi/lo tiles, fp32 accumulate)", "data": "synthetic",
         "config": {"workload": f"{YAML} x {P} multi-starts per GPU: NLP eval g + nnz(dg/dw) + f + grad f, SoA fp32 resident in HBM",
                    "problems_per_gpu": P, "sdf_points_per_step_per_gpu": n_pts, "n_w": prob.n_w, "n_g": prob.n_g, "nnz_jac": prob.nnz,
                    "sdf_model": "mlp ReLU 2-128-128-1 (synthetic seeded weights)", "sdf_precision": prec,
@@ -339,9 +340,11 @@ def run_ours(args):
         "best_of_batch": {"merit": best_val, "global_index": best_idx},
     }
     if world == 1 and not args.no_cpu_baseline:
-        rate, dt, threads = time_cpu(args.cpu_problems, 3, 1)
+        cpu_steps = 7
+        rate, dt, threads = time_cpu(args.cpu_problems, cpu_steps, 1)
         cb = {"value": rate, "unit": UNIT, "cores": threads, "host_cpus": os.cpu_count(), "kind": "port",
-              "sample": f"{args.cpu_problems} problems/step x 3 steps ({dt * 3:.1f} s); numpy fp64 assembly + torch-CPU fp32 batched SDF on all host threads"}
+              "sample": f"{args.cpu_problems} of the {P} problems per step x {cpu_steps} steps ({dt * cpu_steps:.1f} s of CPU work); numpy fp64 assembly "
+                        "(oracle.nlp_oracle) + torch-CPU fp32 batched SDF forward + analytic reverse on all host threads"}
         a = reference_call_pattern_rate()
         if a is not None:
             cb["reference_call_pattern_points_per_s_1thread"] = a
@@ -361,7 +364,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--problems", type=int, default=65536, help="multi-start problems per GPU")
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tc3xf16"])
-    ap.add_argument("--cpu-problems", type=int, default=2048, help="problems per CPU-baseline step (bounded sample)")
+    ap.add_argument("--cpu-problems", type=int, default=8192, help="problems per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

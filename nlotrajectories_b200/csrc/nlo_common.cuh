@@ -53,9 +53,10 @@ struct nlo_sdf_model {
   size_t n_w;
   // tensor-path operand images (built on demand by sdf_tc.cu)
   void* d_tc;                // W1 split into fp16 hi | lo images in UMMA core-matrix order
-  size_t tc_bytes;
+  size_t tc_bytes;           // bytes of the images; a ring of 64 tile counters (dynamic tile scheduling) follows them
+  unsigned tc_seq;           // launches so far (selects the counter)
   float tc_params[8];        // TcParams of sdf_tc.cu (scales and bounds)
-  float tc_const[648];       // TcConst of sdf_tc.cu (small vectors handed to the kernel as a __grid_constant__ parameter)
+  float tc_const[776];       // TcConst of sdf_tc.cu (small vectors handed to the kernel as a __grid_constant__ parameter)
   // scratch for the host-buffer entry points
   float* d_io; size_t io_cap;        // device staging
   float* h_io; size_t h_cap;         // pinned staging
@@ -101,6 +102,49 @@ __device__ __forceinline__ void nlo_phi_d2(float a, int act, float prm, float& d
     case NLO_ACT_SIN: { float s, c; sincosf(prm * a, &s, &c); d = prm * c; d2 = -prm * prm * s; } break;
     case NLO_ACT_COS_SCALE: { float s, c; sincosf(a, &s, &c); d = -prm * s; d2 = -prm * c; } break;
     default: d = 1.f; d2 = 0.f; break;
+  }
+}
+
+// ---- SFU sine / cosine behind an exact-enough range reduction (tensor path, sdf_tc.cu) -----------------------
+// The Fourier-feature and SIREN layers (core/nn_architectures.py:8-39) evaluate cos / sin at |a| up to ~10^2
+// (shipped model: |W| up to 24).  sinf / cosf cost ~30-50 instructions each; here the argument is reduced to
+// [-pi, pi] with two FMAs against 2*pi = hi + lo (absolute error ~2e-7: one rounding of a result of magnitude <= pi)
+// and handed to MUFU.SIN / MUFU.COS (absolute error 2^-21.4 on that interval).  Both are below the error the
+// reference's own fp32 evaluation of `a` carries at that magnitude (ulp(50) = 3.8e-6).
+__device__ __forceinline__ float nlo_reduce_2pi(float a) {
+  const float kk = fmaf(a, 0.15915494309189535f, 12582912.f);     // round-to-nearest integer via the 1.5*2^23 trick
+  const float k = kk - 12582912.f;
+  const float r = fmaf(k, -6.2831854820251465f, a);               // fp32(2*pi)
+  return fmaf(k, 1.7484555e-07f, r);                              // fp32(2*pi) - 2*pi
+}
+// (huge arguments: the library's slow path, kept out of line so that unrolled callers stay small)
+static __device__ __noinline__ void nlo_sincos_slow(float a, float* s, float* c) { sincosf(a, s, c); }
+__device__ __forceinline__ void nlo_sincos_fast(float a, float& s, float& c) {
+  if (fabsf(a) > 8192.f) { nlo_sincos_slow(a, &s, &c); return; }
+  const float r = nlo_reduce_2pi(a);
+  s = __sinf(r); c = __cosf(r);
+}
+__device__ __forceinline__ float nlo_cos_fast(float a) {
+  if (fabsf(a) > 8192.f) { float s, c; nlo_sincos_slow(a, &s, &c); return c; }
+  return __cosf(nlo_reduce_2pi(a));
+}
+__device__ __forceinline__ float nlo_sin_fast(float a) {
+  if (fabsf(a) > 8192.f) { float s, c; nlo_sincos_slow(a, &s, &c); return s; }
+  return __sinf(nlo_reduce_2pi(a));
+}
+// activations of the tensor path: identical to nlo_phi / nlo_phi_d except for the SFU trigonometry above
+__device__ __forceinline__ float nlo_phi_tc(float a, int act, float prm) {
+  switch (act) {
+    case NLO_ACT_SIN: return nlo_sin_fast(prm * a);
+    case NLO_ACT_COS_SCALE: return nlo_cos_fast(a) * prm;
+    default: return nlo_phi(a, act, prm);
+  }
+}
+__device__ __forceinline__ void nlo_phi_d_tc(float a, int act, float prm, float& v, float& d) {
+  switch (act) {
+    case NLO_ACT_SIN: { float s, c; nlo_sincos_fast(prm * a, s, c); v = s; d = prm * c; } break;
+    case NLO_ACT_COS_SCALE: { float s, c; nlo_sincos_fast(a, s, c); v = prm * c; d = -prm * s; } break;
+    default: nlo_phi_d(a, act, prm, v, d); break;
   }
 }
 

@@ -7,19 +7,24 @@
 // (scripts/run_benchmark.py:65 with benchmarks/*.yaml model: hidden_dim 128, num_hidden_layers 2) and
 // the shipped FourierMLP-128 (_l4c_generated/nn_sdf.pt).
 //
-// Persistent CTAs of 256 threads, two per SM (so one CTA's SIMT phases overlap the other's MMAs);
-// tile = 128 points == the 128 TMEM lanes; a point is owned by two threads (one per half of the columns)
-// that meet only to add three partial sums per point through shared memory.  The small vectors (W0, b0, b1, w2) sit in __constant__ memory and every loop is
-// fully unrolled, so they enter the arithmetic as constant-bank operands and shared memory is left to
-// the tensor core's B-operand fetches:
+// One persistent CTA of 512 threads per SM; its threads form independent tile groups (H = 128: two groups of 256
+// threads, two threads per point; H = 64: four groups of 128) that share one shared-memory copy of the operand images
+// and each own 2H tensor-memory columns, an mbarrier and a named barrier.  Tile = 128 points == the 128 TMEM lanes;
+// tiles are handed out by a global counter (SMs do not all run at the same speed).  While one group's MMAs run, the
+// other groups' SIMT phases fill the SM; an MMA-issue lock keeps the groups' GEMMs first-come-first-served.
+// The small vectors (W0, b0, b1, w2) sit in __constant__ memory and every loop is fully unrolled, so they enter the
+// arithmetic as constant-bank operands and shared memory is left to the tensor core's B-operand fetches:
 //   layer 0 (SIMT)   h0 = phi0(W0 p + b0)  -> row-scaled, split into fp16 hi/lo -> tcgen05.st -> A (TMEM)
 //   GEMM 1 (tcgen05) Z1[128 x H] = H0 . W1^T   3 passes (lo.hi, hi.lo, hi.hi), B = W1 K-major in smem
-//   epilogue 1       tcgen05.ld Z1; s = w2.phi(z1+b1)+b2; g1 = sbar*w2*phi'(z1+b1) -> hi/lo -> A (TMEM)
-//   GEMM 2 (tcgen05) G0[128 x H] = G1 . W1     the same smem bytes read through an MN-major descriptor
-//   epilogue 2       tcgen05.ld G0; g0 = G0 * phi0'(a0); J = g0 . W0
+//   epilogue 1       tcgen05.ld Z1; s = w2.phi(z1+b1)+b2; g1 = w2*phi'(z1+b1) -> A (TMEM)
+//   GEMM 2 (tcgen05) G0[128 x H] = G1 . W1
+//                      ReLU hidden layer: G1 = mask . diag(w2), so A = the 0/1 mask (exact in fp16, hi only) and
+//                      B = V = diag(w2) W1 (its own hi/lo images): 2 passes instead of 3 and no split in epilogue 1;
+//                      other activations: 3 passes over the W1 image read through an MN-major descriptor
+//   epilogue 2       tcgen05.ld G0; g0 = G0 * phi0'(a0); J = sbar * g0 . W0   (the adjoint seed is applied last)
 // fp16 has tf32's 11 significant bits at twice the MMA rate and half the bytes; its narrow exponent is
-// handled by exact power-of-two scaling: W1 by one global factor (host), every A row (= point) by its own
-// factor from a cheap bound on the row, both undone in the epilogue.
+// handled by exact power-of-two scaling: W1 and V by one global factor each (host), every A row (= point) by its own
+// factor from a cheap bound on the row, all undone in the epilogues.
 // W1*S is split once on the host into fp16 hi + fp16 lo, each stored in UMMA core-matrix order (no swizzle):
 // element (n,k) at ((k/8)*(H/8) + n/8)*128 + (n%8)*16 + (k%8)*2 bytes, which is simultaneously the
 // canonical K-major layout of B(n,k) = W1[n][k] (LBO = 16H, SBO = 128) and the canonical MN-major layout
@@ -54,17 +59,6 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t a = smem_u32(bar);
-  uint32_t ok;
-  do {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // D[tmem] (+)= A[tmem] . B[smem descriptor], kind::f16, issued by one thread
 __device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -131,7 +125,7 @@ __device__ __forceinline__ void row_scale(float bound, float& sc, float& inv) {
 
 template <int A>
 __device__ __forceinline__ void act_vd(float a, int rt, float prm, float& v, float& d) {
-  if (A >= 0) nlo_phi_d(a, A, prm, v, d); else nlo_phi_d(a, rt, prm, v, d);
+  if (A >= 0) nlo_phi_d_tc(a, A, prm, v, d); else nlo_phi_d_tc(a, rt, prm, v, d);
 }
 // upper bound of |phi(a)| given |a| <= ba, and of |phi'|
 __device__ __forceinline__ float act_bound(int act, float prm, float ba) {
@@ -141,47 +135,42 @@ __device__ __forceinline__ float act_bound(int act, float prm, float ba) {
     default: return ba;
   }
 }
-__device__ __forceinline__ float act_dbound(int act, float prm) {
-  switch (act) {
-    case NLO_ACT_SIGMOID: return 0.25f;
-    case NLO_ACT_SIN: case NLO_ACT_COS_SCALE: return fabsf(prm);
-    default: return 1.f;
-  }
-}
-
 constexpr int TILE = 128;          // points per tile == TMEM lanes
 
 struct TcParams {          // built by nlo_sdf_tc_prepare
-  float inv_sw;            // 1 / (power-of-two scale applied to W1 in the fp16 images)
-  float max_w0x, max_w0y, max_b0, max_w2;
+  float inv_sw;            // 1 / (power-of-two scale applied to W1 in its fp16 images)
+  float inv_sv;            // 1 / (power-of-two scale applied to V = diag(w2) W1 in its fp16 images)
+  float inv_sc1;           // 1 / (power-of-two scale folded into w2s, the generic reverse-pass seed vector)
+  float max_w0x, max_w0y, max_b0;
 };
 // Small vectors of the network live in __constant__ memory: with fully unrolled loops every use is an FFMA/FMUL
 // with a constant-bank operand (c[3][imm]) - no load instruction and no shared-memory bandwidth (which the tensor
 // core needs for its B-operand fetches).  One copy per device context; nlo_sdf_tc_launch re-uploads it (after a
 // device-wide sync) whenever a different model is evaluated.
 struct TcConst {
-  float w0x[128], w0y[128], b0[128], b1[128], w2[128];
+  float w0x[128], w0y[128], b0[128], b1[128], w2[128], w2s[128];
   float bout;
 };
 __constant__ TcConst cst;
 
+// One persistent CTA of 512 threads per SM.  Its threads form NGROUPS independent tile groups (H = 128: two groups of
+// 256 threads, two threads per point; H = 64: four groups of 128 threads) - each group owns 2H tensor-memory columns,
+// one mbarrier and one named barrier, and walks its own tiles; the groups meet only at the MMA-issue lock.  While one
+// group's MMAs run, the other groups' SIMT phases fill the SM.  All groups share one copy of the operand images.
 template <int H>
 struct TcCfg {
   static constexpr int IMG_HALFS = H * H;                           // one fp16 image
-  static constexpr size_t BYTES = (size_t)2 * IMG_HALFS * 2 + 2 * 128 * 2 * 4 + 16;
-  static constexpr uint32_t TMEM_COLS = 2 * H;                      // A hi H/2 | A lo H/2 | D H   (power of two)
-  // H = 128: TMEM allows two tiles per SM, so two threads share a point (256-thread CTAs) to have 16 warps per SM;
-  // H = 64: four tiles per SM fit, one thread per point (128-thread CTAs).
-  static constexpr int SPLIT = (H >= 128) ? 2 : 1;
-  static constexpr int THREADS = TILE * SPLIT;
-  static constexpr int CTAS_PER_SM = (512 / TMEM_COLS) > 4 ? 4 : (512 / TMEM_COLS);
+  static constexpr uint32_t TMEM_COLS = 2 * H;                      // per group: A hi H/2 | A lo H/2 | D H
+  static constexpr int SPLIT = (H >= 128) ? 2 : 1;                  // threads per point
+  static constexpr int GROUP_THREADS = TILE * SPLIT;
+  static constexpr int NGROUPS = 512 / TMEM_COLS;
+  static constexpr int THREADS = NGROUPS * GROUP_THREADS;           // 512
+  static constexpr size_t bytes(bool relu_hidden) {
+    return (size_t)(relu_hidden ? 4 : 2) * IMG_HALFS * 2 + (size_t)NGROUPS * 2 * TILE * 2 * 4 + NGROUPS * 8 + 16 + NGROUPS * 4;
+  }
 };
 
 template <int N> struct TmemIO;
-template <> struct TmemIO<32> {
-  __device__ static __forceinline__ void ld(uint32_t a, uint32_t (&v)[32]) { tmem_ld32(a, v); }
-  __device__ static __forceinline__ void st(uint32_t a, const uint32_t (&v)[32]) { tmem_st32(a, v); }
-};
 template <> struct TmemIO<16> {
   __device__ static __forceinline__ void ld(uint32_t a, uint32_t (&v)[16]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -197,32 +186,70 @@ template <> struct TmemIO<16> {
 };
 
 struct TileCtx {
-  uint32_t tmem_base, lane_base, sB_hi, sB_lo, mbar_addr;
+  uint32_t tmem_base, lane_base, sB_hi, sB_lo, sV_hi, sV_lo, mbar_addr, bar_id;
+  int* lock;
+  unsigned int* ctr;       // global tile counter (dynamic scheduling) or nullptr (static striding)
+  uint32_t* next_slot;     // the group's next tile index, fetched while GEMM 1 runs
+  uint32_t ctr_bias;
   int act0, act;
-  float prm0, prm, inv_sw, max_w0x, max_w0y, max_b0, g1_bound;
-  long long* dbg;          // optional phase timeline (NLO_B200_TC_TIMELINE): 8 clock stamps per tile of CTA 0 / 1
+  float prm0, prm, inv_sw, unscale2, max_w0x, max_w0y, max_b0;
+  long long* dbg;          // optional phase timeline (NLO_B200_TC_TIMELINE): clock stamps per tile of CTA 0, groups 0 / 1
 };
 
-// one thread issues the 3 x (H/16) MMAs of a GEMM and commits them to the mbarrier
-template <int H>
-__device__ __forceinline__ void issue_gemm(const TileCtx& c, bool fwd) {
+// named barrier of one tile group
+template <int NT>
+__device__ __forceinline__ void group_bar(uint32_t id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NT) : "memory"); }
+
+__device__ __forceinline__ bool elect_one(uint32_t mask) {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, %1;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred) : "r"(mask));
+  return pred != 0;
+}
+template <int H, bool RELU_BWD>
+__device__ __forceinline__ void issue_mmas(const TileCtx& c, bool fwd) {
   constexpr uint32_t COL_AHI = 0, COL_ALO = H / 2, COL_D = H;
-  constexpr uint32_t IDESC_FWD = umma_idesc_f16(TILE, H, 0), IDESC_BWD = umma_idesc_f16(TILE, H, 1);
-  tc_fence_after();
-  const uint32_t lbo = fwd ? 16u * H : 128u, sbo = fwd ? 128u : 16u * H;
-  const uint32_t kstep_bytes = fwd ? 32u * H : 256u;     // 16 k: two K-adjacent core matrices
-  const uint32_t idesc = fwd ? IDESC_FWD : IDESC_BWD;
+  constexpr uint32_t IDESC_K = umma_idesc_f16(TILE, H, 0), IDESC_MN = umma_idesc_f16(TILE, H, 1);
+  if (!fwd && RELU_BWD) {
 #pragma unroll
-  for (int pass = 0; pass < 3; ++pass) {               // smallest terms first: lo.hi, hi.lo, hi.hi
-    const uint32_t a_col = (pass == 0) ? COL_ALO : COL_AHI;
-    const uint32_t b_base = (pass == 1) ? c.sB_lo : c.sB_hi;
+    for (int pass = 0; pass < 2; ++pass) {               // smaller term first: mask.lo, mask.hi
+      const uint32_t b_base = (pass == 0) ? c.sV_lo : c.sV_hi;
 #pragma unroll
-    for (int ks = 0; ks < H / 16; ++ks) {
-      tc_mma_f16_ts(c.tmem_base + COL_D, c.tmem_base + a_col + ks * 8, umma_desc(b_base + ks * kstep_bytes, lbo, sbo), idesc,
-                    (pass | ks) != 0);
+      for (int ks = 0; ks < H / 16; ++ks)
+        tc_mma_f16_ts(c.tmem_base + COL_D, c.tmem_base + COL_AHI + ks * 8, umma_desc(b_base + ks * 32u * H, 16u * H, 128u), IDESC_K,
+                      (pass | ks) != 0);
+    }
+  } else {
+    const uint32_t lbo = fwd ? 16u * H : 128u, sbo = fwd ? 128u : 16u * H;
+    const uint32_t kstep_bytes = fwd ? 32u * H : 256u;     // 16 k: two K-adjacent core matrices
+    const uint32_t idesc = fwd ? IDESC_K : IDESC_MN;
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {               // smallest terms first: lo.hi, hi.lo, hi.hi
+      const uint32_t a_col = (pass == 0) ? COL_ALO : COL_AHI;
+      const uint32_t b_base = (pass == 1) ? c.sB_lo : c.sB_hi;
+#pragma unroll
+      for (int ks = 0; ks < H / 16; ++ks)
+        tc_mma_f16_ts(c.tmem_base + COL_D, c.tmem_base + a_col + ks * 8, umma_desc(b_base + ks * kstep_bytes, lbo, sbo), idesc,
+                      (pass | ks) != 0);
     }
   }
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(c.mbar_addr) : "memory");
+}
+// Lane 0 of the group issues the MMAs of a GEMM and commits them to the group's mbarrier.  The CTA-wide lock makes the
+// groups' GEMMs run first-come-first-served instead of interleaved instruction by instruction (tcgen05.mma issue
+// blocks while the tensor queue is full, so two concurrent issuers stretch both GEMMs to the sum of the two).
+// The MMAs sit under elect.sync (single-lane mask): ptxas then emits them on the uniform datapath, 2 instructions per
+// MMA, instead of wrapping each one in a ~16-instruction R2UR waterfall loop.  Measured on B200 (G points/s, ReLU
+// H=128 / H=64): this form 6.39 / 15.97; plain single lane 6.02 / 12.54; whole warp converged + elect 5.54 / 15.15.
+template <int H, bool RELU_BWD>
+__device__ __forceinline__ void issue_gemm(const TileCtx& c, bool fwd, long long* dbg) {
+  tc_fence_after();
+  while (atomicCAS(c.lock, 0, 1) != 0) { }
+  if (dbg) dbg[fwd ? 10 : 11] = clock64();
+  if (elect_one(1u)) issue_mmas<H, RELU_BWD>(c, fwd);
+  __threadfence_block();
+  atomicExch(c.lock, 0);
+  // next tile of this group: the atomic's latency hides behind the GEMM that was just issued
+  if (fwd && c.ctr) *c.next_slot = atomicAdd(c.ctr, 1u) + c.ctr_bias;
 }
 __device__ __forceinline__ void mbar_wait_addr(uint32_t a, uint32_t parity) {
   uint32_t ok;
@@ -231,9 +258,13 @@ __device__ __forceinline__ void mbar_wait_addr(uint32_t a, uint32_t parity) {
                  : "=r"(ok) : "r"(a), "r"(parity) : "memory");
   } while (!ok);
 }
+__device__ __forceinline__ uint32_t pack_f16(float v0, float v1) {
+  const __half2 p = __floats2half2_rn(v0, v1);
+  return *reinterpret_cast<const uint32_t*>(&p);
+}
 
-// One tile (128 points).  Two threads own a point: HALF 0 (warps 0-3) the low half of the neurons / D columns,
-// HALF 1 (warps 4-7) the high half; they meet only to add three partial sums per point through shared memory.
+// One tile (128 points) of one group.  SPLIT = 2: two threads own a point - HALF 0 the low half of the neurons / D
+// columns, HALF 1 the high half; they meet only to add three partial sums per point through shared memory.
 // Deliberately NOT inlined into the persistent loop: the constants are loop-invariant, and an inlined body makes
 // the compiler hoist hundreds of them into registers (and spill) instead of feeding them to the arithmetic from
 // the constant bank.
@@ -244,11 +275,15 @@ __device__ __noinline__ uint32_t sdf_tc_tile(TileCtx c, uint32_t phase, float px
   constexpr int HH = H / SPLIT;                    // neurons per thread
   constexpr int C0 = HALF * HH;                    // first neuron / D column of this thread
   constexpr int NCH = HH / 32;                     // 32-neuron chunks per thread
+  constexpr int NT = TILE * SPLIT;                 // threads of the group
+  constexpr bool RH = (ACT == NLO_ACT_RELU);       // ReLU hidden layer: mask x V reverse GEMM
   constexpr uint32_t COL_AHI = HALF * (HH / 2), COL_ALO = H / 2 + HALF * (HH / 2), COL_D = H + C0;
-  const int pt = threadIdx.x & (TILE - 1);
-  long long* dbg = (c.dbg && (threadIdx.x & 127) == 0) ? c.dbg + HALF * 8 : nullptr;
+  const int tg = threadIdx.x % NT;
+  const int pt = tg & (TILE - 1);
+  long long* dbg = (c.dbg && pt == 0) ? c.dbg + HALF * 16 : nullptr;
 #define TC_STAMP(i) do { if (dbg) dbg[i] = clock64(); } while (0)
   TC_STAMP(0);
+  if (dbg) { unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); dbg[12] = (long long)gt; }
   // ---- layer 0 -> A operand (row-scaled fp16 hi/lo) ------------------------------------------------------------
   float sc0, inv0;
   row_scale(act_bound(c.act0, c.prm0, fmaf(fabsf(px), c.max_w0x, fmaf(fabsf(py), c.max_w0y, c.max_b0))) + 1e-30f, sc0, inv0);
@@ -261,7 +296,7 @@ __device__ __noinline__ uint32_t sdf_tc_tile(TileCtx c, uint32_t phase, float px
       for (int e = 0; e < 2; ++e) {
         const int k = C0 + cc * 32 + 2 * q + e;
         const float a = fmaf(cst.w0x[k], px, fmaf(cst.w0y[k], py, cst.b0[k]));
-        if (ACT0 >= 0) v[e] = nlo_phi(a, ACT0, c.prm0) * sc0; else v[e] = nlo_phi(a, c.act0, c.prm0) * sc0;
+        if (ACT0 >= 0) v[e] = nlo_phi_tc(a, ACT0, c.prm0) * sc0; else v[e] = nlo_phi_tc(a, c.act0, c.prm0) * sc0;
       }
       split_pack_f16(v[0], v[1], hi[q], lo[q]);
     }
@@ -278,19 +313,18 @@ __device__ __noinline__ uint32_t sdf_tc_tile(TileCtx c, uint32_t phase, float px
   TC_STAMP(1);
   tc_wait_st();
   tc_fence_before();
-  __syncthreads();
-  if (threadIdx.x == 0) issue_gemm<H>(c, true);
+  group_bar<NT>(c.bar_id);
+  TC_STAMP(8);
+  if (tg == 0) issue_gemm<H, RH>(c, true, dbg);
   TC_STAMP(2);
   mbar_wait_addr(c.mbar_addr, phase); phase ^= 1;
   tc_fence_after();
   TC_STAMP(3);
 
-  // ---- epilogue 1: value, and g1 -> A operand ------------------------------------------------------------------
+  // ---- epilogue 1: value, and the reverse seed g1 = w2 * phi'(z1) -> A operand (the adjoint seed sbar is linear ----
+  // ---- in everything downstream and multiplies the Jacobian at the very end)                                   ----
   float s = HALF == 0 ? cst.bout : 0.f;
   const float unscale1 = inv0 * c.inv_sw;
-  float sc1, inv1;
-  row_scale(fabsf(seed) * c.g1_bound + 1e-30f, sc1, inv1);
-  const float seed_sc = seed * sc1;
   auto epi1 = [&](int cc) {
     uint32_t z[32];
     tmem_ld32(c.lane_base + COL_D + cc * 32, z);
@@ -302,16 +336,22 @@ __device__ __noinline__ uint32_t sdf_tc_tile(TileCtx c, uint32_t phase, float px
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int j = C0 + cc * 32 + 2 * q + e;
-        float v, d;
-        act_vd<ACT>(fmaf(__uint_as_float(z[2 * q + e]), unscale1, cst.b1[j]), c.act, c.prm, v, d);
-        s = fmaf(cst.w2[j], v, s);
-        g[e] = seed_sc * cst.w2[j] * d;
+        const float zz = fmaf(__uint_as_float(z[2 * q + e]), unscale1, cst.b1[j]);
+        if (RH) {
+          s = fmaf(cst.w2[j], fmaxf(zz, 0.f), s);
+          g[e] = zz > 0.f ? 1.f : 0.f;                     // exact in fp16: the w2 factor lives in V = diag(w2) W1
+        } else {
+          float v, d;
+          act_vd<ACT>(zz, c.act, c.prm, v, d);
+          s = fmaf(cst.w2[j], v, s);
+          g[e] = cst.w2s[j] * d;
+        }
       }
-      split_pack_f16(g[0], g[1], hi[q], lo[q]);
+      if (RH) hi[q] = pack_f16(g[0], g[1]); else split_pack_f16(g[0], g[1], hi[q], lo[q]);
     }
     if (want_jac) {
       TmemIO<16>::st(c.lane_base + COL_AHI + cc * 16, hi);
-      TmemIO<16>::st(c.lane_base + COL_ALO + cc * 16, lo);
+      if (!RH) TmemIO<16>::st(c.lane_base + COL_ALO + cc * 16, lo);
     }
   };
   if (FULL) {
@@ -326,8 +366,9 @@ __device__ __noinline__ uint32_t sdf_tc_tile(TileCtx c, uint32_t phase, float px
     TC_STAMP(4);
     tc_wait_st();
     tc_fence_before();
-    __syncthreads();
-    if (threadIdx.x == 0) issue_gemm<H>(c, false);
+    group_bar<NT>(c.bar_id);
+    TC_STAMP(9);
+    if (tg == 0) issue_gemm<H, RH>(c, false, dbg);
     TC_STAMP(5);
     mbar_wait_addr(c.mbar_addr, phase); phase ^= 1;
     tc_fence_after();
@@ -355,7 +396,7 @@ __device__ __noinline__ uint32_t sdf_tc_tile(TileCtx c, uint32_t phase, float px
 #pragma unroll 1
       for (int cc = 0; cc < NCH; ++cc) epi2(cc);
     }
-    const float unscale2 = inv1 * c.inv_sw;
+    const float unscale2 = seed * c.unscale2;
     jx *= unscale2; jy *= unscale2;
   }
   TC_STAMP(7);
@@ -364,7 +405,7 @@ __device__ __noinline__ uint32_t sdf_tc_tile(TileCtx c, uint32_t phase, float px
     if (j_ptr) { j_ptr[0] = jx; j_ptr[jy_off] = jy; }
     // the next tile's tcgen05.st / MMA must not overtake this tile's TMEM reads
     tc_fence_before();
-    __syncthreads();
+    group_bar<NT>(c.bar_id);
     tc_fence_after();
     return phase;
   }
@@ -373,7 +414,7 @@ __device__ __noinline__ uint32_t sdf_tc_tile(TileCtx c, uint32_t phase, float px
   if (HALF == 0) { mine[0] = jy; } else { mine[0] = s; mine[1] = jx; }
   // (this barrier also keeps the next tile's tcgen05.st / MMA from overtaking this tile's TMEM reads)
   tc_fence_before();
-  __syncthreads();
+  group_bar<NT>(c.bar_id);
   tc_fence_after();
   const float* other = part + ((1 - HALF) * TILE + pt) * 2;
   if (HALF == 0) {
@@ -382,86 +423,106 @@ __device__ __noinline__ uint32_t sdf_tc_tile(TileCtx c, uint32_t phase, float px
   } else {
     if (j_ptr) *j_ptr = jy + other[0];
   }
+  // `part` is rewritten by the next tile only after its first group barrier, which every thread reaches after these reads
   return phase;
 }
 
 template <int H, int ACT0, int ACT>
-__global__ void __launch_bounds__(TcCfg<H>::THREADS, TcCfg<H>::CTAS_PER_SM)
+__global__ void __launch_bounds__(TcCfg<H>::THREADS, 1)
 sdf_tc_kernel(SdfNetDev net, TcParams prm_tc, const __half* __restrict__ bimg, const float* __restrict__ x,
               const float* __restrict__ y, const float* __restrict__ sbar, size_t n, float* __restrict__ s_out,
-              float* __restrict__ jx_out, float* __restrict__ jy_out, long long* __restrict__ dbg) {
+              float* __restrict__ jx_out, float* __restrict__ jy_out, unsigned int* __restrict__ tile_ctr, long long* __restrict__ dbg) {
+  using Cfg = TcCfg<H>;
+  constexpr bool RH = (ACT == NLO_ACT_RELU);
+  constexpr int NIMG = RH ? 4 : 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __half* sB = reinterpret_cast<__half*>(smem_raw);                  // hi image | lo image
-  float* sPart = reinterpret_cast<float*>(smem_raw + (size_t)2 * TcCfg<H>::IMG_HALFS * 2);   // [2][TILE][2]
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(sPart + 2 * TILE * 2);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+  __half* sB = reinterpret_cast<__half*>(smem_raw);                  // W1 hi | W1 lo | (V hi | V lo)
+  float* sPart = reinterpret_cast<float*>(smem_raw + (size_t)NIMG * Cfg::IMG_HALFS * 2);   // [NGROUPS][2][TILE][2]
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(sPart + Cfg::NGROUPS * 2 * TILE * 2);       // [NGROUPS]
+  int* lock = reinterpret_cast<int*>(mbar + Cfg::NGROUPS);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lock + 1);
+  uint32_t* next_tile = tmem_slot + 1;                                                      // [NGROUPS]
   const int t = threadIdx.x, warp = t >> 5;
-  const int half = warp >> 2;
-  const int pt = t & (TILE - 1);
+  const int grp = t / Cfg::GROUP_THREADS, tg = t % Cfg::GROUP_THREADS;
+  const int half = (tg >> 5) >> 2;
+  const int pt = tg & (TILE - 1);
 
-  // ---- one-time setup: operand images to smem, barrier, tensor memory ---------------------------------------
+  // ---- one-time setup: operand images to smem, barriers, lock, tensor memory ---------------------------------
   {
     const uint4* src = reinterpret_cast<const uint4*>(bimg);
     uint4* dst = reinterpret_cast<uint4*>(sB);
-    for (int i = t; i < 2 * TcCfg<H>::IMG_HALFS / 8; i += TcCfg<H>::THREADS) dst[i] = src[i];
-    if (t == 0) mbar_init(mbar, 1);
+    for (int i = t; i < NIMG * Cfg::IMG_HALFS / 8; i += Cfg::THREADS) dst[i] = src[i];
+    if (t == 0) {
+      for (int g = 0; g < Cfg::NGROUPS; ++g) mbar_init(mbar + g, 1);
+      *lock = 0;
+    }
     fence_async_smem();                          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
   }
-  if (warp == 0) tmem_alloc(tmem_slot, TcCfg<H>::TMEM_COLS);
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   TileCtx c;
-  c.tmem_base = *tmem_slot;
+  const uint32_t tmem_all = *tmem_slot;
+  c.tmem_base = tmem_all + (uint32_t)grp * Cfg::TMEM_COLS;
   c.lane_base = c.tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-  c.sB_hi = smem_u32(sB); c.sB_lo = smem_u32(sB + TcCfg<H>::IMG_HALFS);
-  c.mbar_addr = smem_u32(mbar);
+  c.sB_hi = smem_u32(sB); c.sB_lo = smem_u32(sB + Cfg::IMG_HALFS);
+  c.sV_hi = smem_u32(sB + 2 * Cfg::IMG_HALFS); c.sV_lo = smem_u32(sB + 3 * Cfg::IMG_HALFS);
+  c.mbar_addr = smem_u32(mbar + grp);
+  c.bar_id = 1 + grp;
+  c.lock = lock;
+  c.ctr = tile_ctr; c.next_slot = next_tile + grp; c.ctr_bias = gridDim.x * Cfg::NGROUPS;
   c.act0 = ACT0 >= 0 ? ACT0 : net.act0; c.act = ACT >= 0 ? ACT : net.act;
   c.prm0 = net.p0; c.prm = net.p; c.inv_sw = prm_tc.inv_sw;
+  c.unscale2 = RH ? prm_tc.inv_sv : prm_tc.inv_sc1 * prm_tc.inv_sw;
   c.max_w0x = prm_tc.max_w0x; c.max_w0y = prm_tc.max_w0y; c.max_b0 = prm_tc.max_b0;
-  c.g1_bound = prm_tc.max_w2 * act_dbound(c.act, c.prm);
   const bool want_jac = (jx_out != nullptr) || (jy_out != nullptr);
-  constexpr bool FULL = (ACT0 == NLO_ACT_RELU && ACT == NLO_ACT_RELU);
+  constexpr bool FULL = (ACT0 >= 0 && ACT >= 0);   // compile-time activations: unrolled, vectors as constant-bank operands
+  float* part = sPart + grp * (2 * TILE * 2);
   uint32_t phase = 0;
+  if (dbg && t == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); dbg[2 * 64 * 32 + blockIdx.x * 4 + 0] = (long long)gt; dbg[2 * 64 * 32 + blockIdx.x * 4 + 2] = clock64(); }
   const size_t n_tiles = (n + TILE - 1) / TILE;
   int it = 0;
-  for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-    // timeline: CTAs 0 and gridDim/2 (same SM on a 2-CTA/SM launch is not guaranteed; smid is recorded), first 64 tiles
-    c.dbg = (dbg && it < 64 && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2)) ? dbg + ((blockIdx.x ? 1 : 0) * 64 + it) * 16 : nullptr;
+  // tiles: the first one by position, the rest from the global counter (SMs do not all run at the same speed; static
+  // striding left the slowest 25 % behind) - or by striding when no counter is given (small launches)
+  for (size_t tile = (size_t)blockIdx.x * Cfg::NGROUPS + grp; tile < n_tiles; ++it) {
+    // timeline: groups 0 and 1 of CTA 0, first 64 tiles
+    c.dbg = (dbg && (it & 15) == 0 && (it >> 4) < 64 && blockIdx.x == 0 && grp < 2) ? dbg + (grp * 64 + (it >> 4)) * 32 : nullptr;
     const size_t i = tile * TILE + pt;
     const bool valid = i < n;
     const size_t ic = valid ? i : n - 1;
     const float px = x[ic], py = y[ic], seed = sbar ? sbar[ic] : 1.f;
-    if (TcCfg<H>::SPLIT == 1) {
+    if (Cfg::SPLIT == 1) {
       // jx and jy are both written by the one owner of the point (both non-null whenever a Jacobian is requested through this path)
-      phase = sdf_tc_tile<H, ACT0, ACT, FULL, 1, 0>(c, phase, px, py, seed, want_jac, sPart, (valid && s_out) ? s_out + i : nullptr,
+      phase = sdf_tc_tile<H, ACT0, ACT, FULL, 1, 0>(c, phase, px, py, seed, want_jac, part, (valid && s_out) ? s_out + i : nullptr,
                                                     (valid && jx_out) ? jx_out + i : nullptr, jy_out - jx_out);
     } else if (half == 0) {
-      phase = sdf_tc_tile<H, ACT0, ACT, FULL, TcCfg<H>::SPLIT, 0>(c, phase, px, py, seed, want_jac, sPart,
-                                                                  (valid && s_out) ? s_out + i : nullptr,
-                                                                  (valid && jx_out) ? jx_out + i : nullptr, 0);
+      phase = sdf_tc_tile<H, ACT0, ACT, FULL, Cfg::SPLIT, 0>(c, phase, px, py, seed, want_jac, part,
+                                                             (valid && s_out) ? s_out + i : nullptr,
+                                                             (valid && jx_out) ? jx_out + i : nullptr, 0);
     } else {
-      phase = sdf_tc_tile<H, ACT0, ACT, FULL, TcCfg<H>::SPLIT, TcCfg<H>::SPLIT - 1>(c, phase, px, py, seed, want_jac, sPart, nullptr,
-                                                                                   (valid && jy_out) ? jy_out + i : nullptr, 0);
+      phase = sdf_tc_tile<H, ACT0, ACT, FULL, Cfg::SPLIT, Cfg::SPLIT - 1>(c, phase, px, py, seed, want_jac, part, nullptr,
+                                                                          (valid && jy_out) ? jy_out + i : nullptr, 0);
     }
+    tile = tile_ctr ? (size_t)next_tile[grp] : tile + (size_t)gridDim.x * Cfg::NGROUPS;
   }
+  tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(c.tmem_base, TcCfg<H>::TMEM_COLS);
+  if (dbg && t == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); dbg[2 * 64 * 32 + blockIdx.x * 4 + 1] = (long long)gt; dbg[2 * 64 * 32 + blockIdx.x * 4 + 3] = clock64(); }
+  if (warp == 0) tmem_dealloc(tmem_all, 512);
 }
 
 unsigned long long g_const_owner[64] = {0};   // per device: uid of the model whose vectors sit in `cst`
 
 template <int H, int ACT0, int ACT>
 int launch_tc(nlo_sdf_model* m, const float* x, const float* y, const float* sbar, size_t n, float* s, float* jx, float* jy, cudaStream_t st) {
+  using Cfg = TcCfg<H>;
   auto kfn = sdf_tc_kernel<H, ACT0, ACT>;
-  // CTAS_PER_SM CTAs share an SM (tensor memory: 512 columns): pad the smem request so that no more fit
-  size_t smem = TcCfg<H>::BYTES;
-  const size_t floor_smem = (size_t)(227 * 1024) / (TcCfg<H>::CTAS_PER_SM + 1) + 1024;
-  if (smem < floor_smem) smem = floor_smem;
+  const size_t smem = Cfg::bytes(ACT == NLO_ACT_RELU);
   NLO_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const size_t tiles = (n + TILE - 1) / TILE;
-  const size_t cap = (size_t)m->sm_count * TcCfg<H>::CTAS_PER_SM;
-  const int grid = (int)(tiles < cap ? tiles : cap);
+  const size_t want = (tiles + Cfg::NGROUPS - 1) / Cfg::NGROUPS;
+  const int grid = (int)(want < (size_t)m->sm_count ? want : (size_t)m->sm_count);   // one persistent CTA per SM
   TcParams prm;
   memcpy(&prm, m->tc_params, sizeof(prm));
   if (g_const_owner[m->device] != m->uid) {
@@ -472,22 +533,46 @@ int launch_tc(nlo_sdf_model* m, const float* x, const float* y, const float* sba
     g_const_owner[m->device] = m->uid;
   }
   long long* dbg = nullptr;
-  if (getenv("NLO_B200_TC_TIMELINE")) {             // debugging aid: dump phase clocks of two CTAs after the launch
-    NLO_CUDA(cudaMalloc(&dbg, 2 * 64 * 16 * sizeof(long long)));
-    NLO_CUDA(cudaMemsetAsync(dbg, 0, 2 * 64 * 16 * sizeof(long long), st));
+  if (getenv("NLO_B200_TC_TIMELINE")) {             // debugging aid: dump phase clocks of two groups after the launch
+    NLO_CUDA(cudaMalloc(&dbg, (2 * 64 * 32 + 4 * 256) * sizeof(long long)));
+    NLO_CUDA(cudaMemsetAsync(dbg, 0, (2 * 64 * 32 + 4 * 256) * sizeof(long long), st));
   }
-  kfn<<<grid, TcCfg<H>::THREADS, smem, st>>>(m->net(), prm, reinterpret_cast<const __half*>(m->d_tc), x, y, sbar, n, s, jx, jy, dbg);
+  unsigned int* ctr = nullptr;
+  if (tiles > (size_t)grid * Cfg::NGROUPS) {         // more than one tile per group: balance dynamically
+    ctr = reinterpret_cast<unsigned int*>(static_cast<char*>(m->d_tc) + m->tc_bytes) + (m->tc_seq++ & 63u);
+    NLO_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st));
+  }
+  kfn<<<grid, Cfg::THREADS, smem, st>>>(m->net(), prm, reinterpret_cast<const __half*>(m->d_tc), x, y, sbar, n, s, jx, jy, ctr, dbg);
   if (dbg) {
-    std::vector<long long> h(2 * 64 * 16);
+    std::vector<long long> h(2 * 64 * 32 + 4 * 256);
     NLO_CUDA(cudaMemcpyAsync(h.data(), dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
     NLO_CUDA(cudaStreamSynchronize(st));
     cudaFree(dbg);
-    for (int cta = 0; cta < 2; ++cta)
+    {
+      const long long* q = h.data() + 2 * 64 * 32;
+      long long t0 = q[0], t1 = q[1], dmin = 1LL << 60, dmax = 0; double mhz_min = 1e9, mhz_max = 0;
+      for (int b = 0; b < grid && b < 256; ++b) {
+        t0 = q[4 * b] < t0 ? q[4 * b] : t0; t1 = q[4 * b + 1] > t1 ? q[4 * b + 1] : t1;
+        const long long d = q[4 * b + 1] - q[4 * b]; dmin = d < dmin ? d : dmin; dmax = d > dmax ? d : dmax;
+        const double mhz = 1e3 * (double)(q[4 * b + 3] - q[4 * b + 2]) / (double)d; mhz_min = mhz < mhz_min ? mhz : mhz_min; mhz_max = mhz > mhz_max ? mhz : mhz_max;
+      }
+      fprintf(stderr, "[tc timeline] kernel %lld ns first-start to last-end; per-CTA duration %lld..%lld ns; per-CTA clock %.0f..%.0f MHz; CTA0 %lld ns\n",
+              t1 - t0, dmin, dmax, mhz_min, mhz_max, q[1] - q[0]);
+    }
+    for (int g = 0; g < 2; ++g)
       for (int it = 8; it < 14; ++it) {
-        const long long* r = h.data() + (cta * 64 + it) * 16;
-        fprintf(stderr, "[tc timeline] cta%d tile%2d half0: L0 %5lld sync+issue %5lld mma1 %5lld E1 %5lld sync+issue %5lld mma2 %5lld E2 %5lld | start-to-start %6lld | half1 L0 %5lld E1 %5lld E2 %5lld\n",
-                cta, it, r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[5] - r[4], r[6] - r[5], r[7] - r[6],
-                (h.data() + (cta * 64 + it + 1) * 16)[0] - r[0], r[9] - r[8], r[12] - r[11], r[15] - r[14]);
+        const long long* r = h.data() + (g * 64 + it) * 32;
+        if (it == 8) {
+          for (int q = 0; q + 8 < 64; q += 8) {
+            const long long* r0 = h.data() + (g * 64 + q) * 32; const long long* r1 = h.data() + (g * 64 + q + 8) * 32;
+            if (r1[0] == 0) break;
+            fprintf(stderr, "[tc timeline] group%d tiles %4d..%4d: %lld cycles in %lld ns -> %.0f MHz, %.0f cycles/tile\n", g, q * 16, (q + 8) * 16,
+                    r1[0] - r0[0], r1[12] - r0[12], 1e3 * (double)(r1[0] - r0[0]) / (double)(r1[12] - r0[12]), (double)(r1[0] - r0[0]) / 128.0);
+          }
+        }
+        fprintf(stderr, "[tc timeline] group%d tile%2d half0: L0 %5lld bar %5lld lock %5lld issue %5lld mma1 %5lld E1 %5lld bar %5lld lock %5lld issue %5lld mma2 %5lld E2 %5lld | start-to-start %6lld | half1 L0 %5lld E1 %5lld E2 %5lld\n",
+                g, it, r[1] - r[0], r[8] - r[1], r[10] - r[8], r[2] - r[10], r[3] - r[2], r[4] - r[3], r[9] - r[4], r[11] - r[9], r[5] - r[11], r[6] - r[5], r[7] - r[6],
+                0LL, r[17] - r[16], r[20] - r[19], r[23] - r[22]);
       }
   }
   NLO_CHECK_LAUNCH();
@@ -500,48 +585,75 @@ bool nlo_sdf_tc_supported(const nlo_sdf_desc* d) {
   return d->n_hidden_mats == 1 && (d->hidden == 64 || d->hidden == 128);
 }
 
-// Scale W1 by a power of two into fp16's range, split into fp16 hi + lo, store both in UMMA core-matrix order.
+// power-of-two scale that puts mx into [2^13, 2^14)
+static float tc_pow2_scale(float mx) {
+  int ex = 0;
+  if (mx > 0.f) frexpf(mx, &ex);                        // mx = f * 2^ex, f in [0.5, 1)
+  return ldexpf(1.f, 14 - ex);
+}
+// element (n, k) of a K-major operand image in UMMA core-matrix order (no swizzle), in halfs
+static size_t tc_img_off(int n, int k, int H) { return ((size_t)(k / 8) * (H / 8) + n / 8) * 64 + (n % 8) * 8 + (k % 8); }
+
+// Scale W1 (and V = diag(w2) W1) by a power of two into fp16's range, split into fp16 hi + lo, store in UMMA
+// core-matrix order: images W1 hi | W1 lo | V hi | V lo.
 int nlo_sdf_tc_prepare(nlo_sdf_model* m, const float* w) {
   const int H = (int)m->desc.hidden;
   const float* W0 = w;
   const float* b0 = w + 2 * H;
   const float* W1 = w + 3 * H;                          // blob order: W0[H][2], b0[H], W1[H][H], b1[H], w_out[H], b_out
-  const float* w2 = W1 + (size_t)H * H + H;
-  float mx = 0.f;
-  for (size_t i = 0; i < (size_t)H * H; ++i) mx = fmaxf(mx, fabsf(W1[i]));
-  int ex = 0;
-  if (mx > 0.f) frexpf(mx, &ex);                        // mx = f * 2^ex, f in [0.5, 1)
-  const float sw = ldexpf(1.f, 14 - ex);                // max |W1| * sw in [2^13, 2^14)
+  const float* b1 = W1 + (size_t)H * H;
+  const float* w2 = b1 + H;
+  float mx = 0.f, mv = 0.f, mw2 = 0.f;
+  for (int j = 0; j < H; ++j) {
+    mw2 = fmaxf(mw2, fabsf(w2[j]));
+    for (int k = 0; k < H; ++k) {
+      mx = fmaxf(mx, fabsf(W1[(size_t)j * H + k]));
+      mv = fmaxf(mv, (float)fabs((double)w2[j] * (double)W1[(size_t)j * H + k]));
+    }
+  }
+  const float sw = tc_pow2_scale(mx), sv = tc_pow2_scale(mv);
+  const int act = (int)m->desc.act;
+  const float dbound = act == NLO_ACT_SIGMOID ? 0.25f : (act == NLO_ACT_SIN || act == NLO_ACT_COS_SCALE) ? fabsf(m->desc.p) : 1.f;
+  const float sc1 = tc_pow2_scale(mw2 * dbound);
   TcParams prm;
-  prm.inv_sw = 1.f / sw;
-  prm.max_w0x = prm.max_w0y = prm.max_b0 = prm.max_w2 = 0.f;
+  prm.inv_sw = 1.f / sw; prm.inv_sv = 1.f / sv; prm.inv_sc1 = 1.f / sc1;
+  prm.max_w0x = prm.max_w0y = prm.max_b0 = 0.f;
   for (int k = 0; k < H; ++k) {
     prm.max_w0x = fmaxf(prm.max_w0x, fabsf(W0[2 * k])); prm.max_w0y = fmaxf(prm.max_w0y, fabsf(W0[2 * k + 1]));
-    prm.max_b0 = fmaxf(prm.max_b0, fabsf(b0[k])); prm.max_w2 = fmaxf(prm.max_w2, fabsf(w2[k]));
+    prm.max_b0 = fmaxf(prm.max_b0, fabsf(b0[k]));
   }
   static_assert(sizeof(TcParams) <= sizeof(m->tc_params), "tc_params too small");
   memcpy(m->tc_params, &prm, sizeof(prm));
   static_assert(sizeof(TcConst) <= sizeof(m->tc_const), "tc_const too small");
   TcConst* cst = reinterpret_cast<TcConst*>(m->tc_const);
   memset(cst, 0, sizeof(TcConst));
-  const float* b1 = W1 + (size_t)H * H;
-  for (int k = 0; k < H; ++k) { cst->w0x[k] = W0[2 * k]; cst->w0y[k] = W0[2 * k + 1]; cst->b0[k] = b0[k]; cst->b1[k] = b1[k]; cst->w2[k] = w2[k]; }
+  for (int k = 0; k < H; ++k) {
+    cst->w0x[k] = W0[2 * k]; cst->w0y[k] = W0[2 * k + 1]; cst->b0[k] = b0[k]; cst->b1[k] = b1[k]; cst->w2[k] = w2[k];
+    cst->w2s[k] = w2[k] * sc1;
+  }
   cst->bout = w2[H];
-  std::vector<__half> img((size_t)2 * H * H);
+  const size_t HH = (size_t)H * H;
+  std::vector<__half> img(4 * HH);
   for (int nn = 0; nn < H; ++nn)
     for (int k = 0; k < H; ++k) {
+      // forward / generic reverse operand: B(n, k) = W1[n][k]
       const float v = W1[(size_t)nn * H + k] * sw;
       const __half hi = __float2half_rn(v);
-      const __half lo = __float2half_rn(v - __half2float(hi));
-      const size_t off = ((size_t)(k / 8) * (H / 8) + nn / 8) * 64 + (nn % 8) * 8 + (k % 8);   // in halfs
+      const size_t off = tc_img_off(nn, k, H);
       img[off] = hi;
-      img[(size_t)H * H + off] = lo;
+      img[HH + off] = __float2half_rn(v - __half2float(hi));
+      // ReLU reverse operand: B'(n' = nn, k' = k) = V[k][nn] = w2[k] W1[k][nn]   (n' = input neuron, k' = hidden neuron)
+      const double vv = (double)w2[k] * (double)W1[(size_t)k * H + nn] * (double)sv;
+      const __half vhi = __float2half_rn((float)vv);
+      img[2 * HH + off] = vhi;
+      img[3 * HH + off] = __float2half_rn((float)(vv - (double)__half2float(vhi)));
     }
   if (m->d_tc) cudaFree(m->d_tc);
   m->d_tc = nullptr;
-  NLO_CUDA(cudaMalloc(&m->d_tc, img.size() * sizeof(__half)));
+  NLO_CUDA(cudaMalloc(&m->d_tc, img.size() * sizeof(__half) + 64 * sizeof(unsigned int)));
   NLO_CUDA(cudaMemcpy(m->d_tc, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice));
   m->tc_bytes = img.size() * sizeof(__half);
+  m->tc_seq = 0;
   return 0;
 }
 
