@@ -151,10 +151,8 @@ __global__ void __launch_bounds__(256) nlp_dyn_kernel(NlpDev L, const float* __r
                                                       float* __restrict__ g, float* __restrict__ jac) {
   using D = Dyn<DYN>;
   constexpr int nx = D::nx, nu = D::nu;
-  const size_t total = (size_t)L.N * P;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-    const int k = (int)(idx / P);
-    const size_t p = idx - (size_t)k * P;
+  const int k = blockIdx.y;                       // interval: uniform per block, no index division
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (size_t)gridDim.x * blockDim.x) {
     float x[nx], xn[nx], u[nu], f[nx], A[D::nA > 0 ? D::nA : 1], B[D::nB];
 #pragma unroll
     for (int i = 0; i < nx; ++i) { x[i] = w[(size_t)(k * nx + i) * ld + p]; xn[i] = w[(size_t)((k + 1) * nx + i) * ld + p]; }
@@ -188,10 +186,8 @@ __global__ void __launch_bounds__(256) nlp_dyn_kernel(NlpDev L, const float* __r
 // ---- rows that are plain copies of a variable (init, terminal, slack >= 0, control box): dg/dw = 1 ----
 __global__ void __launch_bounds__(256) nlp_copy_rows_kernel(NlpDev L, const float* __restrict__ w, size_t P, size_t ld,
                                                             float* __restrict__ g, float* __restrict__ jac) {
-  const size_t total = (size_t)L.n_copy * P;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-    const int r = (int)(idx / P);
-    const size_t p = idx - (size_t)r * P;
+  const int r = blockIdx.y;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (size_t)gridDim.x * blockDim.x) {
     if (g) g[(size_t)L.copy_row[r] * ld + p] = w[(size_t)L.copy_var[r] * ld + p];
     if (jac) jac[(size_t)L.copy_nz[r] * ld + p] = 1.f;
   }
@@ -200,10 +196,8 @@ __global__ void __launch_bounds__(256) nlp_copy_rows_kernel(NlpDev L, const floa
 // ---- K3a: footprint points (core/geometry.py:78-83) ------------------------------------------------------
 __global__ void __launch_bounds__(256) nlp_points_kernel(NlpDev L, const float* __restrict__ w, size_t P, size_t ld,
                                                          float* __restrict__ px, float* __restrict__ py) {
-  const size_t total = (size_t)(L.N + 1) * P;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-    const int k = (int)(idx / P);
-    const size_t p = idx - (size_t)k * P;
+  const int k = blockIdx.y;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (size_t)gridDim.x * blockDim.x) {
     const float x = w[(size_t)(k * L.nx + 0) * ld + p], y = w[(size_t)(k * L.nx + 1) * ld + p];
     if (L.shape == NLO_SHAPE_DOT) { px[(size_t)k * P + p] = x; py[(size_t)k * P + p] = y; continue; }
     float s, c; sincosf(w[(size_t)(k * L.nx + 2) * ld + p], &s, &c);
@@ -236,10 +230,8 @@ __global__ void __launch_bounds__(256) nlp_circles_kernel(NlpDev L, const float*
 __global__ void __launch_bounds__(256) nlp_sdf_rows_kernel(NlpDev L, const float* __restrict__ w, size_t P, size_t ld,
                                                            const float* __restrict__ s, const float* __restrict__ jx,
                                                            const float* __restrict__ jy, float* __restrict__ g, float* __restrict__ jac) {
-  const size_t total = (size_t)(L.N + 1) * P;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-    const int k = (int)(idx / P);
-    const size_t p = idx - (size_t)k * P;
+  const int k = blockIdx.y;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (size_t)gridDim.x * blockDim.x) {
     const int* __restrict__ nz = L.nzmap + L.e_off_sdf + k * L.rows_per_knot * L.nnz_sdf_row;
     if (L.shape == NLO_SHAPE_DOT) {
       const size_t q = (size_t)k * P + p;
@@ -280,56 +272,83 @@ __global__ void __launch_bounds__(256) nlp_sdf_rows_kernel(NlpDev L, const float
 }
 
 // ---- K4: objective and gradient (core/runner.py:80-98) -----------------------------------------------------
+// Objective: a block is 32 problems x 8 knot ranges (problem index fastest -> every load is one 128-byte line per warp);
+// the 8 partial sums of a problem meet in shared memory.
 __global__ void __launch_bounds__(256) nlp_obj_kernel(NlpDev L, const float* __restrict__ w, size_t P, size_t ld, float* __restrict__ f) {
-  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (size_t)gridDim.x * blockDim.x) {
+  __shared__ float part[8][33];
+  const int tx = threadIdx.x & 31, c = threadIdx.x >> 5;
+  for (size_t p0 = (size_t)blockIdx.x * 32; p0 < P; p0 += (size_t)gridDim.x * 32) {
+    const size_t p = p0 + tx;
     float acc = 0.f;
-    float x0 = w[p], y0 = w[ld + p];
-    for (int k = 1; k <= L.N; ++k) {
-      const float x1 = w[(size_t)(k * L.nx) * ld + p], y1 = w[(size_t)(k * L.nx + 1) * ld + p];
-      const float dx = x1 - x0, dy = y1 - y0;
-      acc += sqrtf(dx * dx + dy * dy + NLO_EPS_PATH);
-      x0 = x1; y0 = y1;
+    if (p < P) {
+      const int per = (L.N + 7) / 8;
+      const int k0 = c * per + 1, k1 = min(L.N, (c + 1) * per);
+      if (k0 <= k1) {
+        float x0 = w[(size_t)((k0 - 1) * L.nx) * ld + p], y0 = w[(size_t)((k0 - 1) * L.nx + 1) * ld + p];
+#pragma unroll 4
+        for (int k = k0; k <= k1; ++k) {
+          const float x1 = w[(size_t)(k * L.nx) * ld + p], y1 = w[(size_t)(k * L.nx + 1) * ld + p];
+          const float dx = x1 - x0, dy = y1 - y0;
+          acc += sqrtf(dx * dx + dy * dy + NLO_EPS_PATH);
+          x0 = x1; y0 = y1;
+        }
+      }
+      if (L.use_slack) {
+        const int pers = (L.N + 8) / 8;
+        float ss = 0.f;
+        for (int k = c * pers; k < min(L.N + 1, (c + 1) * pers); ++k) { const float v = w[(size_t)(L.n_X + L.n_U + k) * ld + p]; ss = fmaf(v, v, ss); }
+        acc = fmaf(L.slack_penalty, ss, acc);
+      }
+      if (L.use_smooth) {
+        const int nq = (L.N - 1) * L.nu, perq = (nq + 7) / 8;
+        float uu = 0.f;
+#pragma unroll 4
+        for (int q = c * perq; q < min(nq, (c + 1) * perq); ++q) { const float v = w[(size_t)(L.n_X + q) * ld + p]; uu = fmaf(v, v, uu); }
+        acc = fmaf(L.smooth_weight, uu, acc);
+      }
     }
-    if (L.use_slack) {
-      float ss = 0.f;
-      for (int k = 0; k <= L.N; ++k) { const float v = w[(size_t)(L.n_X + L.n_U + k) * ld + p]; ss = fmaf(v, v, ss); }
-      acc = fmaf(L.slack_penalty, ss, acc);
+    part[c][tx] = acc;
+    __syncthreads();
+    if (c == 0 && p < P) {
+      float t = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) t += part[q][tx];      // fixed order: deterministic
+      f[p] = t;
     }
-    if (L.use_smooth) {
-      float uu = 0.f;
-      for (int q = 0; q < (L.N - 1) * L.nu; ++q) { const float v = w[(size_t)(L.n_X + q) * ld + p]; uu = fmaf(v, v, uu); }
-      acc = fmaf(L.smooth_weight, uu, acc);
-    }
-    f[p] = acc;
+    __syncthreads();
   }
 }
 
+// Gradient: blockIdx.y = knot (uniform per block, no index division); a thread writes every gradient entry that belongs
+// to its (problem, knot): the nx state entries, the nu controls of interval k and the knot's slack.
 __global__ void __launch_bounds__(256) nlp_grad_kernel(NlpDev L, const float* __restrict__ w, size_t P, size_t ld, float* __restrict__ grad) {
-  const size_t total = (size_t)L.n_w * P;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-    const int v = (int)(idx / P);
-    const size_t p = idx - (size_t)v * P;
-    float out = 0.f;
-    if (v < L.n_X) {
-      const int k = v / L.nx, i = v - k * L.nx;
-      if (i < 2) {
-        const float xk = w[(size_t)(k * L.nx) * ld + p], yk = w[(size_t)(k * L.nx + 1) * ld + p];
-        if (k > 0) {
-          const float dx = xk - w[(size_t)((k - 1) * L.nx) * ld + p], dy = yk - w[(size_t)((k - 1) * L.nx + 1) * ld + p];
-          out += (i == 0 ? dx : dy) * rsqrtf(dx * dx + dy * dy + NLO_EPS_PATH);
-        }
-        if (k < L.N) {
-          const float dx = w[(size_t)((k + 1) * L.nx) * ld + p] - xk, dy = w[(size_t)((k + 1) * L.nx + 1) * ld + p] - yk;
-          out -= (i == 0 ? dx : dy) * rsqrtf(dx * dx + dy * dy + NLO_EPS_PATH);
-        }
-      }
-    } else if (v < L.n_X + L.n_U) {
-      const int k = (v - L.n_X) / L.nu;
-      if (L.use_smooth && k < L.N - 1) out = 2.f * L.smooth_weight * w[(size_t)v * ld + p];
-    } else {
-      out = 2.f * L.slack_penalty * w[(size_t)v * ld + p];
+  const int k = blockIdx.y;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (size_t)gridDim.x * blockDim.x) {
+    const float xk = w[(size_t)(k * L.nx) * ld + p], yk = w[(size_t)(k * L.nx + 1) * ld + p];
+    float gx = 0.f, gy = 0.f;
+    if (k > 0) {
+      const float dx = xk - w[(size_t)((k - 1) * L.nx) * ld + p], dy = yk - w[(size_t)((k - 1) * L.nx + 1) * ld + p];
+      const float r = rsqrtf(dx * dx + dy * dy + NLO_EPS_PATH);
+      gx += dx * r; gy += dy * r;
     }
-    grad[(size_t)v * ld + p] = out;
+    if (k < L.N) {
+      const float dx = w[(size_t)((k + 1) * L.nx) * ld + p] - xk, dy = w[(size_t)((k + 1) * L.nx + 1) * ld + p] - yk;
+      const float r = rsqrtf(dx * dx + dy * dy + NLO_EPS_PATH);
+      gx -= dx * r; gy -= dy * r;
+    }
+    grad[(size_t)(k * L.nx) * ld + p] = gx;
+    grad[(size_t)(k * L.nx + 1) * ld + p] = gy;
+    for (int i = 2; i < L.nx; ++i) grad[(size_t)(k * L.nx + i) * ld + p] = 0.f;
+    if (k < L.N) {
+      for (int i = 0; i < L.nu; ++i) {
+        const size_t v = (size_t)(L.n_X + k * L.nu + i);
+        grad[v * ld + p] = (L.use_smooth && k < L.N - 1) ? 2.f * L.smooth_weight * w[v * ld + p] : 0.f;
+      }
+    }
+    if (L.use_slack) {
+      const size_t v = (size_t)(L.n_X + L.n_U + k);
+      grad[v * ld + p] = 2.f * L.slack_penalty * w[v * ld + p];
+    }
   }
 }
 
@@ -396,17 +415,17 @@ int nlo_nlp_launch_assembly(nlo_nlp* p, const NlpScratch& sc, const float* w, si
   const int sm = p->sm_count;
   if (phase == 0) {
     if (g || jac) {
-      const int grid = grid_for((size_t)L.N * P, 256, sm);
+      const unsigned gx = (unsigned)std::min<size_t>((P + 255) / 256, 4096);
       switch (L.dyn) {
-#define NLO_CASE(D) case D: nlp_dyn_kernel<D><<<grid, 256, 0, st>>>(L, w, P, ld, g, jac); break;
+#define NLO_CASE(D) case D: nlp_dyn_kernel<D><<<dim3(gx, (unsigned)L.N), 256, 0, st>>>(L, w, P, ld, g, jac); break;
         NLO_CASE(NLO_DYN_POINT_1ST) NLO_CASE(NLO_DYN_POINT_2ND) NLO_CASE(NLO_DYN_UNICYCLE)
         NLO_CASE(NLO_DYN_UNICYCLE_2ND) NLO_CASE(NLO_DYN_ACKERMANN) NLO_CASE(NLO_DYN_ACKERMANN_2ND)
 #undef NLO_CASE
       }
       NLO_CHECK_LAUNCH();
-      nlp_copy_rows_kernel<<<grid_for((size_t)L.n_copy * P, 256, sm), 256, 0, st>>>(L, w, P, ld, g, jac);
+      nlp_copy_rows_kernel<<<dim3(gx, (unsigned)L.n_copy), 256, 0, st>>>(L, w, P, ld, g, jac);
       NLO_CHECK_LAUNCH();
-      nlp_points_kernel<<<grid_for((size_t)(L.N + 1) * P, 256, sm), 256, 0, st>>>(L, w, P, ld, sc.px, sc.py);
+      nlp_points_kernel<<<dim3(gx, (unsigned)(L.N + 1)), 256, 0, st>>>(L, w, P, ld, sc.px, sc.py);
       NLO_CHECK_LAUNCH();
       if (L.sdf_mode == NLO_SDF_CIRCLES) {
         const size_t n = (size_t)(L.N + 1) * L.nb * P;
@@ -414,11 +433,15 @@ int nlo_nlp_launch_assembly(nlo_nlp* p, const NlpScratch& sc, const float* w, si
         NLO_CHECK_LAUNCH();
       }
     }
-    if (f) { nlp_obj_kernel<<<grid_for(P, 128, sm), 128, 0, st>>>(L, w, P, ld, f); NLO_CHECK_LAUNCH(); }
-    if (grad_f) { nlp_grad_kernel<<<grid_for((size_t)L.n_w * P, 256, sm), 256, 0, st>>>(L, w, P, ld, grad_f); NLO_CHECK_LAUNCH(); }
+    if (f) { nlp_obj_kernel<<<grid_for(P * 8, 256, sm), 256, 0, st>>>(L, w, P, ld, f); NLO_CHECK_LAUNCH(); }
+    if (grad_f) {
+      const dim3 grid((unsigned)std::min<size_t>((P + 255) / 256, 4096), (unsigned)(L.N + 1));
+      nlp_grad_kernel<<<grid, 256, 0, st>>>(L, w, P, ld, grad_f);
+      NLO_CHECK_LAUNCH();
+    }
   } else {
     if (g || jac) {
-      nlp_sdf_rows_kernel<<<grid_for((size_t)(L.N + 1) * P, 256, sm), 256, 0, st>>>(L, w, P, ld, sc.s, sc.jx, sc.jy, g, jac);
+      nlp_sdf_rows_kernel<<<dim3((unsigned)std::min<size_t>((P + 255) / 256, 4096), (unsigned)(L.N + 1)), 256, 0, st>>>(L, w, P, ld, sc.s, sc.jx, sc.jy, g, jac);
       NLO_CHECK_LAUNCH();
     }
   }
