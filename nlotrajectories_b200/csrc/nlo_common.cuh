@@ -159,3 +159,8 @@ bool nlo_sdf_tc_supported(const nlo_sdf_desc* d);
 int nlo_sdf_tc_prepare(nlo_sdf_model* m, const float* weights_host);
 int nlo_sdf_tc_launch(nlo_sdf_model* m, const float* x, const float* y, const float* sbar, size_t n,
                       float* s, float* jx, float* jy, cudaStream_t st);
+// sdf_tc256.cu (reached through the three nlo_sdf_tc_* entry points above)
+bool nlo_sdf_tc256_supported(const nlo_sdf_desc* d);
+int nlo_sdf_tc256_prepare(nlo_sdf_model* m, const float* weights_host);
+int nlo_sdf_tc256_launch(nlo_sdf_model* m, const float* x, const float* y, const float* sbar, size_t n,
+                         float* s, float* jx, float* jy, cudaStream_t st);

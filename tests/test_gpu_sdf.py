@@ -40,6 +40,9 @@ NETS = {
     "siren64x2": lambda: so.synthetic_siren(64, 2, omega0=30.0, seed=7),
     "fourier64_tanh": lambda: so.synthetic_fourier(64, 1, scale=3.0, seed=8, act=so.ACT_TANH),
     "relu16x0": lambda: so.synthetic_mlp(16, 0, seed=9),
+    "fourier256_relu": lambda: so.synthetic_fourier(256, 1, scale=2.0, seed=10),      # H = 256 tensor path, cos features
+    "fourier128_relu": lambda: so.synthetic_fourier(128, 1, scale=2.0, seed=12),
+    "tanh128": lambda: so.synthetic_mlp(128, 1, seed=13, act=so.ACT_TANH),            # generic 3-pass reverse GEMM
 }
 
 
@@ -122,6 +125,27 @@ def test_edge_cases_empty_single_and_host_path(shipped_net, torch_cuda):
     assert out.shape == grid_x.shape
     with pytest.raises(TypeError):
         NNObstacle(None, model).approximated_sdf(1.0, 2.0)
+    model.close()
+
+
+@pytest.mark.parametrize("name", ["relu256", "relu64", "fourier256_relu"])
+@pytest.mark.parametrize("n", [1, 127, 129, 128 * 148 + 5, 128 * 148 * 4 + 77])
+def test_tensor_paths_ragged_sizes(name, n, torch_cuda):
+    """Tile / group / ring bookkeeping of the tensor kernels at sizes around one tile, one tile per SM and a few per SM
+    (static striding for H = 256, counter-scheduled groups for H = 64)."""
+    from nlotrajectories_b200.sdf import LearnedSDF
+    net = NETS[name]()
+    model = LearnedSDF(to_weights(net))
+    assert model.precision == "tc3xf16"
+    P = sample_points(n, seed=100 + n % 97)
+    s_ref, J_ref = so.value_jac(net.astype(np.float64), P.astype(np.float64))
+    for _ in range(2):                                   # twice: barrier phases / counters must be reusable
+        s, J = run_device(model, torch_cuda, P)
+        tie = kink_mask(net, P)
+        assert not close(s, s_ref, TOL).any()
+        assert not (close(J, J_ref, TOL).any(axis=1) & ~tie).any()
+    s_only, _ = run_device(model, torch_cuda, P, want_jac=False)
+    assert np.array_equal(s_only, s)
     model.close()
 
 

@@ -29,11 +29,12 @@ def timed(fn, reps):
     return e0.elapsed_time(e1) / reps
 
 
-def sdf_sweep(max_log=26):
+def sdf_sweep(max_log=28):
     nets = {"relu64": so.synthetic_mlp(64, 1, seed=1), "relu128": so.synthetic_mlp(128, 1, seed=0), "relu256": so.synthetic_mlp(256, 1, seed=2),
             "shipped_fourier128": so.from_npz(REPO / "tests/golden/sdf_shipped_fourier128_weights.npz")}
-    for name, net in nets.items():
-        model = LearnedSDF(to_weights(net))
+    runs = [(name, net, "auto") for name, net in nets.items()] + [("relu128", nets["relu128"], "fp32"), ("relu256", nets["relu256"], "fp32")]
+    for name, net, prec in runs:
+        model = LearnedSDF(to_weights(net), precision=prec)
         for logn in (20, 22, 24, 26, 28):
             if logn > max_log or (model.precision == "fp32" and logn > 22): continue
             n = 1 << logn
@@ -92,6 +93,6 @@ def casadi_latency():
 
 
 if __name__ == "__main__":
-    sdf_sweep(int(sys.argv[1]) if len(sys.argv) > 1 else 26)
+    sdf_sweep(int(sys.argv[1]) if len(sys.argv) > 1 else 28)
     nlp_rows()
     casadi_latency()
