@@ -215,6 +215,16 @@ NLO_API int nlo_nlp_eval(nlo_nlp* p, const float* w, size_t P, size_t ld,
  * out [n_w][ld].  The product a constrained solver needs for the gradient of its (augmented) Lagrangian.        */
 NLO_API int nlo_nlp_jac_tvec(nlo_nlp* p, const float* jac, const float* y, const float* add, size_t P, size_t ld,
                              float* out, void* stream);
+/* Hessian of the Lagrangian  sigma * hess f + sum_r lam_r * hess g_r  (what IPOPT's eval_h asks CasADi's nlp_hess_l
+ * for; core/runner.py:113-125 leaves hessian_approximation at its default "exact").  Built from the second
+ * derivatives of core/dynamics.py:59-148, core/geometry.py:78-117, core/utils.py:28-31, core/runner.py:80-98 and
+ * jac_adj1_nn_sdf (_l4c_generated/nn_sdf.cpp:88-104).  Structural non-zeros of the UPPER triangle in
+ * compressed-column order: colind[n_w+1], row[nnz_hess].
+ *   sigma fp32 [P] or NULL (= 1)     lam fp32 [n_g][ld]     hess fp32 [nnz_hess][ld]                              */
+NLO_API long long nlo_nlp_nnz_hess(const nlo_nlp* p);
+NLO_API int  nlo_nlp_hess_sparsity(const nlo_nlp* p, int32_t* colind, int32_t* row);
+NLO_API int  nlo_nlp_hess(nlo_nlp* p, const float* w, const float* sigma, const float* lam, size_t P, size_t ld,
+                          float* hess, void* stream);
 /* max constraint violation per problem given bounds lbg/ubg (fp32[n_g], device), for best-of selection */
 NLO_API int nlo_nlp_violation(nlo_nlp* p, const float* g, const float* lbg, const float* ubg, size_t P, size_t ld,
                               float* viol, void* stream);

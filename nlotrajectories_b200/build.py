@@ -16,7 +16,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OBJ = PKG / "csrc" / "_obj"
 LIB = PKG / "libnlo_b200.so"
-SOURCES = ["capi.cu", "sdf_simt.cu", "sdf_tc.cu", "sdf_tc256.cu", "nlp_kernels.cu"]
+SOURCES = ["capi.cu", "sdf_simt.cu", "sdf_tc.cu", "sdf_tc256.cu", "nlp_kernels.cu", "nlp_hess.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr",

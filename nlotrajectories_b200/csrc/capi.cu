@@ -428,7 +428,8 @@ int nlo_nlp_create(const nlo_nlp_desc* desc, nlo_sdf_model* model, int device, n
   nlo_nlp* p = new (std::nothrow) nlo_nlp();
   if (!p) return nlo_fail("out of host memory");
   p->desc = *desc; p->model = model; p->device = device;
-  p->d_tables = nullptr;
+  p->d_tables = nullptr; p->d_hmap = nullptr; p->hs_cap_P = 0;
+  p->d_hs[0] = p->d_hs[1] = p->d_hs[2] = nullptr;
   memset(&p->scratch, 0, sizeof(p->scratch));
   memset(p->lane, 0, sizeof(p->lane));
   std::vector<int> nzmap, copy_row, copy_var, copy_emit;
@@ -454,6 +455,14 @@ int nlo_nlp_create(const nlo_nlp_desc* desc, nlo_sdf_model* model, int device, n
   p->L.nzmap = p->d_tables; p->L.copy_row = p->d_tables + nzmap.size();
   p->L.copy_var = p->L.copy_row + nc; p->L.copy_nz = p->L.copy_var + nc; p->L.n_copy = nc;
   p->d_colind = p->d_tables + off_colind; p->d_row = p->d_colind + p->L.n_w + 1;
+  {
+    std::vector<int> hmap;
+    if (nlo_nlp_build_hess_layout(p->L, &p->hrows_ccs, &p->hcols_ccs, &hmap)) { nlo_nlp_destroy(p); return 1; }
+    if (cudaMalloc(&p->d_hmap, hmap.size() * sizeof(int)) != cudaSuccess ||
+        cudaMemcpy(p->d_hmap, hmap.data(), hmap.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
+      nlo_nlp_destroy(p); return nlo_fail("device allocation failed");
+    }
+  }
   for (auto& ln : p->lane)
     if (cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking) != cudaSuccess) { nlo_nlp_destroy(p); return nlo_fail("stream creation failed"); }
   *out = p;
@@ -478,6 +487,8 @@ void nlo_nlp_destroy(nlo_nlp* p) {
   free_scratch(p->scratch);
   for (auto& ln : p->lane) { free_lane_bufs(ln); if (ln.stream) cudaStreamDestroy(ln.stream); }
   if (p->d_tables) cudaFree(p->d_tables);
+  if (p->d_hmap) cudaFree(p->d_hmap);
+  for (float*& b : p->d_hs) { if (b) cudaFree(b); b = nullptr; }
   delete p;
 }
 
@@ -526,6 +537,54 @@ int nlo_nlp_eval(nlo_nlp* p, const float* w, size_t P, size_t ld, float* g, floa
   if (ld < P) return nlo_fail("ld (%zu) < P (%zu)", ld, P);
   NLO_CUDA(cudaSetDevice(p->device));
   return nlp_eval_on(p, p->scratch, w, P, ld, g, jac, f, grad_f, (cudaStream_t)stream);
+}
+
+// ---- Hessian of the Lagrangian (nlp_hess.cu) ------------------------------------------------------------------
+long long nlo_nlp_nnz_hess(const nlo_nlp* p) { return p ? (long long)p->hrows_ccs.size() : -1; }
+
+int nlo_nlp_hess_sparsity(const nlo_nlp* p, int32_t* colind, int32_t* row) {
+  if (!p || !colind || !row) return nlo_fail("null argument");
+  const int n_w = p->L.n_w, nnz = (int)p->hrows_ccs.size();
+  for (int c = 0; c <= n_w; ++c) colind[c] = 0;
+  for (int i = 0; i < nnz; ++i) { colind[p->hcols_ccs[i] + 1]++; row[i] = p->hrows_ccs[i]; }
+  for (int c = 0; c < n_w; ++c) colind[c + 1] += colind[c];
+  return 0;
+}
+
+// second derivatives of piecewise-linear networks vanish identically (what sdf_hess_kernel would compute, exactly)
+static bool sdf_is_piecewise_linear(const nlo_sdf_model* m) {
+  auto lin = [](uint32_t a) { return a == NLO_ACT_RELU || a == NLO_ACT_LEAKY_RELU; };
+  return lin(m->desc.act0) && (m->desc.n_hidden_mats == 0 || lin(m->desc.act));
+}
+
+int nlo_nlp_hess(nlo_nlp* p, const float* w, const float* sigma, const float* lam, size_t P, size_t ld, float* hess, void* stream) {
+  if (!p) return nlo_fail("null nlp");
+  if (P == 0) return 0;
+  if (!w || !lam || !hess) return nlo_fail("null argument");
+  if (ld < P) return nlo_fail("ld (%zu) < P (%zu)", ld, P);
+  NLO_CUDA(cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ensure_scratch(p, p->scratch, P)) return 1;
+  const size_t n = (size_t)(p->L.N + 1) * p->L.nb * P;
+  if (p->hs_cap_P < P) {
+    for (float*& b : p->d_hs) { if (b) cudaFree(b); b = nullptr; }
+    p->hs_cap_P = 0;
+    for (float*& b : p->d_hs) NLO_CUDA(cudaMalloc(&b, n * sizeof(float)));
+    p->hs_cap_P = P;
+  }
+  NlpScratch& sc = p->scratch;
+  if (nlo_nlp_launch_points(p->L, w, P, ld, sc.px, sc.py, st)) return 1;
+  if (p->L.sdf_mode == NLO_SDF_CIRCLES) {
+    if (nlo_nlp_launch_circles_hess(p->L, sc.px, sc.py, n, sc.s, sc.jx, sc.jy, p->d_hs[0], p->d_hs[1], p->d_hs[2], p->sm_count, st)) return 1;
+  } else {
+    if (nlo_sdf_eval(p->model, sc.px, sc.py, nullptr, n, sc.s, sc.jx, sc.jy, st)) return 1;
+    if (sdf_is_piecewise_linear(p->model)) {
+      for (float* b : p->d_hs) NLO_CUDA(cudaMemsetAsync(b, 0, n * sizeof(float), st));
+    } else if (nlo_sdf_hess(p->model, sc.px, sc.py, nullptr, n, p->d_hs[0], p->d_hs[1], p->d_hs[2], st)) {
+      return 1;
+    }
+  }
+  return nlo_nlp_launch_hess(p->L, p->d_hmap, w, sigma, lam, P, ld, sc.s, sc.jx, sc.jy, p->d_hs[0], p->d_hs[1], p->d_hs[2], hess, st);
 }
 
 int nlo_nlp_violation(nlo_nlp* p, const float* g, const float* lbg, const float* ubg, size_t P, size_t ld, float* viol, void* stream) {

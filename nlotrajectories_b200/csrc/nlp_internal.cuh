@@ -3,6 +3,8 @@
 #include "nlo_common.cuh"
 #include <vector>
 
+#define NLO_HESS_SLOTS 19        // Hessian emission slots per knot (nlp_hess.cu)
+
 struct NlpDev {                 // passed by value to kernels
   int dyn, shape, N, nx, nu, nb;
   int use_slack, use_smooth, enforce_heading, sdf_mode, n_circles;
@@ -42,6 +44,10 @@ struct nlo_nlp {
   int* d_tables;                // nzmap | copy_row | copy_var | copy_nz | colind (n_w+1) | row (nnz)
   const int* d_colind; const int* d_row;
   NlpScratch scratch;           // SDF point / value scratch of the device entry point
+  // Hessian of the Lagrangian (nlp_hess.cu)
+  std::vector<int> hrows_ccs, hcols_ccs;   // structural pattern, upper triangle, compressed-column order
+  int* d_hmap;                  // device: [N+1][NLO_HESS_SLOTS] emission slot -> CCS position (or -1)
+  float* d_hs[3]; size_t hs_cap_P;          // SDF Hessian scratch (hxx, hxy, hyy) for hs_cap_P problems
   NlpLane lane[2];              // host entry point: two lanes (streams) process alternating chunks of problems
 };
 
@@ -68,6 +74,13 @@ int nlo_nlp_build_layout(const nlo_nlp_desc* d, NlpDev* L, std::vector<int>* row
 // phase 1: SDF rows (needs p->d_s/d_jx/d_jy)
 int nlo_nlp_launch_assembly(nlo_nlp* p, const NlpScratch& sc, const float* w, size_t P, size_t ld, float* g, float* jac, float* f,
                             float* grad_f, cudaStream_t st, int phase);
+int nlo_nlp_build_hess_layout(const NlpDev& L, std::vector<int>* rows, std::vector<int>* cols, std::vector<int>* hmap);
+int nlo_nlp_launch_points(const NlpDev& L, const float* w, size_t P, size_t ld, float* px, float* py, cudaStream_t st);
+int nlo_nlp_launch_circles_hess(const NlpDev& L, const float* px, const float* py, size_t n, float* s, float* jx, float* jy,
+                                float* hxx, float* hxy, float* hyy, int sm, cudaStream_t st);
+int nlo_nlp_launch_hess(const NlpDev& L, const int* hmap, const float* w, const float* sigma, const float* lam, size_t P, size_t ld,
+                        const float* s, const float* jx, const float* jy, const float* hxx, const float* hxy, const float* hyy,
+                        float* hess, cudaStream_t st);
 int nlo_launch_violation(int n_g, const float* g, const float* lb, const float* ub, size_t P, size_t ld, float* viol, int sm, cudaStream_t st);
 int nlo_launch_jtv(int n_w, const int* colind, const int* row, const float* jac, const float* y, size_t P, size_t ld, const float* add,
                    float* out, int sm, cudaStream_t st);

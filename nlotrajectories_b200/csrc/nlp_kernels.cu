@@ -448,6 +448,12 @@ int nlo_nlp_launch_assembly(nlo_nlp* p, const NlpScratch& sc, const float* w, si
   return 0;
 }
 
+int nlo_nlp_launch_points(const NlpDev& L, const float* w, size_t P, size_t ld, float* px, float* py, cudaStream_t st) {
+  nlp_points_kernel<<<dim3((unsigned)std::min<size_t>((P + 255) / 256, 4096), (unsigned)(L.N + 1)), 256, 0, st>>>(L, w, P, ld, px, py);
+  NLO_CHECK_LAUNCH();
+  return 0;
+}
+
 int nlo_launch_violation(int n_g, const float* g, const float* lb, const float* ub, size_t P, size_t ld, float* viol, int sm, cudaStream_t st) {
   nlp_violation_kernel<<<grid_for(P, 128, sm), 128, 0, st>>>(n_g, g, lb, ub, P, ld, viol);
   NLO_CHECK_LAUNCH();

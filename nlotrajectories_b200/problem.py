@@ -118,6 +118,30 @@ class NlpProblem:
                                                 row.ctypes.data_as(C.POINTER(C.c_int32))))
         return colind, row
 
+    @property
+    def nnz_hess(self) -> int:
+        return int(self._L.nlo_nlp_nnz_hess(self._h))
+
+    def hess_sparsity(self):
+        """Compressed-column pattern of the upper triangle of the Hessian of the Lagrangian: (colind[n_w+1], row[nnz_hess])."""
+        colind = np.zeros(self.n_w + 1, np.int32); row = np.zeros(self.nnz_hess, np.int32)
+        _lib.check(self._L.nlo_nlp_hess_sparsity(self._h, colind.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                 row.ctypes.data_as(C.POINTER(C.c_int32))))
+        return colind, row
+
+    def eval_hess_device(self, w, lam, sigma=None, out=None, P: Optional[int] = None, stream=None):
+        """sigma * hess f + sum_r lam_r hess g_r for every problem (what IPOPT's eval_h needs; core/runner.py:113-125 keeps
+        the exact Hessian).  w (n_w, ld), lam (n_g, ld), sigma (P,) or None (= 1) are torch fp32 CUDA tensors; returns the
+        values (nnz_hess, ld) on ``hess_sparsity()``."""
+        import torch
+        ld = w.shape[1]
+        P = ld if P is None else P
+        if out is None:
+            out = torch.empty((self.nnz_hess, ld), dtype=torch.float32, device=w.device)
+        st = torch.cuda.current_stream(w.device).cuda_stream if stream is None else stream
+        _lib.check(self._L.nlo_nlp_hess(self._h, w.data_ptr(), _lib.ptr(sigma), lam.data_ptr(), P, ld, out.data_ptr(), st))
+        return out
+
     # ---- initial guesses ---------------------------------------------------------------------------------
     def linear_guess(self) -> np.ndarray:
         """``LinearInitializer`` (core/trajectory_initialization.py:54-55) packed as w (U = slack = 0)."""

@@ -147,6 +147,63 @@ def lambdify_reference(opti, net64: so.SdfNet):
     return rows, cols, f_g, f_j, f_f
 
 
+def hessian_reference(opti, net64: so.SdfNet, lam: np.ndarray, sigma: float):
+    """Upper triangle of hess(sigma * f + lam^T g) from the reference's recorded expressions, by symbolic
+    differentiation (the learned SDF's second derivatives are the opaque sdf_dxx/dxy/dyy of the stub, bound to the
+    numpy restatement of jac_adj1_nn_sdf)."""
+    import sympy as sp
+    wsym = opti.w_symbols()
+    index = {s: i for i, s in enumerate(wsym)}
+
+    def _v(fn):
+        def call(x, y):
+            P = np.stack([np.atleast_1d(np.asarray(x, float)), np.atleast_1d(np.asarray(y, float))], axis=-1)
+            out = fn(P)
+            return out[0] if np.ndim(x) == 0 else out
+        return call
+    hs = lambda P: so.jac_adj1(net64, P, np.ones(len(P)))
+    mods = [{"sdf": _v(lambda P: so.forward(net64, P)),
+             "sdf_dx": _v(lambda P: so.value_jac(net64, P)[1][:, 0]), "sdf_dy": _v(lambda P: so.value_jac(net64, P)[1][:, 1]),
+             "sdf_dxx": _v(lambda P: hs(P)[:, 0, 0]), "sdf_dxy": _v(lambda P: hs(P)[:, 0, 1]), "sdf_dyy": _v(lambda P: hs(P)[:, 1, 1])}, "numpy"]
+    acc = {}
+    for coef, e in [(sigma, opti.f)] + [(float(l), e) for l, e in zip(lam, opti.g_rows)]:
+        if coef == 0.0:
+            continue
+        syms = sorted(e.free_symbols, key=lambda s: index[s])
+        for ia, a in enumerate(syms):
+            da = sp.diff(e, a)
+            if da == 0:
+                continue
+            for b in syms[ia:]:
+                if b not in da.free_symbols:
+                    continue
+                d2 = sp.diff(da, b)
+                if d2 != 0:
+                    key = (index[a], index[b])
+                    acc[key] = acc.get(key, 0) + coef * d2
+    keys = sorted(acc, key=lambda rc: (rc[1], rc[0]))
+    fn = sp.lambdify(wsym, [acc[k] for k in keys], modules=mods, cse=True)
+    return np.array([k[0] for k in keys]), np.array([k[1] for k in keys]), fn
+
+
+def make_hess_golden(ref: Path, net: so.SdfNet, names, P: int = 2):
+    net64 = net.astype(np.float64)
+    bench_dir = ref / "src" / "nlotrajectories" / "benchmarks"
+    for name in names:
+        yaml_path = next(bench_dir.glob(f"{name}*.yaml"))
+        raw, opti = record_reference_nlp(ref, yaml_path)
+        spec = no.NlpSpec.from_yaml_dict(raw)
+        rng = np.random.default_rng(11)
+        lam = rng.normal(0, 1, spec.n_g).astype(np.float32).astype(np.float64)
+        sigma = 0.75
+        rows, cols, fn = hessian_reference(opti, net64, lam, sigma)
+        w = golden_w(spec, P, seed=7).astype(np.float32).astype(np.float64)
+        vals = np.array([np.asarray(fn(*wi), float) for wi in w])
+        np.savez(GOLD / f"nlp_hess_{name}.npz", yaml=np.array(yaml_path.name), w=w, lam=lam, sigma=np.float64(sigma),
+                 hess_rows=rows, hess_cols=cols, hess_vals=vals)
+        print(f"{name}: hessian of the Lagrangian, {len(rows)} structurally non-zero upper-triangle entries")
+
+
 def golden_w(spec: no.NlpSpec, P: int, seed: int) -> np.ndarray:
     """Multi-start guesses plus noise on every block so that no Jacobian entry is trivially zero."""
     rng = np.random.default_rng(seed)
@@ -182,14 +239,20 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reference", default="/root/reference")
     ap.add_argument("--only", default="")
+    ap.add_argument("--hessian", action="store_true", help="(re)generate only the Hessian-of-the-Lagrangian fixtures")
     a = ap.parse_args()
     ref = Path(a.reference)
     GOLD.mkdir(parents=True, exist_ok=True)
-    net = make_sdf_golden(ref)
+    net = None if a.hessian else make_sdf_golden(ref)
     names = ["benchmark_1", "benchmark_2", "benchmark_3", "benchmark_4", "benchmark_6"]
     if a.only:
         names = a.only.split(",")
+    if a.hessian:
+        from oracle import sdf_oracle as _so
+        make_hess_golden(ref, _so.from_npz(GOLD / "sdf_shipped_fourier128_weights.npz"), names)
+        return
     make_nlp_golden(ref, net, names)
+    make_hess_golden(ref, net, names)
 
 
 if __name__ == "__main__":

@@ -390,3 +390,196 @@ def multistart_guess(spec: NlpSpec, P: int, seed0: int = 1234) -> np.ndarray:
         Xi[:, :2] += amp * np.sin(np.pi * t)[:, None] * nrm[None, :] + rng.normal(0.0, 0.01, (spec.N + 1, 2))
         w[i, :spec.n_X] = Xi.reshape(-1)
     return w
+
+
+# -------------------------------------------------------------------------------------------------
+# Hessian of the Lagrangian  L(w) = sigma * f(w) + lam^T g(w)      
+# -------------------------------------------------------------------------------------------------
+# IPOPT's default is the exact Hessian (core/runner.py:113-125 sets no hessian_approximation), which CasADi
+# assembles from second derivatives of the same expressions: dynamics (core/dynamics.py), footprint + soft-min
+# (core/geometry.py:78-117, core/utils.py:28-31), the learned SDF's jac_adj1 (_l4c_generated/nn_sdf.cpp:88-104) and
+# the objective (core/runner.py:80-98).  Returned: values of the structural non-zeros of the UPPER triangle in
+# compressed-column order [upstream-memory: CasADi's nlp_hess_l is declared "triu:hess:gamma:x:x"].
+
+# structurally non-zero second derivatives of f(x,u) w.r.t. z = (x, u), pairs (a <= b), u_j at index nx + j
+DYN_H = {
+    "point_1st": [], "point_2nd": [],
+    "unicycle": [(2, 2), (2, 3)],
+    "unicycle_2nd": [(2, 2), (2, 3)],
+    "ackermann": [(2, 2), (2, 4), (3, 3), (3, 4)],
+    "ackermann_2nd": [(2, 2), (2, 4), (3, 3), (3, 4), (3, 6), (3, 7), (4, 6)],
+}
+
+
+def dynamics_hess(spec: NlpSpec, x: np.ndarray, u: np.ndarray, lam: np.ndarray):
+    """sum_i lam_i d2 f_i / dz_a dz_b for the pairs of DYN_H[spec.dynamics] (same order); x (..., nx), lam (..., nx)."""
+    name = spec.dynamics
+    if name in ("point_1st", "point_2nd"):
+        return np.zeros(x.shape[:-1] + (0,))
+    th = x[..., 2]
+    c, s = np.cos(th), np.sin(th)
+    if name in ("unicycle", "unicycle_2nd"):
+        v = u[..., 0] if name == "unicycle" else x[..., 3]
+        out = [-v * (lam[..., 0] * c + lam[..., 1] * s), -lam[..., 0] * s + lam[..., 1] * c]
+    elif name == "ackermann":
+        L = spec.wheelbase
+        psi, v = x[..., 3], u[..., 0]
+        t = np.tan(psi); sec2 = 1 + t * t
+        out = [-v * (lam[..., 0] * c + lam[..., 1] * s), -lam[..., 0] * s + lam[..., 1] * c,
+               lam[..., 2] * v * 2 * t * sec2 / L, lam[..., 2] * sec2 / L]
+    elif name == "ackermann_2nd":
+        L = spec.wheelbase
+        psi, v, pd, a = x[..., 3], x[..., 4], x[..., 6], u[..., 0]
+        t = np.tan(psi); sec2 = 1 + t * t
+        q = 1.0 / (1.0 + psi * psi)
+        dq = -2 * psi * q * q
+        d2q = q * q * (8 * psi * psi * q - 2)
+        l2, l4 = lam[..., 2], lam[..., 4]
+        out = [-v * (lam[..., 0] * c + lam[..., 1] * s), -lam[..., 0] * s + lam[..., 1] * c,
+               l2 * v * 2 * t * sec2 / L + l4 * (pd * v * d2q + a * 2 * t * sec2) / L,
+               l2 * sec2 / L + l4 * pd * dq / L,
+               l4 * v * dq / L, l4 * sec2 / L, l4 * q / L]
+    else:
+        raise ValueError(name)
+    return np.stack(out, axis=-1)
+
+
+def circles_hess(spec: NlpSpec, pts: np.ndarray):
+    """Hessian (n, 3) = (hxx, hxy, hyy) of circles_sdf: soft-min over ||p - c|| - R."""
+    vals, ns, Hs = [], [], []
+    for cx, cy, r, m in spec.circles:
+        dx, dy = pts[:, 0] - cx, pts[:, 1] - cy
+        d = np.sqrt(dx * dx + dy * dy)
+        nx_, ny_ = dx / d, dy / d
+        vals.append(d - (r + m)); ns.append((nx_, ny_))
+        Hs.append(((1 - nx_ * nx_) / d, -nx_ * ny_ / d, (1 - ny_ * ny_) / d))
+    vals = np.stack(vals, axis=0)
+    e = np.exp(-ALPHA * vals)
+    om = e / e.sum(axis=0)
+    mx = sum(om[i] * ns[i][0] for i in range(len(ns))); my = sum(om[i] * ns[i][1] for i in range(len(ns)))
+    hxx = sum(om[i] * (Hs[i][0] - ALPHA * ns[i][0] * ns[i][0]) for i in range(len(ns))) + ALPHA * mx * mx
+    hxy = sum(om[i] * (Hs[i][1] - ALPHA * ns[i][0] * ns[i][1]) for i in range(len(ns))) + ALPHA * mx * my
+    hyy = sum(om[i] * (Hs[i][2] - ALPHA * ns[i][1] * ns[i][1]) for i in range(len(ns))) + ALPHA * my * my
+    return np.stack([hxx, hxy, hyy], axis=-1)
+
+
+def hess_pattern(spec: NlpSpec):
+    """Structural (row, col), row <= col, of the Hessian of the Lagrangian in compressed-column order."""
+    ent = set()
+    nx, nu, N = spec.nx, spec.nu, spec.N
+    zi = lambda a, k: spec.iX(a, k) if a < nx else spec.iU(a - nx, k)
+    pose = [(0, 0), (0, 1), (1, 1)] if spec.shape == "dot" else [(0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2)]
+    for k in range(N + 1):
+        for (a, b) in [(0, 0), (0, 1), (1, 1)] + pose:                 # objective + SDF rows
+            ent.add((spec.iX(a, k), spec.iX(b, k)))
+        if k < N:
+            for (a, b) in DYN_H[spec.dynamics]:
+                ent.add((zi(a, k), zi(b, k)))
+            for a in (0, 1):
+                for b in (0, 1):
+                    ent.add((spec.iX(a, k), spec.iX(b, k + 1)))           # path length couples neighbouring knots
+            if spec.use_smooth and k < N - 1:
+                for j in range(nu):
+                    ent.add((spec.iU(j, k), spec.iU(j, k)))
+        if spec.use_slack:
+            ent.add((spec.iS(k), spec.iS(k)))
+    ent = sorted(ent, key=lambda rc: (rc[1], rc[0]))
+    assert all(r <= c for r, c in ent)
+    return np.array([r for r, _ in ent]), np.array([c for _, c in ent])
+
+
+def eval_hess_lag(spec: NlpSpec, w: np.ndarray, sigma: np.ndarray, lam: np.ndarray,
+                  sdf: Optional[Callable] = None, sdf_hess: Optional[Callable] = None):
+    """Values (P, nnz_h) of the upper triangle of  sigma * hess f + sum_r lam_r * hess g_r  on ``hess_pattern``.
+
+    ``sdf(points) -> (s, grad (n,2))`` and ``sdf_hess(points) -> (n,3) = (hxx, hxy, hyy)`` are the learned SDF
+    (l4casadi mode); ignored in casadi mode.  sigma: (P,), lam: (P, n_g).
+    """
+    w = np.asarray(w, dtype=np.float64)
+    P = w.shape[0]
+    sigma = np.broadcast_to(np.asarray(sigma, dtype=np.float64), (P,))
+    lam = np.asarray(lam, dtype=np.float64)
+    X, U, S = unpack(spec, w)
+    nx, nu, N = spec.nx, spec.nu, spec.N
+    rows, cols = hess_pattern(spec)
+    pos = {(int(r), int(c)): i for i, (r, c) in enumerate(zip(rows, cols))}
+    H = np.zeros((P, len(rows)))
+
+    def add(r, c, v):
+        H[:, pos[(r, c) if r <= c else (c, r)]] += v
+    zi = lambda a, k: spec.iX(a, k) if a < nx else spec.iU(a - nx, k)
+    # row offsets (SURVEY.md Appendix A.2)
+    off_dyn = nx + len(spec.terminal_idx)
+    off_sdf = off_dyn + N * nx + ((N + 1) if spec.use_slack else 0)
+    # dynamics: g = x_{k+1} - x_k - dt f  ->  -dt * sum_i lam_i hess f_i
+    lam_dyn = lam[:, off_dyn:off_dyn + N * nx].reshape(P, N, nx)
+    hd = dynamics_hess(spec, X[:, :-1, :], U, lam_dyn)
+    for n, (a, b) in enumerate(DYN_H[spec.dynamics]):
+        for k in range(N):
+            add(zi(a, k), zi(b, k), -spec.dt * hd[:, k, n])
+    # SDF rows
+    pts, dpts = _footprint(spec, X)
+    nb = pts.shape[2]
+    flat = pts.reshape(-1, 2)
+    if spec.sdf_mode == "casadi":
+        s, gr = circles_sdf(spec, flat)
+        hs = circles_hess(spec, flat)
+    else:
+        s, gr = sdf(flat)
+        hs = sdf_hess(flat)
+    s = np.asarray(s, np.float64).reshape(P, N + 1, nb)
+    gr = np.asarray(gr, np.float64).reshape(P, N + 1, nb, 2)
+    hs = np.asarray(hs, np.float64).reshape(P, N + 1, nb, 3)
+    jx, jy = gr[..., 0], gr[..., 1]
+    hxx, hxy, hyy = hs[..., 0], hs[..., 1], hs[..., 2]
+    tx, ty = dpts[..., 0], dpts[..., 1]
+    if spec.shape == "dot":
+        ux = uy = np.zeros_like(tx)
+    else:
+        ux, uy = -(pts[..., 0] - X[..., 0:1]), -(pts[..., 1] - X[..., 1:2])       # d2 p / d theta2
+    d3 = np.stack([jx, jy, jx * tx + jy * ty], axis=-1)                            # grad of s(p(q)) w.r.t. q = (x, y, theta)
+    ax, ay = hxx * tx + hxy * ty, hxy * tx + hyy * ty
+    # per-point 3x3 symmetric block, order (00, 01, 02, 11, 12, 22)
+    Hb = np.stack([hxx, hxy, ax, hyy, ay, tx * ax + ty * ay + jx * ux + jy * uy], axis=-1)
+    pairs = [(0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2)]
+    if spec.shape == "dot":
+        lam_s = lam[:, off_sdf:off_sdf + N + 1]
+        blk = lam_s[..., None] * Hb[:, :, 0, :]
+    elif spec.use_slack:
+        lam_s = lam[:, off_sdf:off_sdf + N + 1]
+        e = np.exp(-ALPHA * s)
+        om = e / e.sum(axis=-1, keepdims=True)
+        mean = (om[..., None] * d3).sum(axis=2)                                    # (P, N+1, 3)
+        blk = np.zeros((P, N + 1, 6))
+        for n, (a, b) in enumerate(pairs):
+            second = (om * d3[..., a] * d3[..., b]).sum(axis=2)
+            blk[..., n] = (om * Hb[..., n]).sum(axis=2) - ALPHA * (second - mean[..., a] * mean[..., b])
+        blk = lam_s[..., None] * blk
+    else:
+        lam_s = lam[:, off_sdf:off_sdf + (N + 1) * nb].reshape(P, N + 1, nb)
+        blk = (lam_s[..., None] * Hb).sum(axis=2)
+    for n, (a, b) in enumerate(pairs):
+        if spec.shape == "dot" and (a == 2 or b == 2):
+            continue
+        for k in range(N + 1):
+            add(spec.iX(a, k), spec.iX(b, k), blk[:, k, n])
+    # objective (core/runner.py:80-98)
+    dx, dy = X[:, 1:, 0] - X[:, :-1, 0], X[:, 1:, 1] - X[:, :-1, 1]
+    r2 = dx * dx + dy * dy + EPS_PATH
+    r3 = r2 * np.sqrt(r2)
+    M = {(0, 0): (r2 - dx * dx) / r3, (0, 1): -dx * dy / r3, (1, 1): (r2 - dy * dy) / r3}
+    for k in range(N):
+        for (a, b), v in M.items():
+            add(spec.iX(a, k), spec.iX(b, k), sigma * v[:, k])
+            add(spec.iX(a, k + 1), spec.iX(b, k + 1), sigma * v[:, k])
+        for a in (0, 1):
+            for b in (0, 1):
+                add(spec.iX(a, k), spec.iX(b, k + 1), -sigma * M[(min(a, b), max(a, b))][:, k])
+    if spec.use_slack:
+        for k in range(N + 1):
+            add(spec.iS(k), spec.iS(k), sigma * 2.0 * spec.slack_penalty)
+    if spec.use_smooth:
+        for k in range(N - 1):
+            for j in range(nu):
+                add(spec.iU(j, k), spec.iU(j, k), sigma * 2.0 * spec.smooth_weight)
+    return H

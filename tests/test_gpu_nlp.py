@@ -195,3 +195,91 @@ def test_violation_and_transposes(library):
     lib.check(L.nlo_transpose_to_aos(soa.data_ptr(), back.data_ptr(), P, 45, 80, torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     assert torch.equal(soa[:, :P], a.T) and torch.equal(back, a)
+
+
+# ---- Hessian of the Lagrangian -------------------------------------------------------------------
+def _hess_device(prob, w32, lam32, sigma32):
+    import torch
+    P = w32.shape[0]
+    wd = torch.from_numpy(np.ascontiguousarray(w32.T)).cuda()
+    ld_ = torch.from_numpy(np.ascontiguousarray(lam32.T)).cuda()
+    sg = None if sigma32 is None else torch.from_numpy(sigma32).cuda()
+    H = prob.eval_hess_device(wd, ld_, sg)
+    torch.cuda.synchronize()
+    return H.cpu().numpy().T.copy()                    # (P, nnz_hess)
+
+
+@pytest.mark.parametrize("name", BENCHES)
+def test_hessian_golden_from_reference_expressions(name, shipped_net, library):
+    """fp32 CUDA Hessian of the Lagrangian vs second derivatives of the reference's own recorded expressions
+    (tests/golden/nlp_hess_*.npz, oracle/make_golden.py --hessian): same pattern, values to 1e-5 of the output scale."""
+    z = np.load(GOLDEN / f"nlp_hess_{name}.npz")
+    cfg, model, prob = make_problem(name, shipped_net)
+    colind, row = prob.hess_sparsity()
+    cols = np.repeat(np.arange(prob.n_w), np.diff(colind))
+    assert prob.nnz_hess == len(z["hess_rows"])
+    assert np.array_equal(row, z["hess_rows"]) and np.array_equal(cols, z["hess_cols"])
+    w = z["w"].astype(np.float32)
+    P = w.shape[0]
+    lam = np.broadcast_to(z["lam"].astype(np.float32), (P, prob.n_g)).copy()
+    sigma = np.full(P, float(z["sigma"]), np.float32)
+    H = _hess_device(prob, w, lam, sigma)
+    ref = z["hess_vals"]
+    spec = no.NlpSpec.from_yaml_dict(yaml.safe_load(open(bench_yaml(name))))
+    # entries of knots whose footprint touches a ReLU kink are discontinuous: excluded like the Jacobian's
+    ok = np.ones_like(ref, bool)
+    if model is not None:
+        rows_tie = sdf_row_ties(spec, shipped_net, w.astype(np.float64), spec.nx + len(spec.terminal_idx) + spec.N * spec.nx
+                                + ((spec.N + 1) if spec.use_slack else 0))
+        nrow = (spec.N + 1) * spec.sdf_rows_per_knot
+        off = spec.n_g - spec.n_U - nrow
+        k_tie = rows_tie[:, off:off + nrow].reshape(P, spec.N + 1, -1).any(axis=2)
+        knot_of_row = np.where(row < spec.n_X, row // spec.nx, -1)
+        for i in range(P):
+            ok[i, np.isin(knot_of_row, np.nonzero(k_tie[i])[0])] = False
+    scale = max(1.0, np.abs(ref).max())
+    err = np.abs(H - ref)
+    assert ok.mean() > 0.95
+    assert (err[ok] <= 1e-5 * scale).all(), (err[ok].max(), scale)
+
+
+@pytest.mark.parametrize("name", ["benchmark_1", "benchmark_3", "benchmark_6"])
+@pytest.mark.parametrize("netname", ["fourier64_tanh", "relu128"])
+def test_hessian_batch_matches_oracle(name, netname, library):
+    """Ragged batch against the fp64 oracle: a smooth network (FP32 general path + K1b Hessian kernel) and the
+    benchmark-shaped ReLU network (tensor path; its second derivatives vanish identically)."""
+    net = so.synthetic_fourier(64, 1, scale=3.0, seed=8, act=so.ACT_TANH) if netname == "fourier64_tanh" else so.synthetic_mlp(128, 1, seed=0)
+    cfg, model, prob = make_problem(name, net)
+    spec = no.NlpSpec.from_yaml_dict(yaml.safe_load(open(bench_yaml(name))))
+    P = 77
+    rng = np.random.default_rng(5)
+    w = prob.multistart_guess(P)
+    w[:, spec.n_X:spec.n_X + spec.n_U] = rng.normal(0, 0.5, (P, spec.n_U))
+    w[:, 2:spec.n_X:spec.nx] += rng.normal(0, 0.2, (P, spec.N + 1)).astype(np.float32)
+    lam = rng.normal(0, 1, (P, prob.n_g)).astype(np.float32)
+    sigma = rng.uniform(0.5, 1.5, P).astype(np.float32)
+    H = _hess_device(prob, w, lam, sigma)
+    n64 = net.astype(np.float64)
+    sdf_h = lambda Q: (lambda Hm: np.stack([Hm[:, 0, 0], Hm[:, 0, 1], Hm[:, 1, 1]], -1))(so.jac_adj1(n64, Q, np.ones(len(Q))))
+    ref = no.eval_hess_lag(spec, w.astype(np.float64), sigma.astype(np.float64), lam.astype(np.float64),
+                           lambda Q: so.value_jac(n64, Q), sdf_h)
+    assert H.shape == ref.shape
+    ok = np.ones_like(ref, bool)
+    if model is not None and netname == "relu128":
+        rows_tie = sdf_row_ties(spec, net, w.astype(np.float64), spec.nx + len(spec.terminal_idx) + spec.N * spec.nx
+                                + ((spec.N + 1) if spec.use_slack else 0))
+        nrow = (spec.N + 1) * spec.sdf_rows_per_knot
+        off = spec.n_g - spec.n_U - nrow
+        k_tie = rows_tie[:, off:off + nrow].reshape(P, spec.N + 1, -1).any(axis=2)
+        _, row = prob.hess_sparsity()
+        knot_of_row = np.where(row < spec.n_X, row // spec.nx, -1)
+        for i in range(P):
+            ok[i, np.isin(knot_of_row, np.nonzero(k_tie[i])[0])] = False
+    scale = np.maximum(1.0, np.abs(ref).max(axis=1, keepdims=True))
+    err = np.abs(H - ref) / scale
+    assert ok.mean() > 0.9
+    assert (err[ok] <= 1e-5).all(), err[ok].max()
+    # sigma == NULL means 1
+    H1 = _hess_device(prob, w, lam, None)
+    Hs = _hess_device(prob, w, lam, np.ones(P, np.float32))
+    assert np.array_equal(H1, Hs)

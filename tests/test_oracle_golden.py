@@ -100,3 +100,20 @@ def test_nlp_oracle_jacobian_by_finite_differences(shipped_net):
         e = np.zeros((1, spec.n_w)); e[0, v] = eps
         fd = (no.eval_f_grad(spec, w + e)[0] - no.eval_f_grad(spec, w - e)[0])[0] / (2 * eps)
         np.testing.assert_allclose(gr[0, v], fd, atol=2e-6)
+
+
+@pytest.mark.parametrize("name", ["benchmark_1", "benchmark_2", "benchmark_3", "benchmark_4", "benchmark_6"])
+def test_hessian_oracle_matches_reference_expressions(name, shipped_net):
+    """Hessian of the Lagrangian: the numpy restatement against second derivatives of the reference's own recorded
+    expressions (oracle/make_golden.py --hessian): identical structural pattern (upper triangle, CCS) and values."""
+    z = np.load(GOLDEN / f"nlp_hess_{name}.npz")
+    spec = no.NlpSpec.from_yaml_dict(yaml.safe_load(open(bench_yaml(name))))
+    net = shipped_net.astype(np.float64)
+    rows, cols = no.hess_pattern(spec)
+    assert np.array_equal(rows, z["hess_rows"]) and np.array_equal(cols, z["hess_cols"])
+    w = z["w"]
+    lam = np.broadcast_to(z["lam"], (w.shape[0], spec.n_g))
+    sdf_h = lambda Q: (lambda H: np.stack([H[:, 0, 0], H[:, 0, 1], H[:, 1, 1]], -1))(so.jac_adj1(net, Q, np.ones(len(Q))))
+    H = no.eval_hess_lag(spec, w, float(z["sigma"]), lam, lambda Q: so.value_jac(net, Q), sdf_h)
+    scale = max(1.0, np.abs(z["hess_vals"]).max())
+    assert np.abs(H - z["hess_vals"]).max() <= 1e-9 * scale, np.abs(H - z["hess_vals"]).max()
