@@ -170,6 +170,8 @@ int nlo_sdf_hess(nlo_sdf_model* m, const float* x, const float* y, const float* 
   if (n == 0) return 0;
   if (!x || !y) return nlo_fail("null coordinate array");
   NLO_CUDA(cudaSetDevice(m->device));
+  if (m->prec == NLO_PREC_TC_3XF16 && hxx && hxy && hyy && nlo_sdf_tc_hess_supported(m))
+    return nlo_sdf_tc_hess_launch(m, x, y, sbar, n, nullptr, nullptr, nullptr, hxx, hxy, hyy, (cudaStream_t)stream);
   return nlo_sdf_simt_hess_launch(m, x, y, sbar, n, hxx, hxy, hyy, (cudaStream_t)stream);
 }
 
@@ -220,7 +222,7 @@ int nlo_sdf_hess_host(nlo_sdf_model* m, const float* x, const float* y, const fl
   NLO_CUDA(cudaMemcpyAsync(d, x, n * sizeof(float), cudaMemcpyHostToDevice, st));
   NLO_CUDA(cudaMemcpyAsync(d + n, y, n * sizeof(float), cudaMemcpyHostToDevice, st));
   if (sbar) NLO_CUDA(cudaMemcpyAsync(d + 2 * n, sbar, n * sizeof(float), cudaMemcpyHostToDevice, st));
-  if (nlo_sdf_simt_hess_launch(m, d, d + n, sbar ? d + 2 * n : nullptr, n, d + 3 * n, d + 4 * n, d + 5 * n, st)) return 1;
+  if (nlo_sdf_hess(m, d, d + n, sbar ? d + 2 * n : nullptr, n, d + 3 * n, d + 4 * n, d + 5 * n, st)) return 1;
   if (hxx) NLO_CUDA(cudaMemcpyAsync(hxx, d + 3 * n, n * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (hxy) NLO_CUDA(cudaMemcpyAsync(hxy, d + 4 * n, n * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (hyy) NLO_CUDA(cudaMemcpyAsync(hyy, d + 5 * n, n * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -577,6 +579,11 @@ int nlo_nlp_hess(nlo_nlp* p, const float* w, const float* sigma, const float* la
   if (p->L.sdf_mode == NLO_SDF_CIRCLES) {
     if (nlo_nlp_launch_circles_hess(p->L, sc.px, sc.py, n, sc.s, sc.jx, sc.jy, p->d_hs[0], p->d_hs[1], p->d_hs[2], p->sm_count, st)) return 1;
   } else {
+    if (p->model->prec == NLO_PREC_TC_3XF16 && nlo_sdf_tc_hess_supported(p->model)) {
+      // one fused launch: value, Jacobian and Hessian of every footprint point
+      if (nlo_sdf_tc_hess_launch(p->model, sc.px, sc.py, nullptr, n, sc.s, sc.jx, sc.jy, p->d_hs[0], p->d_hs[1], p->d_hs[2], st)) return 1;
+      return nlo_nlp_launch_hess(p->L, p->d_hmap, w, sigma, lam, P, ld, sc.s, sc.jx, sc.jy, p->d_hs[0], p->d_hs[1], p->d_hs[2], hess, st);
+    }
     if (nlo_sdf_eval(p->model, sc.px, sc.py, nullptr, n, sc.s, sc.jx, sc.jy, st)) return 1;
     if (sdf_is_piecewise_linear(p->model)) {
       for (float* b : p->d_hs) NLO_CUDA(cudaMemsetAsync(b, 0, n * sizeof(float), st));

@@ -148,6 +148,17 @@ __device__ __forceinline__ void nlo_phi_d_tc(float a, int act, float prm, float&
   }
 }
 
+// second derivative from the value v = phi(a) and first derivative d = phi'(a) (no further transcendental)
+__device__ __forceinline__ float nlo_phi_d2_from_vd(int act, float prm, float v, float d) {
+  switch (act) {
+    case NLO_ACT_TANH: return -2.f * v * d;
+    case NLO_ACT_SIGMOID: return d * (1.f - 2.f * v);
+    case NLO_ACT_SIN: return -prm * prm * v;
+    case NLO_ACT_COS_SCALE: return -v;
+    default: return 0.f;
+  }
+}
+
 // ---- kernels' host-side launchers (one per .cu) -------------------------------------------------
 // sdf_simt.cu
 int nlo_sdf_simt_launch(nlo_sdf_model* m, const float* x, const float* y, const float* sbar, size_t n,
@@ -159,6 +170,9 @@ bool nlo_sdf_tc_supported(const nlo_sdf_desc* d);
 int nlo_sdf_tc_prepare(nlo_sdf_model* m, const float* weights_host);
 int nlo_sdf_tc_launch(nlo_sdf_model* m, const float* x, const float* y, const float* sbar, size_t n,
                       float* s, float* jx, float* jy, cudaStream_t st);
+bool nlo_sdf_tc_hess_supported(const nlo_sdf_model* m);
+int nlo_sdf_tc_hess_launch(nlo_sdf_model* m, const float* x, const float* y, const float* sbar, size_t n,
+                           float* s, float* jx, float* jy, float* hxx, float* hxy, float* hyy, cudaStream_t st);
 // sdf_tc256.cu (reached through the three nlo_sdf_tc_* entry points above)
 bool nlo_sdf_tc256_supported(const nlo_sdf_desc* d);
 int nlo_sdf_tc256_prepare(nlo_sdf_model* m, const float* weights_host);

@@ -72,7 +72,7 @@ struct TcCfg {
   static constexpr int NGROUPS = 512 / TMEM_COLS;
   static constexpr int THREADS = NGROUPS * GROUP_THREADS;           // 512
   static constexpr size_t bytes(bool relu_hidden) {
-    return (size_t)(relu_hidden ? 4 : 2) * IMG_HALFS * 2 + (size_t)NGROUPS * 2 * TILE * 2 * 4 + NGROUPS * 8 + 16 + NGROUPS * 4;
+    return (size_t)(relu_hidden ? 4 : 2) * IMG_HALFS * 2 + (size_t)NGROUPS * 2 * TILE * 4 * 4 + NGROUPS * 8 + 16 + NGROUPS * 4;
   }
 };
 
@@ -97,6 +97,7 @@ struct TileCtx {
   unsigned int* ctr;       // global tile counter (dynamic scheduling) or nullptr (static striding)
   uint32_t* next_slot;     // the group's next tile index, fetched while GEMM 1 runs
   uint32_t ctr_bias;
+  ptrdiff_t hxy_off, hyy_off;   // hxy / hyy outputs relative to hxx (HESS variants)
   int act0, act;
   float prm0, prm, inv_sw, unscale2, max_w0x, max_w0y, max_b0;
   long long* dbg;          // optional phase timeline (NLO_B200_TC_TIMELINE): clock stamps per tile of CTA 0, groups 0 / 1
@@ -174,10 +175,12 @@ __device__ __forceinline__ uint32_t pack_f16(float v0, float v1) {
 // Deliberately NOT inlined into the persistent loop: the constants are loop-invariant, and an inlined body makes
 // the compiler hoist hundreds of them into registers (and spill) instead of feeding them to the arithmetic from
 // the constant bank.
-template <int H, int ACT0, int ACT, bool FULL, int SPLIT, int HALF>
+// HESS (ReLU hidden layer only): also sbar * Hessian.  With phi'' = 0 in the hidden layer the forward-over-reverse
+// tangents need no further GEMM: H = sum_k G0[k] phi0''(a0[k]) W0[k,:] W0[k,:]^T, and G0 is what epilogue 2 already holds.
+template <int H, int ACT0, int ACT, bool FULL, int SPLIT, int HALF, bool HESS>
 __device__ __noinline__ uint32_t sdf_tc_tile(TileCtx c, uint32_t phase, float px, float py, float seed, bool want_jac,
                                              float* __restrict__ part, float* __restrict__ s_ptr, float* __restrict__ j_ptr,
-                                             ptrdiff_t jy_off) {
+                                             ptrdiff_t jy_off, float* __restrict__ h_ptr) {
   constexpr int HH = H / SPLIT;                    // neurons per thread
   constexpr int C0 = HALF * HH;                    // first neuron / D column of this thread
   constexpr int NCH = HH / 32;                     // 32-neuron chunks per thread
@@ -267,7 +270,7 @@ __device__ __noinline__ uint32_t sdf_tc_tile(TileCtx c, uint32_t phase, float px
 #pragma unroll 1
     for (int cc = 0; cc < NCH; ++cc) epi1(cc);
   }
-  float jx = 0.f, jy = 0.f;
+  float jx = 0.f, jy = 0.f, hxx = 0.f, hxy = 0.f, hyy = 0.f;
   if (want_jac) {
     TC_STAMP(4);
     tc_wait_st();
@@ -293,6 +296,11 @@ __device__ __noinline__ uint32_t sdf_tc_tile(TileCtx c, uint32_t phase, float px
         const float g0 = __uint_as_float(gz[q]) * d;
         jx = fmaf(g0, cst.w0x[k], jx);
         jy = fmaf(g0, cst.w0y[k], jy);
+        if (HESS) {
+          const float tt = __uint_as_float(gz[q]) * nlo_phi_d2_from_vd(ACT0 >= 0 ? ACT0 : c.act0, c.prm0, v, d);
+          const float tx = tt * cst.w0x[k], ty = tt * cst.w0y[k];
+          hxx = fmaf(tx, cst.w0x[k], hxx); hxy = fmaf(tx, cst.w0y[k], hxy); hyy = fmaf(ty, cst.w0y[k], hyy);
+        }
       }
     };
     if (FULL) {
@@ -304,47 +312,53 @@ __device__ __noinline__ uint32_t sdf_tc_tile(TileCtx c, uint32_t phase, float px
     }
     const float unscale2 = seed * c.unscale2;
     jx *= unscale2; jy *= unscale2;
+    if (HESS) { hxx *= unscale2; hxy *= unscale2; hyy *= unscale2; }
   }
   TC_STAMP(7);
   if (SPLIT == 1) {
     if (s_ptr) *s_ptr = s;
     if (j_ptr) { j_ptr[0] = jx; j_ptr[jy_off] = jy; }
+    if (HESS && h_ptr) { h_ptr[0] = hxx; h_ptr[c.hxy_off] = hxy; h_ptr[c.hyy_off] = hyy; }
     // the next tile's tcgen05.st / MMA must not overtake this tile's TMEM reads
     tc_fence_before();
     group_bar<NT>(c.bar_id);
     tc_fence_after();
     return phase;
   }
-  // ---- hand the other half what it stores: HALF 0 writes s and jx, HALF 1 writes jy ------------------------------
-  float* mine = part + (HALF * TILE + pt) * 2;
-  if (HALF == 0) { mine[0] = jy; } else { mine[0] = s; mine[1] = jx; }
+  // ---- hand the other half what it stores: HALF 0 writes s, jx (hxx, hxy), HALF 1 writes jy (hyy) ------------------
+  float* mine = part + (HALF * TILE + pt) * 4;
+  if (HALF == 0) { mine[0] = jy; if (HESS) mine[1] = hyy; }
+  else { mine[0] = s; mine[1] = jx; if (HESS) { mine[2] = hxx; mine[3] = hxy; } }
   // (this barrier also keeps the next tile's tcgen05.st / MMA from overtaking this tile's TMEM reads)
   tc_fence_before();
   group_bar<NT>(c.bar_id);
   tc_fence_after();
-  const float* other = part + ((1 - HALF) * TILE + pt) * 2;
+  const float* other = part + ((1 - HALF) * TILE + pt) * 4;
   if (HALF == 0) {
     if (s_ptr) *s_ptr = s + other[0];
     if (j_ptr) *j_ptr = jx + other[1];
+    if (HESS && h_ptr) { h_ptr[0] = hxx + other[2]; h_ptr[c.hxy_off] = hxy + other[3]; }
   } else {
     if (j_ptr) *j_ptr = jy + other[0];
+    if (HESS && h_ptr) h_ptr[c.hyy_off] = hyy + other[1];
   }
   // `part` is rewritten by the next tile only after its first group barrier, which every thread reaches after these reads
   return phase;
 }
 
-template <int H, int ACT0, int ACT>
+template <int H, int ACT0, int ACT, bool HESS>
 __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1)
 sdf_tc_kernel(SdfNetDev net, TcParams prm_tc, const __half* __restrict__ bimg, const float* __restrict__ x,
               const float* __restrict__ y, const float* __restrict__ sbar, size_t n, float* __restrict__ s_out,
-              float* __restrict__ jx_out, float* __restrict__ jy_out, unsigned int* __restrict__ tile_ctr, long long* __restrict__ dbg) {
+              float* __restrict__ jx_out, float* __restrict__ jy_out, float* __restrict__ hxx_out, float* __restrict__ hxy_out,
+              float* __restrict__ hyy_out, unsigned int* __restrict__ tile_ctr, long long* __restrict__ dbg) {
   using Cfg = TcCfg<H>;
   constexpr bool RH = (ACT == NLO_ACT_RELU);
   constexpr int NIMG = RH ? 4 : 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __half* sB = reinterpret_cast<__half*>(smem_raw);                  // W1 hi | W1 lo | (V hi | V lo)
-  float* sPart = reinterpret_cast<float*>(smem_raw + (size_t)NIMG * Cfg::IMG_HALFS * 2);   // [NGROUPS][2][TILE][2]
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(sPart + Cfg::NGROUPS * 2 * TILE * 2);       // [NGROUPS]
+  float* sPart = reinterpret_cast<float*>(smem_raw + (size_t)NIMG * Cfg::IMG_HALFS * 2);   // [NGROUPS][2][TILE][4]
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(sPart + Cfg::NGROUPS * 2 * TILE * 4);       // [NGROUPS]
   int* lock = reinterpret_cast<int*>(mbar + Cfg::NGROUPS);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lock + 1);
   uint32_t* next_tile = tmem_slot + 1;                                                      // [NGROUPS]
@@ -382,9 +396,10 @@ sdf_tc_kernel(SdfNetDev net, TcParams prm_tc, const __half* __restrict__ bimg, c
   c.prm0 = net.p0; c.prm = net.p; c.inv_sw = prm_tc.inv_sw;
   c.unscale2 = RH ? prm_tc.inv_sv : prm_tc.inv_sc1 * prm_tc.inv_sw;
   c.max_w0x = prm_tc.max_w0x; c.max_w0y = prm_tc.max_w0y; c.max_b0 = prm_tc.max_b0;
-  const bool want_jac = (jx_out != nullptr) || (jy_out != nullptr);
+  const bool want_jac = (jx_out != nullptr) || (jy_out != nullptr) || HESS;
   constexpr bool FULL = (ACT0 >= 0 && ACT >= 0);   // compile-time activations: unrolled, vectors as constant-bank operands
-  float* part = sPart + grp * (2 * TILE * 2);
+  float* part = sPart + grp * (2 * TILE * 4);
+  c.hxy_off = HESS ? hxy_out - hxx_out : 0; c.hyy_off = HESS ? hyy_out - hxx_out : 0;
   uint32_t phase = 0;
   if (dbg && t == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); dbg[2 * 64 * 32 + blockIdx.x * 4 + 0] = (long long)gt; dbg[2 * 64 * 32 + blockIdx.x * 4 + 2] = clock64(); }
   const size_t n_tiles = (n + TILE - 1) / TILE;
@@ -400,15 +415,18 @@ sdf_tc_kernel(SdfNetDev net, TcParams prm_tc, const __half* __restrict__ bimg, c
     const float px = x[ic], py = y[ic], seed = sbar ? sbar[ic] : 1.f;
     if (Cfg::SPLIT == 1) {
       // jx and jy are both written by the one owner of the point (both non-null whenever a Jacobian is requested through this path)
-      phase = sdf_tc_tile<H, ACT0, ACT, FULL, 1, 0>(c, phase, px, py, seed, want_jac, part, (valid && s_out) ? s_out + i : nullptr,
-                                                    (valid && jx_out) ? jx_out + i : nullptr, jy_out - jx_out);
+      phase = sdf_tc_tile<H, ACT0, ACT, FULL, 1, 0, HESS>(c, phase, px, py, seed, want_jac, part, (valid && s_out) ? s_out + i : nullptr,
+                                                          (valid && jx_out) ? jx_out + i : nullptr, jy_out - jx_out,
+                                                          (HESS && valid) ? hxx_out + i : nullptr);
     } else if (half == 0) {
-      phase = sdf_tc_tile<H, ACT0, ACT, FULL, Cfg::SPLIT, 0>(c, phase, px, py, seed, want_jac, part,
-                                                             (valid && s_out) ? s_out + i : nullptr,
-                                                             (valid && jx_out) ? jx_out + i : nullptr, 0);
+      phase = sdf_tc_tile<H, ACT0, ACT, FULL, Cfg::SPLIT, 0, HESS>(c, phase, px, py, seed, want_jac, part,
+                                                                   (valid && s_out) ? s_out + i : nullptr,
+                                                                   (valid && jx_out) ? jx_out + i : nullptr, 0,
+                                                                   (HESS && valid) ? hxx_out + i : nullptr);
     } else {
-      phase = sdf_tc_tile<H, ACT0, ACT, FULL, Cfg::SPLIT, Cfg::SPLIT - 1>(c, phase, px, py, seed, want_jac, part, nullptr,
-                                                                          (valid && jy_out) ? jy_out + i : nullptr, 0);
+      phase = sdf_tc_tile<H, ACT0, ACT, FULL, Cfg::SPLIT, Cfg::SPLIT - 1, HESS>(c, phase, px, py, seed, want_jac, part, nullptr,
+                                                                                (valid && jy_out) ? jy_out + i : nullptr, 0,
+                                                                                (HESS && valid) ? hxx_out + i : nullptr);
     }
     tile = tile_ctr ? (size_t)next_tile[grp] : tile + (size_t)gridDim.x * Cfg::NGROUPS;
   }
@@ -420,10 +438,11 @@ sdf_tc_kernel(SdfNetDev net, TcParams prm_tc, const __half* __restrict__ bimg, c
 
 unsigned long long g_const_owner[64] = {0};   // per device: uid of the model whose vectors sit in `cst`
 
-template <int H, int ACT0, int ACT>
-int launch_tc(nlo_sdf_model* m, const float* x, const float* y, const float* sbar, size_t n, float* s, float* jx, float* jy, cudaStream_t st) {
+template <int H, int ACT0, int ACT, bool HESS = false>
+int launch_tc(nlo_sdf_model* m, const float* x, const float* y, const float* sbar, size_t n, float* s, float* jx, float* jy, cudaStream_t st,
+              float* hxx = nullptr, float* hxy = nullptr, float* hyy = nullptr) {
   using Cfg = TcCfg<H>;
-  auto kfn = sdf_tc_kernel<H, ACT0, ACT>;
+  auto kfn = sdf_tc_kernel<H, ACT0, ACT, HESS>;
   const size_t smem = Cfg::bytes(ACT == NLO_ACT_RELU);
   NLO_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const size_t tiles = (n + TILE - 1) / TILE;
@@ -448,7 +467,7 @@ int launch_tc(nlo_sdf_model* m, const float* x, const float* y, const float* sba
     ctr = reinterpret_cast<unsigned int*>(static_cast<char*>(m->d_tc) + m->tc_bytes) + (m->tc_seq++ & 63u);
     NLO_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st));
   }
-  kfn<<<grid, Cfg::THREADS, smem, st>>>(m->net(), prm, reinterpret_cast<const __half*>(m->d_tc), x, y, sbar, n, s, jx, jy, ctr, dbg);
+  kfn<<<grid, Cfg::THREADS, smem, st>>>(m->net(), prm, reinterpret_cast<const __half*>(m->d_tc), x, y, sbar, n, s, jx, jy, hxx, hxy, hyy, ctr, dbg);
   if (dbg) {
     std::vector<long long> h(2 * 64 * 32 + 4 * 256);
     NLO_CUDA(cudaMemcpyAsync(h.data(), dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
@@ -562,6 +581,21 @@ int nlo_sdf_tc_prepare(nlo_sdf_model* m, const float* w) {
   m->tc_bytes = img.size() * sizeof(__half);
   m->tc_seq = 0;
   return 0;
+}
+
+// Fused value + Jacobian + Hessian on the tensor path: networks whose hidden layer is ReLU and whose first layer is the
+// cosine feature map (the shipped FourierMLP shape).  jx/jy must both be given or both be NULL.
+bool nlo_sdf_tc_hess_supported(const nlo_sdf_model* m) {
+  return m->d_tc && m->desc.n_hidden_mats == 1 && (m->desc.hidden == 64 || m->desc.hidden == 128) &&
+         m->desc.act0 == NLO_ACT_COS_SCALE && m->desc.act == NLO_ACT_RELU;
+}
+int nlo_sdf_tc_hess_launch(nlo_sdf_model* m, const float* x, const float* y, const float* sbar, size_t n,
+                           float* s, float* jx, float* jy, float* hxx, float* hxy, float* hyy, cudaStream_t st) {
+  if (n == 0) return 0;
+  if (!nlo_sdf_tc_hess_supported(m)) return nlo_fail("tensor-tile Hessian: unsupported network");
+  if (!hxx || !hxy || !hyy) return nlo_fail("tensor-tile Hessian: all three outputs are required");
+  if (m->desc.hidden == 128) return launch_tc<128, NLO_ACT_COS_SCALE, NLO_ACT_RELU, true>(m, x, y, sbar, n, s, jx, jy, st, hxx, hxy, hyy);
+  return launch_tc<64, NLO_ACT_COS_SCALE, NLO_ACT_RELU, true>(m, x, y, sbar, n, s, jx, jy, st, hxx, hxy, hyy);
 }
 
 int nlo_sdf_tc_launch(nlo_sdf_model* m, const float* x, const float* y, const float* sbar, size_t n,

@@ -105,6 +105,35 @@ def test_hessian_matches_oracle(name, torch_cuda):
     model.close()
 
 
+@pytest.mark.parametrize("name", ["shipped_fourier128", "fourier128_relu", "fourier64_relu"])
+def test_hessian_on_the_tensor_path(name, shipped_net, torch_cuda):
+    """Networks with a ReLU hidden layer: the Hessian comes out of the tensor kernel's second epilogue (no extra GEMM).
+    Checked against the fp64 oracle (kink-adjacent points excluded and counted) and against the FP32 K1b kernel."""
+    torch = torch_cuda
+    from nlotrajectories_b200.sdf import LearnedSDF
+    net = shipped_net if name == "shipped_fourier128" else (NETS[name]() if name in NETS else so.synthetic_fourier(64, 1, scale=2.0, seed=14))
+    model = LearnedSDF(to_weights(net))
+    assert model.precision == "tc3xf16"
+    n = 50_021
+    P = sample_points(n, seed=6)
+    sbar = np.random.default_rng(4).uniform(0.5, 1.5, n).astype(np.float32)
+    x, y, sb = (torch.from_numpy(a.copy()).cuda() for a in (P[:, 0], P[:, 1], sbar))
+    hxx, hxy, hyy = (t.cpu().numpy() for t in model.hess(x, y, sb))
+    H_ref = so.jac_adj1(net.astype(np.float64), P.astype(np.float64), sbar.astype(np.float64))
+    tie = kink_mask(net, P)
+    assert tie.mean() < 2e-2
+    scale = max(1.0, np.abs(H_ref).max())
+    for got, ref in ((hxx, H_ref[:, 0, 0]), (hxy, H_ref[:, 0, 1]), (hyy, H_ref[:, 1, 1])):
+        assert np.abs(got - ref)[~tie].max() <= 2e-5 * scale, (np.abs(got - ref)[~tie].max(), scale)
+    ref32 = LearnedSDF(to_weights(net), precision="fp32")
+    gxx, gxy, gyy = (t.cpu().numpy() for t in ref32.hess(x, y, sb))
+    assert np.abs(gxx - hxx)[~tie].max() <= 4e-5 * scale and np.abs(gyy - hyy)[~tie].max() <= 4e-5 * scale
+    # host entry point takes the same route
+    h2 = model.hess_host(P[:1000, 0].copy(), P[:1000, 1].copy(), sbar[:1000])
+    assert np.array_equal(h2[0], hxx[:1000]) and np.array_equal(h2[2], hyy[:1000])
+    model.close(); ref32.close()
+
+
 def test_edge_cases_empty_single_and_host_path(shipped_net, torch_cuda):
     torch = torch_cuda
     from nlotrajectories_b200.sdf import LearnedSDF, NNObstacle
