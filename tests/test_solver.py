@@ -1,0 +1,55 @@
+"""Batched interior-point solver: the caller on top of the evaluation hot path.
+CPU: the solver logic on the numpy oracle.  GPU: the same solver over the CUDA evaluation + Hessian kernels."""
+import numpy as np
+import pytest
+import yaml
+
+from conftest import bench_yaml
+from oracle import nlp_oracle as no
+from solver_util import OracleEvaluator
+
+B1_OPT = 1.50352      # benchmark_1 optimum at the reference's tolerance (tol 1e-4, final barrier 1e-5); SLSQP: 1.50342
+
+
+def _solve_cpu(P, max_iter=200):
+    import torch
+    from nlotrajectories_b200.solver import BatchedIPSolver
+    spec = no.NlpSpec.from_yaml_dict(yaml.safe_load(open(bench_yaml("benchmark_1"))))
+    lb, ub = no.bounds(spec)
+    w0 = no.multistart_guess(spec, P)
+    res = BatchedIPSolver(OracleEvaluator(spec), lb, ub, max_iter=max_iter).solve(torch.from_numpy(w0))
+    return spec, lb, ub, res
+
+
+def test_interior_point_on_the_oracle_benchmark_1():
+    spec, lb, ub, res = _solve_cpu(2)
+    assert bool(res.converged.all())
+    f = res.f.numpy()
+    assert np.all(np.abs(f - B1_OPT) < 2e-4), f
+    assert np.all(res.violation.numpy() < 1e-6)
+    # first-order optimality with the returned multipliers: grad f + J^T lam = 0
+    g, jv = no.eval_g_jac(spec, res.w.numpy())
+    _, gr = no.eval_f_grad(spec, res.w.numpy())
+    rows, cols, _ = no.jac_pattern(spec)
+    for i in range(2):
+        r = gr[i].copy()
+        np.add.at(r, cols, jv[i] * res.lam.numpy()[i, rows])
+        assert np.abs(r).max() < 5e-3
+
+
+@pytest.mark.gpu
+def test_interior_point_on_the_gpu_path_matches_cpu_solution(library):
+    import torch
+    from nlotrajectories_b200.config import Config
+    from nlotrajectories_b200.problem import NlpProblem
+    from nlotrajectories_b200.solver import BatchedIPSolver, DeviceEvaluator
+    prob = NlpProblem.from_config(Config.load(bench_yaml("benchmark_1")), None)
+    lb, ub = prob.bounds()
+    P = 16
+    w0 = prob.multistart_guess(P).astype(np.float64)
+    res = BatchedIPSolver(DeviceEvaluator(prob), lb, ub, max_iter=200).solve(torch.from_numpy(w0).cuda())
+    ok = res.converged.cpu().numpy()
+    f = res.f.cpu().numpy()
+    assert ok.mean() >= 0.5, ok
+    assert np.all(np.abs(f[ok] - B1_OPT) < 3e-4), f[ok]
+    assert np.all(res.violation.cpu().numpy()[ok] < 1e-5)
