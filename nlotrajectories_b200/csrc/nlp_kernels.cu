@@ -146,12 +146,13 @@ template <> struct Dyn<NLO_DYN_ACKERMANN_2ND> { static constexpr int nx = 7, nu 
     A[7] = (a * sec2 - 2.f * psi * v * pd * q * q) * iL; A[8] = pd * q * iL; A[9] = v * q * iL;
     B[0] = t * iL; B[1] = 1.f; B[2] = 1.f; } };
 
+// The kernels below are written as device bodies that take their row / knot index k (uniform per block); one fused launch
+// (nlp_phase0_kernel) runs them all, selecting the role by blockIdx.y range.
 template <int DYN>
-__global__ void __launch_bounds__(256) nlp_dyn_kernel(NlpDev L, const float* __restrict__ w, size_t P, size_t ld,
-                                                      float* __restrict__ g, float* __restrict__ jac) {
+__device__ __forceinline__ void nlp_dyn_body(const NlpDev& L, const float* __restrict__ w, size_t P, size_t ld,
+                                             float* __restrict__ g, float* __restrict__ jac, const int k) {
   using D = Dyn<DYN>;
   constexpr int nx = D::nx, nu = D::nu;
-  const int k = blockIdx.y;                       // interval: uniform per block, no index division
   for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (size_t)gridDim.x * blockDim.x) {
     float x[nx], xn[nx], u[nu], f[nx], A[D::nA > 0 ? D::nA : 1], B[D::nB];
 #pragma unroll
@@ -184,9 +185,8 @@ __global__ void __launch_bounds__(256) nlp_dyn_kernel(NlpDev L, const float* __r
 }
 
 // ---- rows that are plain copies of a variable (init, terminal, slack >= 0, control box): dg/dw = 1 ----
-__global__ void __launch_bounds__(256) nlp_copy_rows_kernel(NlpDev L, const float* __restrict__ w, size_t P, size_t ld,
-                                                            float* __restrict__ g, float* __restrict__ jac) {
-  const int r = blockIdx.y;
+__device__ __forceinline__ void nlp_copy_rows_body(const NlpDev& L, const float* __restrict__ w, size_t P, size_t ld,
+                                                   float* __restrict__ g, float* __restrict__ jac, const int r) {
   for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (size_t)gridDim.x * blockDim.x) {
     if (g) g[(size_t)L.copy_row[r] * ld + p] = w[(size_t)L.copy_var[r] * ld + p];
     if (jac) jac[(size_t)L.copy_nz[r] * ld + p] = 1.f;
@@ -194,9 +194,8 @@ __global__ void __launch_bounds__(256) nlp_copy_rows_kernel(NlpDev L, const floa
 }
 
 // ---- K3a: footprint points (core/geometry.py:78-83) ------------------------------------------------------
-__global__ void __launch_bounds__(256) nlp_points_kernel(NlpDev L, const float* __restrict__ w, size_t P, size_t ld,
-                                                         float* __restrict__ px, float* __restrict__ py) {
-  const int k = blockIdx.y;
+__device__ __forceinline__ void nlp_points_body(const NlpDev& L, const float* __restrict__ w, size_t P, size_t ld,
+                                                float* __restrict__ px, float* __restrict__ py, const int k) {
   for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (size_t)gridDim.x * blockDim.x) {
     const float x = w[(size_t)(k * L.nx + 0) * ld + p], y = w[(size_t)(k * L.nx + 1) * ld + p];
     if (L.shape == NLO_SHAPE_DOT) { px[(size_t)k * P + p] = x; py[(size_t)k * P + p] = y; continue; }
@@ -274,7 +273,7 @@ __global__ void __launch_bounds__(256) nlp_sdf_rows_kernel(NlpDev L, const float
 // ---- K4: objective and gradient (core/runner.py:80-98) -----------------------------------------------------
 // Objective: a block is 32 problems x 8 knot ranges (problem index fastest -> every load is one 128-byte line per warp);
 // the 8 partial sums of a problem meet in shared memory.
-__global__ void __launch_bounds__(256) nlp_obj_kernel(NlpDev L, const float* __restrict__ w, size_t P, size_t ld, float* __restrict__ f) {
+__device__ __forceinline__ void nlp_obj_body(const NlpDev& L, const float* __restrict__ w, size_t P, size_t ld, float* __restrict__ f) {
   __shared__ float part[8][33];
   const int tx = threadIdx.x & 31, c = threadIdx.x >> 5;
   for (size_t p0 = (size_t)blockIdx.x * 32; p0 < P; p0 += (size_t)gridDim.x * 32) {
@@ -321,8 +320,8 @@ __global__ void __launch_bounds__(256) nlp_obj_kernel(NlpDev L, const float* __r
 
 // Gradient: blockIdx.y = knot (uniform per block, no index division); a thread writes every gradient entry that belongs
 // to its (problem, knot): the nx state entries, the nu controls of interval k and the knot's slack.
-__global__ void __launch_bounds__(256) nlp_grad_kernel(NlpDev L, const float* __restrict__ w, size_t P, size_t ld, float* __restrict__ grad) {
-  const int k = blockIdx.y;
+__device__ __forceinline__ void nlp_grad_body(const NlpDev& L, const float* __restrict__ w, size_t P, size_t ld, float* __restrict__ grad,
+                                              const int k) {
   for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (size_t)gridDim.x * blockDim.x) {
     const float xk = w[(size_t)(k * L.nx) * ld + p], yk = w[(size_t)(k * L.nx + 1) * ld + p];
     float gx = 0.f, gy = 0.f;
@@ -350,6 +349,27 @@ __global__ void __launch_bounds__(256) nlp_grad_kernel(NlpDev L, const float* __
       grad[v * ld + p] = 2.f * L.slack_penalty * w[v * ld + p];
     }
   }
+}
+
+// ---- everything that precedes the SDF evaluation, in ONE launch: blockIdx.y selects the role and its row -----------------
+template <int DYN>
+__global__ void __launch_bounds__(256, 8) nlp_phase0_kernel(NlpDev L, const float* __restrict__ w, size_t P, size_t ld, float* __restrict__ g,
+                                                         float* __restrict__ jac, float* __restrict__ px, float* __restrict__ py,
+                                                         float* __restrict__ f, float* __restrict__ grad, int n_dyn, int n_copy, int n_pts,
+                                                         int n_grad) {
+  int r = blockIdx.y;
+  if (r < n_dyn) { nlp_dyn_body<DYN>(L, w, P, ld, g, jac, r); return; }
+  r -= n_dyn;
+  if (r < n_copy) { nlp_copy_rows_body(L, w, P, ld, g, jac, r); return; }
+  r -= n_copy;
+  if (r < n_pts) { nlp_points_body(L, w, P, ld, px, py, r); return; }
+  r -= n_pts;
+  if (r < n_grad) { nlp_grad_body(L, w, P, ld, grad, r); return; }
+  nlp_obj_body(L, w, P, ld, f);
+}
+__global__ void __launch_bounds__(256) nlp_points_kernel(NlpDev L, const float* __restrict__ w, size_t P, size_t ld,
+                                                         float* __restrict__ px, float* __restrict__ py) {
+  nlp_points_body(L, w, P, ld, px, py, blockIdx.y);
 }
 
 // ---- max bound violation per problem (best-of selection) ----------------------------------------------------
@@ -414,29 +434,22 @@ int nlo_nlp_launch_assembly(nlo_nlp* p, const NlpScratch& sc, const float* w, si
   const NlpDev& L = p->L;
   const int sm = p->sm_count;
   if (phase == 0) {
-    if (g || jac) {
-      const unsigned gx = (unsigned)std::min<size_t>((P + 255) / 256, 4096);
+    const bool gj = g || jac;
+    const int n_dyn = gj ? L.N : 0, n_copy = gj ? L.n_copy : 0, n_pts = gj ? L.N + 1 : 0, n_grad = grad_f ? L.N + 1 : 0, n_obj = f ? 1 : 0;
+    const unsigned rows = (unsigned)(n_dyn + n_copy + n_pts + n_grad + n_obj);
+    if (rows) {
+      const dim3 grid((unsigned)std::min<size_t>((P + 255) / 256, 4096), rows);
       switch (L.dyn) {
-#define NLO_CASE(D) case D: nlp_dyn_kernel<D><<<dim3(gx, (unsigned)L.N), 256, 0, st>>>(L, w, P, ld, g, jac); break;
+#define NLO_CASE(D) case D: nlp_phase0_kernel<D><<<grid, 256, 0, st>>>(L, w, P, ld, g, jac, sc.px, sc.py, f, grad_f, n_dyn, n_copy, n_pts, n_grad); break;
         NLO_CASE(NLO_DYN_POINT_1ST) NLO_CASE(NLO_DYN_POINT_2ND) NLO_CASE(NLO_DYN_UNICYCLE)
         NLO_CASE(NLO_DYN_UNICYCLE_2ND) NLO_CASE(NLO_DYN_ACKERMANN) NLO_CASE(NLO_DYN_ACKERMANN_2ND)
 #undef NLO_CASE
       }
       NLO_CHECK_LAUNCH();
-      nlp_copy_rows_kernel<<<dim3(gx, (unsigned)L.n_copy), 256, 0, st>>>(L, w, P, ld, g, jac);
-      NLO_CHECK_LAUNCH();
-      nlp_points_kernel<<<dim3(gx, (unsigned)(L.N + 1)), 256, 0, st>>>(L, w, P, ld, sc.px, sc.py);
-      NLO_CHECK_LAUNCH();
-      if (L.sdf_mode == NLO_SDF_CIRCLES) {
-        const size_t n = (size_t)(L.N + 1) * L.nb * P;
-        nlp_circles_kernel<<<grid_for(n, 256, sm), 256, 0, st>>>(L, sc.px, sc.py, n, sc.s, sc.jx, sc.jy);
-        NLO_CHECK_LAUNCH();
-      }
     }
-    if (f) { nlp_obj_kernel<<<grid_for(P * 8, 256, sm), 256, 0, st>>>(L, w, P, ld, f); NLO_CHECK_LAUNCH(); }
-    if (grad_f) {
-      const dim3 grid((unsigned)std::min<size_t>((P + 255) / 256, 4096), (unsigned)(L.N + 1));
-      nlp_grad_kernel<<<grid, 256, 0, st>>>(L, w, P, ld, grad_f);
+    if (gj && L.sdf_mode == NLO_SDF_CIRCLES) {
+      const size_t n = (size_t)(L.N + 1) * L.nb * P;
+      nlp_circles_kernel<<<grid_for(n, 256, sm), 256, 0, st>>>(L, sc.px, sc.py, n, sc.s, sc.jx, sc.jy);
       NLO_CHECK_LAUNCH();
     }
   } else {
