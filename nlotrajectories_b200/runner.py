@@ -45,7 +45,25 @@ class RunBenchmark:
         """g, dg/dw values (CCS order), f, grad f for a (P, n_w) batch held on the host."""
         return self.problem.eval_host(w)
 
-    def run(self):
-        raise NotImplementedError(
-            "the IPOPT solve of core/runner.py:112-133 is the caller of this hot path and is not part of it; "
-            "use evaluate() / NlpProblem.eval_device() as the callbacks of a solver")
+    def run(self, P: int = 64, first: int = 0, max_iter: int = 300, tol: float = 1e-4, verbose: bool = False):
+        """The reference's ``run()`` (core/runner.py:44-153) for a batch of P multi-start problems: every start is solved by
+        the batched interior point of ``solver.py`` (tol 1e-4 and the exact Hessian, like the IPOPT options at
+        core/runner.py:112-125) and the best converged start is returned in the reference's shape:
+        ``(X_opt (nx, N+1), U_opt (nu, N), result, X_init (N+1, nx), status)`` with status "success" or "failed"
+        (core/runner.py:134-153 returns the last iterate with "failed" when IPOPT does not converge; so does this)."""
+        import torch
+        from .solver import BatchedIPSolver, DeviceEvaluator
+        pr = self.problem
+        w0 = self.initial_guess(P, first).astype(np.float64)
+        lb, ub = pr.bounds()
+        dev = torch.device("cuda", pr.device)
+        res = BatchedIPSolver(DeviceEvaluator(pr), lb, ub, tol=tol, max_iter=max_iter, verbose=verbose).solve(torch.from_numpy(w0).to(dev))
+        f = res.f.cpu().numpy(); ok = res.converged.cpu().numpy(); viol = res.violation.cpu().numpy()
+        score = np.where(ok, f, f + 1e3 * (1.0 + viol))             # converged starts first, by objective
+        best = int(np.argmin(score))
+        w = res.w[best].cpu().numpy()
+        X_opt = w[:pr.n_X].reshape(pr.N + 1, pr.nx).T.copy()
+        U_opt = w[pr.n_X:pr.n_X + pr.n_U].reshape(pr.N, pr.nu).T.copy()
+        X_init = w0[best, :pr.n_X].reshape(pr.N + 1, pr.nx)
+        res.best = best
+        return X_opt, U_opt, res, X_init, ("success" if ok[best] else "failed")

@@ -53,3 +53,22 @@ def test_interior_point_on_the_gpu_path_matches_cpu_solution(library):
     assert ok.mean() >= 0.5, ok
     assert np.all(np.abs(f[ok] - B1_OPT) < 3e-4), f[ok]
     assert np.all(res.violation.cpu().numpy()[ok] < 1e-5)
+
+
+@pytest.mark.gpu
+def test_run_benchmark_run_returns_reference_shapes(library):
+    """RunBenchmark.run() mirrors core/runner.py:9-153: (X_opt (nx, N+1), U_opt (nu, N), result, X_init, status)."""
+    from nlotrajectories_b200.runner import RunBenchmark
+    rb = RunBenchmark(dynamics="point_2nd", geometry="dot", x0=[0.0, 0.0, 0.0, 0.0], x_goal=[1.0, 1.0, 0.0, 0.0], N=40, dt=0.1,
+                      sdf_func=[(0.5, 0.5, 0.2, 0.05)], control_bounds=((-1.0, 1.0), (-1.0, 1.0)), use_slack=True, slack_penalty=50,
+                      enforce_heading=False)                       # benchmark_1_dot_circle.yaml
+    X_opt, U_opt, res, X_init, status = rb.run(P=8, max_iter=200)
+    assert X_opt.shape == (4, 41) and U_opt.shape == (2, 40) and X_init.shape == (41, 4)
+    assert status == "success"
+    np.testing.assert_allclose(X_opt[:, 0], [0, 0, 0, 0], atol=1e-5)
+    np.testing.assert_allclose(X_opt[[0, 1, 3], -1], [1, 1, 0], atol=1e-5)          # terminal row skips state 2 (runner.py:54-56)
+    assert np.all(np.abs(U_opt) <= 1.0 + 1e-5)
+    d = np.hypot(X_opt[0] - 0.5, X_opt[1] - 0.5)
+    assert d.min() >= 0.25 - 1e-4                                                     # radius + margin
+    path = np.sqrt(np.diff(X_opt[0]) ** 2 + np.diff(X_opt[1]) ** 2 + 1e-8).sum()
+    assert abs(path - B1_OPT) < 3e-4
