@@ -67,6 +67,18 @@ class SdfWeights:
         return SdfWeights.pack(str(z["kind"]), z["W0"], z["b0"], [(z[f"W{l+1}"], z[f"b{l+1}"]) for l in range(M)],
                                z["w_out"], float(z["b_out"]), int(z["act0"]), int(z["act"]), float(z["p0"]), float(z["p"]))
 
+    def save_npz(self, path) -> None:
+        """The layout ``from_npz`` reads (also what oracle/sdf_oracle.py's to_npz / from_npz use)."""
+        H, M = self.hidden, self.n_hidden_mats
+        b = self.blob
+        d = {"kind": np.array(self.kind), "n_hidden_mats": np.int64(M), "act0": np.int64(self.act0), "act": np.int64(self.act),
+             "p0": np.float64(self.p0), "p": np.float64(self.p), "W0": b[:2 * H].reshape(H, 2), "b0": b[2 * H:3 * H]}
+        o = 3 * H
+        for l in range(M):
+            d[f"W{l + 1}"] = b[o:o + H * H].reshape(H, H); d[f"b{l + 1}"] = b[o + H * H:o + H * H + H]; o += H * H + H
+        d["w_out"] = b[o:o + H]; d["b_out"] = np.float64(b[o + H])
+        np.savez(path, **d)
+
     @staticmethod
     def from_torchscript(path) -> "SdfWeights":
         """Traced FourierMLP artefact written by l4casadi (``nn_sdf.pt``): constants c0..c5 with
