@@ -61,10 +61,11 @@ def solve_benchmark(config_path: Path, batch: int = 64, weights: str | None = No
     res = BatchedIPSolver(DeviceEvaluator(prob), lb, ub, verbose=verbose and rank == 0).solve(w0)
     torch.cuda.synchronize()
     dt = time.time() - t0
-    score = torch.where(res.converged, res.f, res.f + 1e3 * (1.0 + res.violation)).float()
+    usable = res.converged | (res.stalled & (res.violation <= 1e-4))
+    score = torch.where(usable, res.f, res.f + 1e3 * (1.0 + res.violation)).float()
     best_val, best_idx, w_best = select_best(score, res.w.float().T.contiguous(), lo, prob.n_w)
     out = {"config": str(config_path), "batch": batch, "world": world, "solver": "batched interior point (tol 1e-4, exact Hessian)",
-           "solve_s_rank0": dt, "converged_fraction_rank0": float(res.converged.float().mean().item()),
+           "solve_s_rank0": dt, "converged_fraction_rank0": float(res.converged.float().mean().item()), "stalled_feasible_fraction_rank0": float(res.stalled.float().mean().item()),
            "best_objective": best_val, "best_start": best_idx}
     if rank == 0 and verbose:
         print(json.dumps(out))

@@ -59,11 +59,12 @@ class RunBenchmark:
         dev = torch.device("cuda", pr.device)
         res = BatchedIPSolver(DeviceEvaluator(pr), lb, ub, tol=tol, max_iter=max_iter, verbose=verbose).solve(torch.from_numpy(w0).to(dev))
         f = res.f.cpu().numpy(); ok = res.converged.cpu().numpy(); viol = res.violation.cpu().numpy()
-        score = np.where(ok, f, f + 1e3 * (1.0 + viol))             # converged starts first, by objective
+        usable = ok | (res.stalled.cpu().numpy() & (viol <= tol))   # converged, or feasible and stationary in f (ReLU kinks)
+        score = np.where(usable, f, f + 1e3 * (1.0 + viol))         # usable starts first, by objective
         best = int(np.argmin(score))
         w = res.w[best].cpu().numpy()
         X_opt = w[:pr.n_X].reshape(pr.N + 1, pr.nx).T.copy()
         U_opt = w[pr.n_X:pr.n_X + pr.n_U].reshape(pr.N, pr.nu).T.copy()
         X_init = w0[best, :pr.n_X].reshape(pr.N + 1, pr.nx)
         res.best = best
-        return X_opt, U_opt, res, X_init, ("success" if ok[best] else "failed")
+        return X_opt, U_opt, res, X_init, ("success" if usable[best] else "failed")

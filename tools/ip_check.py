@@ -33,9 +33,12 @@ res = BatchedIPSolver(ev, lb, ub, verbose=True, max_iter=300).solve(torch.from_n
 torch.cuda.synchronize()
 dt = time.time() - t0
 f = res.f.cpu().numpy(); v = res.violation.cpu().numpy(); ok = res.converged.cpu().numpy(); its = res.iterations.cpu().numpy()
-best = np.where(ok, f, np.inf).argmin()
-print(f"{name}: P={P} batched IP on GPU: {dt:.1f} s, {ev.evals} batched evaluations; converged {ok.mean() * 100:.1f}% (iterations median {np.median(its[ok]) if ok.any() else -1:.0f}); "
-      f"f over converged min/med/max {f[ok].min():.6f} / {np.median(f[ok]):.6f} / {f[ok].max():.6f}; best start {best} f={f[best]:.6f} viol={v[best]:.1e}", flush=True)
+stl = res.stalled.cpu().numpy()
+use = ok | (stl & (v <= 1e-4))
+best = np.where(use, f, np.inf).argmin()
+q = lambda m: f"{f[m].min():.6f} / {np.median(f[m]):.6f} / {f[m].max():.6f}" if m.any() else "-"
+print(f"{name}: P={P} batched IP on GPU: {dt:.1f} s, {ev.evals} batched evaluations; converged {ok.mean() * 100:.1f}% (iterations median {np.median(its[ok]) if ok.any() else -1:.0f}), "
+      f"stalled-feasible {stl.mean() * 100:.1f}%; f over converged min/med/max {q(ok)}; over stalled-feasible {q(stl)}; best start {best} f={f[best]:.6f} viol={v[best]:.1e}", flush=True)
 # CPU: same algorithm on the fp64 oracle, and SLSQP, for the first n_ref starts
 cpu = BatchedIPSolver(OracleEvaluator(spec, net), lb, ub, max_iter=300).solve(torch.from_numpy(w0[:n_ref]))
 n64 = net.astype(np.float64) if net is not None else None
@@ -56,5 +59,5 @@ for i in range(n_ref):
     r = minimize(lambda w: no.eval_f_grad(spec, w[None])[0][0], w0[i], jac=lambda w: no.eval_f_grad(spec, w[None])[1][0],
                  constraints=cons, method="SLSQP", options={"maxiter": 400, "ftol": 1e-10})
     gi = G(r.x); vi = np.maximum(0, np.maximum(lb - gi, gi - ub)).max()
-    print(f"start {i}: GPU IP f={f[i]:.6f} viol={v[i]:.1e} conv={ok[i]} its={its[i]} | CPU IP (oracle fp64) f={cpu.f[i].item():.6f} conv={bool(cpu.converged[i])} "
+    print(f"start {i}: GPU IP f={f[i]:.6f} viol={v[i]:.1e} conv={ok[i]} stalled={stl[i]} its={its[i]} | CPU IP (oracle fp64) f={cpu.f[i].item():.6f} conv={bool(cpu.converged[i])} "
           f"|dw|max={np.abs(cpu.w[i].numpy() - wg[i]).max():.2e} | SLSQP f={r.fun:.6f} viol={vi:.1e} ({r.nit} its, {time.time() - t0:.1f}s) |dw|max={np.abs(r.x - wg[i]).max():.2e}", flush=True)
