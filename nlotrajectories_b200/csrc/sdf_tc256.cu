@@ -8,8 +8,11 @@
 //     MMAs consume them (forward k-step ks: W1hi[ks], W1lo[ks]; reverse: Vlo[ks], Vhi[ks]); a dedicated producer warp
 //     moves them with cp.async.bulk into a 24-slot shared-memory ring (full / empty mbarriers, tcgen05.commit frees
 //     a slot), running ahead of the MMAs across GEMMs and tiles;
-//   * one persistent CTA per SM: 16 compute warps (four threads per point, 64 neurons each) + the producer warp;
-//     lane 0 of warp 0 issues the MMAs (M = 128, N = 256, K = 16) while the compute warps wait;
+//   * one persistent CTA per SM, warp-specialised: 16 compute warps (four threads per point, 64 neurons each), the
+//     producer warp and an MMA-issuer warp (M = 128, N = 256, K = 16).  The k-steps are consumed in an order that lets
+//     half of each GEMM start as soon as every thread has written the first 32-neuron chunk of its A operand, so the
+//     second half of layer 0 / epilogue 1 overlaps the tensor core; the epilogues read all 64 of a thread's D columns
+//     up front, which frees D for the next GEMM (per-warp mbarrier arrivals, no CTA-wide barrier on that path);
 //   * the small vectors sit in shared memory (read as broadcast LDS.128), one code path for all four neuron quarters.
 // Numerics are those of sdf_tc.cu: split-fp16 hi/lo with FP32 accumulation, exact power-of-two scaling, the reverse
 // GEMM as exact 0/1 mask x V (two passes).
@@ -28,7 +31,8 @@ constexpr int H = 256;
 constexpr int TILE = 128;                 // points per tile == TMEM lanes
 constexpr int NQ = 4;                     // threads per point (neuron quarters)
 constexpr int NCOMPUTE = TILE * NQ;       // 512 compute threads
-constexpr int THREADS = NCOMPUTE + 32;    // + producer warp
+constexpr int NCW = NCOMPUTE / 32;          // compute warps
+constexpr int THREADS = NCOMPUTE + 64;    // + producer warp + MMA warp
 constexpr int CHUNK = 8192;               // one K = 16 step of a 256-row operand image
 constexpr int NSLOT = 24;
 constexpr int CHUNKS_FWD = 32, CHUNKS_BWD = 32;
@@ -40,7 +44,7 @@ struct Smem {
   alignas(1024) uint8_t ring[NSLOT][CHUNK];
   alignas(16) float w0x[H], w0y[H], b0[H], b1[H], w2[H];
   float part[NQ][TILE][3];
-  alignas(8) uint64_t full[NSLOT], empty[NSLOT], mma_bar;
+  alignas(8) uint64_t full[NSLOT], empty[NSLOT], mma_bar[2], a_bar[4], dfree_bar[2];
   uint32_t tmem_slot;
 };
 
@@ -77,6 +81,13 @@ __device__ __forceinline__ bool elect_lane0() {
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 1;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
   return pred != 0;
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t a) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory"); }
+// one arrival per compute warp, after every lane's tensor-memory traffic is ordered before the barrier
+__device__ __forceinline__ void warp_arrive(uint32_t a, int lane) {
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(a);
+}
 __device__ __forceinline__ void compute_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NCOMPUTE) : "memory"); }
 __device__ __forceinline__ void st16(uint32_t a, const uint32_t (&v)[16]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};"
@@ -88,38 +99,39 @@ __device__ __forceinline__ uint32_t pack2_f16(float v0, float v1) {
   return *reinterpret_cast<const uint32_t*>(&p);
 }
 
-// lane 0 of warp 0: consume the ring, issue the MMAs of one GEMM, signal mma_bar.  `c` = chunks consumed so far.
+// k-steps in consumption order: a thread's first 32-neuron chunk (cc = 0) covers k-steps {4q, 4q+1}, its second {4q+2, 4q+3}
+// (q = neuron quarter), so half of a GEMM can run as soon as every thread has written its first chunk of the A operand.
+__host__ __device__ constexpr int ks_of(int i) { return ((i & 7) >> 1) * 4 + (i >> 3) * 2 + (i & 1); }   // i = 0..15
+
+// MMA warp, elected lane: consume the ring and issue the MMAs of k-steps order[i0 .. i0+8) of one GEMM.  `c` = chunks consumed so far.
 template <int CL>
-__device__ __forceinline__ void issue_gemm256(Smem* sm, uint32_t tmem, bool fwd, uint32_t& c) {
+__device__ __forceinline__ void issue_half256(Smem* sm, uint32_t tmem, bool fwd, int i0, uint32_t& c) {
   constexpr uint16_t MASK = (uint16_t)((1u << CL) - 1u);
   constexpr uint32_t IDESC = umma_idesc_f16(TILE, H, 0);
   const uint32_t ring = smem_u32(sm->ring), full = smem_u32(sm->full), empty = smem_u32(sm->empty);
-  tc_fence_after();
-  if (elect_lane0()) {
-    for (int ks = 0; ks < H / 16; ++ks) {
-      // first chunk of the k-step: forward W1hi[ks] (A lo and A hi both multiply it); reverse Vlo[ks]
-      uint32_t slot = c % NSLOT;
-      mbar_wait256(full + slot * 8, (c / NSLOT) & 1);
-      tc_fence_after();
-      uint64_t desc = umma_desc(ring + slot * CHUNK, 16u * H, 128u);
-      if (fwd) {
-        tc_mma_f16_ts(tmem + COL_D, tmem + COL_ALO + ks * 8, desc, IDESC, ks != 0);
-        tc_mma_f16_ts(tmem + COL_D, tmem + COL_AHI + ks * 8, desc, IDESC, 1);
-      } else {
-        tc_mma_f16_ts(tmem + COL_D, tmem + COL_AHI + ks * 8, desc, IDESC, ks != 0);
-      }
-      if (CL > 1) tc_commit_mc(empty + slot * 8, MASK); else tc_commit_addr(empty + slot * 8);
-      ++c;
-      // second chunk: forward W1lo[ks]; reverse Vhi[ks]
-      slot = c % NSLOT;
-      mbar_wait256(full + slot * 8, (c / NSLOT) & 1);
-      tc_fence_after();
-      desc = umma_desc(ring + slot * CHUNK, 16u * H, 128u);
+  for (int i = i0; i < i0 + 8; ++i) {
+    const int ks = ks_of(i);
+    // first chunk of the k-step: forward W1hi[ks] (A lo and A hi both multiply it); reverse Vlo[ks]
+    uint32_t slot = c % NSLOT;
+    mbar_wait256(full + slot * 8, (c / NSLOT) & 1);
+    tc_fence_after();
+    uint64_t desc = umma_desc(ring + slot * CHUNK, 16u * H, 128u);
+    if (fwd) {
+      tc_mma_f16_ts(tmem + COL_D, tmem + COL_ALO + ks * 8, desc, IDESC, i != 0);
       tc_mma_f16_ts(tmem + COL_D, tmem + COL_AHI + ks * 8, desc, IDESC, 1);
-      if (CL > 1) tc_commit_mc(empty + slot * 8, MASK); else tc_commit_addr(empty + slot * 8);
-      ++c;
+    } else {
+      tc_mma_f16_ts(tmem + COL_D, tmem + COL_AHI + ks * 8, desc, IDESC, i != 0);
     }
-    tc_commit_addr(smem_u32(&sm->mma_bar));
+    if (CL > 1) tc_commit_mc(empty + slot * 8, MASK); else tc_commit_addr(empty + slot * 8);
+    ++c;
+    // second chunk: forward W1lo[ks]; reverse Vhi[ks]
+    slot = c % NSLOT;
+    mbar_wait256(full + slot * 8, (c / NSLOT) & 1);
+    tc_fence_after();
+    desc = umma_desc(ring + slot * CHUNK, 16u * H, 128u);
+    tc_mma_f16_ts(tmem + COL_D, tmem + COL_AHI + ks * 8, desc, IDESC, 1);
+    if (CL > 1) tc_commit_mc(empty + slot * 8, MASK); else tc_commit_addr(empty + slot * 8);
+    ++c;
   }
 }
 
@@ -154,7 +166,9 @@ sdf_tc256_kernel(SdfNetDev net, Tc256Params prm, const uint8_t* __restrict__ img
     }
     if (t == 0) {
       for (int i = 0; i < NSLOT; ++i) { mbar_init(sm->full + i, 1); mbar_init(sm->empty + i, CL); }
-      mbar_init(&sm->mma_bar, 1);
+      mbar_init(sm->mma_bar + 0, 1); mbar_init(sm->mma_bar + 1, 1);
+      for (int i = 0; i < 4; ++i) mbar_init(sm->a_bar + i, NCW);
+      mbar_init(sm->dfree_bar + 0, NCW); mbar_init(sm->dfree_bar + 1, NCW);
     }
     fence_async_smem();
   }
@@ -165,7 +179,7 @@ sdf_tc256_kernel(SdfNetDev net, Tc256Params prm, const uint8_t* __restrict__ img
   tc_fence_after();
   const uint32_t tmem = sm->tmem_slot;
 
-  if (warp == NCOMPUTE / 32) {
+  if (warp == NCW) {
     // ---- producer: stream the operand chunks in consumption order, as far ahead as the ring allows ------------------
     if (lane == 0) {
       const uint32_t ring = smem_u32(sm->ring), full = smem_u32(sm->full), empty = smem_u32(sm->empty);
@@ -184,14 +198,38 @@ sdf_tc256_kernel(SdfNetDev net, Tc256Params prm, const uint8_t* __restrict__ img
           }
         }
     }
+  } else if (warp == NCW + 1) {
+    // ---- MMA issuer: half a GEMM as soon as the compute warps have written the matching half of the A operand -------
+    if (lane == 0 && elect_lane0()) {
+      const uint32_t a_bar = smem_u32(sm->a_bar), dfree = smem_u32(sm->dfree_bar), mma_bar = smem_u32(sm->mma_bar);
+      uint32_t consumed = 0;
+      for (size_t it = 0; it < my_tiles; ++it) {
+        const uint32_t ph = (uint32_t)(it & 1);
+        // D of the previous tile must have been read: by epilogue 2, or by epilogue 1 when no Jacobian is asked for
+        if (it > 0) mbar_wait256(dfree + (want_jac ? 8 : 0), ph ^ 1);
+        mbar_wait256(a_bar + 0, ph); tc_fence_after();
+        issue_half256<CL>(sm, tmem, true, 0, consumed);
+        mbar_wait256(a_bar + 8, ph); tc_fence_after();
+        issue_half256<CL>(sm, tmem, true, 8, consumed);
+        tc_commit_addr(mma_bar + 0);
+        if (want_jac) {
+          mbar_wait256(dfree + 0, ph);                       // every z of GEMM 1 is in registers: D may be overwritten
+          mbar_wait256(a_bar + 16, ph); tc_fence_after();
+          issue_half256<CL>(sm, tmem, false, 0, consumed);
+          mbar_wait256(a_bar + 24, ph); tc_fence_after();
+          issue_half256<CL>(sm, tmem, false, 8, consumed);
+          tc_commit_addr(mma_bar + 8);
+        }
+      }
+    }
   } else {
     // ---- compute warps ---------------------------------------------------------------------------------------------
     const int q = warp >> 2;                                   // neuron quarter: neurons [64 q, 64 q + 64)
     const int pt = (warp & 3) * 32 + lane;
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const uint32_t mma_bar = smem_u32(&sm->mma_bar);
-    uint32_t phase = 0, consumed = 0;
+    const uint32_t a_bar = smem_u32(sm->a_bar), dfree = smem_u32(sm->dfree_bar), mma_bar = smem_u32(sm->mma_bar);
     for (size_t it = 0; it < my_tiles; ++it) {
+      const uint32_t ph = (uint32_t)(it & 1);
       const size_t tile = blockIdx.x + it * gridDim.x;
       const size_t i = tile * TILE + pt;
       const bool valid = i < n;
@@ -200,7 +238,7 @@ sdf_tc256_kernel(SdfNetDev net, Tc256Params prm, const uint8_t* __restrict__ img
       long long* dg = (dbg && t == 0 && blockIdx.x == 0 && it < 16) ? dbg + it * 8 : nullptr;
 #define T256_STAMP(i) do { if (dg) dg[i] = clock64(); } while (0)
       T256_STAMP(0);
-      // ---- layer 0 -> A operand (row-scaled fp16 hi/lo) ------------------------------------------------------------
+      // ---- layer 0 -> A operand (row-scaled fp16 hi/lo); GEMM 1 starts on the first half while the second is computed ----
       float sc0, inv0;
       row_scale(act_bound(act0, net.p0, fmaf(fabsf(px), prm.max_w0x, fmaf(fabsf(py), prm.max_w0y, prm.max_b0))) + 1e-30f, sc0, inv0);
 #pragma unroll 1
@@ -219,57 +257,60 @@ sdf_tc256_kernel(SdfNetDev net, Tc256Params prm, const uint8_t* __restrict__ img
         }
         st16(lane_base + COL_AHI + q * 32 + cc * 16, hi);
         st16(lane_base + COL_ALO + q * 32 + cc * 16, lo);
+        tc_wait_st();
+        warp_arrive(a_bar + cc * 8, lane);
       }
-      tc_wait_st();
-      tc_fence_before();
-      compute_bar();
       T256_STAMP(1);
-      if (t == 0) issue_gemm256<CL>(sm, tmem, true, consumed);
-      T256_STAMP(2);
-      mbar_wait256(mma_bar, phase); phase ^= 1;
+      mbar_wait256(mma_bar + 0, ph);
       tc_fence_after();
       T256_STAMP(3);
-      // ---- epilogue 1: value, and the 0/1 mask of the ReLU layer -> A operand ---------------------------------------
+      // ---- epilogue 1: value, and the 0/1 mask of the ReLU layer -> A operand.  All 64 pre-activations of this thread are read
+      // ---- first, so that GEMM 2 may overwrite D while the second half of the mask is still being computed -------------------
       float s = q == 0 ? net.w[net.off_bout()] : 0.f;
       const float unscale1 = inv0 * prm.inv_sw;
-#pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int base = q * 64 + cc * 32;
-        uint32_t z[32];
-        tmem_ld32(lane_base + COL_D + base, z);
+      {
+        uint32_t z[2][32];
+        tmem_ld32(lane_base + COL_D + q * 64, z[0]);
+        tmem_ld32(lane_base + COL_D + q * 64 + 32, z[1]);
         tc_wait_ld();
-        uint32_t hi[16];
+        warp_arrive(dfree + 0, lane);
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 bb = *reinterpret_cast<const float4*>(sm->b1 + base + 4 * j4);
-          const float4 ww = *reinterpret_cast<const float4*>(sm->w2 + base + 4 * j4);
-          const float z0 = fmaf(__uint_as_float(z[4 * j4 + 0]), unscale1, bb.x), z1 = fmaf(__uint_as_float(z[4 * j4 + 1]), unscale1, bb.y);
-          const float z2 = fmaf(__uint_as_float(z[4 * j4 + 2]), unscale1, bb.z), z3 = fmaf(__uint_as_float(z[4 * j4 + 3]), unscale1, bb.w);
-          s = fmaf(ww.x, fmaxf(z0, 0.f), s); s = fmaf(ww.y, fmaxf(z1, 0.f), s);
-          s = fmaf(ww.z, fmaxf(z2, 0.f), s); s = fmaf(ww.w, fmaxf(z3, 0.f), s);
-          hi[2 * j4] = pack2_f16(z0 > 0.f ? 1.f : 0.f, z1 > 0.f ? 1.f : 0.f);
-          hi[2 * j4 + 1] = pack2_f16(z2 > 0.f ? 1.f : 0.f, z3 > 0.f ? 1.f : 0.f);
-        }
-        if (want_jac) st16(lane_base + COL_AHI + q * 32 + cc * 16, hi);
-      }
-      float jx = 0.f, jy = 0.f;
-      if (want_jac) {
-        tc_wait_st();
-        tc_fence_before();
-        compute_bar();
-        T256_STAMP(4);
-        if (t == 0) issue_gemm256<CL>(sm, tmem, false, consumed);
-        T256_STAMP(5);
-        mbar_wait256(mma_bar, phase); phase ^= 1;
-        tc_fence_after();
-        T256_STAMP(6);
-        // ---- epilogue 2: through layer 0 to the Jacobian -------------------------------------------------------------
-#pragma unroll 1
         for (int cc = 0; cc < 2; ++cc) {
           const int base = q * 64 + cc * 32;
-          uint32_t gz[32];
-          tmem_ld32(lane_base + COL_D + base, gz);
-          tc_wait_ld();
+          uint32_t hi[16];
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 bb = *reinterpret_cast<const float4*>(sm->b1 + base + 4 * j4);
+            const float4 ww = *reinterpret_cast<const float4*>(sm->w2 + base + 4 * j4);
+            const float z0 = fmaf(__uint_as_float(z[cc][4 * j4 + 0]), unscale1, bb.x), z1 = fmaf(__uint_as_float(z[cc][4 * j4 + 1]), unscale1, bb.y);
+            const float z2 = fmaf(__uint_as_float(z[cc][4 * j4 + 2]), unscale1, bb.z), z3 = fmaf(__uint_as_float(z[cc][4 * j4 + 3]), unscale1, bb.w);
+            s = fmaf(ww.x, fmaxf(z0, 0.f), s); s = fmaf(ww.y, fmaxf(z1, 0.f), s);
+            s = fmaf(ww.z, fmaxf(z2, 0.f), s); s = fmaf(ww.w, fmaxf(z3, 0.f), s);
+            hi[2 * j4] = pack2_f16(z0 > 0.f ? 1.f : 0.f, z1 > 0.f ? 1.f : 0.f);
+            hi[2 * j4 + 1] = pack2_f16(z2 > 0.f ? 1.f : 0.f, z3 > 0.f ? 1.f : 0.f);
+          }
+          if (want_jac) {
+            st16(lane_base + COL_AHI + q * 32 + cc * 16, hi);
+            tc_wait_st();
+            warp_arrive(a_bar + (2 + cc) * 8, lane);
+          }
+        }
+      }
+      T256_STAMP(4);
+      float jx = 0.f, jy = 0.f;
+      if (want_jac) {
+        mbar_wait256(mma_bar + 8, ph);
+        tc_fence_after();
+        T256_STAMP(6);
+        // ---- epilogue 2: through layer 0 to the Jacobian (D is read up front: the next tile's GEMM 1 may then start) ---------
+        uint32_t gz[2][32];
+        tmem_ld32(lane_base + COL_D + q * 64, gz[0]);
+        tmem_ld32(lane_base + COL_D + q * 64 + 32, gz[1]);
+        tc_wait_ld();
+        warp_arrive(dfree + 8, lane);
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int base = q * 64 + cc * 32;
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 wx = *reinterpret_cast<const float4*>(sm->w0x + base + 4 * j4);
@@ -280,7 +321,7 @@ sdf_tc256_kernel(SdfNetDev net, Tc256Params prm, const uint8_t* __restrict__ img
             for (int e = 0; e < 4; ++e) {
               float v, d;
               nlo_phi_d_tc(fmaf(wxs[e], px, fmaf(wys[e], py, bs[e])), act0, net.p0, v, d);
-              const float g0 = __uint_as_float(gz[4 * j4 + e]) * d;
+              const float g0 = __uint_as_float(gz[cc][4 * j4 + e]) * d;
               jx = fmaf(g0, wxs[e], jx); jy = fmaf(g0, wys[e], jy);
             }
           }
@@ -288,12 +329,10 @@ sdf_tc256_kernel(SdfNetDev net, Tc256Params prm, const uint8_t* __restrict__ img
         const float unscale2 = seed * prm.inv_sv;
         jx *= unscale2; jy *= unscale2;
       }
-      // ---- add the four quarters of a point (this barrier also orders this tile's TMEM reads before the next tile's writes) ----
       T256_STAMP(7);
+      // ---- add the four quarters of a point -----------------------------------------------------------------------------
       sm->part[q][pt][0] = s; sm->part[q][pt][1] = jx; sm->part[q][pt][2] = jy;
-      tc_fence_before();
       compute_bar();
-      tc_fence_after();
       if (q == 0 && valid) {
         float r[3];
 #pragma unroll
@@ -302,7 +341,7 @@ sdf_tc256_kernel(SdfNetDev net, Tc256Params prm, const uint8_t* __restrict__ img
         if (jx_out) jx_out[i] = r[1];
         if (jy_out) jy_out[i] = r[2];
       }
-      // `part` is rewritten only after the next tile's first compute barrier, which quarter 0 reaches after these reads
+      compute_bar();                                   // `part` is rewritten by the next tile
     }
   }
   tc_fence_before();
@@ -338,8 +377,8 @@ int launch_tc256_cl(nlo_sdf_model* m, const float* x, const float* y, const floa
     cudaFree(dbg);
     for (int it = 4; it < 8; ++it) {
       const long long* r = h + it * 8;
-      fprintf(stderr, "[tc256 timeline] tile%2d: L0 %5lld issue1 %5lld wait1 %5lld E1 %5lld issue2 %5lld wait2 %5lld E2 %5lld | period %6lld\n", it,
-              r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[5] - r[4], r[6] - r[5], r[7] - r[6], (h + (it + 1) * 8)[0] - r[0]);
+      fprintf(stderr, "[tc256 timeline] tile%2d: L0 %5lld wait-GEMM1 %5lld E1 %5lld wait-GEMM2 %5lld E2 %5lld | period %6lld\n", it,
+              r[1] - r[0], r[3] - r[1], r[4] - r[3], r[6] - r[4], r[7] - r[6], (h + (it + 1) * 8)[0] - r[0]);
     }
   }
   NLO_CHECK_LAUNCH();
@@ -366,8 +405,8 @@ bool nlo_sdf_tc256_supported(const nlo_sdf_desc* d) {
   return d->n_hidden_mats == 1 && d->hidden == 256 && d->act == NLO_ACT_RELU;
 }
 
-// Images in consumption order: chunk 2ks = W1hi[ks], 2ks+1 = W1lo[ks] (forward), 32+2ks = Vlo[ks], 32+2ks+1 = Vhi[ks]
-// (reverse); inside a chunk element (n, kk) of the K = 16 step sits at ((kk/8)*32 + n/8)*128 + (n%8)*16 + (kk%8)*2 bytes
+// Images in consumption order: position i holds k-step ks_of(i); chunk 2i = W1hi[ks], 2i+1 = W1lo[ks] (forward), 32+2i = Vlo[ks],
+// 32+2i+1 = Vhi[ks] (reverse); inside a chunk element (n, kk) of the K = 16 step sits at ((kk/8)*32 + n/8)*128 + (n%8)*16 + (kk%8)*2 bytes
 // (UMMA K-major core-matrix order, no swizzle: LBO = 4096, SBO = 128).
 int nlo_sdf_tc256_prepare(nlo_sdf_model* m, const float* w) {
   const float* W0 = w;
@@ -395,20 +434,21 @@ int nlo_sdf_tc256_prepare(nlo_sdf_model* m, const float* w) {
   auto at = [&](int chunk, int nn, int kk) -> __half& {
     return img[(size_t)chunk * (CHUNK / 2) + ((size_t)(kk / 8) * (H / 8) + nn / 8) * 64 + (nn % 8) * 8 + (kk % 8)];
   };
-  for (int ks = 0; ks < H / 16; ++ks)
+  for (int i = 0; i < H / 16; ++i)                       // consumption position; ks_of(i) = the k-step it holds
     for (int nn = 0; nn < H; ++nn)
       for (int kk = 0; kk < 16; ++kk) {
+        const int ks = ks_of(i);
         const int k = ks * 16 + kk;
         // forward: B(n, k) = W1[n][k]
         const float v = W1[(size_t)nn * H + k] * sw;
         const __half hi = __float2half_rn(v);
-        at(2 * ks, nn, kk) = hi;
-        at(2 * ks + 1, nn, kk) = __float2half_rn(v - __half2float(hi));
+        at(2 * i, nn, kk) = hi;
+        at(2 * i + 1, nn, kk) = __float2half_rn(v - __half2float(hi));
         // reverse: B'(n' = nn, k' = k) = V[k][nn] = w2[k] W1[k][nn]
         const double vv = (double)w2[k] * (double)W1[(size_t)k * H + nn] * (double)sv;
         const __half vhi = __float2half_rn((float)vv);
-        at(CHUNKS_FWD + 2 * ks + 1, nn, kk) = vhi;
-        at(CHUNKS_FWD + 2 * ks, nn, kk) = __float2half_rn((float)(vv - (double)__half2float(vhi)));
+        at(CHUNKS_FWD + 2 * i + 1, nn, kk) = vhi;
+        at(CHUNKS_FWD + 2 * i, nn, kk) = __float2half_rn((float)(vv - (double)__half2float(vhi)));
       }
   if (m->d_tc) cudaFree(m->d_tc);
   m->d_tc = nullptr;
