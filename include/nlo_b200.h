@@ -173,7 +173,8 @@ enum {  /* core/dynamics.py:151-158 */
   NLO_DYN_ACKERMANN = 4, NLO_DYN_ACKERMANN_2ND = 5
 };
 enum { NLO_SHAPE_DOT = 0, NLO_SHAPE_RECTANGLE = 1, NLO_SHAPE_TRIANGLE = 2 };   /* core/geometry.py:17-20 */
-enum { NLO_SDF_LEARNED = 0, NLO_SDF_CIRCLES = 1 };
+enum { NLO_SDF_LEARNED = 0, NLO_SDF_CIRCLES = 1 };      /* CIRCLES = analytic obstacles: soft-min union of circles / squares */
+enum { NLO_OBST_CIRCLE = 0, NLO_OBST_SQUARE = 1 };
 #define NLO_MAX_CIRCLES 8
 
 typedef struct nlo_nlp_desc {
@@ -187,7 +188,8 @@ typedef struct nlo_nlp_desc {
   uint32_t n_circles;
   float dt, slack_penalty, smooth_weight;
   float length, width, wheelbase;
-  float circles[NLO_MAX_CIRCLES][4];   /* cx, cy, radius, margin  (core/sdf/casadi.py:27-41)   */
+  float circles[NLO_MAX_CIRCLES][4];   /* analytic obstacles: cx, cy, radius | size, margin       */
+  uint32_t obstacle_kind[NLO_MAX_CIRCLES]; /* NLO_OBST_CIRCLE (core/sdf/casadi.py:27-41) / NLO_OBST_SQUARE (:48-115) */
 } nlo_nlp_desc;
 
 typedef struct nlo_nlp nlo_nlp;

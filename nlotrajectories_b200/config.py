@@ -176,14 +176,17 @@ class Config:                           # core/config.py:215-222
         with open(path, "r") as fh:
             return Config.parse(yaml.safe_load(fh))
 
-    def circles(self) -> List[Tuple[float, float, float, float]]:
-        """Analytic obstacles for ``solver.mode: casadi``.  The CUDA path covers circles
-        (core/sdf/casadi.py:27-45 via the soft-min union :385-386); other analytic shapes are not on the
-        hot path named by BASELINE.json."""
+    def circles(self) -> List[Tuple[float, float, float, float, int]]:
+        """Analytic obstacles for ``solver.mode: casadi`` as (cx, cy, radius | size, margin, kind): circles (kind 0,
+        core/sdf/casadi.py:27-45) and squares (kind 1, :48-115), combined by the soft-min union (:385-386).  Polygons and
+        rings appear in the shipped benchmarks only behind a learned SDF (mode l4casadi)."""
         out = []
         for o in self.obstacles:
-            if o.type != "circle":
+            c = o.params["center"] if o.type in ("circle", "square") else None
+            if o.type == "circle":
+                out.append((float(c[0]), float(c[1]), float(o.params["radius"]), float(o.params.get("margin", 0.0)), 0))
+            elif o.type == "square":
+                out.append((float(c[0]), float(c[1]), float(o.params["size"]), float(o.params.get("margin", 0.0)), 1))
+            else:
                 raise NotImplementedError(f"solver.mode casadi with obstacle type {o.type!r} is outside the CUDA hot path")
-            c = o.params["center"]
-            out.append((float(c[0]), float(c[1]), float(o.params["radius"]), float(o.params.get("margin", 0.0))))
         return out

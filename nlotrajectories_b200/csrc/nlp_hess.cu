@@ -147,24 +147,13 @@ __global__ void __launch_bounds__(256) nlp_hess_kernel(NlpDev L, const int* __re
   }
 }
 
-// analytic circles + soft-min union: value, gradient and Hessian (core/sdf/casadi.py:33-41, 385-386)
+// analytic circles / squares + soft-min union: value, gradient and Hessian (core/sdf/casadi.py:33-41, 69-115, 385-386)
 __global__ void __launch_bounds__(256) nlp_circles_hess_kernel(NlpDev L, const float* __restrict__ px, const float* __restrict__ py, size_t n,
                                                                float* __restrict__ s, float* __restrict__ jx, float* __restrict__ jy,
                                                                float* __restrict__ hxx, float* __restrict__ hxy, float* __restrict__ hyy) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const float x = px[i], y = py[i];
-    float sum = 0.f, gx = 0.f, gy = 0.f, a = 0.f, b = 0.f, c = 0.f;
-    for (int q = 0; q < L.n_circles; ++q) {
-      const float dx = x - L.circles[q][0], dy = y - L.circles[q][1];
-      const float d = sqrtf(dx * dx + dy * dy), id = 1.f / d, nx = dx * id, ny = dy * id;
-      const float e = expf(-NLO_ALPHA * (d - (L.circles[q][2] + L.circles[q][3])));
-      sum += e; gx += e * nx; gy += e * ny;
-      a += e * ((1.f - nx * nx) * id - NLO_ALPHA * nx * nx); b += e * (-nx * ny * id - NLO_ALPHA * nx * ny);
-      c += e * ((1.f - ny * ny) * id - NLO_ALPHA * ny * ny);
-    }
-    const float inv = 1.f / sum, mx = gx * inv, my = gy * inv;
-    s[i] = -logf(sum) / NLO_ALPHA; jx[i] = mx; jy[i] = my;
-    hxx[i] = a * inv + NLO_ALPHA * mx * mx; hxy[i] = b * inv + NLO_ALPHA * mx * my; hyy[i] = c * inv + NLO_ALPHA * my * my;
+    const NloJet u = nlo_union_jet(L.n_circles, L.okind, L.circles, px[i], py[i]);
+    s[i] = u.v; jx[i] = u.dx; jy[i] = u.dy; hxx[i] = u.dxx; hxy[i] = u.dxy; hyy[i] = u.dyy;
   }
 }
 

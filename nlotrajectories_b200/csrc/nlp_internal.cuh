@@ -16,6 +16,7 @@ struct NlpDev {                 // passed by value to kernels
   float dt, slack_penalty, smooth_weight, wheelbase;
   float bx[4], by[4];
   float circles[NLO_MAX_CIRCLES][4];
+  int okind[NLO_MAX_CIRCLES];
   const int* nzmap;             // device: emission index -> compressed-column position
   const int* copy_row;          // device: rows of g that are copies of a variable
   const int* copy_var;
@@ -50,6 +51,50 @@ struct nlo_nlp {
   float* d_hs[3]; size_t hs_cap_P;          // SDF Hessian scratch (hxx, hxy, hyy) for hs_cap_P problems
   NlpLane lane[2];              // host entry point: two lanes (streams) process alternating chunks of problems
 };
+
+// ---- analytic obstacles (solver.mode casadi): value, gradient and Hessian w.r.t. (x, y) -----------------------------------
+// A small second-order jet pushes the reference's smooth square SDF (core/sdf/casadi.py:69-115: soft |.|, soft max / min with
+// eps = 1e-6) through the chain rule; circles (:33-41) are closed form.
+struct NloJet {
+  float v, dx, dy, dxx, dxy, dyy;
+  __device__ __forceinline__ static NloJet cst(float c) { return {c, 0.f, 0.f, 0.f, 0.f, 0.f}; }
+};
+__device__ __forceinline__ NloJet operator+(const NloJet& a, const NloJet& b) { return {a.v + b.v, a.dx + b.dx, a.dy + b.dy, a.dxx + b.dxx, a.dxy + b.dxy, a.dyy + b.dyy}; }
+__device__ __forceinline__ NloJet operator-(const NloJet& a, const NloJet& b) { return {a.v - b.v, a.dx - b.dx, a.dy - b.dy, a.dxx - b.dxx, a.dxy - b.dxy, a.dyy - b.dyy}; }
+__device__ __forceinline__ NloJet operator*(const NloJet& a, float c) { return {a.v * c, a.dx * c, a.dy * c, a.dxx * c, a.dxy * c, a.dyy * c}; }
+__device__ __forceinline__ NloJet operator*(const NloJet& a, const NloJet& b) {
+  return {a.v * b.v, a.dx * b.v + a.v * b.dx, a.dy * b.v + a.v * b.dy, a.dxx * b.v + 2.f * a.dx * b.dx + a.v * b.dxx,
+          a.dxy * b.v + a.dx * b.dy + a.dy * b.dx + a.v * b.dxy, a.dyy * b.v + 2.f * a.dy * b.dy + a.v * b.dyy};
+}
+__device__ __forceinline__ NloJet nlo_jsqrt(const NloJet& a) {
+  const float r = sqrtf(a.v), f1 = 0.5f / r, f2 = -0.25f / (r * a.v);
+  return {r, f1 * a.dx, f1 * a.dy, f2 * a.dx * a.dx + f1 * a.dxx, f2 * a.dx * a.dy + f1 * a.dxy, f2 * a.dy * a.dy + f1 * a.dyy};
+}
+__device__ __forceinline__ NloJet nlo_obstacle_jet(int kind, const float* c, float x, float y) {
+  if (kind == NLO_OBST_CIRCLE) {
+    const float dx = x - c[0], dy = y - c[1], d = sqrtf(dx * dx + dy * dy), id = 1.f / d, nx = dx * id, ny = dy * id;
+    return {d - (c[2] + c[3]), nx, ny, (1.f - nx * nx) * id, -nx * ny * id, (1.f - ny * ny) * id};
+  }
+  const NloJet X{x - c[0], 1.f, 0.f, 0.f, 0.f, 0.f}, Y{y - c[1], 0.f, 1.f, 0.f, 0.f, 0.f};
+  const NloJet eps = NloJet::cst(1e-6f), half = NloJet::cst(0.5f * c[2] + c[3]), zero = NloJet::cst(0.f);
+  const NloJet d_x = nlo_jsqrt(X * X + eps) - half, d_y = nlo_jsqrt(Y * Y + eps) - half;
+  auto smax = [&](const NloJet& a, const NloJet& b) { return (a + b + nlo_jsqrt((a - b) * (a - b) + eps)) * 0.5f; };
+  auto smin = [&](const NloJet& a, const NloJet& b) { return (a + b - nlo_jsqrt((a - b) * (a - b) + eps)) * 0.5f; };
+  const NloJet xo = smax(d_x, zero), yo = smax(d_y, zero);
+  return nlo_jsqrt(xo * xo + yo * yo) + smin(smax(d_x, d_y), zero);
+}
+// soft-min union (core/sdf/casadi.py:385-386, core/utils.py:28-31) of the obstacles' jets
+__device__ __forceinline__ NloJet nlo_union_jet(int n, const int* kinds, const float (*circles)[4], float x, float y) {
+  float sum = 0.f, gx = 0.f, gy = 0.f, a = 0.f, b = 0.f, c = 0.f;
+  for (int q = 0; q < n; ++q) {
+    const NloJet j = nlo_obstacle_jet(kinds[q], circles[q], x, y);
+    const float e = expf(-NLO_ALPHA * j.v);
+    sum += e; gx += e * j.dx; gy += e * j.dy;
+    a += e * (j.dxx - NLO_ALPHA * j.dx * j.dx); b += e * (j.dxy - NLO_ALPHA * j.dx * j.dy); c += e * (j.dyy - NLO_ALPHA * j.dy * j.dy);
+  }
+  const float inv = 1.f / sum, mx = gx * inv, my = gy * inv;
+  return {-logf(sum) / NLO_ALPHA, mx, my, a * inv + NLO_ALPHA * mx * mx, b * inv + NLO_ALPHA * mx * my, c * inv + NLO_ALPHA * my * my};
+}
 
 // structural A pairs per model, usable in device code after unrolling
 template <int DYN>

@@ -49,7 +49,11 @@ int nlo_nlp_build_layout(const nlo_nlp_desc* d, NlpDev* L, std::vector<int>* row
     return nlo_fail("analytic mode needs 1..%d circles", NLO_MAX_CIRCLES);
   if (l.shape != NLO_SHAPE_DOT && T.nx < 3) return nlo_fail("polygon footprint needs a heading state");
   l.dt = d->dt; l.slack_penalty = d->slack_penalty; l.smooth_weight = d->smooth_weight; l.wheelbase = d->wheelbase;
-  for (int c = 0; c < NLO_MAX_CIRCLES; ++c) for (int q = 0; q < 4; ++q) l.circles[c][q] = d->circles[c][q];
+  for (int c = 0; c < NLO_MAX_CIRCLES; ++c) {
+    for (int q = 0; q < 4; ++q) l.circles[c][q] = d->circles[c][q];
+    if (d->obstacle_kind[c] > NLO_OBST_SQUARE) return nlo_fail("unknown analytic obstacle kind %u", d->obstacle_kind[c]);
+    l.okind[c] = (int)d->obstacle_kind[c];
+  }
   const float hl = 0.5f * d->length, hw = 0.5f * d->width;
   if (l.shape == NLO_SHAPE_DOT) { l.nb = 1; l.bx[0] = l.by[0] = 0.f; }
   else if (l.shape == NLO_SHAPE_RECTANGLE) {            // core/geometry.py:125-135
@@ -207,21 +211,12 @@ __device__ __forceinline__ void nlp_points_body(const NlpDev& L, const float* __
   }
 }
 
-// ---- K5: analytic circles + soft-min union (core/sdf/casadi.py:33-41, 385-386) ----------------------------
+// ---- K5: analytic circles / squares + soft-min union (core/sdf/casadi.py:33-41, 69-115, 385-386) ----------------
 __global__ void __launch_bounds__(256) nlp_circles_kernel(NlpDev L, const float* __restrict__ px, const float* __restrict__ py, size_t n,
                                                           float* __restrict__ s, float* __restrict__ jx, float* __restrict__ jy) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const float x = px[i], y = py[i];
-    float sum = 0.f, gx = 0.f, gy = 0.f;
-    for (int c = 0; c < L.n_circles; ++c) {
-      const float dx = x - L.circles[c][0], dy = y - L.circles[c][1];
-      const float d = sqrtf(dx * dx + dy * dy);
-      const float v = d - (L.circles[c][2] + L.circles[c][3]);
-      const float e = expf(-NLO_ALPHA * v);
-      sum += e; gx += e * dx / d; gy += e * dy / d;
-    }
-    s[i] = -logf(sum) / NLO_ALPHA;
-    jx[i] = gx / sum; jy[i] = gy / sum;
+    const NloJet u = nlo_union_jet(L.n_circles, L.okind, L.circles, px[i], py[i]);
+    s[i] = u.v; jx[i] = u.dx; jy[i] = u.dy;
   }
 }
 

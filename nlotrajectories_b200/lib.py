@@ -26,7 +26,7 @@ class NlpDesc(C.Structure):
                 ("use_smooth", C.c_uint32), ("enforce_heading", C.c_uint32), ("sdf_mode", C.c_uint32),
                 ("n_circles", C.c_uint32), ("dt", C.c_float), ("slack_penalty", C.c_float),
                 ("smooth_weight", C.c_float), ("length", C.c_float), ("width", C.c_float), ("wheelbase", C.c_float),
-                ("circles", (C.c_float * 4) * NLO_MAX_CIRCLES)]
+                ("circles", (C.c_float * 4) * NLO_MAX_CIRCLES), ("obstacle_kind", C.c_uint32 * NLO_MAX_CIRCLES)]
 
 
 _P = C.c_void_p

@@ -62,9 +62,12 @@ class NlpProblem:
         d.n_circles = len(self.circles) if sdf is None else 0
         d.dt, d.slack_penalty, d.smooth_weight = self.dt, self.slack_penalty, self.smooth_weight
         d.length, d.width, d.wheelbase = float(length or 0.0), float(width or 0.0), float(wheelbase or 1.0)
-        for i, c in enumerate(self.circles[:_lib.NLO_MAX_CIRCLES]):
+        if len(self.circles) > _lib.NLO_MAX_CIRCLES:
+            raise ValueError(f"at most {_lib.NLO_MAX_CIRCLES} analytic obstacles")
+        for i, c in enumerate(self.circles):             # (cx, cy, radius | size, margin[, kind: 0 circle, 1 square])
             for q in range(4):
                 d.circles[i][q] = float(c[q])
+            d.obstacle_kind[i] = int(c[4]) if len(c) > 4 else 0
         h = C.c_void_p()
         _lib.check(self._L.nlo_nlp_create(C.byref(d), sdf.handle if sdf is not None else None, device, C.byref(h)))
         self._h = h

@@ -3,7 +3,8 @@ evaluated for P independent multi-start problems on the GPU instead of one symbo
 
 Constructor arguments keep the reference's names and meaning; ``dynamics`` / ``geometry`` are the YAML
 names (``body.dynamic`` / ``body.shape``) instead of CasADi expression builders, ``sdf_func`` is a
-``LearnedSDF`` (solver.mode l4casadi) or a list of circles (solver.mode casadi).
+``LearnedSDF`` (solver.mode l4casadi) or a list of analytic obstacles ``(cx, cy, radius | size, margin[, kind])`` with kind 0 = circle,
+1 = square (solver.mode casadi).
 """
 from __future__ import annotations
 

@@ -65,24 +65,30 @@ class NlpSpec:
     width: Optional[float] = None
     wheelbase: Optional[float] = None
     sdf_mode: str = "l4casadi"       # "l4casadi": learned net; "casadi": analytic soft-min union
-    circles: List[Tuple[float, float, float, float]] = field(default_factory=list)  # (cx, cy, r, margin)
+    circles: List[Tuple[float, float, float, float]] = field(default_factory=list)  # analytic obstacles: (cx, cy, r | size, margin)
+    kinds: List[int] = field(default_factory=list)                                  # 0 = circle, 1 = square (same order)
 
     @staticmethod
     def from_yaml_dict(d: dict) -> "NlpSpec":
         b, s = d["body"], d["solver"]
-        circles = []
+        circles, kinds = [], []
         if s["mode"] == "casadi":
             for o in d["obstacles"]:
-                if o["type"] != "circle":
-                    raise NotImplementedError("oracle covers analytic circles only (SURVEY.md 8(a) a16)")
-                circles.append((float(o["center"][0]), float(o["center"][1]), float(o["radius"]), float(o.get("margin", 0.0))))
+                if o["type"] == "circle":
+                    circles.append((float(o["center"][0]), float(o["center"][1]), float(o["radius"]), float(o.get("margin", 0.0))))
+                    kinds.append(0)
+                elif o["type"] == "square":
+                    circles.append((float(o["center"][0]), float(o["center"][1]), float(o["size"]), float(o.get("margin", 0.0))))
+                    kinds.append(1)
+                else:
+                    raise NotImplementedError("oracle covers analytic circles and squares (benchmarks 1, 2, 5)")
         return NlpSpec(
             dynamics=b["dynamic"], shape=b["shape"], x0=np.array(b["start_state"], float),
             goal=np.array(b["goal_state"], float), control_bounds=[tuple(map(float, cb)) for cb in b["control_bounds"]],
             N=int(s.get("N", 20)), dt=float(s.get("dt", 0.1)), use_slack=bool(s.get("use_slack", False)),
             slack_penalty=float(s.get("slack_penalty", 1000)), use_smooth=bool(s.get("use_smooth", False)),
             smooth_weight=float(s.get("smooth_weight", 10.0)), enforce_heading=bool(s.get("enforce_heading", True)),
-            length=b.get("length"), width=b.get("width"), wheelbase=b.get("wheelbase"), sdf_mode=s["mode"], circles=circles)
+            length=b.get("length"), width=b.get("width"), wheelbase=b.get("wheelbase"), sdf_mode=s["mode"], circles=circles, kinds=kinds)
 
     # -- sizes -----------------------------------------------------------------------------------
     @property
@@ -180,20 +186,86 @@ def dynamics_f(spec: NlpSpec, x: np.ndarray, u: np.ndarray):
 # -------------------------------------------------------------------------------------------------
 # SDF on footprint points
 # -------------------------------------------------------------------------------------------------
-def circles_sdf(spec: NlpSpec, pts: np.ndarray):
-    """MultiObstacle.approximated_sdf over CircleObstacles (core/sdf/casadi.py:33-41, 385-386)."""
-    vals, grads = [], []
-    for cx, cy, r, m in spec.circles:
-        dx, dy = pts[:, 0] - cx, pts[:, 1] - cy
-        d = np.sqrt(dx * dx + dy * dy)
-        vals.append(d - (r + m))
-        grads.append(np.stack([dx / d, dy / d], axis=-1))
-    vals = np.stack(vals, axis=0)                     # (n_obs, n)
+class _Jet:
+    """Value, gradient and Hessian w.r.t. (x, y), element-wise over arrays: enough arithmetic to push the reference's smooth
+    square SDF (core/sdf/casadi.py:69-115) through second order."""
+
+    def __init__(self, v, dx, dy, dxx, dxy, dyy):
+        self.v, self.dx, self.dy, self.dxx, self.dxy, self.dyy = v, dx, dy, dxx, dxy, dyy
+
+    @staticmethod
+    def const(c, like):
+        z = np.zeros_like(like)
+        return _Jet(z + c, z, z, z, z, z)
+
+    def __add__(self, o):
+        o = o if isinstance(o, _Jet) else _Jet.const(o, self.v)
+        return _Jet(self.v + o.v, self.dx + o.dx, self.dy + o.dy, self.dxx + o.dxx, self.dxy + o.dxy, self.dyy + o.dyy)
+
+    def __sub__(self, o):
+        o = o if isinstance(o, _Jet) else _Jet.const(o, self.v)
+        return _Jet(self.v - o.v, self.dx - o.dx, self.dy - o.dy, self.dxx - o.dxx, self.dxy - o.dxy, self.dyy - o.dyy)
+
+    def __mul__(self, o):
+        if not isinstance(o, _Jet):
+            return _Jet(self.v * o, self.dx * o, self.dy * o, self.dxx * o, self.dxy * o, self.dyy * o)
+        return _Jet(self.v * o.v, self.dx * o.v + self.v * o.dx, self.dy * o.v + self.v * o.dy,
+                    self.dxx * o.v + 2 * self.dx * o.dx + self.v * o.dxx,
+                    self.dxy * o.v + self.dx * o.dy + self.dy * o.dx + self.v * o.dxy,
+                    self.dyy * o.v + 2 * self.dy * o.dy + self.v * o.dyy)
+
+    def sqrt(self):
+        r = np.sqrt(self.v)
+        f1, f2 = 0.5 / r, -0.25 / (r * self.v)
+        return _Jet(r, f1 * self.dx, f1 * self.dy, f2 * self.dx * self.dx + f1 * self.dxx,
+                    f2 * self.dx * self.dy + f1 * self.dxy, f2 * self.dy * self.dy + f1 * self.dyy)
+
+
+def _square_jet(x, y, cx, cy, size, margin):
+    """SquareObstacle.approximated_sdf (core/sdf/casadi.py:69-115): soft |.|, soft max / min with eps = 1e-6."""
+    one, zero = np.ones_like(x), np.zeros_like(x)
+    X = _Jet(x - cx, one, zero, zero, zero, zero)
+    Y = _Jet(y - cy, zero, one, zero, zero, zero)
+    half = size / 2 + margin
+    d_x = (X * X + 1e-6).sqrt() - half
+    d_y = (Y * Y + 1e-6).sqrt() - half
+    smax = lambda a, b: (a + b + ((a - b) * (a - b) + 1e-6).sqrt()) * 0.5
+    smin = lambda a, b: (a + b - ((a - b) * (a - b) + 1e-6).sqrt()) * 0.5
+    z = _Jet.const(0.0, x)
+    d_x_out, d_y_out = smax(d_x, z), smax(d_y, z)
+    outside = (d_x_out * d_x_out + d_y_out * d_y_out).sqrt()
+    inside = smin(smax(d_x, d_y), z)
+    return outside + inside
+
+
+def _circle_jet(x, y, cx, cy, r, margin):
+    dx, dy = x - cx, y - cy
+    d = np.sqrt(dx * dx + dy * dy)
+    nx_, ny_ = dx / d, dy / d
+    return _Jet(d - (r + margin), nx_, ny_, (1 - nx_ * nx_) / d, -nx_ * ny_ / d, (1 - ny_ * ny_) / d)
+
+
+def _analytic_union(spec: NlpSpec, pts: np.ndarray):
+    """MultiObstacle.approximated_sdf (core/sdf/casadi.py:385-386): soft_min over the obstacles' smooth SDFs, to second order."""
+    x, y = pts[:, 0], pts[:, 1]
+    kinds = spec.kinds or [0] * len(spec.circles)
+    jets = [(_circle_jet if k == 0 else _square_jet)(x, y, *c) for k, c in zip(kinds, spec.circles)]
+    vals = np.stack([j.v for j in jets], axis=0)
     e = np.exp(-ALPHA * vals)
     ssum = e.sum(axis=0)
+    om = e / ssum
     s = -1.0 / ALPHA * np.log(ssum)                   # soft_min; identity up to rounding for 1 obstacle
-    wgt = e / ssum
-    g = sum(wgt[i][:, None] * grads[i] for i in range(len(grads)))
+    mx = sum(om[i] * jets[i].dx for i in range(len(jets))); my = sum(om[i] * jets[i].dy for i in range(len(jets)))
+    hxx = sum(om[i] * (jets[i].dxx - ALPHA * jets[i].dx * jets[i].dx) for i in range(len(jets))) + ALPHA * mx * mx
+    hxy = sum(om[i] * (jets[i].dxy - ALPHA * jets[i].dx * jets[i].dy) for i in range(len(jets))) + ALPHA * mx * my
+    hyy = sum(om[i] * (jets[i].dyy - ALPHA * jets[i].dy * jets[i].dy) for i in range(len(jets))) + ALPHA * my * my
+    return s, np.stack([mx, my], axis=-1), np.stack([hxx, hxy, hyy], axis=-1)
+
+
+def circles_sdf(spec: NlpSpec, pts: np.ndarray):
+    """Analytic mode (solver.mode casadi): value and gradient of the soft-min union (circles: core/sdf/casadi.py:33-41; squares:
+    :69-115)."""
+    s, g, _ = _analytic_union(spec, pts)
     return s, g
 
 
@@ -445,22 +517,8 @@ def dynamics_hess(spec: NlpSpec, x: np.ndarray, u: np.ndarray, lam: np.ndarray):
 
 
 def circles_hess(spec: NlpSpec, pts: np.ndarray):
-    """Hessian (n, 3) = (hxx, hxy, hyy) of circles_sdf: soft-min over ||p - c|| - R."""
-    vals, ns, Hs = [], [], []
-    for cx, cy, r, m in spec.circles:
-        dx, dy = pts[:, 0] - cx, pts[:, 1] - cy
-        d = np.sqrt(dx * dx + dy * dy)
-        nx_, ny_ = dx / d, dy / d
-        vals.append(d - (r + m)); ns.append((nx_, ny_))
-        Hs.append(((1 - nx_ * nx_) / d, -nx_ * ny_ / d, (1 - ny_ * ny_) / d))
-    vals = np.stack(vals, axis=0)
-    e = np.exp(-ALPHA * vals)
-    om = e / e.sum(axis=0)
-    mx = sum(om[i] * ns[i][0] for i in range(len(ns))); my = sum(om[i] * ns[i][1] for i in range(len(ns)))
-    hxx = sum(om[i] * (Hs[i][0] - ALPHA * ns[i][0] * ns[i][0]) for i in range(len(ns))) + ALPHA * mx * mx
-    hxy = sum(om[i] * (Hs[i][1] - ALPHA * ns[i][0] * ns[i][1]) for i in range(len(ns))) + ALPHA * mx * my
-    hyy = sum(om[i] * (Hs[i][2] - ALPHA * ns[i][1] * ns[i][1]) for i in range(len(ns))) + ALPHA * my * my
-    return np.stack([hxx, hxy, hyy], axis=-1)
+    """Hessian (n, 3) = (hxx, hxy, hyy) of the analytic soft-min union."""
+    return _analytic_union(spec, pts)[2]
 
 
 def hess_pattern(spec: NlpSpec):

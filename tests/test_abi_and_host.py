@@ -135,7 +135,9 @@ def test_config_parses_reference_yamls_unchanged():
     assert (c6.body.dynamic, c6.body.shape, c6.solver.N, c6.solver.use_slack, c6.solver.use_smooth) == ("ackermann_2nd", "rectangle", 80, False, True)
     assert c6.solver.initializer.mode == "rrt" and c6.solver.initializer.max_iter == 5000
     c1 = Config.load(bench_yaml("benchmark_1"))
-    assert c1.circles() == [(0.5, 0.5, 0.2, 0.05)]
+    assert c1.circles() == [(0.5, 0.5, 0.2, 0.05, 0)]
+    c5 = Config.load(bench_yaml("benchmark_5"))          # circle + three squares, analytic mode
+    assert [o[4] for o in c5.circles()] == [0, 1, 1, 1] and c5.circles()[2][:4] == (1.1, 0.7, 0.2, 0.01)
     bad = yaml.safe_load(open(bench_yaml("benchmark_1")))
     bad["body"]["control_bounds"] = [-1.0, 1.0]          # the reference's configs/broken.yaml:7 shape
     with pytest.raises(ConfigError):

@@ -11,7 +11,7 @@ from oracle import sdf_oracle as so
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
-BENCHES = ["benchmark_1", "benchmark_2", "benchmark_3", "benchmark_4", "benchmark_6"]
+BENCHES = ["benchmark_1", "benchmark_2", "benchmark_3", "benchmark_4", "benchmark_5", "benchmark_6"]
 
 
 def make_problem(name, net):

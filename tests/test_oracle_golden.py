@@ -54,7 +54,7 @@ def test_sdf_oracle_derivatives_by_finite_differences(kind):
         np.testing.assert_allclose(H[:, :, d], fdh, atol=1e-5)
 
 
-@pytest.mark.parametrize("name", ["benchmark_1", "benchmark_2", "benchmark_3", "benchmark_4", "benchmark_6"])
+@pytest.mark.parametrize("name", ["benchmark_1", "benchmark_2", "benchmark_3", "benchmark_4", "benchmark_5", "benchmark_6"])
 def test_nlp_oracle_matches_reference_assembly(name, shipped_net):
     z = np.load(GOLDEN / f"nlp_{name}.npz")
     spec = no.NlpSpec.from_yaml_dict(yaml.safe_load(open(bench_yaml(name))))
@@ -102,7 +102,7 @@ def test_nlp_oracle_jacobian_by_finite_differences(shipped_net):
         np.testing.assert_allclose(gr[0, v], fd, atol=2e-6)
 
 
-@pytest.mark.parametrize("name", ["benchmark_1", "benchmark_2", "benchmark_3", "benchmark_4", "benchmark_6"])
+@pytest.mark.parametrize("name", ["benchmark_1", "benchmark_2", "benchmark_3", "benchmark_4", "benchmark_5", "benchmark_6"])
 def test_hessian_oracle_matches_reference_expressions(name, shipped_net):
     """Hessian of the Lagrangian: the numpy restatement against second derivatives of the reference's own recorded
     expressions (oracle/make_golden.py --hessian): identical structural pattern (upper triangle, CCS) and values."""
