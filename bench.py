@@ -203,7 +203,7 @@ def run_ours(args):
     import torch.distributed as dist
     from nlotrajectories_b200 import lib
     from nlotrajectories_b200.config import Config
-    from nlotrajectories_b200.distributed import init_process_group, merit, select_best
+    from nlotrajectories_b200.distributed import bind_to_gpu_numa, init_process_group, merit, select_best
     from nlotrajectories_b200.problem import NlpProblem
     from nlotrajectories_b200.sdf import LearnedSDF, SdfWeights
 
@@ -212,6 +212,7 @@ def run_ours(args):
     rank, local_rank, world = init_process_group("nccl")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_cpus = bind_to_gpu_numa(local_rank) if world > 1 else 0      # before any pinned allocation
     L = lib.load()
     peaks, peak_src = load_peaks()
     net = synthetic_net()
@@ -327,7 +328,8 @@ def run_ours(args):
         "nlp_evals_per_s": world * P / (ms_per_step * 1e-3),
         "clocks": clocks,
         "e2e": {"value": world * n_pts / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_s * 1e3, "api": "nlo_nlp_eval_host (pinned host buffers, problem-major)"},
+                "ms_per_step": e2e_s * 1e3, "api": "nlo_nlp_eval_host (pinned host buffers, problem-major)",
+                "cpu_affinity": (f"rank pinned to the {numa_cpus} CPUs NVML reports local to its GPU" if numa_cpus else "unchanged")},
         "gpu_launches": launches,
         "roofline": {"kernel": "sdf_tc_kernel" if prec == "tc3xf16" else "sdf_simt_kernel", "bound": bound, "achieved": achieved,
                      "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,

@@ -236,7 +236,6 @@ static nlo_sdf_model* g_model = nullptr;
 static bool g_model_owned = false;
 static long long g_batch = 0;
 static std::vector<long long> g_sp[8];
-static std::vector<float> g_hbuf;
 
 int nlo_casadi_bind(nlo_sdf_model* m) {
   std::lock_guard<std::mutex> lk(g_mu);
@@ -268,18 +267,40 @@ static nlo_sdf_model* casadi_model() {
   return m;
 }
 
+// Staging for the CasADi externals: pinned, device-mapped host memory.  Small calls (the reference's pattern is ONE 1x2 point per
+// call, nn_sdf.cpp:57-104) skip every memcpy: the kernel reads its inputs from and writes its results to this buffer directly
+// (zero-copy over PCIe), so a call costs one launch and one stream synchronisation.
+static float* g_pin = nullptr;
+static size_t g_pin_cap = 0;
+static int ensure_pin(size_t floats) {
+  if (g_pin_cap >= floats) return 0;
+  if (g_pin) cudaFreeHost(g_pin);
+  g_pin = nullptr; g_pin_cap = 0;
+  const size_t want = floats < 4096 ? 4096 : floats;
+  NLO_CUDA(cudaHostAlloc(&g_pin, want * sizeof(float), cudaHostAllocMapped | cudaHostAllocPortable));
+  g_pin_cap = want;
+  return 0;
+}
+constexpr size_t NLO_ZERO_COPY_MAX = 16384;      // points per call up to which the zero-copy form is used
+
 // mode 0: value, 1: jac, 2: adj1, 3: jac_adj1.  in: x[P], y[P] doubles (column-major P x 2).
 static int casadi_eval(int mode, long long P, const double* p, const double* seed, double* out) {
   std::lock_guard<std::mutex> lk(g_mu);
   nlo_sdf_model* m = casadi_model();
   if (!m) { fprintf(stderr, "[nlo_b200] %s\n", g_err); return 1; }
   const size_t n = (size_t)P;
-  g_hbuf.resize(6 * n);
-  float* hx = g_hbuf.data(); float* hy = hx + n; float* hs = hy + n; float* o0 = hs + n; float* o1 = o0 + n; float* o2 = o1 + n;
+  if (cudaSetDevice(m->device) != cudaSuccess || ensure_pin(6 * n)) { fprintf(stderr, "[nlo_b200] %s\n", g_err); return 1; }
+  float* hx = g_pin; float* hy = hx + n; float* hs = hy + n; float* o0 = hs + n; float* o1 = o0 + n; float* o2 = o1 + n;
   for (size_t i = 0; i < n; ++i) { hx[i] = p ? (float)p[i] : 0.f; hy[i] = p ? (float)p[n + i] : 0.f; hs[i] = seed ? (float)seed[i] : 0.f; }
   const bool use_seed = (mode == 2 || mode == 3);   // NULL seed == zeros (CasADi convention)
   int rc;
-  if (mode == 0) rc = nlo_sdf_eval_host(m, hx, hy, nullptr, n, o0, nullptr, nullptr);
+  if (n <= NLO_ZERO_COPY_MAX) {
+    // unified addressing: the pinned, mapped buffer is valid as a device pointer
+    if (mode == 0) rc = nlo_sdf_eval(m, hx, hy, nullptr, n, o0, nullptr, nullptr, m->stream);
+    else if (mode == 1 || mode == 2) rc = nlo_sdf_eval(m, hx, hy, use_seed ? hs : nullptr, n, nullptr, o0, o1, m->stream);
+    else rc = nlo_sdf_hess(m, hx, hy, hs, n, o0, o1, o2, m->stream);
+    if (!rc && cudaStreamSynchronize(m->stream) != cudaSuccess) rc = nlo_fail("stream synchronisation failed");
+  } else if (mode == 0) rc = nlo_sdf_eval_host(m, hx, hy, nullptr, n, o0, nullptr, nullptr);
   else if (mode == 1 || mode == 2) rc = nlo_sdf_eval_host(m, hx, hy, use_seed ? hs : nullptr, n, nullptr, o0, o1);
   else rc = nlo_sdf_hess_host(m, hx, hy, hs, n, o0, o1, o2);
   if (rc) { fprintf(stderr, "[nlo_b200] %s\n", g_err); return 1; }

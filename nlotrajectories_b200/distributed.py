@@ -39,6 +39,30 @@ def init_process_group(backend: str = "nccl"):
     return rank, local_rank, world
 
 
+def bind_to_gpu_numa(device_index: int) -> int:
+    """Pin this process to the CPU cores NVML reports as local to the GPU, so that pinned host buffers are first-touched
+    on the GPU's own NUMA node (the host-buffer path moves 1.5 GB per step per GPU: with 8 ranks the host side is the
+    bound).  Returns the number of CPUs in the new affinity mask, 0 if nothing was changed."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            n_cpu = os.cpu_count() or 1
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+            cpus = [64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1 and 64 * w + b < n_cpu]
+            allowed = os.sched_getaffinity(0)
+            cpus = [c for c in cpus if c in allowed]
+            if cpus and len(cpus) < len(allowed):
+                os.sched_setaffinity(0, cpus)
+                return len(cpus)
+        finally:
+            pynvml.nvmlShutdown()
+    except Exception:
+        pass
+    return 0
+
+
 def merit(f, viol, feas_tol: float = 1e-4, penalty: float = 1e3):
     """Scalar used to rank candidates: the objective, plus a large penalty on constraint violation beyond tol."""
     import torch
