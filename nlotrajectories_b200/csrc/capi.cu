@@ -451,7 +451,7 @@ int nlo_nlp_create(const nlo_nlp_desc* desc, nlo_sdf_model* model, int device, n
   nlo_nlp* p = new (std::nothrow) nlo_nlp();
   if (!p) return nlo_fail("out of host memory");
   p->desc = *desc; p->model = model; p->device = device;
-  p->d_tables = nullptr; p->d_hmap = nullptr; p->hs_cap_P = 0;
+  p->d_tables = nullptr; p->d_hmap = nullptr; p->hs_cap_P = 0; p->zc = nullptr; p->zc_cap = 0;
   p->d_hs[0] = p->d_hs[1] = p->d_hs[2] = nullptr;
   memset(&p->scratch, 0, sizeof(p->scratch));
   memset(p->lane, 0, sizeof(p->lane));
@@ -511,6 +511,7 @@ void nlo_nlp_destroy(nlo_nlp* p) {
   for (auto& ln : p->lane) { free_lane_bufs(ln); if (ln.stream) cudaStreamDestroy(ln.stream); }
   if (p->d_tables) cudaFree(p->d_tables);
   if (p->d_hmap) cudaFree(p->d_hmap);
+  if (p->zc) cudaFreeHost(p->zc);
   for (float*& b : p->d_hs) { if (b) cudaFree(b); b = nullptr; }
   delete p;
 }
@@ -661,11 +662,38 @@ static int ensure_lane(nlo_nlp* p, NlpLane& ln, size_t P) {
 // Host-buffer evaluation, problem-major rows.  The batch is cut into chunks that alternate between two lanes
 // (streams): while one lane's results travel device->host, the other lane's inputs travel host->device and its
 // kernels run, so PCIe is busy in both directions and the GPU work hides behind the copies.
+// Small batches (the reference's own case is ONE problem per IPOPT callback): no memcpy and no device transpose.  The decision
+// vectors are laid out variable-major in pinned, device-mapped memory by the CPU, the kernels read and write that memory directly
+// (zero-copy), and the CPU scatters the results back: three launches and one stream synchronisation per call.
+static int nlp_eval_host_small(nlo_nlp* p, const float* w_host, size_t P, float* g_host, float* jac_host, float* f_host, float* grad_host) {
+  const NlpDev& L = p->L;
+  const size_t n_in = (size_t)L.n_w * P, n_out = ((size_t)L.n_g + L.nnz + L.n_w + 1) * P;
+  if (p->zc_cap < n_in + n_out) {
+    if (p->zc) cudaFreeHost(p->zc);
+    p->zc = nullptr; p->zc_cap = 0;
+    NLO_CUDA(cudaHostAlloc(&p->zc, (n_in + n_out) * sizeof(float), cudaHostAllocMapped | cudaHostAllocPortable));
+    p->zc_cap = n_in + n_out;
+  }
+  float* w = p->zc; float* g = w + n_in; float* jac = g + (size_t)L.n_g * P; float* grad = jac + (size_t)L.nnz * P; float* f = grad + (size_t)L.n_w * P;
+  for (size_t i = 0; i < P; ++i) for (int v = 0; v < L.n_w; ++v) w[(size_t)v * P + i] = w_host[i * L.n_w + v];
+  cudaStream_t st = p->lane[0].stream;
+  if (nlp_eval_on(p, p->lane[0].scratch, w, P, P, g_host ? g : nullptr, jac_host ? jac : nullptr, f_host ? f : nullptr, grad_host ? grad : nullptr, st)) return 1;
+  NLO_CUDA(cudaStreamSynchronize(st));
+  for (size_t i = 0; i < P; ++i) {
+    if (g_host) for (int r = 0; r < L.n_g; ++r) g_host[i * L.n_g + r] = g[(size_t)r * P + i];
+    if (jac_host) for (int z = 0; z < L.nnz; ++z) jac_host[i * L.nnz + z] = jac[(size_t)z * P + i];
+    if (grad_host) for (int v = 0; v < L.n_w; ++v) grad_host[i * L.n_w + v] = grad[(size_t)v * P + i];
+    if (f_host) f_host[i] = f[i];
+  }
+  return 0;
+}
+
 int nlo_nlp_eval_host(nlo_nlp* p, const float* w_host, size_t P, float* g_host, float* jac_host, float* f_host, float* grad_host) {
   if (!p) return nlo_fail("null nlp");
   if (P == 0) return 0;
   if (!w_host) return nlo_fail("null w");
   NLO_CUDA(cudaSetDevice(p->device));
+  if (P <= 8) return nlp_eval_host_small(p, w_host, P, g_host, jac_host, f_host, grad_host);
   const NlpDev& L = p->L;
   size_t chunk = (P + 7) / 8;
   if (chunk < 2048) chunk = 2048;

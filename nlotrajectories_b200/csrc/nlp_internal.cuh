@@ -49,6 +49,7 @@ struct nlo_nlp {
   std::vector<int> hrows_ccs, hcols_ccs;   // structural pattern, upper triangle, compressed-column order
   int* d_hmap;                  // device: [N+1][NLO_HESS_SLOTS] emission slot -> CCS position (or -1)
   float* d_hs[3]; size_t hs_cap_P;          // SDF Hessian scratch (hxx, hxy, hyy) for hs_cap_P problems
+  float* zc; size_t zc_cap;                 // pinned, device-mapped staging of the small-batch host entry point (floats)
   NlpLane lane[2];              // host entry point: two lanes (streams) process alternating chunks of problems
 };
 
