@@ -107,6 +107,7 @@ FLOP_PER_POINT = 4 * (3 * 128 + 128 * 128)      # value + Jacobi
 # under profiles/ (profiles/r1_sdf_tc_kernel.md): 170.6 MB read + 207.1 MB written for 21,233,664 points (algorithmic: 20 B/point)
 NCU_DRAM_BYTES_PER_POINT = 17.8
 BYTES_PER_EVAL = (727 + 1057 + 3225) * 4        # read w, write g and nnz(J) = 20,036 B / problem-eval
+DYN_BYTES_PER_PROBLEM = (567 + 160 + 560 + 2080) * 4   # K2 on benchmark_6 = 13,468 B / problem
 POINTS_PER_PROBLEM = 324
 
 
@@ -265,6 +266,17 @@ def run_ours(args):
     k1.record()
     torch.cuda.synchronize()
     k_ms = k0.elapsed_time(k1) / args.steps
+    # K2 alone (Euler defects + banded Jacobian values): the HBM-bound kernel of the path
+    for _ in range(3):
+        prob.eval_dynamics_device(w, g, jac)
+    torch.cuda.synchronize()
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d0.record()
+    for _ in range(args.steps):
+        prob.eval_dynamics_device(w, g, jac)
+    d1.record()
+    torch.cuda.synchronize()
+    dyn_ms = d0.elapsed_time(d1) / args.steps
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -337,6 +349,10 @@ def run_ours(args):
                      "algorithmic_bytes_per_launch": 20 * n_pts,
                      "flop_per_point": FLOP_PER_POINT, "points_per_launch": n_pts, "kernel_ms": k_ms, "peak_source": peak_note,
                      "kernel_share_of_step": k_ms / ms_per_step,
+                     "dynamics_kernel_hbm": {"kernel": "nlp_phase0_kernel (defect rows only)", "algorithmic_bytes_per_launch": DYN_BYTES_PER_PROBLEM * P,
+                                             "kernel_ms": dyn_ms, "achieved_gbs": DYN_BYTES_PER_PROBLEM * P / (dyn_ms * 1e-3) / 1e9,
+                                             "peak_gbs": peaks["hbm_gbs"], "frac": DYN_BYTES_PER_PROBLEM * P / (dyn_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                             "note": "SURVEY.md 8(d): read (N+1)nx + N nu, write N nx residuals + 26 N Jacobian values per problem"},
                      "step_hbm": {"algorithmic_bytes_per_step": BYTES_PER_EVAL * P, "achieved_gbs": BYTES_PER_EVAL * P / (ms_per_step * 1e-3) / 1e9,
                                   "peak_gbs": peaks["hbm_gbs"]}},
         "best_of_batch": {"merit": best_val, "global_index": best_idx},

@@ -213,6 +213,9 @@ NLO_API int  nlo_nlp_jac_sparsity(const nlo_nlp* p, int32_t* colind, int32_t* ro
  * Any output may be NULL.  ld >= P.  Asynchronous on `stream`.                                 */
 NLO_API int nlo_nlp_eval(nlo_nlp* p, const float* w, size_t P, size_t ld,
                          float* g, float* jac, float* f, float* grad_f, void* stream);
+/* K2 alone: only the Euler defect rows of g (core/runner.py:59-64) and their dg/dw values are written - the HBM-bound kernel
+ * bench.py times in isolation for its achieved-GB/s figure.  Same layouts as nlo_nlp_eval; g / jac may be NULL.              */
+NLO_API int nlo_nlp_eval_dynamics(nlo_nlp* p, const float* w, size_t P, size_t ld, float* g, float* jac, void* stream);
 /* out = add + (dg/dw)^T y for every problem: jac [nnz][ld] (CCS values from nlo_nlp_eval), y [n_g][ld], add [n_w][ld] or NULL,
  * out [n_w][ld].  The product a constrained solver needs for the gradient of its (augmented) Lagrangian.        */
 NLO_API int nlo_nlp_jac_tvec(nlo_nlp* p, const float* jac, const float* y, const float* add, size_t P, size_t ld,

@@ -616,6 +616,15 @@ int nlo_nlp_hess(nlo_nlp* p, const float* w, const float* sigma, const float* la
   return nlo_nlp_launch_hess(p->L, p->d_hmap, w, sigma, lam, P, ld, sc.s, sc.jx, sc.jy, p->d_hs[0], p->d_hs[1], p->d_hs[2], hess, st);
 }
 
+// Only the Euler defect rows of g and their Jacobian values (K2): what the HBM roofline of the dynamics kernel is measured on.
+int nlo_nlp_eval_dynamics(nlo_nlp* p, const float* w, size_t P, size_t ld, float* g, float* jac, void* stream) {
+  if (!p || !w) return nlo_fail("null argument");
+  if (P == 0) return 0;
+  if (ld < P) return nlo_fail("ld (%zu) < P (%zu)", ld, P);
+  NLO_CUDA(cudaSetDevice(p->device));
+  return nlo_nlp_launch_dynamics(p->L, w, P, ld, g, jac, (cudaStream_t)stream);
+}
+
 int nlo_nlp_violation(nlo_nlp* p, const float* g, const float* lbg, const float* ubg, size_t P, size_t ld, float* viol, void* stream) {
   if (!p || !g || !lbg || !ubg || !viol) return nlo_fail("null argument");
   NLO_CUDA(cudaSetDevice(p->device));

@@ -121,6 +121,7 @@ int nlo_nlp_build_layout(const nlo_nlp_desc* d, NlpDev* L, std::vector<int>* row
 int nlo_nlp_launch_assembly(nlo_nlp* p, const NlpScratch& sc, const float* w, size_t P, size_t ld, float* g, float* jac, float* f,
                             float* grad_f, cudaStream_t st, int phase);
 int nlo_nlp_build_hess_layout(const NlpDev& L, std::vector<int>* rows, std::vector<int>* cols, std::vector<int>* hmap);
+int nlo_nlp_launch_dynamics(const NlpDev& L, const float* w, size_t P, size_t ld, float* g, float* jac, cudaStream_t st);
 int nlo_nlp_launch_points(const NlpDev& L, const float* w, size_t P, size_t ld, float* px, float* py, cudaStream_t st);
 int nlo_nlp_launch_circles_hess(const NlpDev& L, const float* px, const float* py, size_t n, float* s, float* jx, float* jy,
                                 float* hxx, float* hxy, float* hyy, int sm, cudaStream_t st);

@@ -456,6 +456,19 @@ int nlo_nlp_launch_assembly(nlo_nlp* p, const NlpScratch& sc, const float* w, si
   return 0;
 }
 
+// K2 alone (Euler defects + their Jacobian values): the HBM-bound kernel the roofline report times in isolation
+int nlo_nlp_launch_dynamics(const NlpDev& L, const float* w, size_t P, size_t ld, float* g, float* jac, cudaStream_t st) {
+  const dim3 grid((unsigned)std::min<size_t>((P + 255) / 256, 4096), (unsigned)L.N);
+  switch (L.dyn) {
+#define NLO_CASE(D) case D: nlp_phase0_kernel<D><<<grid, 256, 0, st>>>(L, w, P, ld, g, jac, nullptr, nullptr, nullptr, nullptr, L.N, 0, 0, 0); break;
+    NLO_CASE(NLO_DYN_POINT_1ST) NLO_CASE(NLO_DYN_POINT_2ND) NLO_CASE(NLO_DYN_UNICYCLE)
+    NLO_CASE(NLO_DYN_UNICYCLE_2ND) NLO_CASE(NLO_DYN_ACKERMANN) NLO_CASE(NLO_DYN_ACKERMANN_2ND)
+#undef NLO_CASE
+  }
+  NLO_CHECK_LAUNCH();
+  return 0;
+}
+
 int nlo_nlp_launch_points(const NlpDev& L, const float* w, size_t P, size_t ld, float* px, float* py, cudaStream_t st) {
   nlp_points_kernel<<<dim3((unsigned)std::min<size_t>((P + 255) / 256, 4096), (unsigned)(L.N + 1)), 256, 0, st>>>(L, w, P, ld, px, py);
   NLO_CHECK_LAUNCH();

@@ -64,6 +64,7 @@ SIGNATURES = {
     "nlo_nlp_n_sdf_points": (_LL, [_P]),
     "nlo_nlp_jac_sparsity": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "nlo_nlp_eval": (C.c_int, [_P, _F, _SZ, _SZ, _F, _F, _F, _F, _P]),
+    "nlo_nlp_eval_dynamics": (C.c_int, [_P, _F, _SZ, _SZ, _F, _F, _P]),
     "nlo_nlp_nnz_hess": (_LL, [_P]),
     "nlo_nlp_hess_sparsity": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "nlo_nlp_hess": (C.c_int, [_P, _F, _F, _F, _SZ, _SZ, _F, _P]),

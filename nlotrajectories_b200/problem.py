@@ -180,6 +180,14 @@ class NlpProblem:
         st = torch.cuda.current_stream(w.device).cuda_stream if stream is None else stream
         _lib.check(self._L.nlo_nlp_eval(self._h, w.data_ptr(), P, ld, _lib.ptr(g), _lib.ptr(jac), _lib.ptr(f), _lib.ptr(grad_f), st))
 
+    def eval_dynamics_device(self, w, g=None, jac=None, P: Optional[int] = None, stream=None):
+        """K2 alone: the Euler defect rows of g and their Jacobian values (same SoA layouts as ``eval_device``)."""
+        import torch
+        ld = w.shape[1]
+        P = ld if P is None else P
+        st = torch.cuda.current_stream(w.device).cuda_stream if stream is None else stream
+        _lib.check(self._L.nlo_nlp_eval_dynamics(self._h, w.data_ptr(), P, ld, _lib.ptr(g), _lib.ptr(jac), st))
+
     def alloc_outputs(self, P: int, device=None):
         import torch
         dev = torch.device("cuda", self.device) if device is None else device

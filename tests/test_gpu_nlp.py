@@ -283,3 +283,25 @@ def test_hessian_batch_matches_oracle(name, netname, library):
     H1 = _hess_device(prob, w, lam, None)
     Hs = _hess_device(prob, w, lam, np.ones(P, np.float32))
     assert np.array_equal(H1, Hs)
+
+
+def test_dynamics_only_entry_point_matches_full_evaluation(library):
+    """nlo_nlp_eval_dynamics (K2 alone, the kernel bench.py times for the HBM figure) writes exactly the defect rows of g and their
+    Jacobian values and nothing else."""
+    import torch
+    net = so.synthetic_mlp(128, 1, seed=0)
+    cfg, model, prob = make_problem("benchmark_6", net)
+    P = 515
+    w = torch.from_numpy(prob.multistart_guess(P)).cuda().T.contiguous()
+    g, jac, f, grad = prob.alloc_outputs(P)
+    prob.eval_device(w, g, jac, f, grad)
+    g2 = torch.full_like(g, float("nan")); jac2 = torch.full_like(jac, float("nan"))
+    prob.eval_dynamics_device(w, g2, jac2)
+    torch.cuda.synchronize()
+    spec = no.NlpSpec.from_yaml_dict(yaml.safe_load(open(bench_yaml("benchmark_6"))))
+    off = spec.nx + len(spec.terminal_idx)
+    rows = slice(off, off + spec.N * spec.nx)
+    assert torch.equal(g2[rows], g[rows]) and bool(torch.isnan(g2[:off]).all()) and bool(torch.isnan(g2[off + spec.N * spec.nx:]).all())
+    written = ~torch.isnan(jac2[:, 0])
+    assert int(written.sum()) == spec.N * 26                  # SURVEY.md Appendix A: 26 non-zeros per Ackermann interval
+    assert torch.equal(jac2[written], jac[written])
