@@ -164,12 +164,22 @@ int nlo_sdf_eval(nlo_sdf_model* m, const float* x, const float* y, const float* 
   return nlo_sdf_simt_launch(m, x, y, sbar, n, s, jx, jy, st);
 }
 
+// second derivatives of piecewise-linear networks vanish identically (what sdf_hess_kernel would compute, exactly)
+static bool sdf_is_piecewise_linear(const nlo_sdf_model* m) {
+  auto lin = [](uint32_t a) { return a == NLO_ACT_RELU || a == NLO_ACT_LEAKY_RELU; };
+  return lin(m->desc.act0) && (m->desc.n_hidden_mats == 0 || lin(m->desc.act));
+}
+
 int nlo_sdf_hess(nlo_sdf_model* m, const float* x, const float* y, const float* sbar, size_t n,
                  float* hxx, float* hxy, float* hyy, void* stream) {
   if (!m) return nlo_fail("null model");
   if (n == 0) return 0;
   if (!x || !y) return nlo_fail("null coordinate array");
   NLO_CUDA(cudaSetDevice(m->device));
+  if (sdf_is_piecewise_linear(m)) {
+    for (float* b : {hxx, hxy, hyy}) if (b) NLO_CUDA(cudaMemsetAsync(b, 0, n * sizeof(float), (cudaStream_t)stream));
+    return 0;
+  }
   if (m->prec == NLO_PREC_TC_3XF16 && hxx && hxy && hyy && nlo_sdf_tc_hess_supported(m))
     return nlo_sdf_tc_hess_launch(m, x, y, sbar, n, nullptr, nullptr, nullptr, hxx, hxy, hyy, (cudaStream_t)stream);
   return nlo_sdf_simt_hess_launch(m, x, y, sbar, n, hxx, hxy, hyy, (cudaStream_t)stream);
@@ -573,12 +583,6 @@ int nlo_nlp_hess_sparsity(const nlo_nlp* p, int32_t* colind, int32_t* row) {
   for (int i = 0; i < nnz; ++i) { colind[p->hcols_ccs[i] + 1]++; row[i] = p->hrows_ccs[i]; }
   for (int c = 0; c < n_w; ++c) colind[c + 1] += colind[c];
   return 0;
-}
-
-// second derivatives of piecewise-linear networks vanish identically (what sdf_hess_kernel would compute, exactly)
-static bool sdf_is_piecewise_linear(const nlo_sdf_model* m) {
-  auto lin = [](uint32_t a) { return a == NLO_ACT_RELU || a == NLO_ACT_LEAKY_RELU; };
-  return lin(m->desc.act0) && (m->desc.n_hidden_mats == 0 || lin(m->desc.act));
 }
 
 int nlo_nlp_hess(nlo_nlp* p, const float* w, const float* sigma, const float* lam, size_t P, size_t ld, float* hess, void* stream) {

@@ -242,13 +242,15 @@ __device__ __noinline__ uint32_t sdf_tc_tile(TileCtx c, uint32_t phase, float px
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
       float g[2];
+      uint32_t mask = 0u;                                  // RH: the pair of fp16 0 / 1 values, built from the two predicates
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int j = C0 + cc * 32 + 2 * q + e;
         const float zz = fmaf(__uint_as_float(z[2 * q + e]), unscale1, cst.b1[j]);
         if (RH) {
-          s = fmaf(cst.w2[j], fmaxf(zz, 0.f), s);
-          g[e] = zz > 0.f ? 1.f : 0.f;                     // exact in fp16: the w2 factor lives in V = diag(w2) W1
+          // one predicate serves the value (predicated FFMA instead of max + FFMA) and the mask, which is exact in fp16:
+          // the w2 factor of the reverse seed lives in V = diag(w2) W1
+          if (zz > 0.f) { s = fmaf(cst.w2[j], zz, s); mask |= (e == 0 ? 0x3C00u : 0x3C000000u); }
         } else {
           float v, d;
           act_vd<ACT>(zz, c.act, c.prm, v, d);
@@ -256,7 +258,7 @@ __device__ __noinline__ uint32_t sdf_tc_tile(TileCtx c, uint32_t phase, float px
           g[e] = cst.w2s[j] * d;
         }
       }
-      if (RH) hi[q] = pack_f16(g[0], g[1]); else split_pack_f16(g[0], g[1], hi[q], lo[q]);
+      if (RH) hi[q] = mask; else split_pack_f16(g[0], g[1], hi[q], lo[q]);
     }
     if (want_jac) {
       TmemIO<16>::st(c.lane_base + COL_AHI + cc * 16, hi);
@@ -291,6 +293,11 @@ __device__ __noinline__ uint32_t sdf_tc_tile(TileCtx c, uint32_t phase, float px
       for (int q = 0; q < 32; ++q) {
         const int k = C0 + cc * 32 + q;
         const float a = fmaf(cst.w0x[k], px, fmaf(cst.w0y[k], py, cst.b0[k]));
+        if (ACT0 == NLO_ACT_RELU && !HESS) {
+          // phi0' is 0 / 1: two predicated FFMAs instead of a compare-to-float, a multiply and two FFMAs
+          if (a > 0.f) { jx = fmaf(__uint_as_float(gz[q]), cst.w0x[k], jx); jy = fmaf(__uint_as_float(gz[q]), cst.w0y[k], jy); }
+          continue;
+        }
         float v, d;
         act_vd<ACT0>(a, c.act0, c.prm0, v, d);
         const float g0 = __uint_as_float(gz[q]) * d;

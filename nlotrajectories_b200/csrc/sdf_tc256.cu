@@ -284,10 +284,13 @@ sdf_tc256_kernel(SdfNetDev net, Tc256Params prm, const uint8_t* __restrict__ img
             const float4 ww = *reinterpret_cast<const float4*>(sm->w2 + base + 4 * j4);
             const float z0 = fmaf(__uint_as_float(z[cc][4 * j4 + 0]), unscale1, bb.x), z1 = fmaf(__uint_as_float(z[cc][4 * j4 + 1]), unscale1, bb.y);
             const float z2 = fmaf(__uint_as_float(z[cc][4 * j4 + 2]), unscale1, bb.z), z3 = fmaf(__uint_as_float(z[cc][4 * j4 + 3]), unscale1, bb.w);
-            s = fmaf(ww.x, fmaxf(z0, 0.f), s); s = fmaf(ww.y, fmaxf(z1, 0.f), s);
-            s = fmaf(ww.z, fmaxf(z2, 0.f), s); s = fmaf(ww.w, fmaxf(z3, 0.f), s);
-            hi[2 * j4] = pack2_f16(z0 > 0.f ? 1.f : 0.f, z1 > 0.f ? 1.f : 0.f);
-            hi[2 * j4 + 1] = pack2_f16(z2 > 0.f ? 1.f : 0.f, z3 > 0.f ? 1.f : 0.f);
+            // one predicate per neuron serves the value (predicated FFMA) and the fp16 0 / 1 mask
+            uint32_t m0 = 0u, m1 = 0u;
+            if (z0 > 0.f) { s = fmaf(ww.x, z0, s); m0 |= 0x3C00u; }
+            if (z1 > 0.f) { s = fmaf(ww.y, z1, s); m0 |= 0x3C000000u; }
+            if (z2 > 0.f) { s = fmaf(ww.z, z2, s); m1 |= 0x3C00u; }
+            if (z3 > 0.f) { s = fmaf(ww.w, z3, s); m1 |= 0x3C000000u; }
+            hi[2 * j4] = m0; hi[2 * j4 + 1] = m1;
           }
           if (want_jac) {
             st16(lane_base + COL_AHI + q * 32 + cc * 16, hi);
@@ -319,6 +322,12 @@ sdf_tc256_kernel(SdfNetDev net, Tc256Params prm, const uint8_t* __restrict__ img
             const float wxs[4] = {wx.x, wx.y, wx.z, wx.w}, wys[4] = {wy.x, wy.y, wy.z, wy.w}, bs[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
+              if (ACT0 == NLO_ACT_RELU) {          // phi0' is 0 / 1: predicated FFMAs
+                if (fmaf(wxs[e], px, fmaf(wys[e], py, bs[e])) > 0.f) {
+                  jx = fmaf(__uint_as_float(gz[cc][4 * j4 + e]), wxs[e], jx); jy = fmaf(__uint_as_float(gz[cc][4 * j4 + e]), wys[e], jy);
+                }
+                continue;
+              }
               float v, d;
               nlo_phi_d_tc(fmaf(wxs[e], px, fmaf(wys[e], py, bs[e])), act0, net.p0, v, d);
               const float g0 = __uint_as_float(gz[cc][4 * j4 + e]) * d;
