@@ -297,10 +297,12 @@ __global__ void __launch_bounds__(256) sdf_hess_kernel(SdfNetDev net, const floa
 //     (row stride 132 floats: conflict-free for both the row-wise 128-bit stores and the broadcast loads);
 //   * weights stream from L2 in slabs of 16 rows through a cp.async double buffer - W_l^T rows going forward,
 //     W_l rows going back - so the width is not limited by shared memory (H = 256: 256 KB of weights);
-//   * thread (tx, ty) accumulates 8 points (8*ty..) x TN neurons (tx + 16c) in registers: per k it issues
-//     2 broadcast LDS.128 + TN LDS.32 for 8*TN FMAs.
+//   * thread (tx, ty) accumulates 8 points (8*ty..) x TN neurons (4 consecutive ones per 64-wide group: 64g + 4tx + 0..3) in
+//     registers: per k it issues 2 broadcast LDS.128 for the points + TN/4 LDS.128 for the weights for 8*TN FMAs.
 // Pre-activations of intermediate layers (M >= 2) go to a tile-private global scratch.
 constexpr int GT_P = 128, GT_S = 132, GT_KS = 16, GT_THREADS = 256;
+// column (neuron) owned by accumulator slot c of thread tx
+__device__ __forceinline__ int gt_col(int tx, int c) { return 64 * (c >> 2) + 4 * tx + (c & 3); }
 
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
@@ -335,7 +337,10 @@ __device__ __forceinline__ void gemm_tile(const float* __restrict__ Wg, const fl
       const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
       float bv[TN];
 #pragma unroll
-      for (int c = 0; c < TN; ++c) bv[c] = Wcur[kk * H + tx + 16 * c];
+      for (int g = 0; g < TN / 4; ++g) {
+        const float4 w4 = *reinterpret_cast<const float4*>(Wcur + kk * H + 64 * g + 4 * tx);
+        bv[4 * g + 0] = w4.x; bv[4 * g + 1] = w4.y; bv[4 * g + 2] = w4.z; bv[4 * g + 3] = w4.w;
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -396,7 +401,7 @@ sdf_gemm_kernel(SdfNetDev net, const float* __restrict__ wt, const float* __rest
       const float* bl = gw + net.off_b(l);
 #pragma unroll
       for (int c = 0; c < TN; ++c) {
-        const int nn = tx + 16 * c;
+        const int nn = gt_col(tx, c);
         const float bb = bl[nn];
         float o[8];
         if (l < M) {
@@ -436,7 +441,7 @@ sdf_gemm_kernel(SdfNetDev net, const float* __restrict__ wt, const float* __rest
         if (l > 1) {
 #pragma unroll
           for (int c = 0; c < TN; ++c) {
-            const int kk = tx + 16 * c;
+            const int kk = gt_col(tx, c);
             const float* zrow = tile_ws + ((size_t)(l - 2) * H + kk) * GT_P + p0;
             float o[8];
 #pragma unroll
@@ -452,7 +457,7 @@ sdf_gemm_kernel(SdfNetDev net, const float* __restrict__ wt, const float* __rest
           for (int i = 0; i < 8; ++i) { jx[i] = 0.f; jy[i] = 0.f; }
 #pragma unroll
           for (int c = 0; c < TN; ++c) {
-            const int kk = tx + 16 * c;
+            const int kk = gt_col(tx, c);
             const float wx = W0[2 * kk], wy = W0[2 * kk + 1], bb = b0[kk];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
