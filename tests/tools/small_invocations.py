@@ -1,8 +1,8 @@
-"""Small invocations of every tensor-path kernel and the NLP kernels, for compute-sanitizer (memcheck / racecheck)."""
+"""Small invocations of every tensor-path kernel and the NLP kernels (a quick smoke of all kernel variants on a GPU box)."""
 import sys
 from pathlib import Path
 import numpy as np
-REPO = Path(__file__).resolve().parents[1]
+REPO = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(REPO)); sys.path.insert(0, str(REPO / "tests"))
 import torch
 from oracle import sdf_oracle as so

@@ -2,7 +2,7 @@
 import sys
 from pathlib import Path
 import numpy as np
-REPO = Path(__file__).resolve().parents[1]
+REPO = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(REPO)); sys.path.insert(0, str(REPO / "tests"))
 import torch
 from oracle import sdf_oracle as so
