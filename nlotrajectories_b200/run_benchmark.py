@@ -55,7 +55,11 @@ def solve_benchmark(config_path: Path, batch: int = 64, weights: str | None = No
     prob = NlpProblem.from_config(cfg, sdf, device=local_rank)
     lo, hi = shard_range(batch, rank, world)
     dev = torch.device("cuda", local_rank)
-    w0 = torch.from_numpy(prob.multistart_guess(hi - lo, first=lo).astype(np.float64)).to(dev)
+    if cfg.solver.initializer.mode == "rrt":                     # the YAML's initializer (scripts/run_benchmark.py:114-127), one seed per start
+        from .initializer import rrt_multistart
+        w0 = torch.from_numpy(rrt_multistart(cfg, hi - lo, first=lo).astype(np.float64)).to(dev)
+    else:
+        w0 = torch.from_numpy(prob.multistart_guess(hi - lo, first=lo).astype(np.float64)).to(dev)
     lb, ub = prob.bounds()
     t0 = time.time()
     res = BatchedIPSolver(DeviceEvaluator(prob), lb, ub, verbose=verbose and rank == 0).solve(w0)

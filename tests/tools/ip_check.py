@@ -18,7 +18,8 @@ from nlotrajectories_b200.solver import BatchedIPSolver, DeviceEvaluator
 name = sys.argv[1] if len(sys.argv) > 1 else "benchmark_1"
 P = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 n_ref = int(sys.argv[3]) if len(sys.argv) > 3 else 2
-weights = sys.argv[4] if len(sys.argv) > 4 else None
+weights = sys.argv[4] if len(sys.argv) > 4 and sys.argv[4] != "-" else None
+init = sys.argv[5] if len(sys.argv) > 5 else "multistart"          # "multistart" (seeded lateral offsets) | "rrt" (seeded planner per start)
 ypath = next((REPO / "nlotrajectories_b200/benchmarks").glob(name + "*.yaml"))
 cfg = Config.load(ypath)
 spec = no.NlpSpec.from_yaml_dict(yaml.safe_load(open(ypath)))
@@ -26,7 +27,13 @@ net = so.from_npz(weights) if weights else None
 model = LearnedSDF(to_weights(net)) if cfg.solver.mode == "l4casadi" else None
 prob = NlpProblem.from_config(cfg, model)
 lb, ub = prob.bounds()
-w0 = prob.multistart_guess(P).astype(np.float64)
+if init == "rrt":
+    from nlotrajectories_b200.initializer import rrt_multistart
+    t0 = time.time()
+    w0 = rrt_multistart(cfg, P).astype(np.float64)
+    print(f"{name}: {P} RRT initial guesses in {time.time() - t0:.1f} s (host)", flush=True)
+else:
+    w0 = prob.multistart_guess(P).astype(np.float64)
 ev = DeviceEvaluator(prob)
 t0 = time.time()
 res = BatchedIPSolver(ev, lb, ub, verbose=True, max_iter=300).solve(torch.from_numpy(w0).cuda())
