@@ -138,7 +138,7 @@ def build_model(cfg: Config):
     return net
 
 
-def train(cfg: Config, n_samples=200_000, epochs=100, batch_size=2048, lr=1e-3, seed=0, x_range=(-0.5, 1.5), y_range=(-0.5, 1.5),
+def train(cfg: Config, n_samples=200_000, epochs=100, batch_size=256, lr=1e-3, seed=0, x_range=(-0.5, 1.5), y_range=(-0.5, 1.5),
           patience=10, min_delta=1e-4, device=None, verbose=True):
     import torch
     torch.manual_seed(seed)
@@ -206,9 +206,10 @@ def main():
     ap.add_argument("--samples", type=int, default=200_000)
     ap.add_argument("--epochs", type=int, default=100)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--batch-size", type=int, default=256, help="the reference's value (core/sdf/l4casadi.py:89)")
     a = ap.parse_args()
     cfg = Config.load(Path(a.config))
-    net, info = train(cfg, n_samples=a.samples, epochs=a.epochs, seed=a.seed)
+    net, info = train(cfg, n_samples=a.samples, epochs=a.epochs, seed=a.seed, batch_size=a.batch_size)
     w = SdfWeights.from_state_dict(cfg.model.type, net.state_dict(), activation_function=cfg.model.activation_function,
                                    omega_0=cfg.model.omega_0)
     (w.save_nlow if a.out.endswith(".nlow") else w.save_npz)(a.out)
