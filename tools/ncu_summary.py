@@ -44,8 +44,8 @@ def launches(src, dst):
         f.write("| kernel | launches | total ms | share |\n|---|---|---|---|\n")
         for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"| `{n}` | {c} | {t / 1e6:.3f} | {100 * t / tot:.1f}% |\n")
-        # one step: from a dyn kernel to the next dyn kernel
-        idx = [i for i, (n, _) in enumerate(seq) if n.startswith("nlp_dyn_kernel")]
+        # one step: from one assembly (phase-0) launch to the next
+        idx = [i for i, (n, _) in enumerate(seq) if n.startswith("nlp_phase0_kernel") or n.startswith("nlp_dyn_kernel")]
         if len(idx) > 4:
             a, b = idx[3], idx[4]
             step = seq[a:b]
