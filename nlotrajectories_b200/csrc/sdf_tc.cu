@@ -611,14 +611,21 @@ int nlo_sdf_tc_launch(nlo_sdf_model* m, const float* x, const float* y, const fl
   if (m->desc.hidden == 256) return nlo_sdf_tc256_launch(m, x, y, sbar, n, s, jx, jy, st);
   if (!m->d_tc) return nlo_fail("tensor-tile operands were not prepared");
   const int H = (int)m->desc.hidden, a0 = (int)m->desc.act0, a = (int)m->desc.act;
+#define NLO_TC_ONE(HH, A0, A1) if (a0 == A0 && a == A1) return launch_tc<HH, A0, A1>(m, x, y, sbar, n, s, jx, jy, st)
+  // compile-time activation pairs of the layer zoo (core/nn_architectures.py:42-100, l4casadi's naive MLP): unrolled tile bodies with
+  // constant-bank operands; anything else runs the generic instantiation (run-time activation switch, ~10x slower)
 #define NLO_TC(HH)                                                                                                 \
   do {                                                                                                             \
-    if (a0 == NLO_ACT_RELU && a == NLO_ACT_RELU) return launch_tc<HH, NLO_ACT_RELU, NLO_ACT_RELU>(m, x, y, sbar, n, s, jx, jy, st);          \
-    if (a0 == NLO_ACT_COS_SCALE && a == NLO_ACT_RELU) return launch_tc<HH, NLO_ACT_COS_SCALE, NLO_ACT_RELU>(m, x, y, sbar, n, s, jx, jy, st); \
+    NLO_TC_ONE(HH, NLO_ACT_RELU, NLO_ACT_RELU); NLO_TC_ONE(HH, NLO_ACT_COS_SCALE, NLO_ACT_RELU);                    \
+    NLO_TC_ONE(HH, NLO_ACT_TANH, NLO_ACT_TANH); NLO_TC_ONE(HH, NLO_ACT_SIGMOID, NLO_ACT_SIGMOID);                   \
+    NLO_TC_ONE(HH, NLO_ACT_LEAKY_RELU, NLO_ACT_LEAKY_RELU); NLO_TC_ONE(HH, NLO_ACT_COS_SCALE, NLO_ACT_TANH);        \
+    NLO_TC_ONE(HH, NLO_ACT_COS_SCALE, NLO_ACT_SIGMOID); NLO_TC_ONE(HH, NLO_ACT_COS_SCALE, NLO_ACT_LEAKY_RELU);      \
+    NLO_TC_ONE(HH, NLO_ACT_SIN, NLO_ACT_SIN);                                                                       \
     return launch_tc<HH, -1, -1>(m, x, y, sbar, n, s, jx, jy, st);                                                 \
   } while (0)
   if (H == 128) NLO_TC(128);
   if (H == 64) NLO_TC(64);
 #undef NLO_TC
+#undef NLO_TC_ONE
   return nlo_fail("tensor-tile path: unsupported width %d", H);
 }

@@ -42,8 +42,16 @@ NETS = {
     "relu16x0": lambda: so.synthetic_mlp(16, 0, seed=9),
     "fourier256_relu": lambda: so.synthetic_fourier(256, 1, scale=2.0, seed=10),      # H = 256 tensor path, cos features
     "fourier128_relu": lambda: so.synthetic_fourier(128, 1, scale=2.0, seed=12),
-    "tanh128": lambda: so.synthetic_mlp(128, 1, seed=13, act=so.ACT_TANH),            # generic 3-pass reverse GEMM
+    "tanh128": lambda: so.synthetic_mlp(128, 1, seed=13, act=so.ACT_TANH),            # generic 3-pass reverse GEMM, SFU tanh
+    "sigmoid128": lambda: so.synthetic_mlp(128, 1, seed=15, act=so.ACT_SIGMOID),
+    "leaky128": lambda: so.synthetic_mlp(128, 1, seed=16, act=so.ACT_LEAKY_RELU),
+    "siren64x1": lambda: so.synthetic_siren(64, 1, omega0=30.0, seed=17),             # (sin, sin) on the tensor path
+    "fourier128_sigmoid": lambda: so.synthetic_fourier(128, 1, scale=2.0, seed=18, act=so.ACT_SIGMOID),
+    "fourier64_leaky": lambda: so.synthetic_fourier(64, 1, scale=2.0, seed=19, act=so.ACT_LEAKY_RELU),
+    "tanh_sigmoid_mix64": None,                                                      # placeholder replaced below: run-time (generic) instantiation
 }
+NETS["tanh_sigmoid_mix64"] = lambda: (lambda n: so.SdfNet(n.kind, n.W0, n.b0, n.hidden, n.w_out, n.b_out, so.ACT_TANH, so.ACT_SIGMOID, n.p0, n.p))(
+    so.synthetic_mlp(64, 1, seed=20, act=so.ACT_TANH))
 
 
 @pytest.mark.parametrize("precision", ["fp32", "auto"])

@@ -12,7 +12,8 @@ H = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 prec = sys.argv[2] if len(sys.argv) > 2 else "tc3xf16"
 logn = int(sys.argv[3]) if len(sys.argv) > 3 else 24
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 10
-net = so.synthetic_mlp(H, 1, seed=0)
+act = {"relu": so.ACT_RELU, "tanh": so.ACT_TANH, "sigmoid": so.ACT_SIGMOID, "leaky": so.ACT_LEAKY_RELU}[sys.argv[5] if len(sys.argv) > 5 else "relu"]
+net = so.synthetic_mlp(H, 1, seed=0, act=act)
 model = LearnedSDF(to_weights(net), precision=prec)
 n = 1 << logn
 x = torch.rand(n, device="cuda") * 2 - 0.5; y = torch.rand(n, device="cuda") * 2 - 0.5
