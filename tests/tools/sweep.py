@@ -32,11 +32,15 @@ def timed(fn, reps):
 def sdf_sweep(max_log=28):
     nets = {"relu64": so.synthetic_mlp(64, 1, seed=1), "relu128": so.synthetic_mlp(128, 1, seed=0), "relu256": so.synthetic_mlp(256, 1, seed=2),
             "shipped_fourier128": so.from_npz(REPO / "tests/golden/sdf_shipped_fourier128_weights.npz")}
-    runs = [(name, net, "auto") for name, net in nets.items()] + [("relu128", nets["relu128"], "fp32"), ("relu256", nets["relu256"], "fp32")]
+    zoo = {"tanh128": so.synthetic_mlp(128, 1, seed=13, act=so.ACT_TANH), "sigmoid128": so.synthetic_mlp(128, 1, seed=15, act=so.ACT_SIGMOID),
+           "leaky128": so.synthetic_mlp(128, 1, seed=16, act=so.ACT_LEAKY_RELU), "siren64x1": so.synthetic_siren(64, 1, omega0=30.0, seed=17),
+           "fourier128_tanh": so.synthetic_fourier(128, 1, scale=2.0, seed=21, act=so.ACT_TANH)}
+    runs = ([(name, net, "auto") for name, net in nets.items()] + [("relu128", nets["relu128"], "fp32"), ("relu256", nets["relu256"], "fp32")]
+            + [(name, net, "zoo") for name, net in zoo.items()])
     for name, net, prec in runs:
-        model = LearnedSDF(to_weights(net), precision=prec)
+        model = LearnedSDF(to_weights(net), precision="auto" if prec == "zoo" else prec)
         for logn in (20, 22, 24, 26, 28):
-            if logn > max_log or (model.precision == "fp32" and logn > 22): continue
+            if logn > max_log or (model.precision == "fp32" and logn > 22) or (prec == "zoo" and logn != 24): continue
             n = 1 << logn
             x = torch.rand(n, device="cuda") * 2 - 0.5; y = torch.rand(n, device="cuda") * 2 - 0.5; sb = torch.rand(n, device="cuda") + 0.5
             out = (torch.empty_like(x), torch.empty_like(x), torch.empty_like(x))
