@@ -38,6 +38,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 namespace {
 
@@ -444,6 +445,7 @@ sdf_tc_kernel(SdfNetDev net, TcParams prm_tc, const __half* __restrict__ bimg, c
 }
 
 unsigned long long g_const_owner[64] = {0};   // per device: uid of the model whose vectors sit in `cst`
+std::mutex g_const_mu;                        // check owner -> (sync + upload) -> launch is one critical section per process
 
 template <int H, int ACT0, int ACT, bool HESS = false>
 int launch_tc(nlo_sdf_model* m, const float* x, const float* y, const float* sbar, size_t n, float* s, float* jx, float* jy, cudaStream_t st,
@@ -457,6 +459,7 @@ int launch_tc(nlo_sdf_model* m, const float* x, const float* y, const float* sba
   const int grid = (int)(want < (size_t)m->sm_count ? want : (size_t)m->sm_count);   // one persistent CTA per SM
   TcParams prm;
   memcpy(&prm, m->tc_params, sizeof(prm));
+  std::lock_guard<std::mutex> lk(g_const_mu);   // another host thread must not swap the constants between this check and the launch
   if (g_const_owner[m->device] != m->uid) {
     // A different model's vectors sit in constant memory: drain whatever may still read them, then upload ours
     // synchronously so that launches on any stream see them.  Rare (model switch), so the device-wide sync is fine.
@@ -471,7 +474,7 @@ int launch_tc(nlo_sdf_model* m, const float* x, const float* y, const float* sba
   }
   unsigned int* ctr = nullptr;
   if (tiles > (size_t)grid * Cfg::NGROUPS) {         // more than one tile per group: balance dynamically
-    ctr = reinterpret_cast<unsigned int*>(static_cast<char*>(m->d_tc) + m->tc_bytes) + (m->tc_seq++ & 63u);
+    ctr = reinterpret_cast<unsigned int*>(static_cast<char*>(m->d_tc) + m->tc_bytes) + (__atomic_fetch_add(&m->tc_seq, 1u, __ATOMIC_RELAXED) & 63u);
     NLO_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st));
   }
   kfn<<<grid, Cfg::THREADS, smem, st>>>(m->net(), prm, reinterpret_cast<const __half*>(m->d_tc), x, y, sbar, n, s, jx, jy, hxx, hxy, hyy, ctr, dbg);

@@ -229,8 +229,10 @@ class BatchedIPSolver:
     inequality rows, log barrier, exact Hessian, ell-1 merit line search, monotone barrier update.  Each iteration
     costs one batched evaluation + one batched Hessian + one batched dense KKT solve (n_w + n_eq unknowns)."""
 
-    def __init__(self, evaluator, lbg, ubg, tol: float = 1e-4, max_iter: int = 300, mu0: float = 0.1, verbose: bool = False):
+    def __init__(self, evaluator, lbg, ubg, tol: float = 1e-4, max_iter: int = 300, mu0: float = 0.1, verbose: bool = False,
+                 ls_multipliers: bool = True):
         self.ev, self.tol, self.max_iter, self.mu0, self.verbose = evaluator, tol, max_iter, mu0, verbose
+        self.ls_multipliers = ls_multipliers
         self.lbg, self.ubg = np.asarray(lbg, np.float64), np.asarray(ubg, np.float64)
 
     def solve(self, w0) -> IPResult:
@@ -413,6 +415,16 @@ class BatchedIPSolver:
             z_l = torch.where(has_l, torch.minimum(torch.maximum(z_l, mu[:, None] / (kap * dl(s))), kap * mu[:, None] / dl(s)), z_l)
             z_u = torch.where(has_u, torch.minimum(torch.maximum(z_u, mu[:, None] / (kap * du(s))), kap * mu[:, None] / du(s)), z_u)
             f, grad, g, J = ev.eval(w)
+            if nE and self.ls_multipliers:
+                # least-squares equality multipliers at the new point: min |grad + JI^T lam_I + JE^T lam_E|^2.  The Newton update
+                # rho (JE dw + r_cE) explodes where the linearised equalities are inconsistent (rank-deficient JE at a standstill),
+                # and a huge lam_E makes the Hessian of the Lagrangian hugely indefinite for every later iteration.
+                JE_n = J[:, iE, :]
+                r_n = grad + torch.einsum("prw,pr->pw", J[:, iI, :], z_u - z_l)
+                A = torch.einsum("pew,pfw->pef", JE_n, JE_n)
+                A = A + (1e-8 * torch.clamp(A.diagonal(dim1=1, dim2=2).amax(1), min=1.0))[:, None, None] * torch.eye(nE, dtype=torch.float64, device=dev)
+                lam_ls = -torch.linalg.solve(A, torch.einsum("pew,pw->pe", JE_n, r_n)[:, :, None])[:, :, 0]
+                lam_E = torch.where(done[:, None], lam_E, lam_ls)
         viol = torch.clamp(torch.maximum(lb_all - g, g - ub_all), min=0.0).amax(1)
         lam = torch.zeros((P, ev.n_g), dtype=torch.float64, device=dev)
         lam[:, iE] = lam_E; lam[:, iI] = z_u - z_l

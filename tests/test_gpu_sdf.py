@@ -287,3 +287,37 @@ def test_two_tensor_path_models_alternating_and_streams(torch_cuda):
             assert not (close(J, refs[i][1], TOL).any(axis=1) & ~ties[i]).any()
     for m in models:
         m.close()
+
+
+def test_two_host_threads_share_the_tensor_path(torch_cuda):
+    """Two host threads, each evaluating its own model on its own stream at the same time: the check of the
+    __constant__ owner, the re-upload and the launch are one critical section, and the tile counters are handed
+    out atomically, so every result must still match the oracle."""
+    import threading
+    torch = torch_cuda
+    from nlotrajectories_b200.sdf import LearnedSDF
+    nets = [so.synthetic_mlp(128, 1, seed=31), so.synthetic_mlp(128, 1, seed=32)]
+    models = [LearnedSDF(to_weights(n)) for n in nets]
+    P = sample_points(40000, seed=5)
+    refs = [so.value_jac(n.astype(np.float64), P.astype(np.float64))[0] for n in nets]
+    x = torch.from_numpy(P[:, 0].copy()).cuda(); y = torch.from_numpy(P[:, 1].copy()).cuda()
+    torch.cuda.synchronize()
+    bad = [0, 0]
+
+    def work(i):
+        torch.cuda.set_device(0)
+        st = torch.cuda.Stream()
+        for _ in range(40):
+            with torch.cuda.stream(st):
+                s, _, _ = models[i].eval(x, y)
+            st.synchronize()
+            bad[i] += int(close(s.cpu().numpy(), refs[i], TOL).sum())
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert bad == [0, 0]
+    for m in models:
+        m.close()
