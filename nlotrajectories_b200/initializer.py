@@ -126,10 +126,49 @@ class RRTInitializer:
         return traj
 
 
-def rrt_multistart(cfg, P: int, first: int = 0, seed0: int = 1234) -> np.ndarray:
+def lift_path(X: np.ndarray, dynamic: str, dt: float, wheelbase: Optional[float] = None, control_bounds=None):
+    """Fill the states the planner leaves at zero from the geometry of its (x, y) path, so that the forward-Euler defects of
+    the position rows vanish: heading = direction of p[k+1] - p[k], speed = |p[k+1] - p[k]| / dt, turn rate / steering angle
+    from the heading differences.  Not in the reference (its guess keeps zeros, core/trajectory_initialization.py:228-231); used
+    by the batched solve, whose interior point has no restoration phase to recover from a kinematically inconsistent start.
+    Returns (X, U) with U (N, nu) the controls the dynamics read directly (zeros elsewhere); the caller restores the pinned start state."""
+    X = X.copy()
+    n = X.shape[0]
+    d = np.diff(X[:, :2], axis=0)
+    d = np.vstack([d, d[-1:]])
+    speed = np.linalg.norm(d, axis=1) / dt
+    th = np.unwrap(np.arctan2(d[:, 1], d[:, 0]))
+    om = np.append(np.diff(th), 0.0) / dt
+    nu = {"point_1st": 2, "point_2nd": 2, "unicycle": 2, "unicycle_2nd": 2, "ackermann": 2, "ackermann_2nd": 2}[dynamic]
+    U = np.zeros((n - 1, nu))
+    if dynamic == "point_1st":
+        U[:, 0:2] = d[:-1] / dt
+    elif dynamic == "point_2nd":
+        X[:, 2:4] = d / dt
+    elif dynamic == "unicycle":
+        X[:, 2] = th
+        U[:, 0], U[:, 1] = speed[:-1], om[:-1]
+    elif dynamic == "unicycle_2nd":
+        X[:, 2], X[:, 3], X[:, 4] = th, speed, om
+    else:
+        L = float(wheelbase)
+        psi = np.arctan(L * om / np.maximum(speed, 1e-6))
+        X[:, 2], X[:, 3] = th, psi
+        if dynamic == "ackermann":
+            U[:, 0], U[:, 1] = speed[:-1], (np.append(np.diff(psi), 0.0) / dt)[:-1]
+        else:
+            X[:, 4] = speed                                  # the slot the reference's model reads as v (core/dynamics.py:131-148)
+            X[:, 6] = np.append(np.diff(psi), 0.0) / dt
+    if control_bounds is not None:
+        for i, (lo, hi) in enumerate(control_bounds):
+            U[:, i] = np.clip(U[:, i], 0.95 * lo, 0.95 * hi)
+    return X, U
+
+
+def rrt_multistart(cfg, P: int, first: int = 0, seed0: int = 1234, lift: bool = False) -> np.ndarray:
     """(P, n_w) initial decision vectors for a benchmark config: start i plans its own RRT path with seed ``seed0 + first + i``
     over the exact SDF of the YAML's obstacles (X from the planner, U and slack zero: core/runner.py:106-108).  Starts whose planner
-    fails within ``max_iter`` fall back to the straight line."""
+    fails within ``max_iter`` fall back to the straight line.  ``lift=True`` fills heading / speed / steering from the path (``lift_path``)."""
     from .problem import DYN_DIMS
     from .train import scene_sdf
     b, s = cfg.body, cfg.solver
@@ -153,5 +192,9 @@ def rrt_multistart(cfg, P: int, first: int = 0, seed0: int = 1234) -> np.ndarray
             X = planner.get_initial_guess()
         except RuntimeError:
             X = np.linspace(np.asarray(b.start_state, float), np.asarray(b.goal_state, float), N + 1)
+        if lift:
+            X, U = lift_path(X, b.dynamic, s.dt, getattr(b, "wheelbase", None), b.control_bounds)
+            X[0] = np.asarray(b.start_state, float)              # pinned by the NLP (core/runner.py:60)
+            w[i, n_X:n_X + n_U] = U.reshape(-1)
         w[i, :n_X] = X.reshape(-1)
     return w

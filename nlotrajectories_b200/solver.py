@@ -210,6 +210,69 @@ class DeviceEvaluator:
         return H
 
 
+class ElasticEvaluator:
+    """Elastic mode for the one-sided inequality rows (exact l1 penalty, the device SNOPT-style codes use where IPOPT would
+    enter its restoration phase): row r becomes ``g_r(w) + p_r >= lb_r`` (``g_r(w) - p_r <= ub_r``) with a new variable
+    ``p_r >= 0`` that costs ``penalty * p_r``.  Every start is then strictly feasible for the inequality rows, and a solution
+    with ``p <= tol`` satisfies the original KKT conditions (multipliers below ``penalty``).  Wraps any evaluator with the
+    ``eval`` / ``hess`` interface; ``split(w)`` returns the original variables and the elastic ones."""
+
+    def __init__(self, ev, lbg, ubg, penalty: float = 100.0):
+        lbg, ubg = np.asarray(lbg, np.float64), np.asarray(ubg, np.float64)
+        lo_only = np.isfinite(lbg) & ~np.isfinite(ubg)
+        up_only = np.isfinite(ubg) & ~np.isfinite(lbg)
+        self.rows = np.nonzero(lo_only | up_only)[0]
+        self.sign = np.where(lo_only[self.rows], 1.0, -1.0)
+        self.ev, self.penalty = ev, float(penalty)
+        self.m = len(self.rows)
+        self.n_w0, self.n_g0 = ev.n_w, ev.n_g
+        self.n_w, self.n_g = ev.n_w + self.m, ev.n_g + self.m
+        self.lbg = np.concatenate([lbg, np.zeros(self.m)])
+        self.ubg = np.concatenate([ubg, np.full(self.m, np.inf)])
+
+    @property
+    def evals(self):
+        return self.ev.evals
+
+    def split(self, w):
+        return w[:, :self.n_w0], w[:, self.n_w0:]
+
+    def initial(self, w0, margin: float = 1e-2):
+        """Append elastic variables that make every elastic row satisfied with ``margin`` to spare."""
+        import torch
+        _, _, g, _ = self.ev.eval(w0, want_jac=False)
+        rows = torch.from_numpy(self.rows).to(w0.device); sign = torch.from_numpy(self.sign).to(w0.device)
+        bound = torch.from_numpy(np.where(self.sign > 0, self.lbg[self.rows], self.ubg[self.rows])).to(w0.device)
+        short = sign * (bound - g[:, rows].double())                       # > 0 where the row is violated
+        return torch.cat([w0, torch.clamp(short, min=0.0) + margin], dim=1)
+
+    def eval(self, w, want_jac=True):
+        import torch
+        w0, p = self.split(w)
+        f, grad, g, J = self.ev.eval(w0.contiguous(), want_jac)
+        P, dev = w.shape[0], w.device
+        rows = torch.from_numpy(self.rows).to(dev); sign = torch.from_numpy(self.sign).to(dev)
+        g2 = torch.cat([g, p], dim=1)
+        g2[:, rows] += sign * p
+        f2 = f + self.penalty * p.sum(1)
+        if not want_jac:
+            return f2, None, g2, None
+        grad2 = torch.cat([grad, torch.full((P, self.m), self.penalty, dtype=grad.dtype, device=dev)], dim=1)
+        J2 = torch.zeros((P, self.n_g, self.n_w), dtype=J.dtype, device=dev)
+        J2[:, :self.n_g0, :self.n_w0] = J
+        idx = torch.arange(self.m, device=dev)
+        J2[:, rows, self.n_w0 + idx] = sign
+        J2[:, self.n_g0 + idx, self.n_w0 + idx] = 1.0
+        return f2, grad2, g2, J2
+
+    def hess(self, w, sigma, lam):
+        import torch
+        H = self.ev.hess(w[:, :self.n_w0].contiguous(), sigma, lam[:, :self.n_g0].contiguous())
+        H2 = torch.zeros((w.shape[0], self.n_w, self.n_w), dtype=H.dtype, device=w.device)
+        H2[:, :self.n_w0, :self.n_w0] = H
+        return H2
+
+
 @dataclass
 class IPResult:
     w: "object"            # (P, n_w) fp64

@@ -50,3 +50,26 @@ def test_rrt_raises_like_the_reference_when_no_path_exists():
     p = RRTInitializer(11, [0, 0], [1, 0], 0.1, wall, [[0, -1], [1, 1]], rectangle=False, max_iter=200, seed=0)
     with pytest.raises(RuntimeError, match="RRT failed"):
         p.get_initial_guess()
+
+
+@pytest.mark.parametrize("name", ["benchmark_3", "benchmark_5"])
+def test_lifted_guess_zeroes_the_position_defects(name):
+    """lift_path: heading and speed read off the planned path make the forward-Euler defects of the (x, y) rows vanish
+    (up to the clipping of the controls), the pinned start state is restored."""
+    import yaml
+    from oracle import nlp_oracle as no
+    from nlotrajectories_b200.config import Config
+    from nlotrajectories_b200.initializer import rrt_multistart
+    from conftest import bench_yaml
+    cfg = Config.load(bench_yaml(name))
+    spec = no.NlpSpec.from_yaml_dict(yaml.safe_load(open(bench_yaml(name))))
+    w_flat = rrt_multistart(cfg, 2, lift=False).astype(np.float64)
+    w_lift = rrt_multistart(cfg, 2, lift=True).astype(np.float64)
+    np.testing.assert_allclose(w_lift[:, :spec.nx], np.tile(np.asarray(cfg.body.start_state, float), (2, 1)), atol=1e-6)
+    X0, U0, _ = no.unpack(spec, w_flat)
+    X1, U1, _ = no.unpack(spec, w_lift)
+    np.testing.assert_allclose(X1[:, 1:, :2], X0[:, 1:, :2], atol=1e-6)        # the planned positions are kept
+    def pos_defect(X, U):
+        f, _, _ = no.dynamics_f(spec, X[:, :-1], U)
+        return np.abs(X[:, 1:, :2] - X[:, :-1, :2] - spec.dt * f[..., :2])[:, 1:]   # knot 0 holds the pinned start heading
+    assert pos_defect(X1, U1).max() < 0.2 * pos_defect(X0, U0).max()

@@ -72,3 +72,43 @@ def test_run_benchmark_run_returns_reference_shapes(library):
     assert d.min() >= 0.25 - 1e-4                                                     # radius + margin
     path = np.sqrt(np.diff(X_opt[0]) ** 2 + np.diff(X_opt[1]) ** 2 + 1e-8).sum()
     assert abs(path - B1_OPT) < 3e-4
+
+
+def test_ackermann_with_slack_converges_from_rest_on_the_oracle():
+    """benchmark_5: the linearised dynamics are inconsistent at the all-zero guess (vehicle at rest); the least-squares equality
+    multipliers keep the Hessian of the Lagrangian bounded and both starts reach tol 1e-4."""
+    import torch
+    from nlotrajectories_b200.solver import BatchedIPSolver
+    spec = no.NlpSpec.from_yaml_dict(yaml.safe_load(open(bench_yaml("benchmark_5"))))
+    lb, ub = no.bounds(spec)
+    w0 = no.multistart_guess(spec, 2)
+    res = BatchedIPSolver(OracleEvaluator(spec), lb, ub, max_iter=200).solve(torch.from_numpy(w0))
+    assert bool(res.converged.all()), res.kkt_error
+    assert np.all(np.abs(res.f.numpy() - 1.6205) < 2e-3), res.f
+    assert np.all(res.violation.numpy() < 1e-4)
+
+
+def test_elastic_evaluator_reproduces_the_plain_solution():
+    """Exact l1 penalty on the one-sided inequality rows: with a penalty above the multipliers the elastic variables end at
+    zero (to the barrier's share) and the objective is the plain problem's."""
+    import torch
+    from nlotrajectories_b200.solver import BatchedIPSolver, ElasticEvaluator
+    spec = no.NlpSpec.from_yaml_dict(yaml.safe_load(open(bench_yaml("benchmark_1"))))
+    lb, ub = no.bounds(spec)
+    w0 = torch.from_numpy(no.multistart_guess(spec, 2))
+    ev = ElasticEvaluator(OracleEvaluator(spec), lb, ub, penalty=100.0)
+    assert ev.n_w == spec.n_w + ev.m and ev.n_g == spec.n_g + ev.m and ev.m > 0
+    w1 = ev.initial(w0)
+    # the wrapped functions: value rows shifted by p, Jacobian / Hessian blocks consistent with finite differences
+    f, grad, g, J = ev.eval(w1)
+    h = 1e-6
+    d = torch.from_numpy(np.random.default_rng(0).standard_normal(w1.shape))
+    f2, _, g2, _ = ev.eval(w1 + h * d, want_jac=False)
+    f0, _, g0, _ = ev.eval(w1 - h * d, want_jac=False)
+    assert torch.allclose((f2 - f0) / (2 * h), (grad * d).sum(1), atol=1e-5)
+    assert torch.allclose((g2 - g0) / (2 * h), torch.einsum("prw,pw->pr", J, d), atol=1e-5)
+    res = BatchedIPSolver(ev, ev.lbg, ev.ubg, max_iter=200).solve(w1)
+    assert bool(res.converged.all())
+    w, p = ev.split(res.w)
+    assert float(p.max()) < 1e-4
+    assert np.all(np.abs(res.f.numpy() - B1_OPT) < 2e-2)

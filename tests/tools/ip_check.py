@@ -27,10 +27,10 @@ net = so.from_npz(weights) if weights else None
 model = LearnedSDF(to_weights(net)) if cfg.solver.mode == "l4casadi" else None
 prob = NlpProblem.from_config(cfg, model)
 lb, ub = prob.bounds()
-if init == "rrt":
+if init.startswith("rrt"):
     from nlotrajectories_b200.initializer import rrt_multistart
     t0 = time.time()
-    w0 = rrt_multistart(cfg, P).astype(np.float64)
+    w0 = rrt_multistart(cfg, P, lift=init == "rrt_lift").astype(np.float64)
     print(f"{name}: {P} RRT initial guesses in {time.time() - t0:.1f} s (host)", flush=True)
 else:
     w0 = prob.multistart_guess(P).astype(np.float64)
@@ -46,6 +46,8 @@ best = np.where(use, f, np.inf).argmin()
 q = lambda m: f"{f[m].min():.6f} / {np.median(f[m]):.6f} / {f[m].max():.6f}" if m.any() else "-"
 print(f"{name}: P={P} batched IP on GPU: {dt:.1f} s, {ev.evals} batched evaluations; converged {ok.mean() * 100:.1f}% (iterations median {np.median(its[ok]) if ok.any() else -1:.0f}), "
       f"stalled-feasible {stl.mean() * 100:.1f}%; f over converged min/med/max {q(ok)}; over stalled-feasible {q(stl)}; best start {best} f={f[best]:.6f} viol={v[best]:.1e}", flush=True)
+if n_ref == 0:
+    sys.exit(0)
 # CPU: same algorithm on the fp64 oracle, and SLSQP, for the first n_ref starts
 cpu = BatchedIPSolver(OracleEvaluator(spec, net), lb, ub, max_iter=300).solve(torch.from_numpy(w0[:n_ref]))
 n64 = net.astype(np.float64) if net is not None else None
