@@ -41,11 +41,12 @@ def synthetic_weights(cfg: Config, seed: int = 0) -> SdfWeights:
                            m.omega_0, m.omega_0)
 
 
-def solve_benchmark(config_path: Path, batch: int = 64, weights: str | None = None, precision: str = "auto", verbose: bool = True):
+def solve_benchmark(config_path: Path, batch: int = 64, weights: str | None = None, precision: str = "auto", verbose: bool = True,
+                    lift: bool = False, elastic: float | None = None):
     """``--solve``: every start of this rank's shard goes through the batched interior point (solver.py); the best
     converged objective across ranks is selected with the same all-gather + broadcast as the evaluation path."""
     import torch
-    from .solver import BatchedIPSolver, DeviceEvaluator
+    from .solver import BatchedIPSolver, DeviceEvaluator, solve_elastic
     rank, local_rank, world = init_process_group("nccl")
     torch.cuda.set_device(local_rank)
     cfg = Config.load(config_path)
@@ -57,12 +58,15 @@ def solve_benchmark(config_path: Path, batch: int = 64, weights: str | None = No
     dev = torch.device("cuda", local_rank)
     if cfg.solver.initializer.mode == "rrt":                     # the YAML's initializer (scripts/run_benchmark.py:114-127), one seed per start
         from .initializer import rrt_multistart
-        w0 = torch.from_numpy(rrt_multistart(cfg, hi - lo, first=lo).astype(np.float64)).to(dev)
+        w0 = torch.from_numpy(rrt_multistart(cfg, hi - lo, first=lo, lift=lift).astype(np.float64)).to(dev)
     else:
         w0 = torch.from_numpy(prob.multistart_guess(hi - lo, first=lo).astype(np.float64)).to(dev)
     lb, ub = prob.bounds()
     t0 = time.time()
-    res = BatchedIPSolver(DeviceEvaluator(prob), lb, ub, verbose=verbose and rank == 0).solve(w0)
+    if elastic:
+        res = solve_elastic(DeviceEvaluator(prob), lb, ub, w0, penalty=float(elastic), verbose=verbose and rank == 0)
+    else:
+        res = BatchedIPSolver(DeviceEvaluator(prob), lb, ub, verbose=verbose and rank == 0).solve(w0)
     torch.cuda.synchronize()
     dt = time.time() - t0
     usable = res.converged | (res.stalled & (res.violation <= 1e-4))
@@ -124,9 +128,11 @@ def main():
     ap.add_argument("--weights", type=str, default=None, help="SDF weights (.nlow, .npz, TorchScript .pt or state_dict .pt)")
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tc3xf16"])
     ap.add_argument("--solve", action="store_true", help="solve every start (batched interior point) instead of evaluating the initial guesses")
+    ap.add_argument("--lift", action="store_true", help="--solve: fill heading / speed / steering of the RRT guesses from the planned path")
+    ap.add_argument("--elastic", type=float, default=None, metavar="PENALTY", help="--solve: elastic mode (exact l1 penalty) on the inequality rows")
     a = ap.parse_args()
     if a.solve:
-        solve_benchmark(Path(a.config), min(a.batch, 512), a.weights, a.precision)
+        solve_benchmark(Path(a.config), min(a.batch, 512), a.weights, a.precision, lift=a.lift, elastic=a.elastic)
     else:
         run_benchmark(Path(a.config), a.batch, a.weights, a.precision)
     import torch.distributed as dist

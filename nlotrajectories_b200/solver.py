@@ -492,3 +492,18 @@ class BatchedIPSolver:
         lam = torch.zeros((P, ev.n_g), dtype=torch.float64, device=dev)
         lam[:, iE] = lam_E; lam[:, iI] = z_u - z_l
         return IPResult(w=w, f=f, violation=viol, kkt_error=err0, iterations=iters, converged=done & ~stalled, lam=lam, stalled=stalled)
+
+
+def solve_elastic(evaluator, lbg, ubg, w0, penalty: float = 1000.0, **solver_kw) -> IPResult:
+    """Solve in elastic mode and report in the original problem's terms: ``w`` / ``lam`` without the elastic parts, ``f`` without
+    the penalty, ``violation`` including what the elastic variables still absorb (a start whose ``p`` stays above tol is locally
+    infeasible, not converged)."""
+    import torch
+    el = ElasticEvaluator(evaluator, lbg, ubg, penalty)
+    tol = solver_kw.get("tol", 1e-4)
+    res = BatchedIPSolver(el, el.lbg, el.ubg, **solver_kw).solve(el.initial(w0))
+    w, p = el.split(res.w)
+    viol = torch.maximum(res.violation, p.amax(1) if el.m else torch.zeros_like(res.violation))
+    feasible = viol <= tol
+    return IPResult(w=w.contiguous(), f=res.f - penalty * p.sum(1), violation=viol, kkt_error=res.kkt_error, iterations=res.iterations,
+                    converged=res.converged & feasible, lam=res.lam[:, :el.n_g0].contiguous(), stalled=res.stalled & feasible)

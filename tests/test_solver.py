@@ -112,3 +112,17 @@ def test_elastic_evaluator_reproduces_the_plain_solution():
     w, p = ev.split(res.w)
     assert float(p.max()) < 1e-4
     assert np.all(np.abs(res.f.numpy() - B1_OPT) < 2e-2)
+
+
+def test_solve_elastic_reports_in_original_terms():
+    import torch
+    from nlotrajectories_b200.solver import solve_elastic
+    spec = no.NlpSpec.from_yaml_dict(yaml.safe_load(open(bench_yaml("benchmark_1"))))
+    lb, ub = no.bounds(spec)
+    w0 = torch.from_numpy(no.multistart_guess(spec, 2))
+    res = solve_elastic(OracleEvaluator(spec), lb, ub, w0, penalty=100.0, max_iter=200)
+    assert res.w.shape == (2, spec.n_w) and res.lam.shape == (2, spec.n_g)
+    assert bool(res.converged.all())
+    f_orig, _ = no.eval_f_grad(spec, res.w.numpy())
+    np.testing.assert_allclose(res.f.numpy(), f_orig, atol=1e-9)
+    assert np.all(np.abs(f_orig - B1_OPT) < 2e-3)
