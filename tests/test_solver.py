@@ -126,3 +126,32 @@ def test_solve_elastic_reports_in_original_terms():
     f_orig, _ = no.eval_f_grad(spec, res.w.numpy())
     np.testing.assert_allclose(res.f.numpy(), f_orig, atol=1e-9)
     assert np.all(np.abs(f_orig - B1_OPT) < 2e-3)
+
+
+@pytest.mark.gpu
+def test_benchmark_6_solves_on_the_gpu_path_with_the_trained_network(library):
+    """The headline YAML end to end: learned ReLU SDF (weights trained by train.py at the YAML's sample count), RRT guesses lifted
+    from the path, batched interior point over the tensor-core SDF kernels (values, Jacobian and the fused Hessian route)."""
+    import torch
+    from gpu_util import to_weights
+    from oracle import sdf_oracle as so
+    from conftest import GOLDEN
+    from nlotrajectories_b200.config import Config
+    from nlotrajectories_b200.initializer import rrt_multistart
+    from nlotrajectories_b200.problem import NlpProblem
+    from nlotrajectories_b200.sdf import LearnedSDF
+    from nlotrajectories_b200.solver import BatchedIPSolver, DeviceEvaluator
+    cfg = Config.load(bench_yaml("benchmark_6"))
+    model = LearnedSDF(to_weights(so.from_npz(str(GOLDEN / "sdf_benchmark_6_relu128.npz"))))
+    prob = NlpProblem.from_config(cfg, model)
+    lb, ub = prob.bounds()
+    w0 = rrt_multistart(cfg, 8, lift=True).astype(np.float64)
+    res = BatchedIPSolver(DeviceEvaluator(prob), lb, ub, max_iter=200).solve(torch.from_numpy(w0).cuda())
+    usable = (res.converged | res.stalled).cpu().numpy() & (res.violation.cpu().numpy() <= 1e-4)
+    assert usable.mean() >= 0.5, (res.kkt_error, res.violation)
+    f = res.f.cpu().numpy()[usable]
+    assert abs(f.min() - 9.30927) < 5e-3, f
+    # the solution respects the learned SDF at every footprint point and the control bounds
+    g = DeviceEvaluator(prob).eval(res.w, want_jac=False)[2].cpu().numpy()[usable]
+    assert np.all(g >= lb[None] - 1e-4) and np.all(g <= ub[None] + 1e-4)
+    model.close()

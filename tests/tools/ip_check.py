@@ -19,7 +19,7 @@ name = sys.argv[1] if len(sys.argv) > 1 else "benchmark_1"
 P = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 n_ref = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 weights = sys.argv[4] if len(sys.argv) > 4 and sys.argv[4] != "-" else None
-init = sys.argv[5] if len(sys.argv) > 5 else "multistart"          # "multistart" (seeded lateral offsets) | "rrt" (seeded planner per start)
+init = sys.argv[5] if len(sys.argv) > 5 else "multistart"          # "multistart" (seeded lateral offsets) | "rrt" (seeded planner per start) | "rrt_lift"
 ypath = next((REPO / "nlotrajectories_b200/benchmarks").glob(name + "*.yaml"))
 cfg = Config.load(ypath)
 spec = no.NlpSpec.from_yaml_dict(yaml.safe_load(open(ypath)))
@@ -36,7 +36,12 @@ else:
     w0 = prob.multistart_guess(P).astype(np.float64)
 ev = DeviceEvaluator(prob)
 t0 = time.time()
-res = BatchedIPSolver(ev, lb, ub, verbose=True, max_iter=300).solve(torch.from_numpy(w0).cuda())
+elastic = float(sys.argv[6]) if len(sys.argv) > 6 else 0.0          # > 0: elastic mode with this penalty
+if elastic > 0:
+    from nlotrajectories_b200.solver import solve_elastic
+    res = solve_elastic(ev, lb, ub, torch.from_numpy(w0).cuda(), penalty=elastic, verbose=True, max_iter=300)
+else:
+    res = BatchedIPSolver(ev, lb, ub, verbose=True, max_iter=300).solve(torch.from_numpy(w0).cuda())
 torch.cuda.synchronize()
 dt = time.time() - t0
 f = res.f.cpu().numpy(); v = res.violation.cpu().numpy(); ok = res.converged.cpu().numpy(); its = res.iterations.cpu().numpy()
