@@ -81,7 +81,7 @@ def solve_benchmark(config_path: Path, batch: int = 64, weights: str | None = No
 
 
 def run_benchmark(config_path: Path, batch: int = 4096, weights: str | None = None, precision: str = "auto",
-                  repeats: int = 3, verbose: bool = True):
+                  repeats: int = 3, verbose: bool = True, sdf_metrics: bool = False):
     import torch
     rank, local_rank, world = init_process_group("nccl")
     torch.cuda.set_device(local_rank)
@@ -116,6 +116,11 @@ def run_benchmark(config_path: Path, batch: int = 4096, weights: str | None = No
     out = {"config": str(config_path), "batch": batch, "world": world, "n_w": prob.n_w, "n_g": prob.n_g, "nnz_jac": prob.nnz,
            "sdf_points_per_eval": prob.n_sdf_points if sdf is not None else 0, "precision": sdf.precision if sdf else None,
            "eval_ms_rank0": dt * 1e3, "problem_evals_per_s_rank0": P / dt, "best_merit": best_val, "best_start": best_idx}
+    if sdf_metrics and sdf is not None and rank == 0:              # scripts/run_benchmark.py:34-46, 203-205 (1000^2 grid)
+        from .metrics import compute_metrics
+        from .train import scene_sdf
+        names = ("mse", "iou", "hausdorff", "chamfer", "surface_loss")
+        out["sdf_metrics"] = dict(zip(names, compute_metrics(sdf, scene_sdf(cfg))))
     if rank == 0 and verbose:
         print(json.dumps(out))
     return out, w_best.cpu().numpy()
@@ -130,11 +135,12 @@ def main():
     ap.add_argument("--solve", action="store_true", help="solve every start (batched interior point) instead of evaluating the initial guesses")
     ap.add_argument("--lift", action="store_true", help="--solve: fill heading / speed / steering of the RRT guesses from the planned path")
     ap.add_argument("--elastic", type=float, default=None, metavar="PENALTY", help="--solve: elastic mode (exact l1 penalty) on the inequality rows")
+    ap.add_argument("--sdf-metrics", action="store_true", help="also report the learned SDF's quality metrics on the 1000^2 grid")
     a = ap.parse_args()
     if a.solve:
         solve_benchmark(Path(a.config), min(a.batch, 512), a.weights, a.precision, lift=a.lift, elastic=a.elastic)
     else:
-        run_benchmark(Path(a.config), a.batch, a.weights, a.precision)
+        run_benchmark(Path(a.config), a.batch, a.weights, a.precision, sdf_metrics=a.sdf_metrics)
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():
         dist.destroy_process_group()

@@ -235,14 +235,45 @@ def make_nlp_golden(ref: Path, net: so.SdfNet, names, P: int = 3):
         print(f"{name}: n_w={spec.n_w} n_g={len(opti.g_rows)} nnz={len(rows)}")
 
 
+def make_metrics_golden(ref: Path):
+    """The reference's own core/metrics.py (numpy + torch only, importable here) on small seeded fields: a circle's exact SDF
+    as target, smooth perturbations of it as predictions, plus the empty-band / empty-occupancy corner cases."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_metrics", ref / "src/nlotrajectories/core/metrics.py")
+    rm = importlib.util.module_from_spec(spec); spec.loader.exec_module(rm)
+    n = 96
+    x = np.linspace(-1.0, 2.0, n); X, Y = np.meshgrid(x, x)
+    target = np.hypot(X - 0.5, Y - 0.4) - 0.45
+    out = {"X": X, "Y": Y, "target": target}
+    rng = np.random.default_rng(7)
+    cases = {"shifted": np.hypot(X - 0.53, Y - 0.38) - 0.43,
+             "wavy": target + 0.03 * np.sin(7 * X) * np.cos(5 * Y),
+             "noisy": target + 0.02 * rng.standard_normal(target.shape),
+             "far": target + 5.0}                                        # no surface band, no occupancy in the prediction
+    for name, pred in cases.items():
+        eps = 0.04
+        vals = [rm.mse(target, pred), rm.iou(target, pred, threshold=0.0), rm.hausdorff(pred, target, X, Y, eps=eps),
+                rm.chamfer(pred, target, X, Y, eps=eps), rm.surface_loss(target, pred, eps=eps)]
+        out["pred_" + name] = pred
+        out["vals_" + name] = np.array([np.nan if v is None else float(v) for v in vals])
+    out["eps"] = np.array(0.04)
+    out["iou_both_empty"] = np.array(float(rm.iou(target + 5.0, target + 6.0)))
+    np.savez_compressed(GOLD / "metrics_reference.npz", **out)
+    print("wrote", GOLD / "metrics_reference.npz", {k: v for k, v in out.items() if k.startswith("vals_")})
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reference", default="/root/reference")
     ap.add_argument("--only", default="")
     ap.add_argument("--hessian", action="store_true", help="(re)generate only the Hessian-of-the-Lagrangian fixtures")
+    ap.add_argument("--metrics", action="store_true", help="(re)generate only the SDF-quality metric fixtures")
     a = ap.parse_args()
     ref = Path(a.reference)
     GOLD.mkdir(parents=True, exist_ok=True)
+    if a.metrics:
+        make_metrics_golden(ref)
+        return
     net = None if a.hessian else make_sdf_golden(ref)
     names = ["benchmark_1", "benchmark_2", "benchmark_3", "benchmark_4", "benchmark_6"]
     if a.only:
