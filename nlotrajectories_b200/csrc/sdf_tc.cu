@@ -399,7 +399,7 @@ sdf_tc_kernel(SdfNetDev net, TcParams prm_tc, const __half* __restrict__ bimg, c
   c.mbar_addr = smem_u32(mbar + grp);
   c.bar_id = 1 + grp;
   c.lock = lock;
-  c.ctr = tile_ctr; c.next_slot = next_tile + grp; c.ctr_bias = gridDim.x * Cfg::NGROUPS;
+  c.ctr = tile_ctr; c.next_slot = next_tile + grp; c.ctr_bias = 2 * gridDim.x * Cfg::NGROUPS;
   c.act0 = ACT0 >= 0 ? ACT0 : net.act0; c.act = ACT >= 0 ? ACT : net.act;
   c.prm0 = net.p0; c.prm = net.p; c.inv_sw = prm_tc.inv_sw;
   c.unscale2 = RH ? prm_tc.inv_sv : prm_tc.inv_sc1 * prm_tc.inv_sw;
@@ -414,7 +414,17 @@ sdf_tc_kernel(SdfNetDev net, TcParams prm_tc, const __half* __restrict__ bimg, c
   int it = 0;
   // tiles: the first one by position, the rest from the global counter (SMs do not all run at the same speed; static
   // striding left the slowest 25 % behind) - or by striding when no counter is given (small launches)
+  // The counter runs two tiles ahead: the index of the tile after this one is known when this one starts, so its coordinates
+  // can be pulled towards the SM while this tile computes (the loads at the top of a tile are otherwise an exposed DRAM latency).
+  const size_t stride = (size_t)gridDim.x * Cfg::NGROUPS;
+  size_t tile_next = (size_t)blockIdx.x * Cfg::NGROUPS + grp + stride;
   for (size_t tile = (size_t)blockIdx.x * Cfg::NGROUPS + grp; tile < n_tiles; ++it) {
+    if (tile_next < n_tiles && half == 0) {
+      const size_t in = min(tile_next * TILE + pt, n - 1);
+      asm volatile("prefetch.global.L1 [%0];" :: "l"(x + in));
+      asm volatile("prefetch.global.L1 [%0];" :: "l"(y + in));
+      if (sbar) asm volatile("prefetch.global.L1 [%0];" :: "l"(sbar + in));
+    }
     // timeline: groups 0 and 1 of CTA 0, first 64 tiles
     c.dbg = (dbg && (it & 15) == 0 && (it >> 4) < 64 && blockIdx.x == 0 && grp < 2) ? dbg + (grp * 64 + (it >> 4)) * 32 : nullptr;
     const size_t i = tile * TILE + pt;
@@ -436,7 +446,8 @@ sdf_tc_kernel(SdfNetDev net, TcParams prm_tc, const __half* __restrict__ bimg, c
                                                                                 (valid && jy_out) ? jy_out + i : nullptr, 0,
                                                                                 (HESS && valid) ? hxx_out + i : nullptr);
     }
-    tile = tile_ctr ? (size_t)next_tile[grp] : tile + (size_t)gridDim.x * Cfg::NGROUPS;
+    tile = tile_next;
+    tile_next = tile_ctr ? (size_t)next_tile[grp] : tile_next + stride;
   }
   tc_fence_before();
   __syncthreads();
