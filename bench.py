@@ -105,7 +105,7 @@ def synthetic_net():
 FLOP_PER_POINT = 4 * (3 * 128 + 128 * 128)      # value + Jacobian, 2->128->128->1 = 67,072
 # dram__bytes_read.sum + dram__bytes_write.sum of sdf_tc_kernel per point, from the ncu --set full capture committed
 # under profiles/ (profiles/r1_sdf_tc_kernel.md): 170.6 MB read + 207.1 MB written for 21,233,664 points (algorithmic: 20 B/point)
-NCU_DRAM_BYTES_PER_POINT = 17.8
+NCU_DRAM_BYTES_PER_POINT = 17.2
 BYTES_PER_EVAL = (727 + 1057 + 3225) * 4        # read w, write g and nnz(J) = 20,036 B / problem-eval
 DYN_BYTES_PER_PROBLEM = (567 + 160 + 560 + 2080) * 4   # K2 on benchmark_6 = 13,468 B / problem
 POINTS_PER_PROBLEM = 324
