@@ -165,10 +165,37 @@ def lift_path(X: np.ndarray, dynamic: str, dt: float, wheelbase: Optional[float]
     return X, U
 
 
-def rrt_multistart(cfg, P: int, first: int = 0, seed0: int = 1234, lift: bool = False) -> np.ndarray:
+_PLAN_STATE = None      # (cfg, sdf, body, bounds, lift): set before the worker pool forks, read by the workers
+
+
+def _plan_one(seed: int):
+    cfg, sdf, body, bounds, lift = _PLAN_STATE
+    from .problem import DYN_DIMS
+    b, s = cfg.body, cfg.solver
+    ini = s.initializer
+    N = s.N
+    nu = DYN_DIMS[b.dynamic][1]
+    planner = RRTInitializer(N + 1, b.start_state, b.goal_state, s.dt, sdf, bounds, body_points=body, rectangle=b.shape == "rectangle",
+                             step_size=ini.step_size, max_iter=ini.max_iter, margin=ini.margin, seed=seed)
+    try:
+        X = planner.get_initial_guess()
+    except RuntimeError:
+        X = np.linspace(np.asarray(b.start_state, float), np.asarray(b.goal_state, float), N + 1)
+    U = np.zeros((N, nu))
+    if lift:
+        X, U = lift_path(X, b.dynamic, s.dt, getattr(b, "wheelbase", None), b.control_bounds)
+        X[0] = np.asarray(b.start_state, float)              # pinned by the NLP (core/runner.py:60)
+    return X, U
+
+
+def rrt_multistart(cfg, P: int, first: int = 0, seed0: int = 1234, lift: bool = False, workers: Optional[int] = None) -> np.ndarray:
     """(P, n_w) initial decision vectors for a benchmark config: start i plans its own RRT path with seed ``seed0 + first + i``
     over the exact SDF of the YAML's obstacles (X from the planner, U and slack zero: core/runner.py:106-108).  Starts whose planner
-    fails within ``max_iter`` fall back to the straight line.  ``lift=True`` fills heading / speed / steering from the path (``lift_path``)."""
+    fails within ``max_iter`` fall back to the straight line.  ``lift=True`` fills heading / speed / steering from the path (``lift_path``).
+    The planners are independent: they run on a pool of forked host processes (``workers``, default one per host core up to 32;
+    numpy only - the children never touch CUDA), which is what keeps planning below the batched solve time."""
+    import os
+    global _PLAN_STATE
     from .problem import DYN_DIMS
     from .train import scene_sdf
     b, s = cfg.body, cfg.solver
@@ -176,7 +203,6 @@ def rrt_multistart(cfg, P: int, first: int = 0, seed0: int = 1234, lift: bool = 
     N = s.N
     n_X, n_U = nx * (N + 1), nu * N
     n_w = n_X + n_U + ((N + 1) if s.use_slack else 0)
-    sdf = scene_sdf(cfg)
     if b.shape == "rectangle":
         hl, hw = 0.5 * b.length, 0.5 * b.width
         body = [(-hl, -hw), (-hl, hw), (hl, hw), (hl, -hw)]                  # core/geometry.py:125-135
@@ -184,17 +210,19 @@ def rrt_multistart(cfg, P: int, first: int = 0, seed0: int = 1234, lift: bool = 
         body = None
     ini = s.initializer
     bounds = ini.rrt_bounds if ini.rrt_bounds is not None else [[-0.5, -0.5], [1.5, 1.5]]
+    _PLAN_STATE = (cfg, scene_sdf(cfg), body, bounds, lift)
+    seeds = [seed0 + first + i for i in range(P)]
+    if workers is None:
+        workers = min(32, os.cpu_count() or 1)
+    workers = min(workers, P)
+    if workers > 1 and P >= 4:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(workers) as pool:
+            plans = pool.map(_plan_one, seeds, chunksize=max(1, P // (4 * workers)))
+    else:
+        plans = [_plan_one(sd) for sd in seeds]
     w = np.zeros((P, n_w), np.float32)
-    for i in range(P):
-        planner = RRTInitializer(N + 1, b.start_state, b.goal_state, s.dt, sdf, bounds, body_points=body, rectangle=b.shape == "rectangle",
-                                 step_size=ini.step_size, max_iter=ini.max_iter, margin=ini.margin, seed=seed0 + first + i)
-        try:
-            X = planner.get_initial_guess()
-        except RuntimeError:
-            X = np.linspace(np.asarray(b.start_state, float), np.asarray(b.goal_state, float), N + 1)
-        if lift:
-            X, U = lift_path(X, b.dynamic, s.dt, getattr(b, "wheelbase", None), b.control_bounds)
-            X[0] = np.asarray(b.start_state, float)              # pinned by the NLP (core/runner.py:60)
-            w[i, n_X:n_X + n_U] = U.reshape(-1)
+    for i, (X, U) in enumerate(plans):
         w[i, :n_X] = X.reshape(-1)
+        w[i, n_X:n_X + n_U] = U.reshape(-1)
     return w

@@ -186,6 +186,27 @@ def test_tensor_paths_ragged_sizes(name, n, torch_cuda):
     model.close()
 
 
+@pytest.mark.parametrize("name", ["relu128", "relu64", "fourier128_relu"])
+@pytest.mark.parametrize("tiles_per_group", [1, 2, 3, 5])
+def test_counter_scheduled_tiles_two_ahead(name, tiles_per_group, torch_cuda):
+    """The tile counter of the H = 64 / 128 kernels runs two tiles ahead of the one being computed (the first two tiles of a group
+    come from its position, the rest from the counter; the next tile's coordinates are prefetched): sizes around 1, 2, 3 and 5
+    tiles per group, one point short of and one point past the boundary, must be covered exactly once."""
+    from nlotrajectories_b200.sdf import LearnedSDF
+    net = NETS[name]()
+    model = LearnedSDF(to_weights(net))
+    assert model.precision == "tc3xf16"
+    groups = 148 * (4 if name == "relu64" else 2)
+    for n in (128 * groups * tiles_per_group - 1, 128 * groups * tiles_per_group + 1):
+        P = sample_points(n, seed=7 + tiles_per_group)
+        s_ref, J_ref = so.value_jac(net.astype(np.float64), P.astype(np.float64))
+        s, J = run_device(model, torch_cuda, P)
+        tie = kink_mask(net, P)
+        assert not close(s, s_ref, TOL).any()
+        assert not (close(J, J_ref, TOL).any(axis=1) & ~tie).any()
+    model.close()
+
+
 def test_linearity_of_adjoint_and_full_size_property(torch_cuda):
     """Size-independent properties at sweep size (2^22 points): adj1(sbar) == sbar * jac, and the value
     from a value-only launch equals the value from a value+Jacobian launch bit for bit."""

@@ -73,3 +73,16 @@ def test_lifted_guess_zeroes_the_position_defects(name):
         f, _, _ = no.dynamics_f(spec, X[:, :-1], U)
         return np.abs(X[:, 1:, :2] - X[:, :-1, :2] - spec.dt * f[..., :2])[:, 1:]   # knot 0 holds the pinned start heading
     assert pos_defect(X1, U1).max() < 0.2 * pos_defect(X0, U0).max()
+
+
+def test_pooled_planners_match_the_serial_ones():
+    """rrt_multistart plans on forked host processes; every start owns its seed, so the result does not depend on the pool."""
+    from nlotrajectories_b200.config import Config
+    from nlotrajectories_b200.initializer import rrt_multistart
+    from conftest import bench_yaml
+    cfg = Config.load(bench_yaml("benchmark_3"))
+    a = rrt_multistart(cfg, 6, first=3, workers=1)
+    b = rrt_multistart(cfg, 6, first=3, workers=3)
+    c = rrt_multistart(cfg, 2, first=5, workers=1)
+    assert np.array_equal(a, b)
+    assert np.array_equal(a[2:4], c)                      # start i depends on first + i only: shards of a batch agree with the whole
