@@ -50,17 +50,19 @@ def solve_benchmark(config_path: Path, batch: int = 64, weights: str | None = No
     rank, local_rank, world = init_process_group("nccl")
     torch.cuda.set_device(local_rank)
     cfg = Config.load(config_path)
+    lo, hi = shard_range(batch, rank, world)
+    w0_host = None
+    if cfg.solver.initializer.mode == "rrt":                     # the YAML's initializer (scripts/run_benchmark.py:114-127), one seed per start;
+        from .initializer import rrt_multistart                  # planned on forked host processes, before this process creates its CUDA context
+        w0_host = rrt_multistart(cfg, hi - lo, first=lo, lift=lift).astype(np.float64)
     sdf = None
     if cfg.solver.mode == "l4casadi":
         sdf = LearnedSDF(SdfWeights.load(weights) if weights else synthetic_weights(cfg), device=local_rank, precision=precision)
     prob = NlpProblem.from_config(cfg, sdf, device=local_rank)
-    lo, hi = shard_range(batch, rank, world)
     dev = torch.device("cuda", local_rank)
-    if cfg.solver.initializer.mode == "rrt":                     # the YAML's initializer (scripts/run_benchmark.py:114-127), one seed per start
-        from .initializer import rrt_multistart
-        w0 = torch.from_numpy(rrt_multistart(cfg, hi - lo, first=lo, lift=lift).astype(np.float64)).to(dev)
-    else:
-        w0 = torch.from_numpy(prob.multistart_guess(hi - lo, first=lo).astype(np.float64)).to(dev)
+    if w0_host is None:
+        w0_host = prob.multistart_guess(hi - lo, first=lo).astype(np.float64)
+    w0 = torch.from_numpy(w0_host).to(dev)
     lb, ub = prob.bounds()
     t0 = time.time()
     if elastic:

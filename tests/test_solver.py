@@ -142,10 +142,10 @@ def test_benchmark_6_solves_on_the_gpu_path_with_the_trained_network(library):
     from nlotrajectories_b200.sdf import LearnedSDF
     from nlotrajectories_b200.solver import BatchedIPSolver, DeviceEvaluator
     cfg = Config.load(bench_yaml("benchmark_6"))
+    w0 = rrt_multistart(cfg, 8, lift=True, workers=1).astype(np.float64)      # in-process: this pytest process already holds a CUDA context
     model = LearnedSDF(to_weights(so.from_npz(str(GOLDEN / "sdf_benchmark_6_relu128.npz"))))
     prob = NlpProblem.from_config(cfg, model)
     lb, ub = prob.bounds()
-    w0 = rrt_multistart(cfg, 8, lift=True).astype(np.float64)
     res = BatchedIPSolver(DeviceEvaluator(prob), lb, ub, max_iter=200).solve(torch.from_numpy(w0).cuda())
     usable = (res.converged | res.stalled).cpu().numpy() & (res.violation.cpu().numpy() <= 1e-4)
     assert usable.mean() >= 0.5, (res.kkt_error, res.violation)

@@ -24,15 +24,16 @@ ypath = next((REPO / "nlotrajectories_b200/benchmarks").glob(name + "*.yaml"))
 cfg = Config.load(ypath)
 spec = no.NlpSpec.from_yaml_dict(yaml.safe_load(open(ypath)))
 net = so.from_npz(weights) if weights else None
-model = LearnedSDF(to_weights(net)) if cfg.solver.mode == "l4casadi" else None
-prob = NlpProblem.from_config(cfg, model)
-lb, ub = prob.bounds()
-if init.startswith("rrt"):
+w0 = None
+if init.startswith("rrt"):                                          # host processes fork before the CUDA context exists
     from nlotrajectories_b200.initializer import rrt_multistart
     t0 = time.time()
     w0 = rrt_multistart(cfg, P, lift=init == "rrt_lift").astype(np.float64)
     print(f"{name}: {P} RRT initial guesses in {time.time() - t0:.1f} s (host)", flush=True)
-else:
+model = LearnedSDF(to_weights(net)) if cfg.solver.mode == "l4casadi" else None
+prob = NlpProblem.from_config(cfg, model)
+lb, ub = prob.bounds()
+if w0 is None:
     w0 = prob.multistart_guess(P).astype(np.float64)
 ev = DeviceEvaluator(prob)
 t0 = time.time()
