@@ -293,9 +293,9 @@ class BatchedIPSolver:
     costs one batched evaluation + one batched Hessian + one batched dense KKT solve (n_w + n_eq unknowns)."""
 
     def __init__(self, evaluator, lbg, ubg, tol: float = 1e-4, max_iter: int = 300, mu0: float = 0.1, verbose: bool = False,
-                 ls_multipliers: bool = True):
+                 ls_multipliers: bool = True, compact: bool = True):
         self.ev, self.tol, self.max_iter, self.mu0, self.verbose = evaluator, tol, max_iter, mu0, verbose
-        self.ls_multipliers = ls_multipliers
+        self.ls_multipliers, self.compact = ls_multipliers, compact
         self.lbg, self.ubg = np.asarray(lbg, np.float64), np.asarray(ubg, np.float64)
 
     def solve(self, w0) -> IPResult:
@@ -338,8 +338,32 @@ class BatchedIPSolver:
         err0 = torch.full((P,), float("inf"), dtype=torch.float64, device=dev)
         stalled = torch.zeros(P, dtype=torch.bool, device=dev)
         f_mark = f.clone()
+        # finished starts leave the working set (every 10 iterations, once a quarter of it is done): an iteration costs one
+        # evaluation, one Hessian and one dense KKT solve per ACTIVE start, so a few stragglers no longer pay for the whole batch
+        P0 = P
+        idx = torch.arange(P0, device=dev)
+        out = dict(w=torch.empty((P0, n_w), dtype=torch.float64, device=dev), f=torch.empty(P0, dtype=torch.float64, device=dev),
+                   viol=torch.empty(P0, dtype=torch.float64, device=dev), err=torch.empty(P0, dtype=torch.float64, device=dev),
+                   iters=torch.empty(P0, dtype=torch.int64, device=dev), conv=torch.zeros(P0, dtype=torch.bool, device=dev),
+                   stalled=torch.zeros(P0, dtype=torch.bool, device=dev), lam=torch.empty((P0, ev.n_g), dtype=torch.float64, device=dev))
+
+        def flush(rows):
+            o = idx[rows]
+            out["w"][o] = w[rows]; out["f"][o] = f[rows]; out["err"][o] = err0[rows]; out["iters"][o] = iters[rows]
+            out["viol"][o] = torch.clamp(torch.maximum(lb_all - g[rows], g[rows] - ub_all), min=0.0).amax(1)
+            out["conv"][o] = done[rows] & ~stalled[rows]; out["stalled"][o] = stalled[rows]
+            lam_o = torch.zeros((int(rows.sum()), ev.n_g), dtype=torch.float64, device=dev)
+            lam_o[:, iE] = lam_E[rows]; lam_o[:, iI] = (z_u - z_l)[rows]
+            out["lam"][o] = lam_o
 
         for it in range(self.max_iter):
+            if self.compact and it > 0 and it % 10 == 0 and float(done.float().mean()) >= 0.25:
+                flush(done)
+                keep = ~done
+                (w, s, mu, z_l, z_u, lam_E, nu, iters, delta_w, err0, stalled, f_mark, f, grad, g, J, idx) = (
+                    t[keep] for t in (w, s, mu, z_l, z_u, lam_E, nu, iters, delta_w, err0, stalled, f_mark, f, grad, g, J, idx))
+                done = done[keep]
+                P = int(keep.sum())
             lam_I = z_u - z_l
             lam = torch.zeros((P, ev.n_g), dtype=torch.float64, device=dev)
             lam[:, iE] = lam_E; lam[:, iI] = lam_I
@@ -497,10 +521,9 @@ class BatchedIPSolver:
                 res_nt = (r_n + torch.einsum("pew,pe->pw", JE_n, lam_E)).abs().amax(1)
                 keep_newton = done | (torch.isfinite(res_nt) & (res_nt < res_ls))
                 lam_E = torch.where(keep_newton[:, None], lam_E, lam_ls)
-        viol = torch.clamp(torch.maximum(lb_all - g, g - ub_all), min=0.0).amax(1)
-        lam = torch.zeros((P, ev.n_g), dtype=torch.float64, device=dev)
-        lam[:, iE] = lam_E; lam[:, iI] = z_u - z_l
-        return IPResult(w=w, f=f, violation=viol, kkt_error=err0, iterations=iters, converged=done & ~stalled, lam=lam, stalled=stalled)
+        flush(torch.ones(P, dtype=torch.bool, device=dev))
+        return IPResult(w=out["w"], f=out["f"], violation=out["viol"], kkt_error=out["err"], iterations=out["iters"], converged=out["conv"],
+                        lam=out["lam"], stalled=out["stalled"])
 
 
 def solve_elastic(evaluator, lbg, ubg, w0, penalty: float = 1000.0, **solver_kw) -> IPResult:

@@ -155,3 +155,20 @@ def test_benchmark_6_solves_on_the_gpu_path_with_the_trained_network(library):
     g = DeviceEvaluator(prob).eval(res.w, want_jac=False)[2].cpu().numpy()[usable]
     assert np.all(g >= lb[None] - 1e-4) and np.all(g <= ub[None] + 1e-4)
     model.close()
+
+
+def test_compacting_the_working_set_does_not_change_any_start():
+    """Finished starts leave the working set every 10 iterations; each start's iterates depend on that start alone."""
+    import torch
+    from nlotrajectories_b200.solver import BatchedIPSolver
+    spec = no.NlpSpec.from_yaml_dict(yaml.safe_load(open(bench_yaml("benchmark_1"))))
+    lb, ub = no.bounds(spec)
+    w0 = torch.from_numpy(no.multistart_guess(spec, 6))
+    a = BatchedIPSolver(OracleEvaluator(spec), lb, ub, max_iter=200, compact=True).solve(w0)
+    b = BatchedIPSolver(OracleEvaluator(spec), lb, ub, max_iter=200, compact=False).solve(w0)
+    assert bool(a.converged.all()) and bool(b.converged.all())
+    assert len(set(a.iterations.tolist())) > 1                    # the starts do finish at different iterations
+    assert torch.equal(a.iterations, b.iterations)
+    np.testing.assert_allclose(a.w.numpy(), b.w.numpy(), atol=1e-9)
+    np.testing.assert_allclose(a.f.numpy(), b.f.numpy(), atol=1e-12)
+    np.testing.assert_allclose(a.lam.numpy(), b.lam.numpy(), atol=1e-6)
