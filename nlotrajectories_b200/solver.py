@@ -429,7 +429,10 @@ class BatchedIPSolver:
             def try_solve(dlt):
                 Lc, info = torch.linalg.cholesky_ex(Kc + dlt[:, None, None] * eye_w)
                 good_ = info == 0
-                cand_ = torch.cholesky_solve(rhs_k[:, :, None], torch.where(good_[:, None, None], Lc, eye_w[None]))[:, :, 0]
+                Lc = torch.where(good_[:, None, None], Lc, eye_w[None])
+                # two batched TRSMs: the potrs path behind torch.cholesky_solve runs one slow batched TRSV per triangle
+                y_ = torch.linalg.solve_triangular(Lc, rhs_k[:, :, None], upper=False)
+                cand_ = torch.linalg.solve_triangular(Lc.transpose(1, 2), y_, upper=True)[:, :, 0]
                 good_ = good_ & torch.isfinite(cand_).all(1) & (cand_.abs().amax(1) < 1e3)
                 return cand_, good_
             for attempt in range(16):
@@ -513,7 +516,9 @@ class BatchedIPSolver:
                 r_n = grad + torch.einsum("prw,pr->pw", J[:, iI, :], z_u - z_l)
                 A = torch.einsum("pew,pfw->pef", JE_n, JE_n)
                 A = A + (1e-8 * torch.clamp(A.diagonal(dim1=1, dim2=2).amax(1), min=1.0))[:, None, None] * torch.eye(nE, dtype=torch.float64, device=dev)
-                lam_ls = -torch.linalg.solve(A, torch.einsum("pew,pw->pe", JE_n, r_n)[:, :, None])[:, :, 0]
+                LA = torch.linalg.cholesky_ex(A)[0]                      # SPD by construction (Gram matrix + shift)
+                b_ls = torch.einsum("pew,pw->pe", JE_n, r_n)[:, :, None]
+                lam_ls = -torch.linalg.solve_triangular(LA.transpose(1, 2), torch.linalg.solve_triangular(LA, b_ls, upper=False), upper=True)[:, :, 0]
                 # ... unless the Newton multipliers leave the smaller dual residual: near a solution they are exact, while the
                 # regularised least squares keeps a bias where JE JE^T is nearly singular (B6: 1.15e-4 on a control that barely
                 # enters the dynamics, just above tol)
