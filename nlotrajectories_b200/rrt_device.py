@@ -1,0 +1,176 @@
+"""Batched RRT on the device: the tree search of ``core/trajectory_initialization.py:175-216`` for P planners in
+lock step as torch tensor operations - one sampled point, one nearest-node search, one steer and one collision check per planner per
+iteration, all planners at once.  The exact obstacle SDF (circles, squares, polygons, elliptical half-rings) is evaluated on the
+same device.  Path post-processing (shortcut, corner splitting, cubic spline, optional lifting) stays with ``initializer.py`` on
+the host, where it is a few milliseconds per path.
+
+The host planners of ``initializer.rrt_multistart`` (a pool of forked processes) are the better tool for tens of starts; this one
+is for thousands: its cost per iteration is a handful of launches whatever P is.
+
+Random numbers come from a counter hash of (seed of the start, iteration, draw), so start i depends on ``seed0 + first + i`` only -
+shards of a batch plan the same trees as the whole batch - and not on torch's generator state.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+
+
+# ---- exact SDFs as torch functions of (..., 2) points (same definitions as train.py, which follows core/sdf/casadi.py) ---------
+def _polygon_sdf(pts, poly, margin):
+    import torch
+    a = poly
+    b = torch.roll(poly, -1, dims=0)
+    px, py = pts[..., 0:1], pts[..., 1:2]
+    ex, ey = b[:, 0] - a[:, 0], b[:, 1] - a[:, 1]
+    wx, wy = px - a[:, 0], py - a[:, 1]
+    t = torch.clamp((wx * ex + wy * ey) / torch.clamp(ex * ex + ey * ey, min=1e-300), 0.0, 1.0)
+    d = torch.sqrt(((wx - t * ex) ** 2 + (wy - t * ey) ** 2).amin(dim=-1))
+    cond = (a[:, 1] > py) != (b[:, 1] > py)
+    xint = a[:, 0] + (py - a[:, 1]) * ex / torch.where(ey == 0, torch.ones_like(ey), ey)
+    inside = ((cond & (px < xint)).sum(dim=-1) % 2) == 1
+    return torch.where(inside, -d, d) - margin
+
+
+def torch_scene_sdf(cfg, device, dtype=None):
+    """Exact SDF of the YAML's obstacle list (union = min) as ``f(points (..., 2)) -> (...)`` on ``device``."""
+    import torch
+    from .train import elliptic_ring_points
+    dtype = dtype or torch.float64
+    fns = []
+    for ob in cfg.obstacles:
+        p = ob.params
+        m = float(p.get("margin", 0.0))
+        if ob.type == "circle":
+            c = torch.tensor(p["center"], dtype=dtype, device=device); r = float(p["radius"]) + m
+            fns.append(lambda q, c=c, r=r: torch.linalg.vector_norm(q - c, dim=-1) - r)
+        elif ob.type == "square":
+            c = torch.tensor(p["center"], dtype=dtype, device=device); half = float(p["size"]) / 2 + m
+
+            def sq(q, c=c, half=half):
+                d = (q - c).abs() - half
+                return torch.linalg.vector_norm(torch.clamp(d, min=0.0), dim=-1) + torch.clamp(d.amax(dim=-1), max=0.0)
+            fns.append(sq)
+        elif ob.type in ("polygon", "trapezoid", "elliptical_ring"):
+            if ob.type == "elliptical_ring":
+                pts = elliptic_ring_points(p["center"], p["semi_axes"], p["width"], p.get("angle", np.pi), p.get("num_arc_points", 15),
+                                           p.get("rotation", 0.0))
+            else:
+                pts = p["points"]
+            poly = torch.tensor(np.asarray(pts, float), dtype=dtype, device=device)
+            fns.append(lambda q, poly=poly, m=m: _polygon_sdf(q, poly, m))
+        else:
+            raise NotImplementedError(f"exact SDF of obstacle type {ob.type!r}")
+    return lambda q: torch.stack([f(q) for f in fns], dim=0).amin(dim=0)
+
+
+# ---- counter-hash uniforms ---------------------------------------------------------------------------------------------------
+_M31 = (1 << 31) - 1
+
+
+def _uniform(seed, it: int, k: int):
+    """(P,) uniforms in [0, 1) from int64 seeds: three rounds of a multiply / xor-shift mix kept below 2^62 (no int64 overflow)."""
+    x = (seed * 1103515245 + (it * 40503 + k * 9973 + 12345)) & _M31
+    for mult, add in ((1664525, 1013904223), (22695477, 1), (1103515245, 12345)):
+        x = (x ^ (x >> 15)) & _M31
+        x = (x * mult + add) & _M31
+    x = (x ^ (x >> 13)) & _M31
+    return x.double() / float(1 << 31)
+
+
+def batched_rrt_trees(sdf, start, goal, bounds, P: int, seeds, step_size: float, max_iter: int, inflation: float,
+                      goal_sample_rate: float = 0.05, device=None, check_every: int = 64):
+    """Grow P trees from ``start`` towards ``goal`` (2-vectors).  Returns host arrays ``pos (P, M, 2)``, ``parent (P, M)``,
+    ``final (P,)`` (index of the goal node, -1 where the planner ran out of iterations)."""
+    import torch
+    dev = device
+    f64 = torch.float64
+    M = max_iter + 3                                                  # start + one node per iteration + goal + a scratch slot
+    pos = torch.zeros((P, M, 2), dtype=f64, device=dev)
+    parent = torch.full((P, M), -1, dtype=torch.int64, device=dev)
+    start_t = torch.tensor(np.asarray(start, float)[:2], dtype=f64, device=dev)
+    goal_t = torch.tensor(np.asarray(goal, float)[:2], dtype=f64, device=dev)
+    lo = torch.tensor(np.asarray(bounds, float)[0], dtype=f64, device=dev)
+    hi = torch.tensor(np.asarray(bounds, float)[1], dtype=f64, device=dev)
+    pos[:, 0] = start_t
+    n_nodes = torch.ones(P, dtype=torch.int64, device=dev)
+    final = torch.full((P,), -1, dtype=torch.int64, device=dev)
+    seeds_t = torch.as_tensor(np.asarray(seeds, np.int64), device=dev)
+    rows = torch.arange(P, device=dev)
+    tt = torch.tensor([0.0, 0.5, 1.0], dtype=f64, device=dev)[None, :, None]
+    for it in range(max_iter):
+        active = final < 0
+        if it % check_every == 0 and it > 0 and not bool(active.any()):
+            break
+        to_goal = _uniform(seeds_t, it, 0) < goal_sample_rate
+        sample = lo + (hi - lo) * torch.stack([_uniform(seeds_t, it, 1), _uniform(seeds_t, it, 2)], dim=1)
+        ref = torch.where(to_goal[:, None], goal_t[None, :], sample)
+        n_max = min(M - 1, it + 2)                                    # no tree has more nodes than this yet
+        d2 = ((pos[:, :n_max] - ref[:, None, :]) ** 2).sum(-1)
+        d2 = torch.where(torch.arange(n_max, device=dev)[None, :] < n_nodes[:, None], d2, torch.full_like(d2, float("inf")))
+        near = d2.argmin(dim=1)
+        p_near = pos[rows, near]
+        direction = ref - p_near
+        norm = torch.linalg.vector_norm(direction, dim=1)
+        new = p_near + direction / torch.clamp(norm, min=1e-300)[:, None] * step_size
+        edge = p_near[:, None, :] + (new - p_near)[:, None, :] * tt     # both ends and the midpoint of a step-long edge
+        free = (sdf(edge) >= inflation).all(dim=1)
+        ok = active & free & (norm > 0)
+        slot = torch.where(ok, n_nodes, torch.full_like(n_nodes, M - 1))   # rejected planners write to the scratch slot M - 1
+        pos[rows, slot] = torch.where(ok[:, None], new, pos[rows, slot])
+        parent[rows, slot] = torch.where(ok, near, parent[rows, slot])
+        n_nodes = n_nodes + ok.long()
+        reached = ok & (torch.linalg.vector_norm(new - goal_t[None, :], dim=1) < step_size)
+        gslot = torch.where(reached, n_nodes, torch.full_like(n_nodes, M - 1))
+        pos[rows, gslot] = torch.where(reached[:, None], goal_t[None, :].expand(P, 2), pos[rows, gslot])
+        parent[rows, gslot] = torch.where(reached, n_nodes - 1, parent[rows, gslot])
+        final = torch.where(reached, n_nodes, final)
+        n_nodes = n_nodes + reached.long()
+    return pos.cpu().numpy(), parent.cpu().numpy(), final.cpu().numpy()
+
+
+def rrt_multistart_device(cfg, P: int, first: int = 0, seed0: int = 1234, lift: bool = False, device=None) -> np.ndarray:
+    """``initializer.rrt_multistart`` with the tree search batched on ``device`` (default: CUDA when available, else CPU).  The raw
+    tree paths are shortcut, split at sharp corners, splined and (optionally) lifted on the host exactly like the host planner's."""
+    import torch
+    from .initializer import RRTInitializer, lift_path
+    from .problem import DYN_DIMS
+    from .train import scene_sdf
+    if device is None:
+        device = torch.device("cuda") if torch.cuda.is_available() else torch.device("cpu")
+    b, s = cfg.body, cfg.solver
+    nx, nu = DYN_DIMS[b.dynamic]
+    N = s.N
+    n_X, n_U = nx * (N + 1), nu * N
+    n_w = n_X + n_U + ((N + 1) if s.use_slack else 0)
+    ini = s.initializer
+    bounds = ini.rrt_bounds if ini.rrt_bounds is not None else [[-0.5, -0.5], [1.5, 1.5]]
+    if b.shape == "rectangle":
+        hl, hw = 0.5 * b.length, 0.5 * b.width
+        body = [(-hl, -hw), (-hl, hw), (hl, hw), (hl, -hw)]
+    else:
+        body = None
+    host = RRTInitializer(N + 1, b.start_state, b.goal_state, s.dt, scene_sdf(cfg), bounds, body_points=body, rectangle=b.shape == "rectangle",
+                          step_size=ini.step_size, max_iter=ini.max_iter, margin=ini.margin)
+    seeds = [seed0 + first + i for i in range(P)]
+    pos, parent, final = batched_rrt_trees(torch_scene_sdf(cfg, device), b.start_state, b.goal_state, bounds, P, seeds, ini.step_size,
+                                           ini.max_iter, host.inflation, device=device)
+    w = np.zeros((P, n_w), np.float32)
+    for i in range(P):
+        if final[i] < 0:
+            X = np.linspace(np.asarray(b.start_state, float), np.asarray(b.goal_state, float), N + 1)
+        else:
+            idx, node = [], int(final[i])
+            while node >= 0:
+                idx.append(node); node = int(parent[i, node])
+            path = host._shortcut(host._insert_intermediate_points(pos[i, idx[::-1]]))
+            X = np.zeros((N + 1, nx))
+            X[:, 0:2] = host._spline(path, N + 1)
+        U = np.zeros((N, nu))
+        if lift:
+            X, U = lift_path(X, b.dynamic, s.dt, getattr(b, "wheelbase", None), b.control_bounds)
+            X[0] = np.asarray(b.start_state, float)
+        w[i, :n_X] = X.reshape(-1)
+        w[i, n_X:n_X + n_U] = U.reshape(-1)
+    return w

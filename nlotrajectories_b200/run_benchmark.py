@@ -42,7 +42,7 @@ def synthetic_weights(cfg: Config, seed: int = 0) -> SdfWeights:
 
 
 def solve_benchmark(config_path: Path, batch: int = 64, weights: str | None = None, precision: str = "auto", verbose: bool = True,
-                    lift: bool = False, elastic: float | None = None):
+                    lift: bool = False, elastic: float | None = None, device_rrt: bool = False):
     """``--solve``: every start of this rank's shard goes through the batched interior point (solver.py); the best
     converged objective across ranks is selected with the same all-gather + broadcast as the evaluation path."""
     import torch
@@ -53,8 +53,12 @@ def solve_benchmark(config_path: Path, batch: int = 64, weights: str | None = No
     lo, hi = shard_range(batch, rank, world)
     w0_host = None
     if cfg.solver.initializer.mode == "rrt":                     # the YAML's initializer (scripts/run_benchmark.py:114-127), one seed per start;
-        from .initializer import rrt_multistart                  # planned on forked host processes, before this process creates its CUDA context
-        w0_host = rrt_multistart(cfg, hi - lo, first=lo, lift=lift).astype(np.float64)
+        if device_rrt:                                           # thousands of starts: the tree search batched on the GPU (rrt_device.py)
+            from .rrt_device import rrt_multistart_device
+            w0_host = rrt_multistart_device(cfg, hi - lo, first=lo, lift=lift, device=torch.device("cuda", local_rank)).astype(np.float64)
+        else:
+            from .initializer import rrt_multistart              # planned on forked host processes, before this process creates its CUDA context
+            w0_host = rrt_multistart(cfg, hi - lo, first=lo, lift=lift).astype(np.float64)
     sdf = None
     if cfg.solver.mode == "l4casadi":
         sdf = LearnedSDF(SdfWeights.load(weights) if weights else synthetic_weights(cfg), device=local_rank, precision=precision)
@@ -136,11 +140,12 @@ def main():
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tc3xf16"])
     ap.add_argument("--solve", action="store_true", help="solve every start (batched interior point) instead of evaluating the initial guesses")
     ap.add_argument("--lift", action="store_true", help="--solve: fill heading / speed / steering of the RRT guesses from the planned path")
+    ap.add_argument("--device-rrt", action="store_true", help="--solve: grow the RRT trees of all starts in lock step on the GPU instead of on host processes")
     ap.add_argument("--elastic", type=float, default=None, metavar="PENALTY", help="--solve: elastic mode (exact l1 penalty) on the inequality rows")
     ap.add_argument("--sdf-metrics", action="store_true", help="also report the learned SDF's quality metrics on the 1000^2 grid")
     a = ap.parse_args()
     if a.solve:
-        solve_benchmark(Path(a.config), min(a.batch, 512), a.weights, a.precision, lift=a.lift, elastic=a.elastic)
+        solve_benchmark(Path(a.config), min(a.batch, 512), a.weights, a.precision, lift=a.lift, elastic=a.elastic, device_rrt=a.device_rrt)
     else:
         run_benchmark(Path(a.config), a.batch, a.weights, a.precision, sdf_metrics=a.sdf_metrics)
     import torch.distributed as dist
