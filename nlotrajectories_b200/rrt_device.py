@@ -130,11 +130,37 @@ def batched_rrt_trees(sdf, start, goal, bounds, P: int, seeds, step_size: float,
     return pos.cpu().numpy(), parent.cpu().numpy(), final.cpu().numpy()
 
 
-def rrt_multistart_device(cfg, P: int, first: int = 0, seed0: int = 1234, lift: bool = False, device=None) -> np.ndarray:
+_POST_STATE = None      # (host planner, cfg, lift, nx, nu): set before the post-processing pool forks
+
+
+def _post_one(path):
+    """Raw tree path (or None: planner failed) -> (X, U) like initializer._plan_one."""
+    from .initializer import lift_path
+    host, cfg, lift, nx, nu = _POST_STATE
+    b, s = cfg.body, cfg.solver
+    N = s.N
+    if path is None:
+        X = np.linspace(np.asarray(b.start_state, float), np.asarray(b.goal_state, float), N + 1)
+    else:
+        path = host._shortcut(host._insert_intermediate_points(path))
+        X = np.zeros((N + 1, nx))
+        X[:, 0:2] = host._spline(path, N + 1)
+    U = np.zeros((N, nu))
+    if lift:
+        X, U = lift_path(X, b.dynamic, s.dt, getattr(b, "wheelbase", None), b.control_bounds)
+        X[0] = np.asarray(b.start_state, float)
+    return X, U
+
+
+def rrt_multistart_device(cfg, P: int, first: int = 0, seed0: int = 1234, lift: bool = False, device=None,
+                          workers: Optional[int] = None) -> np.ndarray:
     """``initializer.rrt_multistart`` with the tree search batched on ``device`` (default: CUDA when available, else CPU).  The raw
-    tree paths are shortcut, split at sharp corners, splined and (optionally) lifted on the host exactly like the host planner's."""
+    tree paths are shortcut, split at sharp corners, splined and (optionally) lifted on the host exactly like the host planner's,
+    on a pool of forked processes (numpy only; the children never touch CUDA)."""
+    import os
     import torch
-    from .initializer import RRTInitializer, lift_path
+    global _POST_STATE
+    from .initializer import RRTInitializer
     from .problem import DYN_DIMS
     from .train import scene_sdf
     if device is None:
@@ -156,21 +182,27 @@ def rrt_multistart_device(cfg, P: int, first: int = 0, seed0: int = 1234, lift: 
     seeds = [seed0 + first + i for i in range(P)]
     pos, parent, final = batched_rrt_trees(torch_scene_sdf(cfg, device), b.start_state, b.goal_state, bounds, P, seeds, ini.step_size,
                                            ini.max_iter, host.inflation, device=device)
-    w = np.zeros((P, n_w), np.float32)
+    paths = []
     for i in range(P):
         if final[i] < 0:
-            X = np.linspace(np.asarray(b.start_state, float), np.asarray(b.goal_state, float), N + 1)
-        else:
-            idx, node = [], int(final[i])
-            while node >= 0:
-                idx.append(node); node = int(parent[i, node])
-            path = host._shortcut(host._insert_intermediate_points(pos[i, idx[::-1]]))
-            X = np.zeros((N + 1, nx))
-            X[:, 0:2] = host._spline(path, N + 1)
-        U = np.zeros((N, nu))
-        if lift:
-            X, U = lift_path(X, b.dynamic, s.dt, getattr(b, "wheelbase", None), b.control_bounds)
-            X[0] = np.asarray(b.start_state, float)
+            paths.append(None)
+            continue
+        idx, node = [], int(final[i])
+        while node >= 0:
+            idx.append(node); node = int(parent[i, node])
+        paths.append(pos[i, idx[::-1]])
+    _POST_STATE = (host, cfg, lift, nx, nu)
+    if workers is None:
+        workers = min(32, os.cpu_count() or 1)
+    workers = min(workers, P)
+    if workers > 1 and P >= 8:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(workers) as pool:
+            plans = pool.map(_post_one, paths, chunksize=max(1, P // (4 * workers)))
+    else:
+        plans = [_post_one(pth) for pth in paths]
+    w = np.zeros((P, n_w), np.float32)
+    for i, (X, U) in enumerate(plans):
         w[i, :n_X] = X.reshape(-1)
         w[i, n_X:n_X + n_U] = U.reshape(-1)
     return w
