@@ -60,3 +60,29 @@ def test_multistart_guesses_have_the_reference_shape_and_clear_the_obstacles():
     assert scene_sdf(cfg)(X[..., 0], X[..., 1]).min() > 0
     again = rrt_multistart_device(cfg, 2, first=3, device=CPU)
     np.testing.assert_array_equal(again, w[1:3])
+
+
+@pytest.mark.gpu
+def test_trees_on_the_gpu_are_valid_and_feed_the_solver(library):
+    """The same tensor program on CUDA: every start of benchmark_3 finds a path whose spline clears the obstacles, and the guesses
+    go straight into the batched interior point."""
+    from gpu_util import to_weights
+    from oracle import sdf_oracle as so
+    from conftest import GOLDEN
+    from nlotrajectories_b200.problem import NlpProblem
+    from nlotrajectories_b200.sdf import LearnedSDF
+    from nlotrajectories_b200.solver import BatchedIPSolver, DeviceEvaluator
+    cfg = Config.load(bench_yaml("benchmark_3"))
+    w0 = rrt_multistart_device(cfg, 16, device=torch.device("cuda"), workers=1)
+    N, nx = cfg.solver.N, 5
+    X = w0[:, :nx * (N + 1)].reshape(16, N + 1, nx).astype(float)
+    assert scene_sdf(cfg)(X[..., 0], X[..., 1]).min() > 0
+    assert len({tuple(np.round(x[:, :2].ravel(), 6)) for x in X}) == 16          # sixteen different paths
+    model = LearnedSDF(to_weights(so.from_npz(str(GOLDEN / "sdf_benchmark_3_relu128.npz"))))
+    prob = NlpProblem.from_config(cfg, model)
+    lb, ub = prob.bounds()
+    res = BatchedIPSolver(DeviceEvaluator(prob), lb, ub, max_iter=200).solve(torch.from_numpy(w0.astype(np.float64)).cuda())
+    usable = (res.converged | res.stalled).cpu().numpy() & (res.violation.cpu().numpy() <= 1e-4)
+    assert usable.mean() >= 0.5
+    assert abs(res.f.cpu().numpy()[usable].min() - 1.5321) < 5e-3
+    model.close()
