@@ -50,6 +50,9 @@ NETS = {
     "fourier64_leaky": lambda: so.synthetic_fourier(64, 1, scale=2.0, seed=19, act=so.ACT_LEAKY_RELU),
     "tanh_sigmoid_mix64": None,                                                      # placeholder replaced below: run-time (generic) instantiation
 }
+NETS["fourier128_leaky"] = lambda: so.synthetic_fourier(128, 1, scale=2.0, seed=17, act=so.ACT_LEAKY_RELU)   # masked reverse GEMM + column sums
+NETS["tanh_leaky_mix64"] = lambda: (lambda n: so.SdfNet(n.kind, n.W0, n.b0, n.hidden, n.w_out, n.b_out, so.ACT_TANH, so.ACT_LEAKY_RELU, n.p0, n.p))(
+    so.synthetic_mlp(64, 1, seed=18, act=so.ACT_TANH))                                                           # leaky hidden layer on the generic kernel
 NETS["tanh_sigmoid_mix64"] = lambda: (lambda n: so.SdfNet(n.kind, n.W0, n.b0, n.hidden, n.w_out, n.b_out, so.ACT_TANH, so.ACT_SIGMOID, n.p0, n.p))(
     so.synthetic_mlp(64, 1, seed=20, act=so.ACT_TANH))
 
