@@ -4,8 +4,10 @@
     python bench.py --impl reference --gpus N --steps K --warmup W # the CPU reference arm
 
 Workload (BASELINE.json configs[3], the config the metric is quoted on): benchmark_6_ackermann_wave
-with 65,536 multi-start problems resident per GPU (weak scaling: every rank owns its own 65,536
-starts, global indices rank*65536 ...).  One step = one pass of the hot path over the batch:
+with 65,536 multi-start problems IN TOTAL, sharded by problem index over the N GPUs (strong scaling:
+rank r owns [r*65536/N, (r+1)*65536/N)); with N > 1 the same run also measures the
+weak-scaling variant (65,536 starts per GPU) and reports it in a "weak" block beside the headline
+(`--scaling weak` makes that the headline instead).  One step = one pass of the hot path over the batch:
 g(w), all structural non-zeros of dg/dw, f(w), grad f(w) -> 324 learned-SDF value+Jacobian points per
 problem.  The SDF network is the YAML's model (mlp, ReLU, 2->128->128->1) with seeded synthetic weights.
 Prints ONE JSON line on rank 0.
@@ -20,6 +22,12 @@ import sys
 import threading
 import time
 from pathlib import Path
+
+if "reference" in sys.argv[1:]:
+    # the CPU arm uses every host core at every N: torch.distributed.run exports OMP_NUM_THREADS=1 for N > 1, and the BLAS / OpenMP
+    # runtimes read these variables when numpy / torch are first imported
+    for _v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
 
 import numpy as np
 
@@ -103,9 +111,18 @@ def synthetic_net():
 
 
 FLOP_PER_POINT = 4 * (3 * 128 + 128 * 128)      # value + Jacobian, 2->128->128->1 = 67,072
-# dram__bytes_read.sum + dram__bytes_write.sum of sdf_tc_kernel per point, from the ncu --set full capture committed
-# under profiles/ (profiles/r1_sdf_tc_kernel.md): 170.6 MB read + 207.1 MB written for 21,233,664 points (algorithmic: 20 B/point)
-NCU_DRAM_BYTES_PER_POINT = 17.2
+TOTAL_PROBLEMS = 65536                          # BASELINE.json configs[3]
+
+
+def ncu_dram_bytes_per_point():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per SDF point, read from the committed summary of
+    the `ncu --set full` capture (profiles/sdf_tc_kernel_dram.json, written by tools/ncu_summary.py with the capture's point
+    count).  None when the file is absent."""
+    p = REPO / "profiles" / "sdf_tc_kernel_dram.json"
+    if not p.exists():
+        return None, None
+    d = json.loads(p.read_text())
+    return (d["dram_bytes_read"] + d["dram_bytes_write"]) / d["points"], d
 BYTES_PER_EVAL = (727 + 1057 + 3225) * 4        # SURVEY.md 8(d): read w, write g and nnz(J) = 20,036 B / problem-eval
 DYN_BYTES_PER_PROBLEM = (567 + 160 + 560 + 2080) * 4   # SURVEY.md 8(d): K2 on benchmark_6 = 13,468 B / problem
 POINTS_PER_PROBLEM = 324
@@ -120,6 +137,7 @@ def cpu_step_factory(n_problems: int):
     import torch
     import yaml
     from oracle import nlp_oracle as no
+    torch.set_num_threads(os.cpu_count() or 1)           # every host core at every N (torchrun's default is 1 thread per rank)
     net = synthetic_net()
     t = {k: torch.from_numpy(np.asarray(v)) for k, v in net.items()}
     W0t, W1t = t["W0"].T.contiguous(), t["W1"].T.contiguous()
@@ -183,7 +201,7 @@ def run_reference(args):
     cores = os.cpu_count()
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{YAML} NLP eval (g, nnz(dg/dw), f, grad f); CPU sample of {n_problems} multi-start problems per step "
                                f"({n_problems * POINTS_PER_PROBLEM} SDF points), mlp ReLU 2-128-128-1 synthetic weights"},
@@ -204,7 +222,7 @@ def run_ours(args):
     import torch.distributed as dist
     from nlotrajectories_b200 import lib
     from nlotrajectories_b200.config import Config
-    from nlotrajectories_b200.distributed import bind_to_gpu_numa, init_process_group, merit, select_best
+    from nlotrajectories_b200.distributed import bind_to_gpu_numa, init_process_group, merit, select_best, shard_range
     from nlotrajectories_b200.problem import NlpProblem
     from nlotrajectories_b200.sdf import LearnedSDF, SdfWeights
 
@@ -220,39 +238,94 @@ def run_ours(args):
     weights = SdfWeights.pack("mlp", net["W0"], net["b0"], [(net["W1"], net["b1"])], net["w_out"], float(net["b_out"]), 0, 0)
     model = LearnedSDF(weights, device=local_rank, precision=args.precision)
     prob = NlpProblem.from_config(Config.load(REPO / "nlotrajectories_b200" / "benchmarks" / YAML), model, device=local_rank)
-    P = args.problems
-    first = rank * P
-    w_host = prob.multistart_guess(P, first=first)                       # (P, n_w) problem-major, seeded
-    w_pin = torch.empty((P, prob.n_w), dtype=torch.float32).pin_memory()
-    w_pin.copy_(torch.from_numpy(w_host))
-    w = w_pin.to(dev).T.contiguous()                                      # SoA (n_w, P), resident in HBM
-    g, jac, f, grad = prob.alloc_outputs(P, dev)
-    n_pts = P * prob.n_sdf_points
-
-    def step():
-        prob.eval_device(w, g, jac, f, grad)
+    steps, warmup = args.steps, max(args.warmup, 3)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def measure(P, first, n_steps, with_e2e):
+        """Device-resident and host-buffer timing of this rank's shard of P problems (global indices first..first+P-1)."""
+        w_host = prob.multistart_guess(P, first=first)                   # (P, n_w) problem-major, seeded by global index
+        w_pin = torch.empty((P, prob.n_w), dtype=torch.float32).pin_memory()
+        w_pin.copy_(torch.from_numpy(w_host))
+        w = w_pin.to(dev).T.contiguous()                                  # SoA (n_w, P), resident in HBM
+        g, jac, f, grad = prob.alloc_outputs(P, dev)
+        prob.reserve(P)
+        for _ in range(warmup):
+            prob.eval_device(w, g, jac, f, grad)
+        barrier()
+        l0 = L.nlo_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(n_steps):
+            prob.eval_device(w, g, jac, f, grad)
+        e1.record()
+        barrier()
+        out = {"P": P, "w": w, "g": g, "f": f, "launches": int(L.nlo_launch_count() - l0), "w_pin": w_pin,
+               "ms_per_step": max_over_ranks(e0.elapsed_time(e1)) / n_steps,
+               "resident_bytes": (w.numel() + g.numel() + jac.numel() + grad.numel()) * 4}
+        if with_e2e:
+            out.update(measure_e2e(P, w_pin))
+        return out
+
+    def measure_e2e(P, w_pin):
+        """Host buffers in, host buffers out, through the C-ABI host entry points; synchronous calls, wall clock, max over ranks."""
+        res = {}
+        w_np = w_pin.numpy()
+        e2e_steps = max(2, min(steps, 5))
+        pin = lambda shape: torch.empty(shape, dtype=torch.float32).pin_memory().numpy()
+        lay = prob.compact_layout()
+        full = {"g": pin((P, prob.n_g)), "jac": pin((P, prob.nnz)), "f": pin((P,)), "grad_f": pin((P, prob.n_w))}
+        comp = {"g": pin((P, len(lay["g_var_rows"]))), "jac": pin((P, len(lay["jac_var_nz"]))), "f": pin((P,)),
+                "grad_f": pin((P, len(lay["grad_var_idx"])))}
+        for name, call, bufs in (("full", lambda: prob.eval_host(w_np, out=full), full),
+                                 ("compact", lambda: prob.eval_host_compact(w_np, out=comp), comp)):
+            call()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                call()                                                    # synchronous: results are in host memory on return
+            barrier()
+            res[name] = {"s": max_over_ranks((time.perf_counter() - t0) / e2e_steps), "h2d": int(w_np.nbytes),
+                         "d2h": int(sum(v.nbytes for v in bufs.values()))}
+        return {"e2e": res}
+
     sampler = ClockSampler(local_rank)          # samples SM clocks / throttle reasons across every timed region below
     sampler.start()
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    l0 = L.nlo_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
-    launches = int(L.nlo_launch_count() - l0)
-    ms = e0.elapsed_time(e1)
-    # dominant kernel alone (the fused learned-SDF value+Jacobian kernel on this step's footprint points)
+    # ---- headline: the 65,536-start batch sharded over the ranks (strong), or 65,536 per rank (weak) ---------------------
+    total = args.problems
+    lo, hi = shard_range(total, rank, world)
+    weak = None
+    if args.scaling == "strong":
+        head = measure(hi - lo, lo, steps, with_e2e=True)
+        if world > 1:                            # the weak-scaling variant beside it (fewer steps: it is a side note)
+            weak = measure(total, rank * total, max(5, steps // 4), with_e2e=False)
+    else:
+        lo = rank * total
+        head = measure(total, lo, steps, with_e2e=True)
+    P = head["P"]
+    w, g, f = head["w"], head["g"], head["f"]
+    n_pts = P * prob.n_sdf_points
+    pts_total = int(sum_over_ranks(n_pts))
+    ms_per_step = head["ms_per_step"]
+    value = pts_total / (ms_per_step * 1e-3)
+
+    # ---- the dominant kernel alone (the fused learned-SDF value+Jacobian kernel on this rank's footprint points) ---------
     xs = torch.rand(n_pts, device=dev) * 2 - 0.5
     ys = torch.rand(n_pts, device=dev) * 2 - 0.5
     so_, jx_, jy_ = torch.empty_like(xs), torch.empty_like(xs), torch.empty_like(xs)
@@ -261,50 +334,26 @@ def run_ours(args):
     torch.cuda.synchronize()
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         model.eval(xs, ys, out=(so_, jx_, jy_))
     k1.record()
     torch.cuda.synchronize()
-    k_ms = k0.elapsed_time(k1) / args.steps
+    k_ms = k0.elapsed_time(k1) / steps
     # K2 alone (Euler defects + banded Jacobian values): the HBM-bound kernel of the path
+    jac_d = torch.empty((prob.nnz, P), dtype=torch.float32, device=dev)
     for _ in range(3):
-        prob.eval_dynamics_device(w, g, jac)
+        prob.eval_dynamics_device(w, g, jac_d)
     torch.cuda.synchronize()
     d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     d0.record()
-    for _ in range(args.steps):
-        prob.eval_dynamics_device(w, g, jac)
+    for _ in range(steps):
+        prob.eval_dynamics_device(w, g, jac_d)
     d1.record()
     torch.cuda.synchronize()
-    dyn_ms = d0.elapsed_time(d1) / args.steps
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    ms_per_step = ms / args.steps
-    value = world * n_pts / (ms_per_step * 1e-3)
-
-    # ---- end to end: host buffers in, host buffers out, through the C-ABI host entry point --------------------
-    out_pin = {"g": torch.empty((P, prob.n_g), dtype=torch.float32).pin_memory().numpy(),
-               "jac": torch.empty((P, prob.nnz), dtype=torch.float32).pin_memory().numpy(),
-               "f": torch.empty((P,), dtype=torch.float32).pin_memory().numpy(),
-               "grad_f": torch.empty((P, prob.n_w), dtype=torch.float32).pin_memory().numpy()}
-    w_np = w_pin.numpy()
-    e2e_steps = max(2, min(args.steps, 5))
-    prob.eval_host(w_np, out=out_pin)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        prob.eval_host(w_np, out=out_pin)                                  # synchronous: results are in host memory on return
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
+    dyn_ms = d0.elapsed_time(d1) / steps
+    del jac_d
+    prob.eval_device(w, g, None, f, None)       # g again in full (the K2 timing above rewrote only its defect rows)
     clocks = sampler.stop()
-    h2d = int(w_np.nbytes)
-    d2h = int(sum(v.nbytes for v in out_pin.values()))
 
     # ---- best-of-batch selection (the only collective on the path; outside the timed region) ------------------
     lb, ub = prob.bounds()
@@ -312,7 +361,7 @@ def run_ours(args):
     lbd = torch.from_numpy(np.clip(lb, -big, big).astype(np.float32)).to(dev)
     ubd = torch.from_numpy(np.clip(ub, -big, big).astype(np.float32)).to(dev)
     viol = prob.violation(g, lbd, ubd)
-    best_val, best_idx, _ = select_best(merit(f, viol), w, first, prob.n_w)
+    best_val, best_idx, _ = select_best(merit(f, viol), w, lo, prob.n_w)
 
     if rank != 0:
         return
@@ -328,24 +377,35 @@ def run_ours(args):
         bound = "fp32_simt"
         peak_note = f"FP32 FMA pipe = SMs x 128 lanes x 2 x {sm_mhz:.0f} MHz (median SM clock sampled during the run)"
     achieved = FLOP_PER_POINT * n_pts / (k_ms * 1e-3) / 1e12
+    dram_pp, dram_src = ncu_dram_bytes_per_point() if prec == "tc3xf16" else (None, None)
+    e2e, e2e_full = head["e2e"]["compact"], head["e2e"]["full"]
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32" if prec == "fp32" else "f32 (tcgen05 split-fp16 hi/lo tiles, fp32 accumulate)", "data": "synthetic",
-        "config": {"workload": f"{YAML} x {P} multi-starts per GPU: NLP eval g + nnz(dg/dw) + f + grad f, SoA fp32 resident in HBM",
-                   "problems_per_gpu": P, "sdf_points_per_step_per_gpu": n_pts, "n_w": prob.n_w, "n_g": prob.n_g, "nnz_jac": prob.nnz,
-                   "sdf_model": "mlp ReLU 2-128-128-1 (synthetic seeded weights)", "sdf_precision": prec,
-                   "l2": f"inputs {w.numel() * 4 / 1e6:.0f} MB + outputs {(g.numel() + jac.numel() + grad.numel()) * 4 / 1e6:.0f} MB per step exceed the 126 MB L2",
+        "config": {"workload": (f"{YAML} x {total} multi-starts " + ("sharded by problem index over the GPUs" if args.scaling == "strong" else "per GPU")
+                                + ": NLP eval g + nnz(dg/dw) + f + grad f, SoA fp32 resident in HBM"),
+                   "problems_total": pts_total // prob.n_sdf_points, "problems_per_gpu": P,
+                   "sdf_points_per_step_per_gpu": n_pts, "n_w": prob.n_w, "n_g": prob.n_g, "nnz_jac": prob.nnz,
+                   "sdf_model": "mlp ReLU 2-128-128-1 (synthetic: numpy default_rng(0), W ~ N(0, 1/fan_in), b ~ 0.1 N(0, 1))", "sdf_precision": prec,
+                   "l2": f"inputs + outputs resident per GPU {head['resident_bytes'] / 1e6:.0f} MB per step (every byte read or written once per step) vs the 126 MB L2",
                    "parallelism": f"problem-sharded x{world}, no data-path collective"},
-        "nlp_evals_per_s": world * P / (ms_per_step * 1e-3),
+        "nlp_evals_per_s": pts_total / prob.n_sdf_points / (ms_per_step * 1e-3),
         "clocks": clocks,
-        "e2e": {"value": world * n_pts / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_s * 1e3, "api": "nlo_nlp_eval_host (pinned host buffers, problem-major)",
+        "e2e": {"value": pts_total / e2e["s"], "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                "ms_per_step": e2e["s"] * 1e3,
+                "api": "nlo_nlp_eval_host_compact (pinned host buffers, problem-major; returns every entry of g, nnz(dg/dw), grad f that varies with w - "
+                       "the rest are copies of w and constants published once by nlo_nlp_compact_layout)",
+                "full_form": {"api": "nlo_nlp_eval_host (every entry, constants included)", "value": pts_total / e2e_full["s"], "ms_per_step": e2e_full["s"] * 1e3,
+                              "h2d_bytes_per_step": e2e_full["h2d"], "d2h_bytes_per_step": e2e_full["d2h"]},
                 "cpu_affinity": (f"rank pinned to the {numa_cpus} CPUs NVML reports local to its GPU" if numa_cpus else "unchanged")},
-        "gpu_launches": launches,
+        "gpu_launches": head["launches"],
         "roofline": {"kernel": "sdf_tc_kernel" if prec == "tc3xf16" else "sdf_simt_kernel", "bound": bound, "achieved": achieved,
                      "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": (NCU_DRAM_BYTES_PER_POINT * n_pts if prec == "tc3xf16" else None), "traffic_unit": "bytes per launch (ncu dram read+write)",
+                     "traffic": (dram_pp * n_pts if dram_pp is not None else None), "traffic_unit": "bytes per launch (ncu dram read+write)",
+                     "traffic_source": (f"profiles/sdf_tc_kernel_dram.json: {dram_src['dram_bytes_read']:.0f} B read + {dram_src['dram_bytes_write']:.0f} B written "
+                                        f"for {dram_src['points']} points ({dram_src.get('source', '')}) = {dram_pp:.2f} B/point, scaled to this launch"
+                                        if dram_src else None),
                      "algorithmic_bytes_per_launch": 20 * n_pts,
                      "flop_per_point": FLOP_PER_POINT, "points_per_launch": n_pts, "kernel_ms": k_ms, "peak_source": peak_note,
                      "kernel_share_of_step": k_ms / ms_per_step,
@@ -355,8 +415,12 @@ def run_ours(args):
                                              "note": "SURVEY.md 8(d): read (N+1)nx + N nu, write N nx residuals + 26 N Jacobian values per problem"},
                      "step_hbm": {"algorithmic_bytes_per_step": BYTES_PER_EVAL * P, "achieved_gbs": BYTES_PER_EVAL * P / (ms_per_step * 1e-3) / 1e9,
                                   "peak_gbs": peaks["hbm_gbs"]}},
-        "best_of_batch": {"merit": best_val, "global_index": best_idx},
+        "best_of_batch": {"merit": best_val, "global_index": best_idx, "note": "selection over the evaluated initial guesses (the collective of the path); "
+                          "solved batches: run-benchmark --solve / tests/tools/solve_check.py"},
     }
+    if weak is not None:
+        line["weak"] = {"problems_per_gpu": weak["P"], "ms_per_step": weak["ms_per_step"], "unit": UNIT,
+                        "value": world * weak["P"] * prob.n_sdf_points / (weak["ms_per_step"] * 1e-3)}
     if world == 1 and not args.no_cpu_baseline:
         cpu_steps = 7
         rate, dt, threads = time_cpu(args.cpu_problems, cpu_steps, 1)
@@ -380,7 +444,9 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--problems", type=int, default=65536, help="multi-start problems per GPU")
+    ap.add_argument("--problems", type=int, default=TOTAL_PROBLEMS, help="multi-start problems: in total (strong) / per GPU (weak)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: --problems in total, sharded over the GPUs (BASELINE configs[3]); weak: --problems per GPU")
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tc3xf16"])
     ap.add_argument("--cpu-problems", type=int, default=8192, help="problems per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

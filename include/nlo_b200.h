@@ -204,6 +204,13 @@ NLO_API long long nlo_nlp_n_sdf_points(const nlo_nlp* p); /* learned-SDF points 
 /* compressed-column pattern of dg/dw: colind[n_w+1], row[nnz]                                  */
 NLO_API int  nlo_nlp_jac_sparsity(const nlo_nlp* p, int32_t* colind, int32_t* row);
 
+/* Scratch of the device entry points (footprint points, SDF values / Jacobians / Hessians of (N+1)*nb*P points) is owned by the
+ * handle: ONE nlo_nlp_eval / nlo_nlp_hess call per handle may be in flight at a time (calls on one stream are ordered and
+ * therefore fine; use one handle per stream for concurrent evaluation).  The scratch grows inside the call when P exceeds
+ * every earlier P (cudaFree + cudaMalloc: synchronises the device and cannot be captured in a CUDA graph);
+ * nlo_nlp_reserve(p, P) sizes it up front so that later calls with <= P problems allocate nothing.                       */
+NLO_API int  nlo_nlp_reserve(nlo_nlp* p, size_t P);
+
 /* Device-resident evaluation of P problems.  Structure-of-arrays, variable-major:
  *   w      fp32 [n_w ][ld]   element (v, problem i) at w[v*ld + i]
  *   g      fp32 [n_g ][ld]
@@ -237,6 +244,30 @@ NLO_API int nlo_nlp_violation(nlo_nlp* p, const float* g, const float* lbg, cons
  * Copies in (pinned staging), transposes on device, evaluates, transposes back, copies out, syncs. */
 NLO_API int nlo_nlp_eval_host(nlo_nlp* p, const float* w_host, size_t P,
                               float* g_host, float* jac_host, float* f_host, float* grad_f_host);
+/* Compact host form.  Of what nlo_nlp_eval_host returns, much does not depend on w at all and the rest of it is a copy of w:
+ *   g      rows that are copies of a variable (x_0 pin, terminal pin, slack >= 0, control box: core/runner.py:50-56,67-69,101-103)
+ *   dg/dw  the +-1 / -dt entries of the Euler defects (core/runner.py:59-64), the 1s of the copy rows and of d(row)/d(slack)
+ *   grad f zero except d/d(x_k, y_k) (path length) and the entries linear in their own variable (slack / control penalties,
+ *          core/runner.py:85-96)
+ * benchmark_6: 1,453 of 3,225 Jacobian values, 173 of 1,057 rows of g and 565 of 727 gradient entries.  A per-problem solver fills
+ * those ONCE (nlo_nlp_compact_layout gives the index lists and values) and asks only for what varies:
+ *   g_var_host    [P][n_g_var]    g[g_var_rows[c]]
+ *   jac_var_host  [P][n_jac_var]  jac[jac_var_nz[c]]       (positions in the CCS order of nlo_nlp_jac_sparsity)
+ *   grad_var_host [P][n_grad_var] grad_f[grad_var_idx[c]]
+ *   f_host        [P]
+ * Everything else follows from the layout:  g[g_copy_rows[i]] = w[g_copy_vars[i]];  jac[jac_const_nz[i]] = jac_const_val[i];
+ * grad_f[grad_lin_idx[i]] = grad_lin_coef[i] * w[grad_lin_idx[i]] (fp32 product, bit-identical to the full form); all other
+ * gradient entries are 0.  Same arithmetic and same kernels as nlo_nlp_eval_host; any output may be NULL.                  */
+typedef struct nlo_nlp_compact_counts_t {
+  long long n_g_var, n_g_copy, n_jac_var, n_jac_const, n_grad_var, n_grad_lin;
+} nlo_nlp_compact_counts_t;
+NLO_API int nlo_nlp_compact_counts(const nlo_nlp* p, nlo_nlp_compact_counts_t* out);
+/* index lists sized by nlo_nlp_compact_counts; any pointer may be NULL                          */
+NLO_API int nlo_nlp_compact_layout(const nlo_nlp* p, int32_t* g_var_rows, int32_t* g_copy_rows, int32_t* g_copy_vars,
+                                   int32_t* jac_var_nz, int32_t* jac_const_nz, float* jac_const_val,
+                                   int32_t* grad_var_idx, int32_t* grad_lin_idx, float* grad_lin_coef);
+NLO_API int nlo_nlp_eval_host_compact(nlo_nlp* p, const float* w_host, size_t P,
+                                      float* g_var_host, float* jac_var_host, float* f_host, float* grad_var_host);
 /* layout helpers on device: [rows][ld] variable-major <-> [P][rows] problem-major              */
 NLO_API int nlo_transpose_to_soa(const float* aos, float* soa, size_t P, size_t rows, size_t ld, void* stream);
 NLO_API int nlo_transpose_to_aos(const float* soa, float* aos, size_t P, size_t rows, size_t ld, void* stream);

@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -24,6 +25,19 @@ int nlo_fail(const char* fmt, ...) {
   return 1;
 }
 void nlo_count_launch(unsigned n) { g_launches += n; }
+
+int nlo_model_stream_slot(nlo_sdf_model* m, cudaStream_t st) {
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  for (int i = 0; i < m->n_slots; ++i) if (m->slot_stream[i] == st) return i;
+  if (m->n_slots == NLO_STREAM_SLOTS) {
+    // every slot belongs to some other stream: drain the device, then nothing in flight owns a slot any more
+    if (cudaDeviceSynchronize() != cudaSuccess) { nlo_fail("device synchronisation failed while recycling stream slots"); return -1; }
+    m->n_slots = 0;
+  }
+  m->slot_stream[m->n_slots] = st;
+  return m->n_slots++;
+}
 
 extern "C" {
 
@@ -134,7 +148,7 @@ void nlo_sdf_destroy(nlo_sdf_model* m) {
   if (m->d_wt) cudaFree(m->d_wt);
   if (m->d_tc) cudaFree(m->d_tc);
   if (m->d_io) cudaFree(m->d_io);
-  if (m->d_ws) cudaFree(m->d_ws);
+  for (float* b : m->d_ws) if (b) cudaFree(b);
   if (m->h_io) cudaFreeHost(m->h_io);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
@@ -466,7 +480,32 @@ int nlo_nlp_create(const nlo_nlp_desc* desc, nlo_sdf_model* model, int device, n
   memset(&p->scratch, 0, sizeof(p->scratch));
   memset(p->lane, 0, sizeof(p->lane));
   std::vector<int> nzmap, copy_row, copy_var, copy_emit;
-  if (nlo_nlp_build_layout(desc, &p->L, &p->rows_ccs, &p->cols_ccs, &nzmap, &copy_row, &copy_var, &copy_emit)) { delete p; return 1; }
+  std::vector<float> const_ccs;
+  p->d_compact = nullptr;
+  if (nlo_nlp_build_layout(desc, &p->L, &p->rows_ccs, &p->cols_ccs, &nzmap, &copy_row, &copy_var, &copy_emit, &const_ccs)) { delete p; return 1; }
+  {
+    // what varies with w and what does not (compact host form)
+    const NlpDev& L = p->L;
+    std::vector<char> is_copy(L.n_g, 0);
+    for (size_t i = 0; i < copy_row.size(); ++i) { is_copy[copy_row[i]] = 1; p->cg_copy_row.push_back(copy_row[i]); p->cg_copy_var.push_back(copy_var[i]); }
+    for (int r = 0; r < L.n_g; ++r) if (!is_copy[r]) p->cg_rows.push_back(r);
+    for (int z = 0; z < L.nnz; ++z) {
+      if (std::isnan(const_ccs[z])) p->cj_nz.push_back(z);
+      else { p->cj_const_nz.push_back(z); p->cj_const_val.push_back(const_ccs[z]); }
+    }
+    for (int k = 0; k <= L.N; ++k) { p->cgr_idx.push_back(k * L.nx); p->cgr_idx.push_back(k * L.nx + 1); }
+    if (L.use_smooth) for (int k = 0; k < L.N - 1; ++k) for (int i = 0; i < L.nu; ++i) {
+      p->cgr_lin_idx.push_back(L.n_X + k * L.nu + i); p->cgr_lin_coef.push_back(2.f * L.smooth_weight);
+    }
+    if (L.use_slack) for (int k = 0; k <= L.N; ++k) { p->cgr_lin_idx.push_back(L.n_X + L.n_U + k); p->cgr_lin_coef.push_back(2.f * L.slack_penalty); }
+    std::vector<int> ct(p->cg_rows);
+    ct.insert(ct.end(), p->cj_nz.begin(), p->cj_nz.end());
+    ct.insert(ct.end(), p->cgr_idx.begin(), p->cgr_idx.end());
+    if (cudaMalloc(&p->d_compact, ct.size() * sizeof(int)) != cudaSuccess ||
+        cudaMemcpy(p->d_compact, ct.data(), ct.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
+      nlo_nlp_destroy(p); return nlo_fail("device allocation failed");
+    }
+  }
   if (cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) { delete p; return nlo_fail("cannot query device"); }
   const int nc = (int)copy_row.size();
   std::vector<int> tables(nzmap);
@@ -521,6 +560,7 @@ void nlo_nlp_destroy(nlo_nlp* p) {
   for (auto& ln : p->lane) { free_lane_bufs(ln); if (ln.stream) cudaStreamDestroy(ln.stream); }
   if (p->d_tables) cudaFree(p->d_tables);
   if (p->d_hmap) cudaFree(p->d_hmap);
+  if (p->d_compact) cudaFree(p->d_compact);
   if (p->zc) cudaFreeHost(p->zc);
   for (float*& b : p->d_hs) { if (b) cudaFree(b); b = nullptr; }
   delete p;
@@ -564,6 +604,23 @@ static int nlp_eval_on(nlo_nlp* p, NlpScratch& sc, const float* w, size_t P, siz
   return 0;
 }
 
+static int ensure_hess_scratch(nlo_nlp* p, size_t P) {
+  if (p->hs_cap_P >= P) return 0;
+  const size_t n = (size_t)(p->L.N + 1) * p->L.nb * P;
+  for (float*& b : p->d_hs) { if (b) cudaFree(b); b = nullptr; }
+  p->hs_cap_P = 0;
+  for (float*& b : p->d_hs) NLO_CUDA(cudaMalloc(&b, n * sizeof(float)));
+  p->hs_cap_P = P;
+  return 0;
+}
+
+int nlo_nlp_reserve(nlo_nlp* p, size_t P) {
+  if (!p) return nlo_fail("null nlp");
+  NLO_CUDA(cudaSetDevice(p->device));
+  if (ensure_scratch(p, p->scratch, P)) return 1;
+  return ensure_hess_scratch(p, P);
+}
+
 int nlo_nlp_eval(nlo_nlp* p, const float* w, size_t P, size_t ld, float* g, float* jac, float* f, float* grad_f, void* stream) {
   if (!p) return nlo_fail("null nlp");
   if (P == 0) return 0;
@@ -594,12 +651,7 @@ int nlo_nlp_hess(nlo_nlp* p, const float* w, const float* sigma, const float* la
   cudaStream_t st = (cudaStream_t)stream;
   if (ensure_scratch(p, p->scratch, P)) return 1;
   const size_t n = (size_t)(p->L.N + 1) * p->L.nb * P;
-  if (p->hs_cap_P < P) {
-    for (float*& b : p->d_hs) { if (b) cudaFree(b); b = nullptr; }
-    p->hs_cap_P = 0;
-    for (float*& b : p->d_hs) NLO_CUDA(cudaMalloc(&b, n * sizeof(float)));
-    p->hs_cap_P = P;
-  }
+  if (ensure_hess_scratch(p, P)) return 1;
   NlpScratch& sc = p->scratch;
   if (nlo_nlp_launch_points(p->L, w, P, ld, sc.px, sc.py, st)) return 1;
   if (p->L.sdf_mode == NLO_SDF_CIRCLES) {
@@ -678,7 +730,9 @@ static int ensure_lane(nlo_nlp* p, NlpLane& ln, size_t P) {
 // Small batches (the reference's own case is ONE problem per IPOPT callback): no memcpy and no device transpose.  The decision
 // vectors are laid out variable-major in pinned, device-mapped memory by the CPU, the kernels read and write that memory directly
 // (zero-copy), and the CPU scatters the results back: three launches and one stream synchronisation per call.
-static int nlp_eval_host_small(nlo_nlp* p, const float* w_host, size_t P, float* g_host, float* jac_host, float* f_host, float* grad_host) {
+// compact: g / jac / grad records hold only the entries listed by nlo_nlp_compact_layout (cg_rows, cj_nz, cgr_idx).
+static int nlp_eval_host_small(nlo_nlp* p, const float* w_host, size_t P, float* g_host, float* jac_host, float* f_host, float* grad_host,
+                               bool compact) {
   const NlpDev& L = p->L;
   const size_t n_in = (size_t)L.n_w * P, n_out = ((size_t)L.n_g + L.nnz + L.n_w + 1) * P;
   if (p->zc_cap < n_in + n_out) {
@@ -692,27 +746,33 @@ static int nlp_eval_host_small(nlo_nlp* p, const float* w_host, size_t P, float*
   cudaStream_t st = p->lane[0].stream;
   if (nlp_eval_on(p, p->lane[0].scratch, w, P, P, g_host ? g : nullptr, jac_host ? jac : nullptr, f_host ? f : nullptr, grad_host ? grad : nullptr, st)) return 1;
   NLO_CUDA(cudaStreamSynchronize(st));
+  const int ng = compact ? (int)p->cg_rows.size() : L.n_g, nj = compact ? (int)p->cj_nz.size() : L.nnz, nr = compact ? (int)p->cgr_idx.size() : L.n_w;
   for (size_t i = 0; i < P; ++i) {
-    if (g_host) for (int r = 0; r < L.n_g; ++r) g_host[i * L.n_g + r] = g[(size_t)r * P + i];
-    if (jac_host) for (int z = 0; z < L.nnz; ++z) jac_host[i * L.nnz + z] = jac[(size_t)z * P + i];
-    if (grad_host) for (int v = 0; v < L.n_w; ++v) grad_host[i * L.n_w + v] = grad[(size_t)v * P + i];
+    if (g_host) for (int r = 0; r < ng; ++r) g_host[i * ng + r] = g[(size_t)(compact ? p->cg_rows[r] : r) * P + i];
+    if (jac_host) for (int z = 0; z < nj; ++z) jac_host[i * nj + z] = jac[(size_t)(compact ? p->cj_nz[z] : z) * P + i];
+    if (grad_host) for (int v = 0; v < nr; ++v) grad_host[i * nr + v] = grad[(size_t)(compact ? p->cgr_idx[v] : v) * P + i];
     if (f_host) f_host[i] = f[i];
   }
   return 0;
 }
 
-int nlo_nlp_eval_host(nlo_nlp* p, const float* w_host, size_t P, float* g_host, float* jac_host, float* f_host, float* grad_host) {
+static int nlp_eval_host_impl(nlo_nlp* p, const float* w_host, size_t P, float* g_host, float* jac_host, float* f_host, float* grad_host,
+                              bool compact) {
   if (!p) return nlo_fail("null nlp");
   if (P == 0) return 0;
   if (!w_host) return nlo_fail("null w");
   NLO_CUDA(cudaSetDevice(p->device));
-  if (P <= 8) return nlp_eval_host_small(p, w_host, P, g_host, jac_host, f_host, grad_host);
+  if (P <= 8) return nlp_eval_host_small(p, w_host, P, g_host, jac_host, f_host, grad_host, compact);
   const NlpDev& L = p->L;
-  size_t chunk = (P + 7) / 8;
+  // chunks: enough of them that the first chunk's upload + kernels (the only part no copy hides) is a small share of the call,
+  // large enough that a chunk's kernels fill the GPU
+  size_t chunk = (P + 15) / 16;
   if (chunk < 2048) chunk = 2048;
   if (chunk > P) chunk = P;
   const size_t n_chunks = (P + chunk - 1) / chunk;
   const int n_lanes = n_chunks > 1 ? 2 : 1;
+  const int ng = compact ? (int)p->cg_rows.size() : L.n_g, nj = compact ? (int)p->cj_nz.size() : L.nnz, nr = compact ? (int)p->cgr_idx.size() : L.n_w;
+  const int* d_cg = p->d_compact; const int* d_cj = d_cg + p->cg_rows.size(); const int* d_cr = d_cj + p->cj_nz.size();
   for (int l = 0; l < n_lanes; ++l) if (ensure_lane(p, p->lane[l], chunk)) return 1;
   for (size_t c = 0; c < n_chunks; ++c) {
     NlpLane& ln = p->lane[c % n_lanes];
@@ -723,20 +783,51 @@ int nlo_nlp_eval_host(nlo_nlp* p, const float* w_host, size_t P, float* g_host, 
     if (nlp_eval_on(p, ln.scratch, ln.d_w, Pc, Pc, g_host ? ln.d_g : nullptr, jac_host ? ln.d_jac : nullptr, f_host ? ln.d_f : nullptr,
                     grad_host ? ln.d_grad : nullptr, st)) return 1;
     if (jac_host) {
-      if (nlo_launch_transpose(ln.d_jac, ln.d_ojac, L.nnz, Pc, Pc, L.nnz, p->sm_count, st)) return 1;
-      NLO_CUDA(cudaMemcpyAsync(jac_host + p0 * L.nnz, ln.d_ojac, (size_t)L.nnz * Pc * sizeof(float), cudaMemcpyDeviceToHost, st));
+      if (compact ? nlo_launch_pack_rows(ln.d_jac, Pc, Pc, d_cj, nj, ln.d_ojac, p->sm_count, st)
+                  : nlo_launch_transpose(ln.d_jac, ln.d_ojac, L.nnz, Pc, Pc, L.nnz, p->sm_count, st)) return 1;
+      NLO_CUDA(cudaMemcpyAsync(jac_host + p0 * nj, ln.d_ojac, (size_t)nj * Pc * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
     if (g_host) {
-      if (nlo_launch_transpose(ln.d_g, ln.d_og, L.n_g, Pc, Pc, L.n_g, p->sm_count, st)) return 1;
-      NLO_CUDA(cudaMemcpyAsync(g_host + p0 * L.n_g, ln.d_og, (size_t)L.n_g * Pc * sizeof(float), cudaMemcpyDeviceToHost, st));
+      if (compact ? nlo_launch_pack_rows(ln.d_g, Pc, Pc, d_cg, ng, ln.d_og, p->sm_count, st)
+                  : nlo_launch_transpose(ln.d_g, ln.d_og, L.n_g, Pc, Pc, L.n_g, p->sm_count, st)) return 1;
+      NLO_CUDA(cudaMemcpyAsync(g_host + p0 * ng, ln.d_og, (size_t)ng * Pc * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
     if (grad_host) {
-      if (nlo_launch_transpose(ln.d_grad, ln.d_ograd, L.n_w, Pc, Pc, L.n_w, p->sm_count, st)) return 1;
-      NLO_CUDA(cudaMemcpyAsync(grad_host + p0 * L.n_w, ln.d_ograd, (size_t)L.n_w * Pc * sizeof(float), cudaMemcpyDeviceToHost, st));
+      if (compact ? nlo_launch_pack_rows(ln.d_grad, Pc, Pc, d_cr, nr, ln.d_ograd, p->sm_count, st)
+                  : nlo_launch_transpose(ln.d_grad, ln.d_ograd, L.n_w, Pc, Pc, L.n_w, p->sm_count, st)) return 1;
+      NLO_CUDA(cudaMemcpyAsync(grad_host + p0 * nr, ln.d_ograd, (size_t)nr * Pc * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
     if (f_host) NLO_CUDA(cudaMemcpyAsync(f_host + p0, ln.d_f, Pc * sizeof(float), cudaMemcpyDeviceToHost, st));
   }
   for (int l = 0; l < n_lanes; ++l) NLO_CUDA(cudaStreamSynchronize(p->lane[l].stream));
+  return 0;
+}
+
+int nlo_nlp_eval_host(nlo_nlp* p, const float* w_host, size_t P, float* g_host, float* jac_host, float* f_host, float* grad_host) {
+  return nlp_eval_host_impl(p, w_host, P, g_host, jac_host, f_host, grad_host, false);
+}
+
+int nlo_nlp_eval_host_compact(nlo_nlp* p, const float* w_host, size_t P, float* g_var_host, float* jac_var_host, float* f_host,
+                              float* grad_var_host) {
+  return nlp_eval_host_impl(p, w_host, P, g_var_host, jac_var_host, f_host, grad_var_host, true);
+}
+
+int nlo_nlp_compact_counts(const nlo_nlp* p, nlo_nlp_compact_counts_t* out) {
+  if (!p || !out) return nlo_fail("null argument");
+  out->n_g_var = (long long)p->cg_rows.size(); out->n_g_copy = (long long)p->cg_copy_row.size();
+  out->n_jac_var = (long long)p->cj_nz.size(); out->n_jac_const = (long long)p->cj_const_nz.size();
+  out->n_grad_var = (long long)p->cgr_idx.size(); out->n_grad_lin = (long long)p->cgr_lin_idx.size();
+  return 0;
+}
+
+int nlo_nlp_compact_layout(const nlo_nlp* p, int32_t* g_var_rows, int32_t* g_copy_rows, int32_t* g_copy_vars, int32_t* jac_var_nz,
+                           int32_t* jac_const_nz, float* jac_const_val, int32_t* grad_var_idx, int32_t* grad_lin_idx, float* grad_lin_coef) {
+  if (!p) return nlo_fail("null nlp");
+  auto put = [](int32_t* dst, const std::vector<int>& v) { if (dst) for (size_t i = 0; i < v.size(); ++i) dst[i] = v[i]; };
+  auto putf = [](float* dst, const std::vector<float>& v) { if (dst) for (size_t i = 0; i < v.size(); ++i) dst[i] = v[i]; };
+  put(g_var_rows, p->cg_rows); put(g_copy_rows, p->cg_copy_row); put(g_copy_vars, p->cg_copy_var);
+  put(jac_var_nz, p->cj_nz); put(jac_const_nz, p->cj_const_nz); putf(jac_const_val, p->cj_const_val);
+  put(grad_var_idx, p->cgr_idx); put(grad_lin_idx, p->cgr_lin_idx); putf(grad_lin_coef, p->cgr_lin_coef);
   return 0;
 }
 

@@ -28,6 +28,7 @@ void nlo_count_launch(unsigned n = 1);
   } while (0)
 
 // ---- model ------------------------------------------------------------------------------------
+#define NLO_STREAM_SLOTS 8
 struct SdfNetDev {           // passed by value to kernels
   const float* w;            // flat blob on device (layout in nlo_b200.h)
   int H, M;
@@ -53,14 +54,18 @@ struct nlo_sdf_model {
   size_t n_w;
   // tensor-path operand images (built on demand by sdf_tc.cu)
   void* d_tc;                // W1 split into fp16 hi | lo images in UMMA core-matrix order
-  size_t tc_bytes;           // bytes of the images; a ring of 64 tile counters (dynamic tile scheduling) follows them
-  unsigned tc_seq;           // launches so far (selects the counter)
+  size_t tc_bytes;           // bytes of the images; NLO_STREAM_SLOTS x {tile counter, finished-CTA counter} follow them (zeroed once;
+                             // the last CTA of a launch resets its pair, so no memset is needed per launch)
   float tc_params[8];        // TcParams of sdf_tc.cu (scales and bounds)
   float tc_const[776];       // TcConst of sdf_tc.cu (small vectors handed to the kernel as a __grid_constant__ parameter)
   // scratch for the host-buffer entry points
   float* d_io; size_t io_cap;        // device staging
   float* h_io; size_t h_cap;         // pinned staging
-  float* d_ws; size_t ws_cap;        // global-memory activation scratch (large nets / hessian)
+  // Per-stream slots: one model is evaluated from several streams at once (the two lanes of nlo_nlp_eval_host, the model's own
+  // stream, caller streams), so everything a launch mutates on the device - the activation workspace of the FP32 paths and the
+  // dynamic tile counter of the tensor path - is owned by the stream that launches it (slot = nlo_model_stream_slot()).
+  cudaStream_t slot_stream[NLO_STREAM_SLOTS]; int n_slots;
+  float* d_ws[NLO_STREAM_SLOTS]; size_t ws_cap[NLO_STREAM_SLOTS];   // global-memory activation scratch (large nets / hessian)
   cudaStream_t stream;               // private stream for host-buffer entry points
   SdfNetDev net() const {
     SdfNetDev n; n.w = d_w; n.H = (int)desc.hidden; n.M = (int)desc.n_hidden_mats;
@@ -169,6 +174,9 @@ __device__ __forceinline__ float nlo_phi_d2_from_vd(int act, float prm, float v,
 }
 
 // ---- kernels' host-side launchers (one per .cu) -------------------------------------------------
+// capi.cu: index of the per-stream slot of `st` in the model (claims a free one; when all are taken by other streams the device is
+// drained and the table starts over).  < 0 on error.
+int nlo_model_stream_slot(nlo_sdf_model* m, cudaStream_t st);
 // sdf_simt.cu
 int nlo_sdf_simt_launch(nlo_sdf_model* m, const float* x, const float* y, const float* sbar, size_t n,
                         float* s, float* jx, float* jy, cudaStream_t st);

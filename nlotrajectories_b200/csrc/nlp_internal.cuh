@@ -32,7 +32,7 @@ struct NlpLane {                // one pipeline lane of nlo_nlp_eval_host
   size_t cap_P;                 // problems per chunk the buffers below hold
   float *d_in, *d_w;            // problem-major staging of w, and its SoA transpose
   float *d_g, *d_jac, *d_f, *d_grad;          // SoA outputs
-  float *d_og, *d_ojac, *d_ograd;             // problem-major staging of the outputs
+  float *d_og, *d_ojac, *d_ograd;             // problem-major staging of the outputs (full or compact records)
   NlpScratch scratch;
 };
 
@@ -50,6 +50,12 @@ struct nlo_nlp {
   int* d_hmap;                  // device: [N+1][NLO_HESS_SLOTS] emission slot -> CCS position (or -1)
   float* d_hs[3]; size_t hs_cap_P;          // SDF Hessian scratch (hxx, hxy, hyy) for hs_cap_P problems
   float* zc; size_t zc_cap;                 // pinned, device-mapped staging of the small-batch host entry point (floats)
+  // compact host form (nlo_nlp_eval_host_compact): only what varies with w travels back
+  std::vector<int> cg_rows, cj_nz, cgr_idx;           // varying rows of g / non-zeros of dg/dw / entries of grad f
+  std::vector<int> cg_copy_row, cg_copy_var;          // g[row] = w[var]
+  std::vector<int> cj_const_nz; std::vector<float> cj_const_val;     // dg/dw[nz] = value for every w
+  std::vector<int> cgr_lin_idx; std::vector<float> cgr_lin_coef;     // grad f[idx] = coef * w[idx]; every other non-varying entry is 0
+  int* d_compact;                                     // device: cg_rows | cj_nz | cgr_idx
   NlpLane lane[2];              // host entry point: two lanes (streams) process alternating chunks of problems
 };
 
@@ -115,7 +121,8 @@ __host__ __device__ constexpr int kDynA(int a, int q) {
 
 int nlo_nlp_build_layout(const nlo_nlp_desc* d, NlpDev* L, std::vector<int>* rows_ccs, std::vector<int>* cols_ccs,
                          std::vector<int>* nzmap, std::vector<int>* copy_row, std::vector<int>* copy_var,
-                         std::vector<int>* copy_emit);
+                         std::vector<int>* copy_emit, std::vector<float>* const_ccs = nullptr);
+int nlo_launch_pack_rows(const float* in, size_t ld_in, size_t P, const int* idx, int n_out, float* out, int sm, cudaStream_t st);
 // phase 0: everything before the SDF evaluation (defects, copy rows, footprint points / circles, f, grad f)
 // phase 1: SDF rows (needs p->d_s/d_jx/d_jy)
 int nlo_nlp_launch_assembly(nlo_nlp* p, const NlpScratch& sc, const float* w, size_t P, size_t ld, float* g, float* jac, float* f,

@@ -21,22 +21,24 @@
 // ---- structural tables -----------------------------------------------------
 namespace {
 
-struct DynTable { int nx, nu, nA, nB; int A[10][2]; int B[4][2]; };
+// A / B: structural (row, column) pairs of df/dx, df/du; Ac / Bc: 1 where the entry is the constant 1 for every (x, u)
+// (Dyn<>::eval below writes exactly 1.f there), 0 where it varies.
+struct DynTable { int nx, nu, nA, nB; int A[10][2]; int B[4][2]; int Ac[10]; int Bc[4]; };
 const DynTable kDyn[6] = {
-    /* point_1st     */ {4, 2, 0, 2, {{0, 0}}, {{0, 0}, {1, 1}}},
-    /* point_2nd     */ {4, 2, 2, 2, {{0, 2}, {1, 3}}, {{2, 0}, {3, 1}}},
-    /* unicycle      */ {3, 2, 2, 3, {{0, 2}, {1, 2}}, {{0, 0}, {1, 0}, {2, 1}}},
-    /* unicycle_2nd  */ {5, 2, 5, 2, {{0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 4}}, {{3, 0}, {4, 1}}},
-    /* ackermann     */ {4, 2, 3, 4, {{0, 2}, {1, 2}, {2, 3}}, {{0, 0}, {1, 0}, {2, 0}, {3, 1}}},
+    /* point_1st     */ {4, 2, 0, 2, {{0, 0}}, {{0, 0}, {1, 1}}, {0}, {1, 1}},
+    /* point_2nd     */ {4, 2, 2, 2, {{0, 2}, {1, 3}}, {{2, 0}, {3, 1}}, {1, 1}, {1, 1}},
+    /* unicycle      */ {3, 2, 2, 3, {{0, 2}, {1, 2}}, {{0, 0}, {1, 0}, {2, 1}}, {0, 0}, {0, 0, 1}},
+    /* unicycle_2nd  */ {5, 2, 5, 2, {{0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 4}}, {{3, 0}, {4, 1}}, {0, 0, 0, 0, 1}, {1, 1}},
+    /* ackermann     */ {4, 2, 3, 4, {{0, 2}, {1, 2}, {2, 3}}, {{0, 0}, {1, 0}, {2, 0}, {3, 1}}, {0, 0, 0}, {0, 0, 0, 1}},
     /* ackermann_2nd */ {7, 2, 10, 3, {{0, 2}, {0, 4}, {1, 2}, {1, 4}, {2, 3}, {2, 4}, {3, 6}, {4, 3}, {4, 4}, {4, 6}},
-                         {{4, 0}, {5, 0}, {6, 1}}},
+                         {{4, 0}, {5, 0}, {6, 1}}, {0, 0, 0, 0, 0, 0, 1, 0, 0, 0}, {0, 1, 1}},
 };
 
 }  // namespace
 
 int nlo_nlp_build_layout(const nlo_nlp_desc* d, NlpDev* L, std::vector<int>* rows_ccs, std::vector<int>* cols_ccs,
                          std::vector<int>* nzmap, std::vector<int>* copy_row, std::vector<int>* copy_var,
-                         std::vector<int>* copy_emit) {
+                         std::vector<int>* copy_emit, std::vector<float>* const_ccs) {
   if (d->dynamics > 5) return nlo_fail("unknown dynamics id %u", d->dynamics);
   if (d->shape > 2) return nlo_fail("unknown shape id %u", d->shape);
   if (d->N < 1) return nlo_fail("N must be >= 1");
@@ -77,30 +79,36 @@ int nlo_nlp_build_layout(const nlo_nlp_desc* d, NlpDev* L, std::vector<int>* row
   l.n_g = l.g_off_ctrl + nu * N;
   // emission order == oracle/nlp_oracle.py::jac_pattern
   std::vector<int> rows, cols;
+  std::vector<float> cval;                     // per emission: the value when it is the same for every w, NAN when it varies
   auto iX = [&](int i, int k) { return k * nx + i; };
   auto iU = [&](int i, int k) { return l.n_X + k * nu + i; };
   auto iS = [&](int k) { return l.n_X + l.n_U + k; };
   int r = 0;
-  auto add_copy = [&](int row, int var) { copy_row->push_back(row); copy_var->push_back(var); copy_emit->push_back((int)rows.size()); rows.push_back(row); cols.push_back(var); };
+  auto add_copy = [&](int row, int var) { copy_row->push_back(row); copy_var->push_back(var); copy_emit->push_back((int)rows.size()); rows.push_back(row); cols.push_back(var); cval.push_back(1.f); };
   for (int i = 0; i < nx; ++i) add_copy(r++, iX(i, 0));
   for (int i = 0; i < nx; ++i) if (l.enforce_heading || i != 2) add_copy(r++, iX(i, N));
   l.e_off_dyn = (int)rows.size();
   for (int k = 0; k < N; ++k) {
-    for (int i = 0; i < nx; ++i) { rows.push_back(r + i); cols.push_back(iX(i, k + 1)); }
-    for (int i = 0; i < nx; ++i) { rows.push_back(r + i); cols.push_back(iX(i, k)); }
-    for (int a = 0; a < T.nA; ++a) if (T.A[a][0] != T.A[a][1]) { rows.push_back(r + T.A[a][0]); cols.push_back(iX(T.A[a][1], k)); }
-    for (int b = 0; b < T.nB; ++b) { rows.push_back(r + T.B[b][0]); cols.push_back(iU(T.B[b][1], k)); }
+    for (int i = 0; i < nx; ++i) { rows.push_back(r + i); cols.push_back(iX(i, k + 1)); cval.push_back(1.f); }
+    for (int i = 0; i < nx; ++i) {
+      bool diag_varies = false;
+      for (int a = 0; a < T.nA; ++a) if (T.A[a][0] == i && T.A[a][1] == i) diag_varies = true;
+      rows.push_back(r + i); cols.push_back(iX(i, k)); cval.push_back(diag_varies ? NAN : -1.f);
+    }
+    for (int a = 0; a < T.nA; ++a) if (T.A[a][0] != T.A[a][1]) { rows.push_back(r + T.A[a][0]); cols.push_back(iX(T.A[a][1], k)); cval.push_back(T.Ac[a] ? -l.dt * 1.f : NAN); }
+    for (int b = 0; b < T.nB; ++b) { rows.push_back(r + T.B[b][0]); cols.push_back(iU(T.B[b][1], k)); cval.push_back(T.Bc[b] ? -l.dt * 1.f : NAN); }
     r += nx;
   }
   if (l.use_slack) for (int k = 0; k <= N; ++k) add_copy(r++, iS(k));
   l.e_off_sdf = (int)rows.size();
   for (int k = 0; k <= N; ++k) {
-    if (l.shape == NLO_SHAPE_DOT) { rows.push_back(r); cols.push_back(iX(0, k)); rows.push_back(r); cols.push_back(iX(1, k)); ++r; }
+    if (l.shape == NLO_SHAPE_DOT) { rows.push_back(r); cols.push_back(iX(0, k)); rows.push_back(r); cols.push_back(iX(1, k)); ++r; cval.push_back(NAN); cval.push_back(NAN); }
     else if (l.use_slack) {
       rows.push_back(r); cols.push_back(iX(0, k)); rows.push_back(r); cols.push_back(iX(1, k));
       rows.push_back(r); cols.push_back(iX(2, k)); rows.push_back(r); cols.push_back(iS(k)); ++r;
+      cval.push_back(NAN); cval.push_back(NAN); cval.push_back(NAN); cval.push_back(1.f);
     } else {
-      for (int c = 0; c < l.nb; ++c) { for (int q = 0; q < 3; ++q) { rows.push_back(r); cols.push_back(iX(q, k)); } ++r; }
+      for (int c = 0; c < l.nb; ++c) { for (int q = 0; q < 3; ++q) { rows.push_back(r); cols.push_back(iX(q, k)); cval.push_back(NAN); } ++r; }
     }
   }
   for (int i = 0; i < nu; ++i) for (int k = 0; k < N; ++k) add_copy(r++, iU(i, k));
@@ -111,6 +119,8 @@ int nlo_nlp_build_layout(const nlo_nlp_desc* d, NlpDev* L, std::vector<int>* row
   std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return cols[a] != cols[b] ? cols[a] < cols[b] : rows[a] < rows[b]; });
   nzmap->assign(l.nnz, 0); rows_ccs->resize(l.nnz); cols_ccs->resize(l.nnz);
   for (int pos = 0; pos < l.nnz; ++pos) { (*nzmap)[perm[pos]] = pos; (*rows_ccs)[pos] = rows[perm[pos]]; (*cols_ccs)[pos] = cols[perm[pos]]; }
+  if ((int)cval.size() != l.nnz) return nlo_fail("internal: constant table size %zu != nnz %d", cval.size(), l.nnz);
+  if (const_ccs) { const_ccs->assign(l.nnz, NAN); for (int pos = 0; pos < l.nnz; ++pos) (*const_ccs)[pos] = cval[perm[pos]]; }
   return 0;
 }
 
@@ -416,6 +426,27 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
   }
 }
 
+// ---- gather + transpose: out[p][c] = in[idx[c]][p]  (variable-major rows picked by an index list -> problem-major records) ----
+__global__ void __launch_bounds__(256) pack_rows_kernel(const float* __restrict__ in, size_t ld_in, size_t P, const int* __restrict__ idx,
+                                                        int n_out, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const size_t tiles_c = ((size_t)n_out + 31) / 32, tiles_p = (P + 31) / 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (size_t tidx = blockIdx.x; tidx < tiles_c * tiles_p; tidx += gridDim.x) {
+    const size_t tp = tidx / tiles_c, tc = tidx - tp * tiles_c;
+    for (int j = ty; j < 32; j += 8) {
+      const size_t c = tc * 32 + j, p = tp * 32 + tx;
+      tile[j][tx] = (c < (size_t)n_out && p < P) ? in[(size_t)idx[c] * ld_in + p] : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+      const size_t p = tp * 32 + j, c = tc * 32 + tx;
+      if (p < P && c < (size_t)n_out) out[p * (size_t)n_out + c] = tile[tx][j];
+    }
+    __syncthreads();
+  }
+}
+
 inline int grid_for(size_t total, int threads, int sm_count) {
   size_t want = (total + threads - 1) / threads;
   size_t cap = (size_t)sm_count * 8;
@@ -484,6 +515,14 @@ int nlo_launch_violation(int n_g, const float* g, const float* lb, const float* 
 int nlo_launch_jtv(int n_w, const int* colind, const int* row, const float* jac, const float* y, size_t P, size_t ld, const float* add,
                    float* out, int sm, cudaStream_t st) {
   nlp_jtv_kernel<<<grid_for((size_t)n_w * P, 256, sm), 256, 0, st>>>(n_w, colind, row, jac, y, P, ld, add, out);
+  NLO_CHECK_LAUNCH();
+  return 0;
+}
+
+int nlo_launch_pack_rows(const float* in, size_t ld_in, size_t P, const int* idx, int n_out, float* out, int sm, cudaStream_t st) {
+  if (P == 0 || n_out == 0) return 0;
+  const size_t tiles = (((size_t)n_out + 31) / 32) * ((P + 31) / 32);
+  pack_rows_kernel<<<(int)std::min<size_t>(tiles, (size_t)sm * 16), 256, 0, st>>>(in, ld_in, P, idx, n_out, out);
   NLO_CHECK_LAUNCH();
   return 0;
 }

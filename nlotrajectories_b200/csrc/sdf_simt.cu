@@ -486,12 +486,18 @@ template <int TN>
 int launch_gemm(nlo_sdf_model* m, const float* x, const float* y, const float* sbar, size_t n, float* s, float* jx, float* jy,
                 cudaStream_t st);
 
-int ensure_ws(nlo_sdf_model* m, size_t bytes) {
-  if (m->ws_cap >= bytes) return 0;
-  if (m->d_ws) cudaFree(m->d_ws);
-  m->d_ws = nullptr; m->ws_cap = 0;
-  NLO_CUDA(cudaMalloc(&m->d_ws, bytes));
-  m->ws_cap = bytes;
+// Activation workspace of the stream that launches: two streams evaluating one model (the lanes of nlo_nlp_eval_host) must not
+// share it - the tail CTAs of one launch and the first CTAs of the next would write the same blocks.
+int ensure_ws(nlo_sdf_model* m, cudaStream_t st, size_t bytes, float** out) {
+  const int slot = nlo_model_stream_slot(m, st);
+  if (slot < 0) return 1;
+  if (m->ws_cap[slot] < bytes) {
+    if (m->d_ws[slot]) cudaFree(m->d_ws[slot]);          // (cudaFree waits for the device: no launch still reads the old block)
+    m->d_ws[slot] = nullptr; m->ws_cap[slot] = 0;
+    NLO_CUDA(cudaMalloc(&m->d_ws[slot], bytes));
+    m->ws_cap[slot] = bytes;
+  }
+  *out = m->d_ws[slot];
   return 0;
 }
 
@@ -502,15 +508,18 @@ int launch_gemm(nlo_sdf_model* m, const float* x, const float* y, const float* s
   SdfNetDev net = m->net();
   const size_t smem = (size_t)(H * GT_S + 2 * GT_KS * H + 3 * GT_P) * sizeof(float);
   auto kfn = sdf_gemm_kernel<TN>;
-  NLO_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static bool attr_set[64] = {false};                    // per device: the attribute call is not free on a 20 us path
+  if (!attr_set[m->device & 63]) {
+    NLO_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set[m->device & 63] = true;
+  }
   const int per_sm = TN <= 8 ? 2 : 1;
   const size_t tiles = (n + GT_P - 1) / GT_P;
   const size_t cap = (size_t)m->sm_count * per_sm;
   const int grid = (int)(tiles < cap ? tiles : cap);
   float* ws = nullptr;
   if (net.M > 1) {
-    if (ensure_ws(m, (size_t)grid * (net.M - 1) * H * GT_P * sizeof(float))) return 1;
-    ws = m->d_ws;
+    if (ensure_ws(m, st, (size_t)grid * (net.M - 1) * H * GT_P * sizeof(float), &ws)) return 1;
   }
   kfn<<<grid, GT_THREADS, smem, st>>>(net, m->d_wt, x, y, sbar, n, s, jx, jy, ws);
   NLO_CHECK_LAUNCH();
@@ -549,8 +558,7 @@ int nlo_sdf_simt_launch(nlo_sdf_model* m, const float* x, const float* y, const 
   int grid = (int)(want < cap ? want : cap);
   float* ws = nullptr;
   if (!s_smem) {
-    if (ensure_ws(m, (size_t)grid * T * per_thread)) return 1;
-    ws = m->d_ws;
+    if (ensure_ws(m, st, (size_t)grid * T * per_thread, &ws)) return 1;
   }
 #define NLO_LAUNCH(WS, SS)                                                                                         \
   do {                                                                                                             \

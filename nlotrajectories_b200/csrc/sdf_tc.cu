@@ -482,6 +482,12 @@ sdf_tc_kernel(SdfNetDev net, TcParams prm_tc, const __half* __restrict__ bimg, c
   }
   tc_fence_before();
   __syncthreads();
+  // The last CTA to finish puts the tile counter back to zero for the next launch on this stream (tile_ctr[1] counts finished
+  // CTAs): no memset per launch.  Every group's atomicAdd on tile_ctr[0] has returned before the barrier above.
+  if (tile_ctr && t == 0) {
+    __threadfence();
+    if (atomicAdd(tile_ctr + 1, 1u) == gridDim.x - 1) { tile_ctr[0] = 0u; tile_ctr[1] = 0u; __threadfence(); }
+  }
   if (dbg && t == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); dbg[2 * 64 * 32 + blockIdx.x * 4 + 1] = (long long)gt; dbg[2 * 64 * 32 + blockIdx.x * 4 + 3] = clock64(); }
   if (warp == 0) tmem_dealloc(tmem_all, 512);
 }
@@ -495,7 +501,11 @@ int launch_tc(nlo_sdf_model* m, const float* x, const float* y, const float* sba
   using Cfg = TcCfg<H>;
   auto kfn = sdf_tc_kernel<H, ACT0, ACT, HESS>;
   const size_t smem = Cfg::bytes(ACT == NLO_ACT_RELU);
-  NLO_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static bool attr_set[64] = {false};                    // per device; the call costs microseconds on the single-problem path
+  if (!attr_set[m->device & 63]) {
+    NLO_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set[m->device & 63] = true;
+  }
   const size_t tiles = (n + TILE - 1) / TILE;
   const size_t want = (tiles + Cfg::NGROUPS - 1) / Cfg::NGROUPS;
   const int grid = (int)(want < (size_t)m->sm_count ? want : (size_t)m->sm_count);   // one persistent CTA per SM
@@ -516,8 +526,10 @@ int launch_tc(nlo_sdf_model* m, const float* x, const float* y, const float* sba
   }
   unsigned int* ctr = nullptr;
   if (tiles > (size_t)grid * Cfg::NGROUPS) {         // more than one tile per group: balance dynamically
-    ctr = reinterpret_cast<unsigned int*>(static_cast<char*>(m->d_tc) + m->tc_bytes) + (__atomic_fetch_add(&m->tc_seq, 1u, __ATOMIC_RELAXED) & 63u);
-    NLO_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st));
+    // the counter pair of the launching stream: launches on one stream are ordered, and the kernel leaves its pair at zero
+    const int slot = nlo_model_stream_slot(m, st);
+    if (slot < 0) return 1;
+    ctr = reinterpret_cast<unsigned int*>(static_cast<char*>(m->d_tc) + m->tc_bytes) + 2 * slot;
   }
   kfn<<<grid, Cfg::THREADS, smem, st>>>(m->net(), prm, reinterpret_cast<const __half*>(m->d_tc), x, y, sbar, n, s, jx, jy, hxx, hxy, hyy, ctr, dbg);
   if (dbg) {
@@ -628,10 +640,10 @@ int nlo_sdf_tc_prepare(nlo_sdf_model* m, const float* w) {
     }
   if (m->d_tc) cudaFree(m->d_tc);
   m->d_tc = nullptr;
-  NLO_CUDA(cudaMalloc(&m->d_tc, img.size() * sizeof(__half) + 64 * sizeof(unsigned int)));
+  NLO_CUDA(cudaMalloc(&m->d_tc, img.size() * sizeof(__half) + 2 * NLO_STREAM_SLOTS * sizeof(unsigned int)));
   NLO_CUDA(cudaMemcpy(m->d_tc, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice));
   m->tc_bytes = img.size() * sizeof(__half);
-  m->tc_seq = 0;
+  NLO_CUDA(cudaMemset(static_cast<char*>(m->d_tc) + m->tc_bytes, 0, 2 * NLO_STREAM_SLOTS * sizeof(unsigned int)));
   return 0;
 }
 

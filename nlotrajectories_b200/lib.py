@@ -29,6 +29,10 @@ class NlpDesc(C.Structure):
                 ("circles", (C.c_float * 4) * NLO_MAX_CIRCLES), ("obstacle_kind", C.c_uint32 * NLO_MAX_CIRCLES)]
 
 
+class CompactCounts(C.Structure):
+    _fields_ = [(n, C.c_longlong) for n in ("n_g_var", "n_g_copy", "n_jac_var", "n_jac_const", "n_grad_var", "n_grad_lin")]
+
+
 _P = C.c_void_p
 _F = C.c_void_p       # float* (device or host address passed as integer)
 _SZ = C.c_size_t
@@ -63,6 +67,7 @@ SIGNATURES = {
     "nlo_nlp_nnz_jac": (_LL, [_P]),
     "nlo_nlp_n_sdf_points": (_LL, [_P]),
     "nlo_nlp_jac_sparsity": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "nlo_nlp_reserve": (C.c_int, [_P, _SZ]),
     "nlo_nlp_eval": (C.c_int, [_P, _F, _SZ, _SZ, _F, _F, _F, _F, _P]),
     "nlo_nlp_eval_dynamics": (C.c_int, [_P, _F, _SZ, _SZ, _F, _F, _P]),
     "nlo_nlp_nnz_hess": (_LL, [_P]),
@@ -71,6 +76,9 @@ SIGNATURES = {
     "nlo_nlp_jac_tvec": (C.c_int, [_P, _F, _F, _F, _SZ, _SZ, _F, _P]),
     "nlo_nlp_violation": (C.c_int, [_P, _F, _F, _F, _SZ, _SZ, _F, _P]),
     "nlo_nlp_eval_host": (C.c_int, [_P, _F, _SZ, _F, _F, _F, _F]),
+    "nlo_nlp_compact_counts": (C.c_int, [_P, C.POINTER(CompactCounts)]),
+    "nlo_nlp_compact_layout": (C.c_int, [_P] + [_F] * 9),
+    "nlo_nlp_eval_host_compact": (C.c_int, [_P, _F, _SZ, _F, _F, _F, _F]),
     "nlo_transpose_to_soa": (C.c_int, [_F, _F, _SZ, _SZ, _SZ, _P]),
     "nlo_transpose_to_aos": (C.c_int, [_F, _F, _SZ, _SZ, _SZ, _P]),
 }

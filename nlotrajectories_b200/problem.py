@@ -188,6 +188,10 @@ class NlpProblem:
         st = torch.cuda.current_stream(w.device).cuda_stream if stream is None else stream
         _lib.check(self._L.nlo_nlp_eval_dynamics(self._h, w.data_ptr(), P, ld, _lib.ptr(g), _lib.ptr(jac), st))
 
+    def reserve(self, P: int) -> None:
+        """Size the handle's device scratch for P problems up front (later evaluations with <= P problems allocate nothing)."""
+        _lib.check(self._L.nlo_nlp_reserve(self._h, P))
+
     def alloc_outputs(self, P: int, device=None):
         import torch
         dev = torch.device("cuda", self.device) if device is None else device
@@ -205,6 +209,66 @@ class NlpProblem:
                 res[k] = np.empty(shapes[k], np.float32)
         _lib.check(self._L.nlo_nlp_eval_host(self._h, w.ctypes.data, P, _lib.ptr(res.get("g")), _lib.ptr(res.get("jac")),
                                              _lib.ptr(res.get("f")), _lib.ptr(res.get("grad_f"))))
+        return res
+
+    # ---- compact host form: only what varies with w travels back over PCIe ----------------------------------------
+    def compact_layout(self) -> dict:
+        """Index lists of ``nlo_nlp_compact_layout``: which rows of g / non-zeros of dg/dw / entries of grad f vary with w
+        (``g_var_rows``, ``jac_var_nz``, ``grad_var_idx``) and how everything else follows (``g_copy_rows/vars``,
+        ``jac_const_nz/val``, ``grad_lin_idx/coef``)."""
+        if getattr(self, "_compact", None) is None:
+            cnt = _lib.CompactCounts()
+            _lib.check(self._L.nlo_nlp_compact_counts(self._h, C.byref(cnt)))
+            i32 = lambda n: np.zeros(int(n), np.int32)
+            f32 = lambda n: np.zeros(int(n), np.float32)
+            lay = dict(g_var_rows=i32(cnt.n_g_var), g_copy_rows=i32(cnt.n_g_copy), g_copy_vars=i32(cnt.n_g_copy),
+                       jac_var_nz=i32(cnt.n_jac_var), jac_const_nz=i32(cnt.n_jac_const), jac_const_val=f32(cnt.n_jac_const),
+                       grad_var_idx=i32(cnt.n_grad_var), grad_lin_idx=i32(cnt.n_grad_lin), grad_lin_coef=f32(cnt.n_grad_lin))
+            order = ("g_var_rows", "g_copy_rows", "g_copy_vars", "jac_var_nz", "jac_const_nz", "jac_const_val", "grad_var_idx",
+                     "grad_lin_idx", "grad_lin_coef")
+            _lib.check(self._L.nlo_nlp_compact_layout(self._h, *[lay[k].ctypes.data for k in order]))
+            self._compact = lay
+        return self._compact
+
+    def eval_host_compact(self, w: np.ndarray, want=("g", "jac", "f", "grad_f"), out=None):
+        """Host problem-major evaluation returning only the varying entries: dict of ``g`` (P, n_g_var), ``jac`` (P, n_jac_var),
+        ``f`` (P,), ``grad_f`` (P, n_grad_var); ``expand_compact`` rebuilds the full arrays."""
+        w = np.ascontiguousarray(w, np.float32)
+        P = w.shape[0]
+        lay = self.compact_layout()
+        res = out if out is not None else {}
+        shapes = {"g": (P, len(lay["g_var_rows"])), "jac": (P, len(lay["jac_var_nz"])), "f": (P,), "grad_f": (P, len(lay["grad_var_idx"]))}
+        for k in want:
+            if k not in res:
+                res[k] = np.empty(shapes[k], np.float32)
+        _lib.check(self._L.nlo_nlp_eval_host_compact(self._h, w.ctypes.data, P, _lib.ptr(res.get("g")), _lib.ptr(res.get("jac")),
+                                                     _lib.ptr(res.get("f")), _lib.ptr(res.get("grad_f"))))
+        return res
+
+    def expand_compact(self, w: np.ndarray, compact: dict) -> dict:
+        """Full (P, n_g) / (P, nnz) / (P, n_w) arrays from a compact result and the decision vectors it was evaluated at
+        (what a per-problem solver does once for the constant parts, then per call for the varying ones)."""
+        w = np.ascontiguousarray(w, np.float32)
+        P = w.shape[0]
+        lay = self.compact_layout()
+        res = {}
+        if "g" in compact:
+            g = np.empty((P, self.n_g), np.float32)
+            g[:, lay["g_var_rows"]] = compact["g"]
+            g[:, lay["g_copy_rows"]] = w[:, lay["g_copy_vars"]]
+            res["g"] = g
+        if "jac" in compact:
+            jac = np.empty((P, self.nnz), np.float32)
+            jac[:, lay["jac_var_nz"]] = compact["jac"]
+            jac[:, lay["jac_const_nz"]] = lay["jac_const_val"][None, :]
+            res["jac"] = jac
+        if "grad_f" in compact:
+            gr = np.zeros((P, self.n_w), np.float32)
+            gr[:, lay["grad_var_idx"]] = compact["grad_f"]
+            gr[:, lay["grad_lin_idx"]] = lay["grad_lin_coef"][None, :] * w[:, lay["grad_lin_idx"]]
+            res["grad_f"] = gr
+        if "f" in compact:
+            res["f"] = compact["f"]
         return res
 
     def jac_tvec(self, jac, y, add=None, out=None, P: Optional[int] = None):
