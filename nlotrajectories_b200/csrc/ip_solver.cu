@@ -1,0 +1,506 @@
+// Batched interior-point solver on the device: the CUDA kernels around the bodies of ip_core.cuh, the
+// backend that ip_solve_loop drives, and the C ABI (nlo_ip_*).  It is the caller on both sides of the evaluation hot path -
+// every iteration is one nlo_nlp_eval, one nlo_nlp_hess, a few value-only evaluations for the line search, and the
+// block-tridiagonal factorisation of the condensed KKT matrix - and replaces what the reference delegates to IPOPT
+// (core/runner.py:112-133).  Nothing leaves the device between the initial upload of the starts and the final download.
+#include "nlo_common.cuh"
+#include "nlp_internal.cuh"
+#include "ip_core.cuh"
+#include "ip_tables.hpp"
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace {
+
+constexpr int IP_TPB = 128;     // threads per block of the one-thread-per-problem kernels
+constexpr int BT_TPB = 64;      // threads per block of the factorisation kernels (shared-memory scratch per thread)
+
+__global__ void __launch_bounds__(IP_TPB) ip_init_kernel(IpTables T, IpState S, IpWork W, size_t P, double mu0, int max_iter) {
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < P) ip_init_body(T, S, W, p, mu0, max_iter);
+}
+__global__ void __launch_bounds__(IP_TPB) ip_residual_kernel(IpTables T, IpState S, IpWork W, size_t P, int it, double tol) {
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int done = 0;
+  if (p < P) done = ip_residual_body(T, S, W, p, it, tol);
+  const int n = __syncthreads_count(done);
+  if (threadIdx.x == 0 && n) atomicAdd(W.counters, n);
+}
+__global__ void __launch_bounds__(IP_TPB) ip_step_kernel(IpTables T, IpState S, IpWork W, size_t P) {
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < P) ip_step_body(T, S, W, p);
+}
+// trial point of the line search, fp32 for the evaluation kernels: one thread per (variable, problem)
+__global__ void __launch_bounds__(256) ip_trial_kernel(IpState S, IpWork W, size_t P, int n_w) {
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const double a = W.alpha[p];
+  for (int c = blockIdx.y; c < n_w; c += gridDim.y)
+    W.wt32[(size_t)c * S.ld + p] = (float)(S.w[(size_t)c * S.ld + p] + a * W.dw[(size_t)c * S.ld + p]);
+}
+__global__ void __launch_bounds__(IP_TPB) ip_merit_kernel(IpTables T, IpState S, IpWork W, size_t P) {
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int rej = 0;
+  if (p < P) rej = ip_merit_body(T, S, W, p);
+  const int n = __syncthreads_count(rej);
+  if (threadIdx.x == 0 && n) atomicAdd(W.counters + 1, n);
+}
+__global__ void __launch_bounds__(IP_TPB) ip_update_kernel(IpTables T, IpState S, IpWork W, size_t P) {
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < P) ip_update_body(T, S, W, p);
+}
+__global__ void __launch_bounds__(IP_TPB) ip_lsq_prep_kernel(IpTables T, IpState S, IpWork W, size_t P) {
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < P) ip_lsq_prep_body(T, S, W, p);
+}
+__global__ void __launch_bounds__(IP_TPB) ip_lsq_choose_kernel(IpTables T, IpState S, IpWork W, size_t P) {
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < P) ip_lsq_choose_body(T, S, W, p);
+}
+__global__ void __launch_bounds__(IP_TPB) ip_flush_kernel(IpTables T, IpState S, IpWork W, IpOut O, size_t P, int only_done) {
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < P && (!only_done || S.done[p])) ip_flush_body(T, S, W, O, p);
+}
+__global__ void __launch_bounds__(256) ip_w32_kernel(IpState S, IpWork W, size_t P, int n_w) {
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  for (int c = blockIdx.y; c < n_w; c += gridDim.y) W.w32[(size_t)c * S.ld + p] = (float)S.w[(size_t)c * S.ld + p];
+}
+// working-set compaction: column keep[q] of every row -> column q
+template <typename V>
+__global__ void __launch_bounds__(256) ip_gather_kernel(const V* __restrict__ src, V* __restrict__ dst, int rows, size_t ld,
+                                                        const int* __restrict__ keep, size_t n_keep) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_keep) return;
+  const size_t from = (size_t)keep[q];
+  for (int r = blockIdx.y; r < rows; r += gridDim.y) dst[(size_t)r * ld + q] = src[(size_t)r * ld + from];
+}
+// [n_in_rows][n_in_cols] (row stride ld_in) -> [n_in_cols][ld_out], with a type conversion
+template <typename A, typename B>
+__global__ void __launch_bounds__(256) ip_transpose_kernel(const A* __restrict__ in, B* __restrict__ out, size_t n_in_rows, size_t n_in_cols,
+                                                           size_t ld_in, size_t ld_out) {
+  __shared__ B tile[32][33];
+  const size_t tiles_c = (n_in_cols + 31) / 32, tiles_r = (n_in_rows + 31) / 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (size_t tidx = blockIdx.x; tidx < tiles_c * tiles_r; tidx += gridDim.x) {
+    const size_t tr = tidx / tiles_c, tc = tidx - tr * tiles_c;
+    for (int j = ty; j < 32; j += 8) {
+      const size_t r = tr * 32 + j, c = tc * 32 + tx;
+      tile[j][tx] = (r < n_in_rows && c < n_in_cols) ? (B)in[r * ld_in + c] : (B)0;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+      const size_t c = tc * 32 + j, r = tr * 32 + tx;
+      if (c < n_in_cols && r < n_in_rows) out[c * ld_out + r] = tile[tx][j];
+    }
+    __syncthreads();
+  }
+}
+
+// ---- block-tridiagonal systems ----------------------------------------------------------------------------------------------
+// one thread per (slot, problem): the slot's terms are summed and written once - no atomics, no scratch
+__global__ void __launch_bounds__(256) bt_assemble_kernel(BtTables B, const float* __restrict__ jac, const float* __restrict__ hess,
+                                                          const double* __restrict__ omega, double* __restrict__ K, size_t P, size_t ld) {
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const int n_slots = B.nb * B.SLK;
+  for (int s = blockIdx.y; s < n_slots; s += gridDim.y) K[(size_t)s * ld + p] = bt_slot_value(B, s, jac, hess, omega, ld, p);
+}
+
+template <int NS, int NXR>
+__global__ void __launch_bounds__(BT_TPB) bt_kkt_kernel(BtTables B, const double* __restrict__ K, double* __restrict__ Lf,
+                                                        const double* __restrict__ rhs, double* __restrict__ dw, double* __restrict__ dw_alt,
+                                                        size_t P, size_t ld, int n_unknown, const double* __restrict__ delta_in,
+                                                        const int* __restrict__ skip, double* __restrict__ dwt_out) {
+  extern __shared__ double bt_smem[];
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  double dwt;
+  bt_kkt_body<NS, NXR>(B, K, Lf, rhs, dw, dw_alt, ld, p, n_unknown, delta_in[p], skip ? skip[p] : 0, &dwt, bt_smem + threadIdx.x, BT_TPB);
+  dwt_out[p] = dwt;
+}
+// plain SPD solve with a per-problem diagonal shift (least-squares multipliers); a failed factorisation keeps `fallback`
+template <int NS, int NXR>
+__global__ void __launch_bounds__(BT_TPB) bt_spd_kernel(BtTables B, const double* __restrict__ K, double* __restrict__ Lf,
+                                                        const double* __restrict__ rhs, double* __restrict__ x, size_t P, size_t ld, int n_unknown,
+                                                        const double* __restrict__ shift, const double* __restrict__ fallback) {
+  extern __shared__ double bt_smem[];
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  if (!bt_solve_attempt<NS, NXR>(B, K, Lf, rhs, x, ld, p, shift[p], HUGE_VAL, bt_smem + threadIdx.x, BT_TPB))
+    for (int e = 0; e < n_unknown; ++e) x[(size_t)e * ld + p] = fallback[(size_t)e * ld + p];
+}
+
+template <int NS, int NXR>
+int launch_bt_kkt(const BtTables& B, const double* K, double* Lf, const double* rhs, double* dw, double* dw_alt, size_t P, size_t ld,
+                  int n_unknown, const double* delta_in, const int* skip, double* dwt_out, int device, cudaStream_t st) {
+  constexpr size_t smem = (size_t)(NXR * NS + NS * (NS + 1) / 2) * BT_TPB * sizeof(double);
+  static bool attr[64] = {false};
+  if (!attr[device & 63]) {
+    NLO_CUDA(cudaFuncSetAttribute(bt_kkt_kernel<NS, NXR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr[device & 63] = true;
+  }
+  bt_kkt_kernel<NS, NXR><<<(unsigned)((P + BT_TPB - 1) / BT_TPB), BT_TPB, smem, st>>>(B, K, Lf, rhs, dw, dw_alt, P, ld, n_unknown, delta_in, skip, dwt_out);
+  NLO_CHECK_LAUNCH();
+  return 0;
+}
+template <int NS, int NXR>
+int launch_bt_spd(const BtTables& B, const double* K, double* Lf, const double* rhs, double* x, size_t P, size_t ld, int n_unknown,
+                  const double* shift, const double* fallback, int device, cudaStream_t st) {
+  constexpr size_t smem = (size_t)(NXR * NS + NS * (NS + 1) / 2) * BT_TPB * sizeof(double);
+  static bool attr[64] = {false};
+  if (!attr[device & 63]) {
+    NLO_CUDA(cudaFuncSetAttribute(bt_spd_kernel<NS, NXR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr[device & 63] = true;
+  }
+  bt_spd_kernel<NS, NXR><<<(unsigned)((P + BT_TPB - 1) / BT_TPB), BT_TPB, smem, st>>>(B, K, Lf, rhs, x, P, ld, n_unknown, shift, fallback);
+  NLO_CHECK_LAUNCH();
+  return 0;
+}
+
+// block sizes of the six dynamics models (core/dynamics.py:151-158) with and without slack: NS = nx + nu + slack, NXR = nx
+#define IP_KKT_SIZES(X) X(5, 3) X(6, 3) X(6, 4) X(7, 4) X(7, 5) X(8, 5) X(9, 7) X(10, 7)
+#define IP_LSQ_SIZES(X) X(3, 3) X(4, 4) X(5, 5) X(7, 7)
+
+}  // namespace
+
+// ---- the solver object ----------------------------------------------------------------------------------------------------
+struct nlo_ip {
+  nlo_nlp* nlp;
+  int device;
+  size_t cap;                        // problems the buffers hold == leading dimension of every array
+  cudaStream_t st;
+  IpHostTables HT;
+  BtHost kkt_h, lsq_h;
+  int* d_itab; double* d_dtab;
+  IpTables T; BtTables KB, LB;
+  size_t state_rows;
+  double* d_state[2]; int* d_istate[2]; int cur;
+  float* d_f32; double* d_f64; int* d_i32;
+  double *d_K, *d_L;
+  double* d_out; int* d_iout;
+  int* d_keep;
+  int* h_pin;                        // pinned: counters[2] + done flags
+  IpState S; IpWork W; IpOut O;
+  IpOptions opt;
+};
+
+namespace {
+
+void ip_bind_state(nlo_ip* s, int which) {
+  const IpTables& T = s->T;
+  const size_t ld = s->cap;
+  double* b = s->d_state[which];
+  IpState& S = s->S;
+  S.ld = ld;
+  S.w = b; b += (size_t)T.n_w * ld;
+  S.s = b; b += (size_t)T.nI * ld;
+  S.zl = b; b += (size_t)T.nI * ld;
+  S.zu = b; b += (size_t)T.nI * ld;
+  S.lamE = b; b += (size_t)T.nE * ld;
+  S.mu = b; b += ld; S.nu = b; b += ld; S.delta_w = b; b += ld; S.err0 = b; b += ld; S.f_mark = b;
+  int* ib = s->d_istate[which];
+  S.iters = ib; S.stalled = ib + ld; S.orig = ib + 2 * ld; S.done = ib + 3 * ld;
+  s->cur = which;
+}
+
+template <typename V>
+int upload(V** dst, const std::vector<V>& v) {
+  NLO_CUDA(cudaMalloc(dst, std::max<size_t>(v.size(), 1) * sizeof(V)));
+  if (!v.empty()) NLO_CUDA(cudaMemcpy(*dst, v.data(), v.size() * sizeof(V), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// the backend ip_solve_loop drives: every method enqueues kernels on the solver's stream; the few that return a count synchronise
+struct GpuBackend {
+  nlo_ip* s;
+  cudaStream_t st;
+  dim3 g1(size_t P) const { return dim3((unsigned)((P + IP_TPB - 1) / IP_TPB)); }
+
+  int read_counter(int which, size_t* out) {
+    NLO_CUDA(cudaMemcpyAsync(s->h_pin, s->W.counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    NLO_CUDA(cudaStreamSynchronize(st));
+    *out = (size_t)s->h_pin[which];
+    return 0;
+  }
+  int eval_full(size_t P) {
+    return nlo_nlp_eval(s->nlp, s->W.w32, P, s->cap, s->W.g, s->W.jac, s->W.f, s->W.grad, st);
+  }
+  int init(size_t P, double mu0, int max_iter) {
+    ip_init_kernel<<<g1(P), IP_TPB, 0, st>>>(s->T, s->S, s->W, P, mu0, max_iter);
+    NLO_CHECK_LAUNCH();
+    return 0;
+  }
+  int residual(size_t P, int it, double tol, size_t* n_done) {
+    NLO_CUDA(cudaMemsetAsync(s->W.counters, 0, 2 * sizeof(int), st));
+    ip_residual_kernel<<<g1(P), IP_TPB, 0, st>>>(s->T, s->S, s->W, P, it, tol);
+    NLO_CHECK_LAUNCH();
+    return read_counter(0, n_done);
+  }
+  int hessian(size_t P) { return nlo_nlp_hess(s->nlp, s->W.w32, nullptr, s->W.lam32, P, s->cap, s->W.hess, st); }
+  int assemble(const BtTables& B, size_t P) {
+    const int n_slots = B.nb * B.SLK;
+    bt_assemble_kernel<<<dim3((unsigned)((P + 255) / 256), (unsigned)std::min(n_slots, 65535)), 256, 0, st>>>(B, s->W.jac, s->W.hess, s->W.omega, s->d_K, P, s->cap);
+    NLO_CHECK_LAUNCH();
+    return 0;
+  }
+  int kkt_solve(size_t P) {
+    if (assemble(s->KB, P)) return 1;
+#define IP_CASE(NS_, NXR_)                                                                                                      \
+    if (s->KB.NS == NS_ && s->KB.NXR == NXR_)                                                                                   \
+      return launch_bt_kkt<NS_, NXR_>(s->KB, s->d_K, s->d_L, s->W.rhs, s->W.dw, s->W.dw_alt, P, s->cap, s->T.n_w, s->S.delta_w, s->S.done, \
+                                      s->W.dwt, s->device, st);
+    IP_KKT_SIZES(IP_CASE)
+#undef IP_CASE
+    return nlo_fail("interior point: no factorisation kernel for stage blocks of %d unknowns (%d states)", s->KB.NS, s->KB.NXR);
+  }
+  int step(size_t P) {
+    ip_step_kernel<<<g1(P), IP_TPB, 0, st>>>(s->T, s->S, s->W, P);
+    NLO_CHECK_LAUNCH();
+    return 0;
+  }
+  int trial(size_t P, size_t* rejected) {
+    ip_trial_kernel<<<dim3((unsigned)((P + 255) / 256), 32), 256, 0, st>>>(s->S, s->W, P, s->T.n_w);
+    NLO_CHECK_LAUNCH();
+    if (nlo_nlp_eval(s->nlp, s->W.wt32, P, s->cap, s->W.gt, nullptr, s->W.ft, nullptr, st)) return 1;
+    NLO_CUDA(cudaMemsetAsync(s->W.counters + 1, 0, sizeof(int), st));
+    ip_merit_kernel<<<g1(P), IP_TPB, 0, st>>>(s->T, s->S, s->W, P);
+    NLO_CHECK_LAUNCH();
+    return read_counter(1, rejected);
+  }
+  int update(size_t P) {
+    ip_update_kernel<<<g1(P), IP_TPB, 0, st>>>(s->T, s->S, s->W, P);
+    NLO_CHECK_LAUNCH();
+    return 0;
+  }
+  int lsq_multipliers(size_t P) {
+    if (s->T.nE == 0) return 0;
+    ip_lsq_prep_kernel<<<g1(P), IP_TPB, 0, st>>>(s->T, s->S, s->W, P);
+    NLO_CHECK_LAUNCH();
+    if (assemble(s->LB, P)) return 1;
+    int rc = -1;
+#define IP_CASE(NS_, NXR_)                                                                                                      \
+    if (rc < 0 && s->LB.NS == NS_)                                                                                              \
+      rc = launch_bt_spd<NS_, NXR_>(s->LB, s->d_K, s->d_L, s->W.v, s->W.lam_ls, P, s->cap, s->T.nE, s->W.eps_ls, s->S.lamE, s->device, st);
+    IP_LSQ_SIZES(IP_CASE)
+#undef IP_CASE
+    if (rc < 0) return nlo_fail("interior point: no multiplier kernel for %d states", s->LB.NS);
+    if (rc) return rc;
+    ip_lsq_choose_kernel<<<g1(P), IP_TPB, 0, st>>>(s->T, s->S, s->W, P);
+    NLO_CHECK_LAUNCH();
+    return 0;
+  }
+  int flush(size_t P, int only_done) {
+    ip_flush_kernel<<<g1(P), IP_TPB, 0, st>>>(s->T, s->S, s->W, s->O, P, only_done);
+    NLO_CHECK_LAUNCH();
+    return 0;
+  }
+  int flush_all(size_t P) { return flush(P, 0); }
+  int compact(size_t P, size_t* newP) {
+    if (flush(P, 1)) return 1;
+    int* h_done = s->h_pin + 2;
+    NLO_CUDA(cudaMemcpyAsync(h_done, s->S.done, P * sizeof(int), cudaMemcpyDeviceToHost, st));
+    NLO_CUDA(cudaStreamSynchronize(st));
+    std::vector<int> keep;
+    keep.reserve(P);
+    for (size_t p = 0; p < P; ++p) if (!h_done[p]) keep.push_back((int)p);
+    *newP = keep.size();
+    if (keep.empty()) return 0;
+    NLO_CUDA(cudaMemcpyAsync(s->d_keep, keep.data(), keep.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    const int other = 1 - s->cur;
+    const unsigned gx = (unsigned)((keep.size() + 255) / 256);
+    ip_gather_kernel<double><<<dim3(gx, 64), 256, 0, st>>>(s->d_state[s->cur], s->d_state[other], (int)s->state_rows, s->cap, s->d_keep, keep.size());
+    NLO_CHECK_LAUNCH();
+    ip_gather_kernel<int><<<dim3(gx, 4), 256, 0, st>>>(s->d_istate[s->cur], s->d_istate[other], 4, s->cap, s->d_keep, keep.size());
+    NLO_CHECK_LAUNCH();
+    NLO_CUDA(cudaStreamSynchronize(st));          // `keep` (pageable) must outlive the copy
+    ip_bind_state(s, other);
+    ip_w32_kernel<<<dim3(gx, 32), 256, 0, st>>>(s->S, s->W, keep.size(), s->T.n_w);
+    NLO_CHECK_LAUNCH();
+    return 0;
+  }
+  void report(size_t P, int it, size_t n_done) { fprintf(stderr, "[nlo_ip] it %3d  active %zu  done %zu\n", it, P, n_done); }
+};
+
+}  // namespace
+
+extern "C" {
+
+void nlo_ip_destroy(nlo_ip* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  void* bufs[] = {s->d_itab, s->d_dtab, s->d_state[0], s->d_state[1], s->d_istate[0], s->d_istate[1], s->d_f32, s->d_f64, s->d_i32,
+                  s->d_K, s->d_L, s->d_out, s->d_iout, s->d_keep};
+  for (void* b : bufs) if (b) cudaFree(b);
+  if (s->h_pin) cudaFreeHost(s->h_pin);
+  if (s->st) cudaStreamDestroy(s->st);
+  delete s;
+}
+
+int nlo_ip_create(nlo_nlp* p, const double* lbg, const double* ubg, size_t max_problems, nlo_ip** out) {
+  if (!out) return nlo_fail("null out");
+  *out = nullptr;
+  if (!p || !lbg || !ubg) return nlo_fail("null argument");
+  if (max_problems == 0) return nlo_fail("max_problems must be positive");
+  NLO_CUDA(cudaSetDevice(p->device));
+  nlo_ip* s = new (std::nothrow) nlo_ip();
+  if (!s) return nlo_fail("out of host memory");
+  s->nlp = p; s->device = p->device; s->cap = (max_problems + 31) / 32 * 32;
+  s->d_itab = nullptr; s->d_dtab = nullptr; s->d_state[0] = s->d_state[1] = nullptr; s->d_istate[0] = s->d_istate[1] = nullptr;
+  s->d_f32 = nullptr; s->d_f64 = nullptr; s->d_i32 = nullptr; s->d_K = s->d_L = nullptr; s->d_out = nullptr; s->d_iout = nullptr;
+  s->d_keep = nullptr; s->h_pin = nullptr; s->st = nullptr;
+  const NlpDev& L = p->L;
+  {
+    std::vector<int> jc(L.n_w + 1, 0), hc(L.n_w + 1, 0);
+    for (int z = 0; z < L.nnz; ++z) jc[p->cols_ccs[z] + 1]++;
+    for (size_t z = 0; z < p->hcols_ccs.size(); ++z) hc[p->hcols_ccs[z] + 1]++;
+    for (int c = 0; c < L.n_w; ++c) { jc[c + 1] += jc[c]; hc[c + 1] += hc[c]; }
+    ip_build_tables(L.n_w, L.n_g, jc.data(), p->rows_ccs.data(), (int)p->hrows_ccs.size(), hc.data(), p->hrows_ccs.data(), lbg, ubg, &s->HT);
+  }
+  IpStages stg = {L.N, L.nx, L.nu, L.use_slack, L.n_term, L.g_off_dyn};
+  if (!ip_build_kkt_system(s->HT, stg, &s->kkt_h)) { std::string e = s->kkt_h.error; nlo_ip_destroy(s); return nlo_fail("interior point: %s", e.c_str()); }
+  if (s->HT.nE > 0 && !ip_build_lsq_system(s->HT, stg, &s->lsq_h)) { std::string e = s->lsq_h.error; nlo_ip_destroy(s); return nlo_fail("interior point: %s", e.c_str()); }
+  // ---- device tables: one int blob, one double blob ----
+  const IpHostTables& H = s->HT;
+  std::vector<int> it;
+  auto push = [&](const std::vector<int>& v) { const size_t off = it.size(); it.insert(it.end(), v.begin(), v.end()); return off; };
+  const size_t o_rkind = push(H.rkind), o_ridx = push(H.ridx), o_colind = push(H.colind), o_row = push(H.row), o_rptr = push(H.rptr),
+               o_rnz = push(H.rnz), o_rcol = push(H.rcol), o_hcolind = push(H.hcolind), o_hrow = push(H.hrow),
+               o_kvar = push(s->kkt_h.var), o_kptr = push(s->kkt_h.term_ptr), o_kterms = push(s->kkt_h.terms),
+               o_lvar = push(s->lsq_h.var), o_lptr = push(s->lsq_h.term_ptr), o_lterms = push(s->lsq_h.terms);
+  std::vector<double> dt(H.lb);
+  dt.insert(dt.end(), H.ub.begin(), H.ub.end());
+  if (upload(&s->d_itab, it) || upload(&s->d_dtab, dt)) { nlo_ip_destroy(s); return 1; }
+  IpTables& T = s->T;
+  T.n_w = H.n_w; T.n_g = H.n_g; T.nnz = H.nnz; T.nnzh = H.nnzh; T.nE = H.nE; T.nI = H.nI;
+  T.rkind = s->d_itab + o_rkind; T.ridx = s->d_itab + o_ridx; T.colind = s->d_itab + o_colind; T.row = s->d_itab + o_row;
+  T.rptr = s->d_itab + o_rptr; T.rnz = s->d_itab + o_rnz; T.rcol = s->d_itab + o_rcol; T.hcolind = s->d_itab + o_hcolind; T.hrow = s->d_itab + o_hrow;
+  T.lb = s->d_dtab; T.ub = s->d_dtab + H.n_g;
+  auto bind_bt = [&](BtTables& B, const BtHost& h, size_t ov, size_t op, size_t ot) {
+    B.nb = h.nb; B.NS = h.NS; B.NXR = h.NXR; B.SLK = h.SLK; B.SLL = h.SLL;
+    B.var = s->d_itab + ov; B.term_ptr = s->d_itab + op; B.terms = s->d_itab + ot;
+  };
+  bind_bt(s->KB, s->kkt_h, o_kvar, o_kptr, o_kterms);
+  bind_bt(s->LB, s->lsq_h, o_lvar, o_lptr, o_lterms);
+  // ---- buffers ----
+  const size_t ld = s->cap;
+  s->state_rows = (size_t)T.n_w + 3 * (size_t)T.nI + T.nE + 5;
+  const size_t f32_rows = 1 + (size_t)T.n_w + T.n_g + T.nnz + T.nnzh + T.n_w + T.n_g + T.n_w + 1 + T.n_g;
+  const size_t f64_rows = (size_t)T.n_g * 2 + T.n_w * 3 + T.nI * 3 + T.nE * 2 + 6;
+  const size_t k_slots = std::max((size_t)s->kkt_h.nb * s->kkt_h.SLK, (size_t)s->lsq_h.nb * s->lsq_h.SLK);
+  const size_t l_slots = std::max((size_t)s->kkt_h.nb * s->kkt_h.SLL, (size_t)s->lsq_h.nb * s->lsq_h.SLL);
+  bool ok = true;
+  for (int b = 0; b < 2 && ok; ++b)
+    ok = cudaMalloc(&s->d_state[b], s->state_rows * ld * sizeof(double)) == cudaSuccess && cudaMalloc(&s->d_istate[b], 4 * ld * sizeof(int)) == cudaSuccess;
+  ok = ok && cudaMalloc(&s->d_f32, f32_rows * ld * sizeof(float)) == cudaSuccess && cudaMalloc(&s->d_f64, f64_rows * ld * sizeof(double)) == cudaSuccess &&
+       cudaMalloc(&s->d_i32, (ld + 8) * sizeof(int)) == cudaSuccess && cudaMalloc(&s->d_K, k_slots * ld * sizeof(double)) == cudaSuccess &&
+       cudaMalloc(&s->d_L, l_slots * ld * sizeof(double)) == cudaSuccess &&
+       cudaMalloc(&s->d_out, ((size_t)T.n_w + T.n_g + 3) * ld * sizeof(double)) == cudaSuccess && cudaMalloc(&s->d_iout, 2 * ld * sizeof(int)) == cudaSuccess &&
+       cudaMalloc(&s->d_keep, ld * sizeof(int)) == cudaSuccess && cudaHostAlloc(&s->h_pin, (ld + 2) * sizeof(int), cudaHostAllocDefault) == cudaSuccess &&
+       cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking) == cudaSuccess;
+  if (!ok) {
+    const double gb = ((2 * s->state_rows + f64_rows + k_slots + l_slots + T.n_w + T.n_g + 3) * 8.0 + f32_rows * 4.0) * ld / 1e9;
+    nlo_ip_destroy(s);
+    return nlo_fail("interior point: device allocation failed (%.1f GB for %zu problems)", gb, max_problems);
+  }
+  IpWork& W = s->W;
+  W.ld = ld;
+  float* f = s->d_f32;
+  W.f = f; f += ld; W.grad = f; f += (size_t)T.n_w * ld; W.g = f; f += (size_t)T.n_g * ld; W.jac = f; f += (size_t)T.nnz * ld;
+  W.hess = f; f += (size_t)T.nnzh * ld; W.w32 = f; f += (size_t)T.n_w * ld; W.lam32 = f; f += (size_t)T.n_g * ld;
+  W.wt32 = f; f += (size_t)T.n_w * ld; W.ft = f; f += ld; W.gt = f;
+  double* d = s->d_f64;
+  W.omega = d; d += (size_t)T.n_g * ld; W.v = d; d += (size_t)T.n_g * ld; W.rhs = d; d += (size_t)T.n_w * ld; W.dw = d; d += (size_t)T.n_w * ld;
+  W.dw_alt = d; d += (size_t)T.n_w * ld; W.ds = d; d += (size_t)T.nI * ld; W.dzl = d; d += (size_t)T.nI * ld; W.dzu = d; d += (size_t)T.nI * ld;
+  W.dlamE = d; d += (size_t)T.nE * ld; W.lam_ls = d; d += (size_t)T.nE * ld;
+  W.dwt = d; d += ld; W.alpha = d; d += ld; W.alpha_d = d; d += ld; W.phi0 = d; d += ld; W.dphi = d; d += ld; W.eps_ls = d; W.viol = nullptr;
+  W.accepted = s->d_i32; W.counters = s->d_i32 + ld;
+  IpOut& O = s->O;
+  O.ld = ld; O.w = s->d_out; O.lam = O.w + (size_t)T.n_w * ld; O.f = O.lam + (size_t)T.n_g * ld; O.viol = O.f + ld; O.err = O.viol + ld;
+  O.iters = s->d_iout; O.status = s->d_iout + ld;
+  ip_bind_state(s, 0);
+  if (nlo_nlp_reserve(p, s->cap)) { nlo_ip_destroy(s); return 1; }
+  *out = s;
+  return 0;
+}
+
+size_t nlo_ip_capacity(const nlo_ip* s) { return s ? s->cap : 0; }
+
+int nlo_ip_solve(nlo_ip* s, const double* w0_host, size_t P, const nlo_ip_options* opt_in, double* w_host, double* f_host, double* viol_host,
+                 double* kkt_err_host, int* iters_host, int* status_host, double* lam_host, nlo_ip_stats* stats_out) {
+  if (!s || !w0_host) return nlo_fail("null argument");
+  if (P == 0) return 0;
+  if (P > s->cap) return nlo_fail("interior point: %zu problems exceed the capacity %zu given to nlo_ip_create", P, s->cap);
+  NLO_CUDA(cudaSetDevice(s->device));
+  IpOptions opt = {1e-4, 300, 0.1, 1, 1, 0};
+  if (opt_in) { opt.tol = opt_in->tol; opt.max_iter = opt_in->max_iter; opt.mu0 = opt_in->mu0; opt.ls_multipliers = opt_in->ls_multipliers;
+                opt.compact = opt_in->compact; opt.verbose = opt_in->verbose; }
+  if (!(opt.tol > 0.0) || opt.max_iter < 1 || !(opt.mu0 > 0.0)) return nlo_fail("interior point: bad options");
+  const IpTables& T = s->T;
+  const size_t ld = s->cap;
+  cudaStream_t st = s->st;
+  ip_bind_state(s, 0);
+  // starts: problem-major doubles on the host -> variable-major doubles + floats on the device (staged through the K buffer)
+  NLO_CUDA(cudaMemcpyAsync(s->d_K, w0_host, P * (size_t)T.n_w * sizeof(double), cudaMemcpyHostToDevice, st));
+  {
+    const size_t tiles = ((size_t)(T.n_w + 31) / 32) * ((P + 31) / 32);
+    ip_transpose_kernel<double, double><<<(unsigned)std::min<size_t>(tiles, 148 * 16), 256, 0, st>>>(s->d_K, s->S.w, P, (size_t)T.n_w, (size_t)T.n_w, ld);
+    NLO_CHECK_LAUNCH();
+    ip_w32_kernel<<<dim3((unsigned)((P + 255) / 256), 32), 256, 0, st>>>(s->S, s->W, P, T.n_w);
+    NLO_CHECK_LAUNCH();
+    std::vector<int> orig(P);
+    for (size_t p = 0; p < P; ++p) orig[p] = (int)p;
+    NLO_CUDA(cudaMemcpyAsync(s->S.orig, orig.data(), P * sizeof(int), cudaMemcpyHostToDevice, st));
+    NLO_CUDA(cudaStreamSynchronize(st));
+  }
+  GpuBackend x{s, st};
+  IpStats stats;
+  if (ip_solve_loop(x, P, opt, &stats)) return 1;
+  // results: variable-major on the device -> problem-major on the host (staged through the K buffer)
+  auto download = [&](const double* soa, int rows, double* host) -> int {
+    if (!host) return 0;
+    const size_t tiles = ((size_t)(rows + 31) / 32) * ((P + 31) / 32);
+    ip_transpose_kernel<double, double><<<(unsigned)std::min<size_t>(tiles, 148 * 16), 256, 0, st>>>(soa, s->d_K, (size_t)rows, P, ld, (size_t)rows);
+    NLO_CHECK_LAUNCH();
+    NLO_CUDA(cudaMemcpyAsync(host, s->d_K, P * (size_t)rows * sizeof(double), cudaMemcpyDeviceToHost, st));
+    NLO_CUDA(cudaStreamSynchronize(st));
+    return 0;
+  };
+  if (download(s->O.w, T.n_w, w_host) || download(s->O.lam, T.n_g, lam_host)) return 1;
+  if (f_host) NLO_CUDA(cudaMemcpyAsync(f_host, s->O.f, P * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (viol_host) NLO_CUDA(cudaMemcpyAsync(viol_host, s->O.viol, P * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (kkt_err_host) NLO_CUDA(cudaMemcpyAsync(kkt_err_host, s->O.err, P * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (iters_host) NLO_CUDA(cudaMemcpyAsync(iters_host, s->O.iters, P * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (status_host) NLO_CUDA(cudaMemcpyAsync(status_host, s->O.status, P * sizeof(int), cudaMemcpyDeviceToHost, st));
+  NLO_CUDA(cudaStreamSynchronize(st));
+  if (stats_out) {
+    stats_out->iterations = stats.iterations; stats_out->evaluations = stats.evaluations; stats_out->hessians = stats.hessians;
+    stats_out->trials = stats.trials; stats_out->compactions = stats.compactions;
+  }
+  return 0;
+}
+
+// One regularised Newton step of the condensed KKT system for inputs that already live on the device (all variable-major, leading
+// dimension ld <= capacity):  (H + J^T diag(omega) J + delta I) dw = rhs  per problem, delta chosen by the inertia test.
+int nlo_ip_kkt_step(nlo_ip* s, const float* jac, const float* hess, const double* omega, const double* rhs, const double* delta_in, size_t P,
+                    size_t ld, double* dw, double* delta_out, void* stream) {
+  if (!s || !jac || !hess || !omega || !rhs || !delta_in || !dw || !delta_out) return nlo_fail("null argument");
+  if (P == 0) return 0;
+  if (ld < P || ld > s->cap) return nlo_fail("interior point: ld (%zu) must lie in [P, capacity %zu]", ld, s->cap);
+  NLO_CUDA(cudaSetDevice(s->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const BtTables& B = s->KB;
+  const int n_slots = B.nb * B.SLK;
+  bt_assemble_kernel<<<dim3((unsigned)((P + 255) / 256), (unsigned)std::min(n_slots, 65535)), 256, 0, st>>>(B, jac, hess, omega, s->d_K, P, ld);
+  NLO_CHECK_LAUNCH();
+#define IP_CASE(NS_, NXR_)                                                                                                      \
+  if (B.NS == NS_ && B.NXR == NXR_)                                                                                             \
+    return launch_bt_kkt<NS_, NXR_>(B, s->d_K, s->d_L, rhs, dw, s->W.dw_alt, P, ld, s->T.n_w, delta_in, nullptr, delta_out, s->device, st);
+  IP_KKT_SIZES(IP_CASE)
+#undef IP_CASE
+  return nlo_fail("interior point: no factorisation kernel for stage blocks of %d unknowns (%d states)", B.NS, B.NXR);
+}
+
+}  // extern "C"

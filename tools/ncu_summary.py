@@ -56,15 +56,20 @@ def launches(src, dst):
     print(open(dst).read())
 
 
-def kernel(src, dst):
-    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+def kernel(src, dst, note=""):
+    """src: a .ncu-rep, or the CSV that `ncu -i rep --page raw --csv` printed on the GPU box (a .ncu-rep of a dozen
+    --set full captures exceeds what gpurun brings back)."""
+    if src.endswith(".csv"):
+        raw = open(src).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     with open(dst, "w") as f:
-        f.write(f"# ncu --set full ({src})\n\n")
+        f.write(f"# ncu --set full ({src})\n\n{note}\n\n" if note else f"# ncu --set full ({src})\n\n")
         for r in rows[2:]:
             name = r[hdr.index("Kernel Name")]
-            f.write(f"## `{name[:110]}`\n\n| metric | value | unit |\n|---|---|---|\n")
+            f.write(f"## launch {r[0]}: `{name[:110]}`  grid {r[hdr.index('Grid Size')]} block {r[hdr.index('Block Size')]}\n\n| metric | value | unit |\n|---|---|---|\n")
             for k in KEEP:
                 if k in hdr:
                     i = hdr.index(k)
@@ -73,5 +78,23 @@ def kernel(src, dst):
     print(open(dst).read())
 
 
+def dram(src, dst, launch_id, points, note=""):
+    """profiles/sdf_tc_kernel_dram.json (read by bench.py for roofline.traffic): DRAM bytes of ONE captured launch and the
+    number of SDF points it processed."""
+    import json
+    rows = list(csv.reader(open(src).read().splitlines()))
+    hdr, units = rows[0], rows[1]
+    r = next(r for r in rows[2:] if r[0] == str(launch_id))
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+    def val(k):
+        i = hdr.index(k)
+        return float(r[i].replace(",", "")) * scale[units[i]]
+    d = {"kernel": r[hdr.index("Kernel Name")][:60], "points": int(points), "dram_bytes_read": val("dram__bytes_read.sum"),
+         "dram_bytes_write": val("dram__bytes_write.sum"), "source": note or src}
+    json.dump(d, open(dst, "w"), indent=1)
+    print(d)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "kernel": kernel, "dram": dram}[sys.argv[1]](*sys.argv[2:])
