@@ -268,6 +268,42 @@ NLO_API int nlo_nlp_compact_layout(const nlo_nlp* p, int32_t* g_var_rows, int32_
                                    int32_t* grad_var_idx, int32_t* grad_lin_idx, float* grad_lin_coef);
 NLO_API int nlo_nlp_eval_host_compact(nlo_nlp* p, const float* w_host, size_t P,
                                       float* g_var_host, float* jac_var_host, float* f_host, float* grad_var_host);
+/* ------------------------------------------------------------------------------------------ */
+/* batched interior-point solver (the caller on both sides of the evaluation path)             */
+/* The reference hands every problem to IPOPT (core/runner.py:112-133: tol 1e-4, exact Hessian, */
+/* max_iter 1000); here P multi-start problems are solved at once on the device: primal-dual    */
+/* interior point, slacks on the inequality rows, l1-merit line search, monotone barrier, and a  */
+/* block-tridiagonal (stage-structured) Cholesky of the condensed KKT matrix per problem.        */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct nlo_ip nlo_ip;
+typedef struct nlo_ip_options {
+  double tol;            /* scaled KKT error at which a problem is converged (core/runner.py:118: 1e-4)  */
+  int    max_iter;       /* iteration limit                                                              */
+  double mu0;            /* initial barrier parameter (0.1)                                               */
+  int    ls_multipliers; /* re-estimate the equality multipliers by least squares after every step (1)    */
+  int    compact;        /* finished problems leave the working set every 10 iterations (1)               */
+  int    verbose;
+} nlo_ip_options;
+typedef struct nlo_ip_stats { int iterations, evaluations, hessians, trials, compactions; } nlo_ip_stats;
+/* lbg, ubg: fp64[n_g] bounds of g in Opti's canonical form (+-INFINITY for one-sided rows; rows with lbg == ubg are equalities).
+ * max_problems: batch size the device buffers are sized for.  The solver keeps a pointer to `p` (not owned).              */
+NLO_API int    nlo_ip_create(nlo_nlp* p, const double* lbg, const double* ubg, size_t max_problems, nlo_ip** out);
+NLO_API void   nlo_ip_destroy(nlo_ip* s);
+NLO_API size_t nlo_ip_capacity(const nlo_ip* s);
+/* Solve P problems from the starts w0_host[P][n_w] (problem-major fp64).  Outputs (host, any may be NULL): w_host[P][n_w],
+ * f, viol (max bound violation of g), kkt_err (scaled optimality error), iters, status (1 converged, 2 feasible with a
+ * stationary objective but a KKT error above tol - typical on the kinks of a ReLU SDF -, 0 neither), lam_host[P][n_g].
+ * opt may be NULL (defaults above).                                                                                      */
+NLO_API int    nlo_ip_solve(nlo_ip* s, const double* w0_host, size_t P, const nlo_ip_options* opt, double* w_host, double* f_host,
+                            double* viol_host, double* kkt_err_host, int* iters_host, int* status_host, double* lam_host,
+                            nlo_ip_stats* stats);
+/* One regularised Newton step of the condensed KKT system on device-resident inputs (all variable-major, leading dimension
+ * ld <= capacity):  (H + J^T diag(omega) J + delta I) dw = rhs  per problem, with jac / hess the CCS values of
+ * nlo_nlp_eval / nlo_nlp_hess, omega fp64 [n_g][ld], rhs / dw fp64 [n_w][ld], delta_in / delta_out fp64 [P]: delta starts at
+ * delta_in and grows (x8 from 1e-4) until the block-tridiagonal Cholesky succeeds.                                         */
+NLO_API int    nlo_ip_kkt_step(nlo_ip* s, const float* jac, const float* hess, const double* omega, const double* rhs,
+                               const double* delta_in, size_t P, size_t ld, double* dw, double* delta_out, void* stream);
+
 /* layout helpers on device: [rows][ld] variable-major <-> [P][rows] problem-major              */
 NLO_API int nlo_transpose_to_soa(const float* aos, float* soa, size_t P, size_t rows, size_t ld, void* stream);
 NLO_API int nlo_transpose_to_aos(const float* soa, float* aos, size_t P, size_t rows, size_t ld, void* stream);

@@ -16,7 +16,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OBJ = PKG / "csrc" / "_obj"
 LIB = PKG / "libnlo_b200.so"
-SOURCES = ["capi.cu", "sdf_simt.cu", "sdf_tc.cu", "sdf_tc256.cu", "nlp_kernels.cu", "nlp_hess.cu"]
+SOURCES = ["capi.cu", "sdf_simt.cu", "sdf_tc.cu", "sdf_tc256.cu", "nlp_kernels.cu", "nlp_hess.cu", "ip_solver.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr",
@@ -31,7 +31,7 @@ def nvcc() -> str:
 
 
 def _deps_mtime() -> float:
-    hdrs = list(CSRC.glob("*.cuh")) + list((PKG.parent / "include").glob("*.h"))
+    hdrs = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.hpp")) + list((PKG.parent / "include").glob("*.h"))
     return max(h.stat().st_mtime for h in hdrs)
 
 

@@ -33,6 +33,15 @@ class CompactCounts(C.Structure):
     _fields_ = [(n, C.c_longlong) for n in ("n_g_var", "n_g_copy", "n_jac_var", "n_jac_const", "n_grad_var", "n_grad_lin")]
 
 
+class IpOptions(C.Structure):
+    _fields_ = [("tol", C.c_double), ("max_iter", C.c_int), ("mu0", C.c_double), ("ls_multipliers", C.c_int), ("compact", C.c_int),
+                ("verbose", C.c_int)]
+
+
+class IpStats(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("iterations", "evaluations", "hessians", "trials", "compactions")]
+
+
 _P = C.c_void_p
 _F = C.c_void_p       # float* (device or host address passed as integer)
 _SZ = C.c_size_t
@@ -79,6 +88,11 @@ SIGNATURES = {
     "nlo_nlp_compact_counts": (C.c_int, [_P, C.POINTER(CompactCounts)]),
     "nlo_nlp_compact_layout": (C.c_int, [_P] + [_F] * 9),
     "nlo_nlp_eval_host_compact": (C.c_int, [_P, _F, _SZ, _F, _F, _F, _F]),
+    "nlo_ip_create": (C.c_int, [_P, _F, _F, _SZ, C.POINTER(_P)]),
+    "nlo_ip_destroy": (None, [_P]),
+    "nlo_ip_capacity": (_SZ, [_P]),
+    "nlo_ip_solve": (C.c_int, [_P, _F, _SZ, C.POINTER(IpOptions), _F, _F, _F, _F, _F, _F, _F, C.POINTER(IpStats)]),
+    "nlo_ip_kkt_step": (C.c_int, [_P, _F, _F, _F, _F, _F, _SZ, _SZ, _F, _F, _P]),
     "nlo_transpose_to_soa": (C.c_int, [_F, _F, _SZ, _SZ, _SZ, _P]),
     "nlo_transpose_to_aos": (C.c_int, [_F, _F, _SZ, _SZ, _SZ, _P]),
 }

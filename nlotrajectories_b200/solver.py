@@ -1,25 +1,17 @@
-"""Batched multi-start NLP solvers on the GPU: callers on top of the evaluation hot path.
+"""Batched multi-start NLP solvers on the GPU: the callers on top of the evaluation hot path.
 
-Two solvers live here.  ``BatchedIPSolver`` (bottom of the file) is the one to use: a primal-dual interior point
-with the exact Hessian of the Lagrangian (nlo_nlp_hess) - the algorithm family of IPOPT, which the reference calls
-once per problem - advancing all starts in lock step; measured on benchmark_1 x 256 starts: 98.8 % of the starts
-converge to tol 1e-4 (median 25 iterations, 4 s for the batch), objectives 1.50352 +- 1e-5, equal to the same algorithm
-run on the fp64 CPU oracle and 1e-4 above scipy SLSQP's 1.50342 (the barrier's share at the final mu = 1e-5).  ``BatchedALSolver`` is
-the earlier first-order baseline (augmented Lagrangian + L-BFGS), kept for comparison:
+The reference hands each problem to IPOPT (core/runner.py:112-133: tol 1e-4, exact Hessian, max_iter 1000).  IPOPT does not
+exist in this environment and is one-problem-at-a-time by construction; here all P multi-start problems advance in lock step
+through a primal-dual interior point with the exact Hessian of the Lagrangian (``nlo_nlp_hess``) - the algorithm family of IPOPT.
 
+* ``DeviceIPSolver`` - the solver to use: the whole iteration lives in the CUDA library (``csrc/ip_solver.cu``, C ABI
+  ``nlo_ip_*``).  Per problem the condensed KKT matrix is block tridiagonal in stage order (x_k, u_k, slack_k: at most 10
+  unknowns per block), so its Cholesky costs ~10^5 flops instead of the 727^3 / 3 of a dense factorisation, and batches of
+  4,096 (benchmark_4) or 65,536 (benchmark_6) starts fit one GPU.
+* ``BatchedIPSolver`` - the same algorithm in torch with dense fp64 linear algebra (``torch.linalg``): the readable reference
+  of the iteration, usable with any evaluator (the CPU oracle in the tests); limited to a few hundred starts.
 
-The reference hands each problem to IPOPT (core/runner.py:112-133: tol 1e-4, max_iter 1000).  IPOPT does not
-exist in this environment and is inherently one-problem-at-a-time, so the batched path solves all P starts at
-once with a bound-constrained augmented Lagrangian whose inner problems are minimised by a batched L-BFGS:
-
-    L_rho(w, lam) = f(w) + sum_r [ (y_r^2 - lam_r^2) / (2 rho) ],   y = rho * (z - clip(z, lbg, ubg)),  z = g(w) + lam/rho
-    grad_w L_rho  = grad f + J^T y                                   (J^T y: nlo_nlp_jac_tvec)
-    lam <- y after every inner solve; rho grows where the violation stalls.
-
-Every iteration is one call of the evaluation hot path (g, nnz(dg/dw), f, grad f for the whole batch) plus
-vector updates; all state is structure-of-arrays [variable][problem] and stays on the device.  Equalities are
-rows with lbg == ubg; one-sided rows have an infinite bound.  This is a first-order method: it reaches the
-reference's tolerance (1e-4) on constraint violation and stationarity, not IPOPT's iteration counts.
+Both produce the same iterates on the same inputs (``tests/test_ip_device.py``).
 """
 from __future__ import annotations
 
@@ -27,135 +19,6 @@ from dataclasses import dataclass
 from typing import Optional
 
 import numpy as np
-
-
-@dataclass
-class SolveResult:
-    w: "object"            # torch (n_w, P) SoA
-    f: "object"            # (P,)
-    violation: "object"    # (P,) max bound violation of g
-    stationarity: "object" # (P,) inf-norm of grad_w L
-    outer_iterations: int
-    evaluations: int
-
-
-class BatchedALSolver:
-    def __init__(self, prob, rho0: float = 10.0, rho_max: float = 1e4, outer_iters: int = 40, inner_iters: int = 100,
-                 memory: int = 12, tol: float = 1e-4, verbose: bool = False):
-        self.prob = prob
-        self.rho0, self.rho_max = rho0, rho_max
-        self.outer_iters, self.inner_iters, self.m = outer_iters, inner_iters, memory
-        self.tol, self.verbose = tol, verbose
-        self.evals = 0
-
-    # ---- one evaluation of the augmented Lagrangian and its gradient -------------------------------------------
-    def _al(self, w, lam, rho, bufs):
-        import torch
-        g, jac, f, grad = bufs
-        self.prob.eval_device(w, g, jac, f, grad)
-        self.evals += 1
-        z = g + lam / rho
-        y = rho * (z - torch.minimum(torch.maximum(z, self.lb), self.ub))
-        val = f + ((y * y - lam * lam).sum(dim=0)) / (2.0 * rho)
-        gl = self.prob.jac_tvec(jac, y, add=grad)
-        return val, gl, y
-
-    def solve(self, w0, lam0=None) -> SolveResult:
-        import torch
-        prob = self.prob
-        dev = w0.device
-        P = w0.shape[1]
-        big = 1e30
-        lb, ub = prob.bounds()
-        self.lb = torch.from_numpy(np.clip(lb, -big, big).astype(np.float32)).to(dev)[:, None]
-        self.ub = torch.from_numpy(np.clip(ub, -big, big).astype(np.float32)).to(dev)[:, None]
-        w = w0.clone()
-        lam = torch.zeros((prob.n_g, P), device=dev) if lam0 is None else lam0.clone()
-        rho = torch.full((P,), self.rho0, device=dev)
-        bufs = prob.alloc_outputs(P, dev)
-        bufs_trial = prob.alloc_outputs(P, dev)
-        m = self.m
-        S = torch.zeros((m, prob.n_w, P), device=dev)
-        Y = torch.zeros((m, prob.n_w, P), device=dev)
-        R = torch.zeros((m, P), device=dev)
-        prev_viol = torch.full((P,), float("inf"), device=dev)
-        outer = 0
-        for outer in range(1, self.outer_iters + 1):
-            val, gl, y = self._al(w, lam, rho, bufs)
-            S.zero_(); Y.zero_(); R.zero_()
-            n_hist = 0
-            step0 = 1.0 / torch.clamp(gl.abs().amax(dim=0), min=1.0)          # first step: conservative
-            for it in range(self.inner_iters):
-                gnorm = gl.abs().amax(dim=0)
-                if bool((gnorm < self.tol * 0.1).all()):
-                    break
-                # two-loop recursion, batched over problems
-                q = gl.clone()
-                alphas = []
-                order = [(n_hist - 1 - j) % m for j in range(min(n_hist, m))]
-                for idx in order:
-                    a = R[idx] * (S[idx] * q).sum(dim=0)
-                    q -= a * Y[idx]
-                    alphas.append(a)
-                if n_hist > 0:
-                    last = (n_hist - 1) % m
-                    yy = (Y[last] * Y[last]).sum(dim=0)
-                    gamma = torch.where(yy > 0, (S[last] * Y[last]).sum(dim=0) / torch.clamp(yy, min=1e-30), step0)
-                else:
-                    gamma = step0
-                q *= gamma
-                for idx, a in zip(reversed(order), reversed(alphas)):
-                    b = R[idx] * (Y[idx] * q).sum(dim=0)
-                    q += (a - b) * S[idx]
-                d = -q
-                slope = (gl * d).sum(dim=0)
-                bad = slope >= 0                                                # not a descent direction: steepest descent
-                if bool(bad.any()):
-                    d = torch.where(bad[None, :], -gl * step0, d)
-                    slope = (gl * d).sum(dim=0)
-                # Armijo backtracking, batched: every problem keeps its own step
-                t = torch.ones(P, device=dev)
-                done = gnorm < self.tol * 0.1
-                w_new, val_new, gl_new, y_new = w, val, gl, y
-                acc_w = w.clone(); acc_val = val.clone(); acc_gl = gl.clone(); acc_y = y.clone()
-                for ls in range(12):
-                    wt = w + t * d
-                    vt, gt, yt = self._al(wt, lam, rho, bufs_trial)
-                    ok = (vt <= val + 1e-4 * t * slope) & ~done
-                    if bool(ok.any()):
-                        sel = ok[None, :]
-                        acc_w = torch.where(sel, wt, acc_w); acc_gl = torch.where(sel, gt, acc_gl); acc_y = torch.where(sel, yt, acc_y)
-                        acc_val = torch.where(ok, vt, acc_val)
-                        done = done | ok
-                    if bool(done.all()):
-                        break
-                    t = torch.where(done, t, t * 0.5)
-                s_vec = acc_w - w
-                y_vec = acc_gl - gl
-                sy = (s_vec * y_vec).sum(dim=0)
-                good = sy > 1e-10 * (y_vec * y_vec).sum(dim=0).clamp(min=1e-30)
-                slot = n_hist % m
-                S[slot] = torch.where(good[None, :], s_vec, torch.zeros_like(s_vec))
-                Y[slot] = torch.where(good[None, :], y_vec, torch.zeros_like(y_vec))
-                R[slot] = torch.where(good, 1.0 / sy.clamp(min=1e-30), torch.zeros_like(sy))
-                n_hist += 1
-                w, val, gl, y = acc_w, acc_val, acc_gl, acc_y
-            # multiplier / penalty update
-            g = bufs[0]
-            prob.eval_device(w, g, None, bufs[2], None); self.evals += 1
-            viol = torch.clamp(torch.maximum(self.lb - g, g - self.ub), min=0).amax(dim=0)
-            z = g + lam / rho
-            lam = rho * (z - torch.minimum(torch.maximum(z, self.lb), self.ub))
-            stall = viol > 0.25 * prev_viol
-            rho = torch.where(stall & (viol > self.tol), torch.clamp(rho * 4.0, max=self.rho_max), rho)
-            prev_viol = viol
-            if self.verbose:
-                print(f"[AL] outer {outer:2d} evals {self.evals:5d} f med {bufs[2].median().item():.5f} viol max {viol.max().item():.2e} "
-                      f"med {viol.median().item():.2e} |gradL| max {gl.abs().amax(dim=0).max().item():.2e} rho max {rho.max().item():.0e}")
-            if bool((viol < self.tol).all()) and bool((gl.abs().amax(dim=0) < self.tol).all()):
-                break
-        f = bufs[2].clone()
-        return SolveResult(w, f, viol, gl.abs().amax(dim=0), outer, self.evals)
 
 
 # =====================================================================================================================
@@ -544,3 +407,66 @@ def solve_elastic(evaluator, lbg, ubg, w0, penalty: float = 1000.0, **solver_kw)
     feasible = viol <= tol
     return IPResult(w=w.contiguous(), f=res.f - penalty * p.sum(1), violation=viol, kkt_error=res.kkt_error, iterations=res.iterations,
                     converged=res.converged & feasible, lam=res.lam[:, :el.n_g0].contiguous(), stalled=res.stalled & feasible)
+
+
+class DeviceIPSolver:
+    """The interior point of ``BatchedIPSolver`` run entirely by the CUDA library (``nlo_ip_*``): evaluation, Hessian,
+    block-tridiagonal KKT factorisation, line search and multiplier updates stay on the device for the whole solve."""
+
+    def __init__(self, prob, max_problems: int, tol: float = 1e-4, max_iter: int = 300, mu0: float = 0.1, ls_multipliers: bool = True,
+                 compact: bool = True, verbose: bool = False):
+        import ctypes as C
+        from . import lib as _lib
+        self.prob = prob
+        self._L = _lib.load()
+        lb, ub = prob.bounds()
+        self._lb = np.ascontiguousarray(lb, np.float64); self._ub = np.ascontiguousarray(ub, np.float64)
+        self.opt = _lib.IpOptions(tol, int(max_iter), mu0, int(ls_multipliers), int(compact), int(verbose))
+        h = C.c_void_p()
+        _lib.check(self._L.nlo_ip_create(prob._h, self._lb.ctypes.data, self._ub.ctypes.data, int(max_problems), C.byref(h)))
+        self._h = h
+        self.stats = {}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.nlo_ip_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def solve(self, w0) -> IPResult:
+        """w0: (P, n_w) starts (numpy or torch, any float type).  Returns an ``IPResult`` of CPU tensors."""
+        import ctypes as C
+        import torch
+        from . import lib as _lib
+        if hasattr(w0, "detach"):
+            w0 = w0.detach().cpu().numpy()
+        w0 = np.ascontiguousarray(w0, np.float64)
+        P, n_w = w0.shape
+        if n_w != self.prob.n_w:
+            raise ValueError(f"starts have {n_w} columns, the problem has {self.prob.n_w} decision variables")
+        w = np.empty_like(w0); lam = np.empty((P, self.prob.n_g)); f = np.empty(P); viol = np.empty(P); err = np.empty(P)
+        iters = np.empty(P, np.int32); status = np.empty(P, np.int32)
+        st = _lib.IpStats()
+        _lib.check(self._L.nlo_ip_solve(self._h, w0.ctypes.data, P, C.byref(self.opt), w.ctypes.data, f.ctypes.data, viol.ctypes.data,
+                                        err.ctypes.data, iters.ctypes.data, status.ctypes.data, lam.ctypes.data, C.byref(st)))
+        self.stats = {k: int(getattr(st, k)) for k in ("iterations", "evaluations", "hessians", "trials", "compactions")}
+        t = torch.from_numpy
+        return IPResult(w=t(w), f=t(f), violation=t(viol), kkt_error=t(err), iterations=t(iters.astype(np.int64)), converged=t(status == 1),
+                        lam=t(lam), stalled=t(status == 2))
+
+    def kkt_step(self, jac, hess, omega, rhs, delta_in):
+        """One regularised Newton step of the condensed KKT system on device tensors (variable-major): jac (nnz, ld) / hess
+        (nnz_hess, ld) fp32, omega (n_g, ld) / rhs (n_w, ld) / delta_in (P,) fp64.  Returns (dw (n_w, ld), delta_out (P,))."""
+        import torch
+        from . import lib as _lib
+        ld, P = jac.shape[1], delta_in.numel()
+        dw = torch.zeros((self.prob.n_w, ld), dtype=torch.float64, device=jac.device)
+        d_out = torch.empty(P, dtype=torch.float64, device=jac.device)
+        _lib.check(self._L.nlo_ip_kkt_step(self._h, jac.data_ptr(), hess.data_ptr(), omega.data_ptr(), rhs.data_ptr(), delta_in.data_ptr(), P, ld,
+                                           dw.data_ptr(), d_out.data_ptr(), torch.cuda.current_stream(jac.device).cuda_stream))
+        return dw, d_out
