@@ -284,7 +284,10 @@ typedef struct nlo_ip_options {
   int    compact;        /* finished problems leave the working set every 10 iterations (1)               */
   int    verbose;
 } nlo_ip_options;
-typedef struct nlo_ip_stats { int iterations, evaluations, hessians, trials, compactions; } nlo_ip_stats;
+typedef struct nlo_ip_stats {
+  int iterations, evaluations, hessians, trials, compactions;   /* batched calls of each kind                              */
+  long long trial_problems;                                     /* problems evaluated by the line-search trials, in total   */
+} nlo_ip_stats;
 /* lbg, ubg: fp64[n_g] bounds of g in Opti's canonical form (+-INFINITY for one-sided rows; rows with lbg == ubg are equalities).
  * max_problems: batch size the device buffers are sized for.  The solver keeps a pointer to `p` (not owned).              */
 NLO_API int    nlo_ip_create(nlo_nlp* p, const double* lbg, const double* ubg, size_t max_problems, nlo_ip** out);

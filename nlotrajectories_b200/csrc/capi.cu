@@ -765,12 +765,15 @@ static int nlp_eval_host_impl(nlo_nlp* p, const float* w_host, size_t P, float* 
   if (P <= 8) return nlp_eval_host_small(p, w_host, P, g_host, jac_host, f_host, grad_host, compact);
   const NlpDev& L = p->L;
   // chunks: enough of them that the first chunk's upload + kernels (the only part no copy hides) is a small share of the call,
-  // large enough that a chunk's kernels fill the GPU
-  size_t chunk = (P + 15) / 16;
-  if (chunk < 2048) chunk = 2048;
+  // large enough that a chunk's kernels fill the GPU.  Measured on B200 (benchmark_6 x 65,536, compact form, ms per call):
+  // 8 chunks / 2 lanes 17.8, 16 / 2 18.1, 32 / 3 16.3, 64 / 4 15.0 (the raw device->host copy of the payload alone: 13.2)
+  static const int want_chunks = [] { const char* e = getenv("NLO_B200_HOST_CHUNKS"); const int v = e ? atoi(e) : 64; return v < 1 ? 1 : v; }();
+  static const int want_lanes = [] { const char* e = getenv("NLO_B200_HOST_LANES"); const int v = e ? atoi(e) : 4; return v < 1 ? 1 : (v > NLO_HOST_LANES ? NLO_HOST_LANES : v); }();
+  size_t chunk = (P + want_chunks - 1) / want_chunks;
+  if (chunk < 1024) chunk = 1024;
   if (chunk > P) chunk = P;
   const size_t n_chunks = (P + chunk - 1) / chunk;
-  const int n_lanes = n_chunks > 1 ? 2 : 1;
+  const int n_lanes = (int)std::min<size_t>(n_chunks, (size_t)want_lanes);
   const int ng = compact ? (int)p->cg_rows.size() : L.n_g, nj = compact ? (int)p->cj_nz.size() : L.nnz, nr = compact ? (int)p->cgr_idx.size() : L.n_w;
   const int* d_cg = p->d_compact; const int* d_cj = d_cg + p->cg_rows.size(); const int* d_cr = d_cj + p->cj_nz.size();
   for (int l = 0; l < n_lanes; ++l) if (ensure_lane(p, p->lane[l], chunk)) return 1;

@@ -53,6 +53,7 @@ struct IpWork {
   double *dwt, *alpha, *alpha_d, *phi0, *dphi, *eps_ls, *viol;
   int *accepted;
   int *counters;                      // [0] problems done, [1] line-search rejections of the current trial
+  int *ls_list[2];                    // problems still in the line search: the list a trial reads and the one it appends to
 };
 
 struct IpOut {                        // final results, indexed by the ORIGINAL problem index
@@ -245,13 +246,14 @@ IP_HD void ip_step_body(const IpTables& T, const IpState& S, const IpWork& W, si
 }
 
 // ---- line search: merit at the trial point; returns 1 if the problem is still not accepted --------------------------------------
-IP_HD int ip_merit_body(const IpTables& T, const IpState& S, const IpWork& W, size_t p) {
+// The trial batch holds only the problems still searching: column q of the trial evaluation (wt32, gt, ft) belongs to problem p.
+IP_HD int ip_merit_body(const IpTables& T, const IpState& S, const IpWork& W, size_t p, size_t q_col) {
   if (W.accepted[p]) return 0;
   const size_t ld = S.ld;
   const double mu = S.mu[p], a = W.alpha[p];
   double c1 = 0.0, bar = 0.0;
   for (int r = 0; r < T.n_g; ++r) {
-    const double gr = (double)W.gt[(size_t)r * ld + p];
+    const double gr = (double)W.gt[(size_t)r * ld + q_col];
     if (T.rkind[r] == 0) { c1 += fabs(gr - T.lb[r]); continue; }
     const size_t q = (size_t)T.ridx[r] * ld + p;
     const double st = S.s[q] + a * W.ds[q];
@@ -259,7 +261,7 @@ IP_HD int ip_merit_body(const IpTables& T, const IpState& S, const IpWork& W, si
     if (ip_finite(T.lb[r])) bar -= mu * log(ip_max(st - T.lb[r], 1e-300));
     if (ip_finite(T.ub[r])) bar -= mu * log(ip_max(T.ub[r] - st, 1e-300));
   }
-  const double phi = (double)W.ft[p] + bar + S.nu[p] * c1;
+  const double phi = (double)W.ft[q_col] + bar + S.nu[p] * c1;
   const double phi0 = W.phi0[p];
   const bool ok = ip_finite(phi) && phi <= phi0 + 1e-4 * a * ip_min(W.dphi[p], 0.0) + 1e-12 * fabs(phi0);
   if (ok) { W.accepted[p] = 1; return 0; }
@@ -554,12 +556,12 @@ IP_HD void bt_kkt_body(const BtTables& B, const double* K, double* Lf, const dou
 // The iteration, written against a backend X that runs each body for problems 0..P-1 (CUDA kernels or host loops)
 // =====================================================================================================================
 struct IpOptions { double tol; int max_iter; double mu0; int ls_multipliers; int compact; int verbose; };
-struct IpStats { int iterations, evaluations, hessians, trials, compactions; };
+struct IpStats { int iterations, evaluations, hessians, trials, compactions; long long trial_problems; };
 
 template <class X>
 int ip_solve_loop(X& x, size_t P0, const IpOptions& opt, IpStats* stats) {
   size_t P = P0;
-  IpStats st = {0, 0, 0, 0, 0};
+  IpStats st = {0, 0, 0, 0, 0, 0};
   if (x.eval_full(P)) return 1;
   ++st.evaluations;
   if (x.init(P, opt.mu0, opt.max_iter)) return 1;
@@ -582,11 +584,14 @@ int ip_solve_loop(X& x, size_t P0, const IpOptions& opt, IpStats* stats) {
     ++st.hessians;
     if (x.kkt_solve(P)) return 1;
     if (x.step(P)) return 1;
+    // backtracking line search: after the first trial only the problems whose step was refused are evaluated again
+    size_t n_ls = P;
     for (int ls = 0; ls < 14; ++ls) {
       size_t rejected = 0;
-      if (x.trial(P, &rejected)) return 1;
-      ++st.trials;
+      if (x.trial(n_ls, ls, &rejected)) return 1;
+      ++st.trials; st.trial_problems += (long long)n_ls;
       if (rejected == 0) break;
+      n_ls = rejected;
     }
     if (x.update(P)) return 1;
     if (x.eval_full(P)) return 1;

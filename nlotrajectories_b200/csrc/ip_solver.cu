@@ -32,20 +32,22 @@ __global__ void __launch_bounds__(IP_TPB) ip_step_kernel(IpTables T, IpState S, 
   const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p < P) ip_step_body(T, S, W, p);
 }
-// trial point of the line search, fp32 for the evaluation kernels: one thread per (variable, problem)
-__global__ void __launch_bounds__(256) ip_trial_kernel(IpState S, IpWork W, size_t P, int n_w) {
-  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P) return;
+// trial points of the line search, fp32 for the evaluation kernels: column q of the trial batch is problem list[q] (or q itself)
+__global__ void __launch_bounds__(256) ip_trial_kernel(IpState S, IpWork W, size_t n, int n_w, const int* __restrict__ list) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const size_t p = list ? (size_t)list[q] : q;
   const double a = W.alpha[p];
   for (int c = blockIdx.y; c < n_w; c += gridDim.y)
-    W.wt32[(size_t)c * S.ld + p] = (float)(S.w[(size_t)c * S.ld + p] + a * W.dw[(size_t)c * S.ld + p]);
+    W.wt32[(size_t)c * S.ld + q] = (float)(S.w[(size_t)c * S.ld + p] + a * W.dw[(size_t)c * S.ld + p]);
 }
-__global__ void __launch_bounds__(IP_TPB) ip_merit_kernel(IpTables T, IpState S, IpWork W, size_t P) {
-  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int rej = 0;
-  if (p < P) rej = ip_merit_body(T, S, W, p);
-  const int n = __syncthreads_count(rej);
-  if (threadIdx.x == 0 && n) atomicAdd(W.counters + 1, n);
+// problems whose trial step is refused are appended to `next` (their order does not matter: every problem is independent)
+__global__ void __launch_bounds__(IP_TPB) ip_merit_kernel(IpTables T, IpState S, IpWork W, size_t n, const int* __restrict__ list,
+                                                          int* __restrict__ next) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const size_t p = list ? (size_t)list[q] : q;
+  if (ip_merit_body(T, S, W, p, q)) next[atomicAdd(W.counters + 1, 1)] = (int)p;
 }
 __global__ void __launch_bounds__(IP_TPB) ip_update_kernel(IpTables T, IpState S, IpWork W, size_t P) {
   const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -261,12 +263,13 @@ struct GpuBackend {
     NLO_CHECK_LAUNCH();
     return 0;
   }
-  int trial(size_t P, size_t* rejected) {
-    ip_trial_kernel<<<dim3((unsigned)((P + 255) / 256), 32), 256, 0, st>>>(s->S, s->W, P, s->T.n_w);
+  int trial(size_t n, int ls, size_t* rejected) {
+    const int* list = ls > 0 ? s->W.ls_list[(ls + 1) & 1] : nullptr;
+    ip_trial_kernel<<<dim3((unsigned)((n + 255) / 256), 32), 256, 0, st>>>(s->S, s->W, n, s->T.n_w, list);
     NLO_CHECK_LAUNCH();
-    if (nlo_nlp_eval(s->nlp, s->W.wt32, P, s->cap, s->W.gt, nullptr, s->W.ft, nullptr, st)) return 1;
+    if (nlo_nlp_eval(s->nlp, s->W.wt32, n, s->cap, s->W.gt, nullptr, s->W.ft, nullptr, st)) return 1;
     NLO_CUDA(cudaMemsetAsync(s->W.counters + 1, 0, sizeof(int), st));
-    ip_merit_kernel<<<g1(P), IP_TPB, 0, st>>>(s->T, s->S, s->W, P);
+    ip_merit_kernel<<<g1(n), IP_TPB, 0, st>>>(s->T, s->S, s->W, n, list, s->W.ls_list[ls & 1]);
     NLO_CHECK_LAUNCH();
     return read_counter(1, rejected);
   }
@@ -395,7 +398,7 @@ int nlo_ip_create(nlo_nlp* p, const double* lbg, const double* ubg, size_t max_p
   for (int b = 0; b < 2 && ok; ++b)
     ok = cudaMalloc(&s->d_state[b], s->state_rows * ld * sizeof(double)) == cudaSuccess && cudaMalloc(&s->d_istate[b], 4 * ld * sizeof(int)) == cudaSuccess;
   ok = ok && cudaMalloc(&s->d_f32, f32_rows * ld * sizeof(float)) == cudaSuccess && cudaMalloc(&s->d_f64, f64_rows * ld * sizeof(double)) == cudaSuccess &&
-       cudaMalloc(&s->d_i32, (ld + 8) * sizeof(int)) == cudaSuccess && cudaMalloc(&s->d_K, k_slots * ld * sizeof(double)) == cudaSuccess &&
+       cudaMalloc(&s->d_i32, (3 * ld + 8) * sizeof(int)) == cudaSuccess && cudaMalloc(&s->d_K, k_slots * ld * sizeof(double)) == cudaSuccess &&
        cudaMalloc(&s->d_L, l_slots * ld * sizeof(double)) == cudaSuccess &&
        cudaMalloc(&s->d_out, ((size_t)T.n_w + T.n_g + 3) * ld * sizeof(double)) == cudaSuccess && cudaMalloc(&s->d_iout, 2 * ld * sizeof(int)) == cudaSuccess &&
        cudaMalloc(&s->d_keep, ld * sizeof(int)) == cudaSuccess && cudaHostAlloc(&s->h_pin, (ld + 2) * sizeof(int), cudaHostAllocDefault) == cudaSuccess &&
@@ -416,7 +419,7 @@ int nlo_ip_create(nlo_nlp* p, const double* lbg, const double* ubg, size_t max_p
   W.dw_alt = d; d += (size_t)T.n_w * ld; W.ds = d; d += (size_t)T.nI * ld; W.dzl = d; d += (size_t)T.nI * ld; W.dzu = d; d += (size_t)T.nI * ld;
   W.dlamE = d; d += (size_t)T.nE * ld; W.lam_ls = d; d += (size_t)T.nE * ld;
   W.dwt = d; d += ld; W.alpha = d; d += ld; W.alpha_d = d; d += ld; W.phi0 = d; d += ld; W.dphi = d; d += ld; W.eps_ls = d; W.viol = nullptr;
-  W.accepted = s->d_i32; W.counters = s->d_i32 + ld;
+  W.accepted = s->d_i32; W.ls_list[0] = s->d_i32 + ld; W.ls_list[1] = s->d_i32 + 2 * ld; W.counters = s->d_i32 + 3 * ld;
   IpOut& O = s->O;
   O.ld = ld; O.w = s->d_out; O.lam = O.w + (size_t)T.n_w * ld; O.f = O.lam + (size_t)T.n_g * ld; O.viol = O.f + ld; O.err = O.viol + ld;
   O.iters = s->d_iout; O.status = s->d_iout + ld;
@@ -477,7 +480,7 @@ int nlo_ip_solve(nlo_ip* s, const double* w0_host, size_t P, const nlo_ip_option
   NLO_CUDA(cudaStreamSynchronize(st));
   if (stats_out) {
     stats_out->iterations = stats.iterations; stats_out->evaluations = stats.evaluations; stats_out->hessians = stats.hessians;
-    stats_out->trials = stats.trials; stats_out->compactions = stats.compactions;
+    stats_out->trials = stats.trials; stats_out->compactions = stats.compactions; stats_out->trial_problems = stats.trial_problems;
   }
   return 0;
 }

@@ -3,6 +3,7 @@
 #include "nlo_common.cuh"
 #include <vector>
 
+#define NLO_HOST_LANES 4
 #define NLO_HESS_SLOTS 19        // Hessian emission slots per knot (nlp_hess.cu)
 
 struct NlpDev {                 // passed by value to kernels
@@ -56,7 +57,7 @@ struct nlo_nlp {
   std::vector<int> cj_const_nz; std::vector<float> cj_const_val;     // dg/dw[nz] = value for every w
   std::vector<int> cgr_lin_idx; std::vector<float> cgr_lin_coef;     // grad f[idx] = coef * w[idx]; every other non-varying entry is 0
   int* d_compact;                                     // device: cg_rows | cj_nz | cgr_idx
-  NlpLane lane[2];              // host entry point: two lanes (streams) process alternating chunks of problems
+  NlpLane lane[NLO_HOST_LANES];  // host entry point: lanes (streams) process alternating chunks of problems
 };
 
 // ---- analytic obstacles (solver.mode casadi): value, gradient and Hessian w.r.t. (x, y) -----------------------------------

@@ -152,17 +152,44 @@ def _post_one(path):
     return X, U
 
 
+def _host_planner(cfg):
+    from .initializer import RRTInitializer
+    from .train import scene_sdf
+    b, s = cfg.body, cfg.solver
+    ini = s.initializer
+    bounds = ini.rrt_bounds if ini.rrt_bounds is not None else [[-0.5, -0.5], [1.5, 1.5]]
+    if b.shape == "rectangle":
+        hl, hw = 0.5 * b.length, 0.5 * b.width
+        body = [(-hl, -hw), (-hl, hw), (hl, hw), (hl, -hw)]
+    else:
+        body = None
+    host = RRTInitializer(s.N + 1, b.start_state, b.goal_state, s.dt, scene_sdf(cfg), bounds, body_points=body, rectangle=b.shape == "rectangle",
+                          step_size=ini.step_size, max_iter=ini.max_iter, margin=ini.margin)
+    return host, bounds
+
+
+def make_post_pool(cfg, lift: bool = False, workers: Optional[int] = None):
+    """Fork the post-processing workers of ``rrt_multistart_device`` (numpy only).  Call it BEFORE the process creates its CUDA
+    context or NCCL threads - forking a process that holds either is unsupported - and hand the pool to ``rrt_multistart_device``."""
+    import multiprocessing as mp
+    import os
+    global _POST_STATE
+    from .problem import DYN_DIMS
+    nx, nu = DYN_DIMS[cfg.body.dynamic]
+    _POST_STATE = (_host_planner(cfg)[0], cfg, lift, nx, nu)
+    return mp.get_context("fork").Pool(workers or min(32, os.cpu_count() or 1))
+
+
 def rrt_multistart_device(cfg, P: int, first: int = 0, seed0: int = 1234, lift: bool = False, device=None,
-                          workers: Optional[int] = None) -> np.ndarray:
+                          workers: Optional[int] = None, pool=None) -> np.ndarray:
     """``initializer.rrt_multistart`` with the tree search batched on ``device`` (default: CUDA when available, else CPU).  The raw
-    tree paths are shortcut, split at sharp corners, splined and (optionally) lifted on the host exactly like the host planner's,
-    on a pool of forked processes (numpy only; the children never touch CUDA)."""
+    tree paths are shortcut, split at sharp corners, splined and (optionally) lifted on the host exactly like the host planner's:
+    on ``pool`` (``make_post_pool``, forked before CUDA was initialised) when given; on a pool forked here when this process has
+    no CUDA context yet; in this process otherwise (a process that holds a CUDA context must not fork)."""
     import os
     import torch
     global _POST_STATE
-    from .initializer import RRTInitializer
     from .problem import DYN_DIMS
-    from .train import scene_sdf
     if device is None:
         device = torch.device("cuda") if torch.cuda.is_available() else torch.device("cpu")
     b, s = cfg.body, cfg.solver
@@ -171,14 +198,8 @@ def rrt_multistart_device(cfg, P: int, first: int = 0, seed0: int = 1234, lift: 
     n_X, n_U = nx * (N + 1), nu * N
     n_w = n_X + n_U + ((N + 1) if s.use_slack else 0)
     ini = s.initializer
-    bounds = ini.rrt_bounds if ini.rrt_bounds is not None else [[-0.5, -0.5], [1.5, 1.5]]
-    if b.shape == "rectangle":
-        hl, hw = 0.5 * b.length, 0.5 * b.width
-        body = [(-hl, -hw), (-hl, hw), (hl, hw), (hl, -hw)]
-    else:
-        body = None
-    host = RRTInitializer(N + 1, b.start_state, b.goal_state, s.dt, scene_sdf(cfg), bounds, body_points=body, rectangle=b.shape == "rectangle",
-                          step_size=ini.step_size, max_iter=ini.max_iter, margin=ini.margin)
+    may_fork = pool is None and not torch.cuda.is_initialized()      # decided before the trees run on the device
+    host, bounds = _host_planner(cfg)
     seeds = [seed0 + first + i for i in range(P)]
     pos, parent, final = batched_rrt_trees(torch_scene_sdf(cfg, device), b.start_state, b.goal_state, bounds, P, seeds, ini.step_size,
                                            ini.max_iter, host.inflation, device=device)
@@ -191,15 +212,18 @@ def rrt_multistart_device(cfg, P: int, first: int = 0, seed0: int = 1234, lift: 
         while node >= 0:
             idx.append(node); node = int(parent[i, node])
         paths.append(pos[i, idx[::-1]])
-    _POST_STATE = (host, cfg, lift, nx, nu)
     if workers is None:
         workers = min(32, os.cpu_count() or 1)
     workers = min(workers, P)
-    if workers > 1 and P >= 8:
+    if pool is not None:
+        plans = pool.map(_post_one, paths, chunksize=max(1, P // (4 * workers)))
+    elif may_fork and str(device) == "cpu" and workers > 1 and P >= 8:
         import multiprocessing as mp
-        with mp.get_context("fork").Pool(workers) as pool:
-            plans = pool.map(_post_one, paths, chunksize=max(1, P // (4 * workers)))
+        _POST_STATE = (host, cfg, lift, nx, nu)
+        with mp.get_context("fork").Pool(workers) as own:
+            plans = own.map(_post_one, paths, chunksize=max(1, P // (4 * workers)))
     else:
+        _POST_STATE = (host, cfg, lift, nx, nu)
         plans = [_post_one(pth) for pth in paths]
     w = np.zeros((P, n_w), np.float32)
     for i, (X, U) in enumerate(plans):

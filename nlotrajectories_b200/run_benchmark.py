@@ -42,23 +42,33 @@ def synthetic_weights(cfg: Config, seed: int = 0) -> SdfWeights:
 
 
 def solve_benchmark(config_path: Path, batch: int = 64, weights: str | None = None, precision: str = "auto", verbose: bool = True,
-                    lift: bool = False, elastic: float | None = None, device_rrt: bool = False):
-    """``--solve``: every start of this rank's shard goes through the batched interior point (solver.py); the best
-    converged objective across ranks is selected with the same all-gather + broadcast as the evaluation path."""
-    import torch
-    from .solver import BatchedIPSolver, DeviceEvaluator, solve_elastic
-    rank, local_rank, world = init_process_group("nccl")
-    torch.cuda.set_device(local_rank)
+                    lift: bool = False, elastic: float | None = None, device_rrt: bool = False, dense: bool = False, max_iter: int = 300):
+    """``--solve``: every start of this rank's shard goes through the interior point - the device solver of the CUDA library
+    (``DeviceIPSolver``: block-tridiagonal KKT kernels, batches of thousands of starts) or, with ``dense`` / ``elastic``, the dense
+    torch solver of ``solver.py`` (a few hundred starts).  The best usable objective across ranks is selected with the same
+    all-gather + broadcast as the evaluation path."""
+    from .distributed import env_rank_world
+    rank, local_rank, world = env_rank_world()
     cfg = Config.load(config_path)
     lo, hi = shard_range(batch, rank, world)
     w0_host = None
-    if cfg.solver.initializer.mode == "rrt":                     # the YAML's initializer (scripts/run_benchmark.py:114-127), one seed per start;
-        if device_rrt:                                           # thousands of starts: the tree search batched on the GPU (rrt_device.py)
-            from .rrt_device import rrt_multistart_device
-            w0_host = rrt_multistart_device(cfg, hi - lo, first=lo, lift=lift, device=torch.device("cuda", local_rank)).astype(np.float64)
-        else:
-            from .initializer import rrt_multistart              # planned on forked host processes, before this process creates its CUDA context
-            w0_host = rrt_multistart(cfg, hi - lo, first=lo, lift=lift).astype(np.float64)
+    if cfg.solver.initializer.mode == "rrt" and not device_rrt:
+        # the YAML's initializer (scripts/run_benchmark.py:114-127), one seed per start, planned on forked host processes BEFORE this
+        # process creates its CUDA context or NCCL threads (forking a process that holds either is unsupported)
+        from .initializer import rrt_multistart
+        w0_host = rrt_multistart(cfg, hi - lo, first=lo, lift=lift).astype(np.float64)
+    post_pool = None
+    if cfg.solver.initializer.mode == "rrt" and device_rrt:      # the post-processing workers fork now, while this process holds no CUDA context
+        from .rrt_device import make_post_pool
+        post_pool = make_post_pool(cfg, lift)
+    import torch
+    from .solver import BatchedIPSolver, DeviceEvaluator, DeviceIPSolver, solve_elastic
+    init_process_group("nccl")
+    torch.cuda.set_device(local_rank)
+    if post_pool is not None:                                    # thousands of starts: the tree search batched on the GPU (rrt_device.py)
+        from .rrt_device import rrt_multistart_device
+        w0_host = rrt_multistart_device(cfg, hi - lo, first=lo, lift=lift, device=torch.device("cuda", local_rank), pool=post_pool).astype(np.float64)
+        post_pool.close(); post_pool.join()
     sdf = None
     if cfg.solver.mode == "l4casadi":
         sdf = LearnedSDF(SdfWeights.load(weights) if weights else synthetic_weights(cfg), device=local_rank, precision=precision)
@@ -66,21 +76,27 @@ def solve_benchmark(config_path: Path, batch: int = 64, weights: str | None = No
     dev = torch.device("cuda", local_rank)
     if w0_host is None:
         w0_host = prob.multistart_guess(hi - lo, first=lo).astype(np.float64)
-    w0 = torch.from_numpy(w0_host).to(dev)
     lb, ub = prob.bounds()
     t0 = time.time()
     if elastic:
-        res = solve_elastic(DeviceEvaluator(prob), lb, ub, w0, penalty=float(elastic), verbose=verbose and rank == 0)
+        res = solve_elastic(DeviceEvaluator(prob), lb, ub, torch.from_numpy(w0_host).to(dev), penalty=float(elastic), verbose=verbose and rank == 0,
+                            max_iter=max_iter)
+        name = "dense batched interior point, elastic mode"
+    elif dense:
+        res = BatchedIPSolver(DeviceEvaluator(prob), lb, ub, verbose=verbose and rank == 0, max_iter=max_iter).solve(torch.from_numpy(w0_host).to(dev))
+        name = "dense batched interior point (torch.linalg)"
     else:
-        res = BatchedIPSolver(DeviceEvaluator(prob), lb, ub, verbose=verbose and rank == 0).solve(w0)
+        res = DeviceIPSolver(prob, max_problems=hi - lo, max_iter=max_iter, verbose=verbose and rank == 0).solve(w0_host)
+        name = "device interior point (block-tridiagonal KKT kernels)"
     torch.cuda.synchronize()
     dt = time.time() - t0
-    usable = res.converged | (res.stalled & (res.violation <= 1e-4))
-    score = torch.where(usable, res.f, res.f + 1e3 * (1.0 + res.violation)).float()
-    best_val, best_idx, w_best = select_best(score, res.w.float().T.contiguous(), lo, prob.n_w)
-    out = {"config": str(config_path), "batch": batch, "world": world, "solver": "batched interior point (tol 1e-4, exact Hessian)",
-           "solve_s_rank0": dt, "converged_fraction_rank0": float(res.converged.float().mean().item()), "stalled_feasible_fraction_rank0": float(res.stalled.float().mean().item()),
-           "best_objective": best_val, "best_start": best_idx}
+    w_res, f_res, v_res = res.w.to(dev), res.f.to(dev), res.violation.to(dev)
+    usable = res.converged.to(dev) | (res.stalled.to(dev) & (v_res <= 1e-4))
+    score = torch.where(usable, f_res, f_res + 1e3 * (1.0 + v_res)).float()
+    best_val, best_idx, w_best = select_best(score, w_res.float().T.contiguous(), lo, prob.n_w)
+    out = {"config": str(config_path), "batch": batch, "world": world, "solver": name + ", tol 1e-4, exact Hessian",
+           "solve_s_rank0": dt, "solves_per_s_rank0": (hi - lo) / dt, "converged_fraction_rank0": float(res.converged.float().mean().item()),
+           "stalled_feasible_fraction_rank0": float(res.stalled.float().mean().item()), "best_objective": best_val, "best_start": best_idx}
     if rank == 0 and verbose:
         print(json.dumps(out))
     return out, w_best.cpu().numpy()
@@ -142,10 +158,17 @@ def main():
     ap.add_argument("--lift", action="store_true", help="--solve: fill heading / speed / steering of the RRT guesses from the planned path")
     ap.add_argument("--device-rrt", action="store_true", help="--solve: grow the RRT trees of all starts in lock step on the GPU instead of on host processes")
     ap.add_argument("--elastic", type=float, default=None, metavar="PENALTY", help="--solve: elastic mode (exact l1 penalty) on the inequality rows")
+    ap.add_argument("--dense", action="store_true", help="--solve: the dense torch solver instead of the device solver (at most 512 starts)")
+    ap.add_argument("--max-iter", type=int, default=300, help="--solve: iteration limit")
     ap.add_argument("--sdf-metrics", action="store_true", help="also report the learned SDF's quality metrics on the 1000^2 grid")
     a = ap.parse_args()
     if a.solve:
-        solve_benchmark(Path(a.config), min(a.batch, 512), a.weights, a.precision, lift=a.lift, elastic=a.elastic, device_rrt=a.device_rrt)
+        batch = a.batch
+        if (a.dense or a.elastic) and batch > 512:
+            print(f"[run-benchmark] --dense / --elastic factorise dense {batch} x n_w^2 fp64 matrices: batch clamped from {batch} to 512", file=sys.stderr)
+            batch = 512
+        solve_benchmark(Path(a.config), batch, a.weights, a.precision, lift=a.lift, elastic=a.elastic, device_rrt=a.device_rrt, dense=a.dense,
+                        max_iter=a.max_iter)
     else:
         run_benchmark(Path(a.config), a.batch, a.weights, a.precision, sdf_metrics=a.sdf_metrics)
     import torch.distributed as dist

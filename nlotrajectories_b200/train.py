@@ -203,13 +203,13 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", required=True)
     ap.add_argument("--out", required=True, help=".nlow or .npz")
-    ap.add_argument("--samples", type=int, default=200_000)
+    ap.add_argument("--samples", type=int, default=None, help="default: the YAML's model.n_samples (scripts/run_benchmark.py:88-96)")
     ap.add_argument("--epochs", type=int, default=100)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--batch-size", type=int, default=256, help="the reference's value (core/sdf/l4casadi.py:89)")
     a = ap.parse_args()
     cfg = Config.load(Path(a.config))
-    net, info = train(cfg, n_samples=a.samples, epochs=a.epochs, seed=a.seed, batch_size=a.batch_size)
+    net, info = train(cfg, n_samples=a.samples if a.samples is not None else cfg.model.n_samples, epochs=a.epochs, seed=a.seed, batch_size=a.batch_size)
     w = SdfWeights.from_state_dict(cfg.model.type, net.state_dict(), activation_function=cfg.model.activation_function,
                                    omega_0=cfg.model.omega_0)
     (w.save_nlow if a.out.endswith(".nlow") else w.save_npz)(a.out)

@@ -88,13 +88,21 @@ struct HostBackend {
     return 1;
   }
   int step(size_t P) { for (size_t p = 0; p < P; ++p) ip_step_body(e.T, e.S, e.W, p); return 0; }
-  int trial(size_t P, size_t* rejected) {
+  int trial(size_t n, int ls, size_t* rejected) {
+    const int* list = ls > 0 ? e.W.ls_list[(ls + 1) & 1] : nullptr;
+    int* next = e.W.ls_list[ls & 1];
     for (int c = 0; c < e.T.n_w; ++c)
-      for (size_t p = 0; p < P; ++p) e.W.wt32[(size_t)c * e.ld + p] = (float)(e.S.w[(size_t)c * e.ld + p] + e.W.alpha[p] * e.W.dw[(size_t)c * e.ld + p]);
-    if (e.eval(e.W.wt32, P, e.ld, e.W.gt, nullptr, e.W.ft, nullptr)) return 1;
-    size_t n = 0;
-    for (size_t p = 0; p < P; ++p) n += ip_merit_body(e.T, e.S, e.W, p);
-    *rejected = n;
+      for (size_t q = 0; q < n; ++q) {
+        const size_t p = list ? (size_t)list[q] : q;
+        e.W.wt32[(size_t)c * e.ld + q] = (float)(e.S.w[(size_t)c * e.ld + p] + e.W.alpha[p] * e.W.dw[(size_t)c * e.ld + p]);
+      }
+    if (e.eval(e.W.wt32, n, e.ld, e.W.gt, nullptr, e.W.ft, nullptr)) return 1;
+    size_t m = 0;
+    for (size_t q = 0; q < n; ++q) {
+      const size_t p = list ? (size_t)list[q] : q;
+      if (ip_merit_body(e.T, e.S, e.W, p, q)) next[m++] = (int)p;
+    }
+    *rejected = m;
     return 0;
   }
   int update(size_t P) { for (size_t p = 0; p < P; ++p) ip_update_body(e.T, e.S, e.W, p); return 0; }
@@ -145,7 +153,7 @@ void setup(Emul& e, int n_w, int n_g, const int* jcolind, const int* jrow, int n
   for (int b = 0; b < 2; ++b) { e.state[b].assign(e.state_rows * ld, 0.0); e.istate[b].assign(4 * ld, 0); }
   const size_t f32_rows = 1 + (size_t)T.n_w + T.n_g + T.nnz + T.nnzh + T.n_w + T.n_g + T.n_w + 1 + T.n_g;
   const size_t f64_rows = (size_t)T.n_g * 2 + T.n_w * 3 + T.nI * 3 + T.nE * 2 + 6;
-  e.f32.assign(f32_rows * ld, 0.f); e.f64.assign(f64_rows * ld, 0.0); e.i32.assign(ld + 8, 0);
+  e.f32.assign(f32_rows * ld, 0.f); e.f64.assign(f64_rows * ld, 0.0); e.i32.assign(3 * ld + 8, 0);
   e.K.assign(std::max((size_t)e.kkt_h.nb * e.kkt_h.SLK, (size_t)e.lsq_h.nb * e.lsq_h.SLK) * ld, 0.0);
   e.L.assign(std::max((size_t)e.kkt_h.nb * e.kkt_h.SLL, (size_t)e.lsq_h.nb * e.lsq_h.SLL) * ld, 0.0);
   e.out.assign(((size_t)T.n_w + T.n_g + 3) * ld, 0.0); e.iout.assign(2 * ld, 0);
@@ -160,7 +168,7 @@ void setup(Emul& e, int n_w, int n_g, const int* jcolind, const int* jrow, int n
   W.dw_alt = d; d += (size_t)T.n_w * ld; W.ds = d; d += (size_t)T.nI * ld; W.dzl = d; d += (size_t)T.nI * ld; W.dzu = d; d += (size_t)T.nI * ld;
   W.dlamE = d; d += (size_t)T.nE * ld; W.lam_ls = d; d += (size_t)T.nE * ld;
   W.dwt = d; d += ld; W.alpha = d; d += ld; W.alpha_d = d; d += ld; W.phi0 = d; d += ld; W.dphi = d; d += ld; W.eps_ls = d; W.viol = nullptr;
-  W.accepted = e.i32.data(); W.counters = e.i32.data() + ld;
+  W.accepted = e.i32.data(); W.ls_list[0] = e.i32.data() + ld; W.ls_list[1] = e.i32.data() + 2 * ld; W.counters = e.i32.data() + 3 * ld;
   IpOut& O = e.O;
   O.ld = ld; O.w = e.out.data(); O.lam = O.w + (size_t)T.n_w * ld; O.f = O.lam + (size_t)T.n_g * ld; O.viol = O.f + ld; O.err = O.viol + ld;
   O.iters = e.iout.data(); O.status = e.iout.data() + ld;
