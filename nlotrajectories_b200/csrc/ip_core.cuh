@@ -67,11 +67,28 @@ IP_HD bool ip_finite(double x) { return x - x == 0.0; }
 IP_HD double ip_max(double a, double b) { return a > b ? a : b; }     // NaN-propagating like torch.maximum is not needed here
 IP_HD double ip_min(double a, double b) { return a < b ? a : b; }
 
+// Every body below is written for a TEAM of workers per problem: worker `part` of `nparts` takes the rows / columns
+// part, part + nparts, ... of each loop, partial results meet in the team's reducer R, and everything that follows a reduction is
+// computed redundantly by all workers, while only worker 0 stores per-problem scalars.  On the device a team is the W warps of a
+// thread block whose 32 lanes are 32 consecutive problems (so every global access stays coalesced along the problem index) and R
+// reduces through shared memory; on the host (tests) a team is one worker and R is the identity.  One thread per problem left the
+// GPU idle: at 4,096 problems the row loops (~1,000 dependent iterations) ran on 32 warps in total.
+struct IpSolo {                         // team of one
+  IP_HD int part() const { return 0; }
+  IP_HD int nparts() const { return 1; }
+  IP_HD double sum(double v) { return v; }
+  IP_HD double max(double v) { return v; }
+  IP_HD double min(double v) { return v; }
+  IP_HD bool any(bool v) { return v; }
+  IP_HD void sync() {}
+};
+
 // ---- initial slacks and multipliers -----------------------------------------------------------------------------------------
-IP_HD void ip_init_body(const IpTables& T, const IpState& S, const IpWork& W, size_t p, double mu0, int max_iter) {
+template <class R>
+IP_HD void ip_init_body(const IpTables& T, const IpState& S, const IpWork& W, size_t p, double mu0, int max_iter, R& red) {
   const size_t ld = S.ld;
   const double push = 1e-2;
-  for (int r = 0; r < T.n_g; ++r) {
+  for (int r = red.part(); r < T.n_g; r += red.nparts()) {
     if (T.rkind[r] == 0) { S.lamE[(size_t)T.ridx[r] * ld + p] = 0.0; continue; }
     const int i = T.ridx[r];
     const double l = T.lb[r], u = T.ub[r];
@@ -88,17 +105,23 @@ IP_HD void ip_init_body(const IpTables& T, const IpState& S, const IpWork& W, si
     S.zl[(size_t)i * ld + p] = hl ? mu0 / (sv - lf) : 0.0;
     S.zu[(size_t)i * ld + p] = hu ? mu0 / (uf - sv) : 0.0;
   }
-  S.mu[p] = mu0; S.nu[p] = 1.0; S.delta_w[p] = 0.0; S.err0[p] = HUGE_VAL; S.f_mark[p] = (double)W.f[p];
-  S.iters[p] = max_iter; S.stalled[p] = 0; S.done[p] = 0;
+  if (red.part() == 0) {
+    S.mu[p] = mu0; S.nu[p] = 1.0; S.delta_w[p] = 0.0; S.err0[p] = HUGE_VAL; S.f_mark[p] = (double)W.f[p];
+    S.iters[p] = max_iter; S.stalled[p] = 0; S.done[p] = 0;
+  }
 }
 
 // ---- residuals, convergence test, barrier update, weights and right-hand side of the condensed system ------------------------
 // Returns 1 when the problem is done after this test.
-IP_HD int ip_residual_body(const IpTables& T, const IpState& S, const IpWork& W, size_t p, int it, double tol) {
+template <class R>
+IP_HD int ip_residual_body(const IpTables& T, const IpState& S, const IpWork& W, size_t p, int it, double tol, R& red) {
   const size_t ld = S.ld;
-  double feas = 0.0, c1 = 0.0, sum_abs = 0.0, sum_z = 0.0, cmax = -HUGE_VAL, cmin = HUGE_VAL;
+  int done = S.done[p];
+  double mu = S.mu[p];
+  const double f_mark = S.f_mark[p];
+  double feas = 0.0, sum_abs = 0.0, sum_z = 0.0, cmax = -HUGE_VAL, cmin = HUGE_VAL;
   bool any_comp = false;
-  for (int r = 0; r < T.n_g; ++r) {
+  for (int r = red.part(); r < T.n_g; r += red.nparts()) {
     const double gr = (double)W.g[(size_t)r * ld + p];
     double lam, rc;
     if (T.rkind[r] == 0) {
@@ -114,42 +137,45 @@ IP_HD int ip_residual_body(const IpTables& T, const IpState& S, const IpWork& W,
       if (ip_finite(T.ub[r])) { const double c = zu * (T.ub[r] - sv); cmax = ip_max(cmax, c); cmin = ip_min(cmin, c); any_comp = true; }
     }
     feas = ip_max(feas, fabs(rc));
-    c1 += fabs(rc);
     sum_abs += fabs(lam);
     W.v[(size_t)r * ld + p] = lam;
     W.lam32[(size_t)r * ld + p] = (float)lam;
   }
+  feas = red.max(feas); sum_abs = red.sum(sum_abs); sum_z = red.sum(sum_z); cmax = red.max(cmax); cmin = red.min(cmin); any_comp = red.any(any_comp);
+  red.sync();                                           // the multipliers written above are read column-wise below
   // dual residual  grad f + J^T lam
   double rd = 0.0;
-  for (int c = 0; c < T.n_w; ++c) {
+  for (int c = red.part(); c < T.n_w; c += red.nparts()) {
     double acc = (double)W.grad[(size_t)c * ld + p];
     for (int z = T.colind[c]; z < T.colind[c + 1]; ++z) acc += (double)W.jac[(size_t)z * ld + p] * W.v[(size_t)T.row[z] * ld + p];
     rd = ip_max(rd, fabs(acc));
   }
+  rd = red.max(rd);
+  red.sync();                                           // ... and overwritten row-wise further down
   const double s_d = ip_max((sum_abs + sum_z) / (double)(T.n_g + 2 * T.nI) / 100.0, 1.0);
   // max_i |comp_i - m| over the bounded slack sides = max(cmax - m, m - cmin)
 #define IP_KKT_ERR(m) ip_max(ip_max(rd / s_d, feas), (any_comp ? ip_max(0.0, ip_max(cmax - (m), (m) - cmin)) : 0.0) / s_d)
   const double err0 = IP_KKT_ERR(0.0);
-  S.err0[p] = err0;
-  int done = S.done[p];
-  if (!done && err0 <= tol) { S.iters[p] = it; done = 1; }
+  int iters = -1, stalled = 0;
+  if (!done && err0 <= tol) { iters = it; done = 1; }
   const double f = (double)W.f[p];
-  if (it > 0 && it % 30 == 0) {
-    if (!done && feas <= tol && fabs(f - S.f_mark[p]) <= 1e-7 * ip_max(fabs(f), 1.0)) { S.iters[p] = it; S.stalled[p] = 1; done = 1; }
-    S.f_mark[p] = f;
-  }
-  S.done[p] = done;
+  const bool mark = it > 0 && it % 30 == 0;
+  if (mark && !done && feas <= tol && fabs(f - f_mark) <= 1e-7 * ip_max(fabs(f), 1.0)) { iters = it; stalled = 1; done = 1; }
   // monotone barrier update
-  double mu = S.mu[p];
   if (!done)
     for (int q = 0; q < 4; ++q) {
       if (!(IP_KKT_ERR(mu) <= 10.0 * mu && mu > tol / 10.0)) break;
       mu = ip_max(ip_min(0.2 * mu, pow(mu, 1.5)), tol / 10.0);
     }
 #undef IP_KKT_ERR
-  S.mu[p] = mu;
+  if (red.part() == 0) {
+    S.err0[p] = err0; S.done[p] = done; S.mu[p] = mu;
+    if (iters >= 0) S.iters[p] = iters;
+    if (stalled) S.stalled[p] = 1;
+    if (mark) S.f_mark[p] = f;
+  }
   // weights of the rows in the condensed matrix and the vector v with  rhs = -(grad f + J^T v)
-  for (int r = 0; r < T.n_g; ++r) {
+  for (int r = red.part(); r < T.n_g; r += red.nparts()) {
     const double gr = (double)W.g[(size_t)r * ld + p];
     double om, v;
     if (T.rkind[r] == 0) {
@@ -166,7 +192,8 @@ IP_HD int ip_residual_body(const IpTables& T, const IpState& S, const IpWork& W,
     W.omega[(size_t)r * ld + p] = om;
     W.v[(size_t)r * ld + p] = v;
   }
-  for (int c = 0; c < T.n_w; ++c) {
+  red.sync();
+  for (int c = red.part(); c < T.n_w; c += red.nparts()) {
     double acc = (double)W.grad[(size_t)c * ld + p];
     for (int z = T.colind[c]; z < T.colind[c + 1]; ++z) acc += (double)W.jac[(size_t)z * ld + p] * W.v[(size_t)T.row[z] * ld + p];
     W.rhs[(size_t)c * ld + p] = -acc;
@@ -175,13 +202,14 @@ IP_HD int ip_residual_body(const IpTables& T, const IpState& S, const IpWork& W,
 }
 
 // ---- the step: multiplier / slack directions, fraction to the boundary, merit parameters --------------------------------------
-IP_HD void ip_step_body(const IpTables& T, const IpState& S, const IpWork& W, size_t p) {
+template <class R>
+IP_HD void ip_step_body(const IpTables& T, const IpState& S, const IpWork& W, size_t p, R& red) {
   const size_t ld = S.ld;
   const double mu = S.mu[p];
   const int done = S.done[p];
   const double tau = ip_max(1.0 - mu, 0.99);
   double a_p = HUGE_VAL, a_d = HUGE_VAL, c1 = 0.0, bar_dir = 0.0, bar0 = 0.0, curv = 0.0;
-  for (int r = 0; r < T.n_g; ++r) {
+  for (int r = red.part(); r < T.n_g; r += red.nparts()) {
     double jd = 0.0;
     for (int t = T.rptr[r]; t < T.rptr[r + 1]; ++t) jd += (double)W.jac[(size_t)T.rnz[t] * ld + p] * W.dw[(size_t)T.rcol[t] * ld + p];
     const double gr = (double)W.g[(size_t)r * ld + p];
@@ -215,10 +243,9 @@ IP_HD void ip_step_body(const IpTables& T, const IpState& S, const IpWork& W, si
       W.ds[q] = ds; W.dzl[q] = dzl; W.dzu[q] = dzu;
     }
   }
-  a_p = ip_min(a_p, 1.0); a_d = ip_min(a_d, 1.0);
   // dw^T H dw over the upper triangle, grad f . dw, |dw|^2
   double gd = 0.0, d2 = 0.0;
-  for (int c = 0; c < T.n_w; ++c) {
+  for (int c = red.part(); c < T.n_w; c += red.nparts()) {
     const double dc = W.dw[(size_t)c * ld + p];
     gd += (double)W.grad[(size_t)c * ld + p] * dc;
     d2 += dc * dc;
@@ -229,6 +256,9 @@ IP_HD void ip_step_body(const IpTables& T, const IpState& S, const IpWork& W, si
     }
     curv += acc * dc;
   }
+  a_p = ip_min(red.min(a_p), 1.0); a_d = ip_min(red.min(a_d), 1.0);
+  c1 = red.sum(c1); bar_dir = red.sum(bar_dir); bar0 = red.sum(bar0); curv = red.sum(curv); gd = red.sum(gd); d2 = red.sum(d2);
+  if (red.part() != 0) return;
   const double dwt = W.dwt[p];
   curv += dwt * d2;
   double dlt = dwt > 0.0 ? dwt / 3.0 : dwt;
@@ -247,40 +277,46 @@ IP_HD void ip_step_body(const IpTables& T, const IpState& S, const IpWork& W, si
 
 // ---- line search: merit at the trial point; returns 1 if the problem is still not accepted --------------------------------------
 // The trial batch holds only the problems still searching: column q of the trial evaluation (wt32, gt, ft) belongs to problem p.
-IP_HD int ip_merit_body(const IpTables& T, const IpState& S, const IpWork& W, size_t p, size_t q_col) {
-  if (W.accepted[p]) return 0;
+// Worker 0 updates accepted / alpha; every worker returns the same verdict.
+template <class R>
+IP_HD int ip_merit_body(const IpTables& T, const IpState& S, const IpWork& W, size_t p, size_t q_col, R& red) {
+  const int was_accepted = W.accepted[p];
   const size_t ld = S.ld;
   const double mu = S.mu[p], a = W.alpha[p];
   double c1 = 0.0, bar = 0.0;
-  for (int r = 0; r < T.n_g; ++r) {
-    const double gr = (double)W.gt[(size_t)r * ld + q_col];
-    if (T.rkind[r] == 0) { c1 += fabs(gr - T.lb[r]); continue; }
-    const size_t q = (size_t)T.ridx[r] * ld + p;
-    const double st = S.s[q] + a * W.ds[q];
-    c1 += fabs(gr - st);
-    if (ip_finite(T.lb[r])) bar -= mu * log(ip_max(st - T.lb[r], 1e-300));
-    if (ip_finite(T.ub[r])) bar -= mu * log(ip_max(T.ub[r] - st, 1e-300));
-  }
+  if (!was_accepted)
+    for (int r = red.part(); r < T.n_g; r += red.nparts()) {
+      const double gr = (double)W.gt[(size_t)r * ld + q_col];
+      if (T.rkind[r] == 0) { c1 += fabs(gr - T.lb[r]); continue; }
+      const size_t q = (size_t)T.ridx[r] * ld + p;
+      const double st = S.s[q] + a * W.ds[q];
+      c1 += fabs(gr - st);
+      if (ip_finite(T.lb[r])) bar -= mu * log(ip_max(st - T.lb[r], 1e-300));
+      if (ip_finite(T.ub[r])) bar -= mu * log(ip_max(T.ub[r] - st, 1e-300));
+    }
+  c1 = red.sum(c1); bar = red.sum(bar);                  // (collectives: reached by every worker of every team, accepted or not)
   const double phi = (double)W.ft[q_col] + bar + S.nu[p] * c1;
   const double phi0 = W.phi0[p];
   const bool ok = ip_finite(phi) && phi <= phi0 + 1e-4 * a * ip_min(W.dphi[p], 0.0) + 1e-12 * fabs(phi0);
-  if (ok) { W.accepted[p] = 1; return 0; }
-  W.alpha[p] = 0.5 * a;
-  return 1;
+  red.sync();                                            // every worker has read accepted / alpha
+  if (was_accepted) return 0;
+  if (red.part() == 0) { if (ok) W.accepted[p] = 1; else W.alpha[p] = 0.5 * a; }
+  return ok ? 0 : 1;
 }
 
 // ---- take the step ------------------------------------------------------------------------------------------------------------
-IP_HD void ip_update_body(const IpTables& T, const IpState& S, const IpWork& W, size_t p) {
+template <class R>
+IP_HD void ip_update_body(const IpTables& T, const IpState& S, const IpWork& W, size_t p, R& red) {
   const size_t ld = S.ld;
   const int done = S.done[p];
-  if (!W.accepted[p]) S.delta_w[p] = ip_min(ip_max(S.delta_w[p] * 10.0, 1e-3), 1e4);
+  if (red.part() == 0 && !W.accepted[p]) S.delta_w[p] = ip_min(ip_max(S.delta_w[p] * 10.0, 1e-3), 1e4);
   const double a = W.alpha[p], adz = done ? 0.0 : W.alpha_d[p], mu = S.mu[p];
-  for (int c = 0; c < T.n_w; ++c) {
+  for (int c = red.part(); c < T.n_w; c += red.nparts()) {
     const double wn = S.w[(size_t)c * ld + p] + a * W.dw[(size_t)c * ld + p];
     S.w[(size_t)c * ld + p] = wn;
     W.w32[(size_t)c * ld + p] = (float)wn;
   }
-  for (int r = 0; r < T.n_g; ++r) {
+  for (int r = red.part(); r < T.n_g; r += red.nparts()) {
     if (T.rkind[r] == 0) { const size_t q = (size_t)T.ridx[r] * ld + p; S.lamE[q] += a * W.dlamE[q]; continue; }
     const size_t q = (size_t)T.ridx[r] * ld + p;
     const double sv = S.s[q] + a * W.ds[q];
@@ -294,9 +330,10 @@ IP_HD void ip_update_body(const IpTables& T, const IpState& S, const IpWork& W, 
 
 // ---- least-squares equality multipliers:  min | grad f + JI^T lam_I + JE^T lam_E |^2  -------------------------------------------
 // r_n = grad f + JI^T (zu - zl)  (kept in W.rhs),  right-hand side -JE r_n (kept in W.v, indexed by equality),  shift of the Gram matrix
-IP_HD void ip_lsq_prep_body(const IpTables& T, const IpState& S, const IpWork& W, size_t p) {
+template <class R>
+IP_HD void ip_lsq_prep_body(const IpTables& T, const IpState& S, const IpWork& W, size_t p, R& red) {
   const size_t ld = S.ld;
-  for (int c = 0; c < T.n_w; ++c) {
+  for (int c = red.part(); c < T.n_w; c += red.nparts()) {
     double acc = (double)W.grad[(size_t)c * ld + p];
     for (int z = T.colind[c]; z < T.colind[c + 1]; ++z) {
       const int r = T.row[z];
@@ -304,8 +341,9 @@ IP_HD void ip_lsq_prep_body(const IpTables& T, const IpState& S, const IpWork& W
     }
     W.rhs[(size_t)c * ld + p] = acc;
   }
+  red.sync();
   double amax = 0.0;
-  for (int r = 0; r < T.n_g; ++r) {
+  for (int r = red.part(); r < T.n_g; r += red.nparts()) {
     if (T.rkind[r] != 0) continue;
     double b = 0.0, d = 0.0;
     for (int t = T.rptr[r]; t < T.rptr[r + 1]; ++t) {
@@ -316,15 +354,17 @@ IP_HD void ip_lsq_prep_body(const IpTables& T, const IpState& S, const IpWork& W
     W.v[(size_t)T.ridx[r] * ld + p] = -b;
     amax = ip_max(amax, d);
   }
-  W.eps_ls[p] = 1e-8 * ip_max(amax, 1.0);
+  amax = red.max(amax);
+  if (red.part() == 0) W.eps_ls[p] = 1e-8 * ip_max(amax, 1.0);
 }
 
 // keep the Newton multipliers where they leave the smaller dual residual, else take the least-squares ones
-IP_HD void ip_lsq_choose_body(const IpTables& T, const IpState& S, const IpWork& W, size_t p) {
+template <class R>
+IP_HD void ip_lsq_choose_body(const IpTables& T, const IpState& S, const IpWork& W, size_t p, R& red) {
   const size_t ld = S.ld;
   double res_ls = 0.0, res_nt = 0.0;
-  bool nt_finite = true;
-  for (int c = 0; c < T.n_w; ++c) {
+  bool nt_bad = false;
+  for (int c = red.part(); c < T.n_w; c += red.nparts()) {
     double a_ls = W.rhs[(size_t)c * ld + p], a_nt = a_ls;
     for (int z = T.colind[c]; z < T.colind[c + 1]; ++z) {
       const int r = T.row[z];
@@ -335,27 +375,33 @@ IP_HD void ip_lsq_choose_body(const IpTables& T, const IpState& S, const IpWork&
       }
     }
     res_ls = ip_max(res_ls, fabs(a_ls));
-    if (!ip_finite(a_nt)) nt_finite = false;
+    if (!ip_finite(a_nt)) nt_bad = true;
     res_nt = ip_max(res_nt, fabs(a_nt));
   }
-  const bool keep_newton = S.done[p] || (nt_finite && res_nt < res_ls);
+  res_ls = red.max(res_ls); res_nt = red.max(res_nt); nt_bad = red.any(nt_bad);
+  red.sync();                                            // every worker has read lamE
+  const bool keep_newton = S.done[p] || (!nt_bad && res_nt < res_ls);
   if (!keep_newton)
-    for (int e = 0; e < T.nE; ++e) S.lamE[(size_t)e * ld + p] = W.lam_ls[(size_t)e * ld + p];
+    for (int e = red.part(); e < T.nE; e += red.nparts()) S.lamE[(size_t)e * ld + p] = W.lam_ls[(size_t)e * ld + p];
 }
 
 // ---- results of problem p -> outputs at its original index ---------------------------------------------------------------------
-IP_HD void ip_flush_body(const IpTables& T, const IpState& S, const IpWork& W, const IpOut& O, size_t p) {
+template <class R>
+IP_HD void ip_flush_body(const IpTables& T, const IpState& S, const IpWork& W, const IpOut& O, size_t p, R& red) {
   const size_t ld = S.ld, o = (size_t)S.orig[p];
   double viol = 0.0;
-  for (int r = 0; r < T.n_g; ++r) {
+  for (int r = red.part(); r < T.n_g; r += red.nparts()) {
     const double gr = (double)W.g[(size_t)r * ld + p];
     viol = ip_max(viol, ip_max(T.lb[r] - gr, gr - T.ub[r]));
     const size_t q = (size_t)T.ridx[r] * ld + p;
     O.lam[(size_t)r * O.ld + o] = T.rkind[r] == 0 ? S.lamE[q] : S.zu[q] - S.zl[q];
   }
-  for (int c = 0; c < T.n_w; ++c) O.w[(size_t)c * O.ld + o] = S.w[(size_t)c * ld + p];
-  O.f[o] = (double)W.f[p]; O.viol[o] = viol; O.err[o] = S.err0[p]; O.iters[o] = S.iters[p];
-  O.status[o] = S.stalled[p] ? 2 : (S.done[p] ? 1 : 0);
+  for (int c = red.part(); c < T.n_w; c += red.nparts()) O.w[(size_t)c * O.ld + o] = S.w[(size_t)c * ld + p];
+  viol = red.max(viol);
+  if (red.part() == 0) {
+    O.f[o] = (double)W.f[p]; O.viol[o] = viol; O.err[o] = S.err0[p]; O.iters[o] = S.iters[p];
+    O.status[o] = S.stalled[p] ? 2 : (S.done[p] ? 1 : 0);
+  }
 }
 
 // =====================================================================================================================
@@ -389,15 +435,43 @@ IP_HD double bt_slot_value(const BtTables& B, int slot, const float* jac, const 
 
 #define BT_LI(i, j) ((i) * ((i) + 1) / 2 + (j))
 
+// Staging of the blocks the sequential sweep reads next.  On the device the matrix (forward sweep) and factor (backward sweep) blocks
+// of the NEXT stage are pulled into the thread's shared-memory column with cp.async while the current stage is computed: with one
+// thread per problem nothing else hides the ~1 us of a global load, and register pressure keeps the compiler from batching ~100
+// independent loads per stage on its own.  On the host (tests) the blocks are read in place.
+template <int NSLOT>
+struct BtStage {
+#if defined(__CUDA_ARCH__)
+  double* buf; int ss;                                        // NSLOT doubles, element stride ss
+  IP_HD void fetch(const double* src, size_t ld, int n) {     // slots 0..n-1 of a block whose slot q lives at src[q * ld]
+    for (int q = 0; q < n; ++q) {
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(buf + (size_t)q * ss);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src + (size_t)q * ld) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  IP_HD void wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+  IP_HD double get(int q) const { return buf[(size_t)q * ss]; }
+#else
+  const double* src; size_t ld;
+  double* buf; int ss;
+  IP_HD void fetch(const double* s, size_t l, int) { src = s; ld = l; }
+  IP_HD void wait() {}
+  IP_HD double get(int q) const { return src[(size_t)q * ld]; }
+#endif
+};
+
 // One factor + solve attempt with `delta` added to the diagonal of every real unknown.  sc: per-thread scratch of
-// NXR * NS + ND doubles with element stride ss (shared memory on the device).  Writes x (indexed by unknown).  Returns true when
-// every pivot was positive and the solution is finite with max |x| < xmax.
+// 2 * (NXR * NS + ND) + NS doubles with element stride ss (shared memory on the device).  Writes x (indexed by unknown).  Returns true
+// when every pivot was positive and the solution is finite with max |x| < xmax.
 template <int NS, int NXR>
 IP_HD bool bt_solve_attempt(const BtTables& B, const double* __restrict__ K, double* __restrict__ Lf, const double* __restrict__ rhs,
                             double* __restrict__ x, size_t ld, size_t p, double delta, double xmax, double* sc, int ss) {
   constexpr int ND = NS * (NS + 1) / 2, NO = NXR * NS, SLK = ND + NO, SLL = ND + NO + NS;
-  double* sLo = sc;                  // L_{k+1,k} rows
-  double* sSn = sc + (size_t)NO * ss;   // Schur complement of the next diagonal block
+  double* sLo = sc;                      // L_{k+1,k} rows
+  double* sSn = sc + (size_t)NO * ss;    // Schur complement of the next diagonal block
+  BtStage<SLL> stage;                    // the next stage's blocks
+  stage.buf = sc + (size_t)(NO + ND) * ss; stage.ss = ss;
   const int nb = B.nb;
   bool ok = true;
   double L[ND], y[NS], dinv[NS];
@@ -409,6 +483,8 @@ IP_HD bool bt_solve_attempt(const BtTables& B, const double* __restrict__ K, dou
     if (u >= 0) { L[BT_LI(i, i)] += delta; y[i] = rhs[(size_t)u * ld + p]; } else y[i] = 0.0;
   }
   for (int k = 0; k < nb; ++k) {
+    // O_k (rows NXR x NS, slots ND.. of block k) and D_{k+1} (slots 0..ND-1 of block k + 1) are contiguous in K: one fetch
+    if (k < nb - 1) stage.fetch(K + ((size_t)k * SLK + ND) * ld + p, ld, NO + ND);
     // Cholesky of the current block in place (row-wise Crout) and y = L^-1 b
 #pragma unroll
     for (int j = 0; j < NS; ++j) {
@@ -439,25 +515,25 @@ IP_HD bool bt_solve_attempt(const BtTables& B, const double* __restrict__ K, dou
     for (int q = 0; q < ND; ++q) Lk[(size_t)q * ld] = L[q];
 #pragma unroll
     for (int i = 0; i < NS; ++i) Lk[(size_t)(ND + NO + i) * ld] = y[i];
+    if (!ok) { stage.wait(); return false; }         // the inertia test failed: the caller retries with a larger delta
     if (k == nb - 1) break;
     // next diagonal block and right-hand side
-    const double* Kn = K + (size_t)(k + 1) * SLK * ld + p;
+    stage.wait();
     double bn[NS];
 #pragma unroll
     for (int i = 0; i < NS; ++i) {
       const int u = B.var[(k + 1) * NS + i];
 #pragma unroll
-      for (int j = 0; j <= i; ++j) sSn[(size_t)BT_LI(i, j) * ss] = Kn[(size_t)BT_LI(i, j) * ld];
+      for (int j = 0; j <= i; ++j) sSn[(size_t)BT_LI(i, j) * ss] = stage.get(NO + BT_LI(i, j));
       if (u >= 0) { sSn[(size_t)BT_LI(i, i) * ss] += delta; bn[i] = rhs[(size_t)u * ld + p]; } else bn[i] = 0.0;
     }
-    const double* Ok = K + ((size_t)k * SLK + ND) * ld + p;
 #pragma unroll
     for (int i = 0; i < NXR; ++i) {
       // row i of L_{k+1,k} = O_k L_kk^-T
       double lo[NS];
 #pragma unroll
       for (int j = 0; j < NS; ++j) {
-        double v = Ok[(size_t)(i * NS + j) * ld];
+        double v = stage.get(i * NS + j);
 #pragma unroll
         for (int m = 0; m < j; ++m) v -= lo[m] * L[BT_LI(j, m)];
         lo[j] = v * dinv[j];
@@ -483,25 +559,27 @@ IP_HD bool bt_solve_attempt(const BtTables& B, const double* __restrict__ K, dou
 #pragma unroll
     for (int i = 0; i < NS; ++i) y[i] = bn[i];
   }
-  // backward pass  x_k = L_kk^-T (y_k - L_{k+1,k}^T x_{k+1})
+  // backward pass  x_k = L_kk^-T (y_k - L_{k+1,k}^T x_{k+1}); the factor blocks of stage k - 1 arrive while stage k is computed
   double xn[NS];
   double amax = 0.0;
   bool fin = true;
 #pragma unroll
   for (int i = 0; i < NS; ++i) xn[i] = 0.0;
+  stage.fetch(Lf + (size_t)(nb - 1) * SLL * ld + p, ld, SLL);
   for (int k = nb - 1; k >= 0; --k) {
-    const double* Lk = Lf + (size_t)k * SLL * ld + p;
+    stage.wait();
     double t[NS];
 #pragma unroll
-    for (int i = 0; i < NS; ++i) t[i] = Lk[(size_t)(ND + NO + i) * ld];
+    for (int i = 0; i < NS; ++i) t[i] = stage.get(ND + NO + i);
     if (k < nb - 1) {
 #pragma unroll
       for (int i = 0; i < NXR; ++i)
 #pragma unroll
-        for (int j = 0; j < NS; ++j) t[j] -= Lk[(size_t)(ND + i * NS + j) * ld] * xn[i];
+        for (int j = 0; j < NS; ++j) t[j] -= stage.get(ND + i * NS + j) * xn[i];
     }
 #pragma unroll
-    for (int q = 0; q < ND; ++q) L[q] = Lk[(size_t)q * ld];
+    for (int q = 0; q < ND; ++q) L[q] = stage.get(q);
+    if (k > 0) stage.fetch(Lf + (size_t)(k - 1) * SLL * ld + p, ld, SLL);
 #pragma unroll
     for (int i = NS - 1; i >= 0; --i) {
       double v = t[i];

@@ -14,23 +14,54 @@
 
 namespace {
 
-constexpr int IP_TPB = 128;     // threads per block of the one-thread-per-problem kernels
+constexpr int IP_TEAM = 8;      // warps per team: a thread block is 32 problems (lanes) x IP_TEAM workers (warps)
 constexpr int BT_TPB = 64;      // threads per block of the factorisation kernels (shared-memory scratch per thread)
 
-__global__ void __launch_bounds__(IP_TPB) ip_init_kernel(IpTables T, IpState S, IpWork W, size_t P, double mu0, int max_iter) {
-  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < P) ip_init_body(T, S, W, p, mu0, max_iter);
+// The team reducer of ip_core.cuh on the device: worker = warp, reductions per lane (= per problem) through shared memory.
+// Lanes beyond the batch take no part in any loop (part() is out of every range) and store nothing, but reach every barrier.
+struct IpBlockRed {
+  double* sm;                    // [IP_TEAM][32]
+  int w, lane;
+  bool act;
+  __device__ __forceinline__ int part() const { return act ? w : (1 << 30); }
+  __device__ __forceinline__ int nparts() const { return IP_TEAM; }
+  template <class Op>
+  __device__ __forceinline__ double reduce(double v, Op op) {
+    sm[w * 32 + lane] = v;
+    __syncthreads();
+    double r = sm[lane];
+#pragma unroll
+    for (int i = 1; i < IP_TEAM; ++i) r = op(r, sm[i * 32 + lane]);
+    __syncthreads();
+    return r;
+  }
+  __device__ __forceinline__ double sum(double v) { return reduce(v, [](double a, double b) { return a + b; }); }
+  __device__ __forceinline__ double max(double v) { return reduce(v, [](double a, double b) { return a > b ? a : b; }); }
+  __device__ __forceinline__ double min(double v) { return reduce(v, [](double a, double b) { return a < b ? a : b; }); }
+  __device__ __forceinline__ bool any(bool v) { return reduce(v ? 1.0 : 0.0, [](double a, double b) { return a > b ? a : b; }) != 0.0; }
+  __device__ __forceinline__ void sync() { __syncthreads(); }
+};
+#define IP_TEAM_SETUP(n_)                                                      \
+  __shared__ double red_sm[IP_TEAM * 32];                                      \
+  const size_t q_ = (size_t)blockIdx.x * 32 + threadIdx.x;                     \
+  IpBlockRed red{red_sm, (int)threadIdx.y, (int)threadIdx.x, q_ < (n_)};       \
+  const size_t qc_ = red.act ? q_ : (n_) - 1        /* inactive lanes read (only) a valid column */
+
+__global__ void __launch_bounds__(32 * IP_TEAM) ip_init_kernel(IpTables T, IpState S, IpWork W, size_t P, double mu0, int max_iter) {
+  IP_TEAM_SETUP(P);
+  ip_init_body(T, S, W, qc_, mu0, max_iter, red);
 }
-__global__ void __launch_bounds__(IP_TPB) ip_residual_kernel(IpTables T, IpState S, IpWork W, size_t P, int it, double tol) {
-  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int done = 0;
-  if (p < P) done = ip_residual_body(T, S, W, p, it, tol);
-  const int n = __syncthreads_count(done);
-  if (threadIdx.x == 0 && n) atomicAdd(W.counters, n);
+__global__ void __launch_bounds__(32 * IP_TEAM) ip_residual_kernel(IpTables T, IpState S, IpWork W, size_t P, int it, double tol) {
+  IP_TEAM_SETUP(P);
+  const int done = ip_residual_body(T, S, W, qc_, it, tol, red);
+  if (threadIdx.y == 0) {
+    const unsigned m = __ballot_sync(0xffffffffu, done && red.act);
+    if (threadIdx.x == 0 && m) atomicAdd(W.counters, __popc(m));
+  }
 }
-__global__ void __launch_bounds__(IP_TPB) ip_step_kernel(IpTables T, IpState S, IpWork W, size_t P) {
-  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < P) ip_step_body(T, S, W, p);
+__global__ void __launch_bounds__(32 * IP_TEAM) ip_step_kernel(IpTables T, IpState S, IpWork W, size_t P) {
+  IP_TEAM_SETUP(P);
+  ip_step_body(T, S, W, qc_, red);
 }
 // trial points of the line search, fp32 for the evaluation kernels: column q of the trial batch is problem list[q] (or q itself)
 __global__ void __launch_bounds__(256) ip_trial_kernel(IpState S, IpWork W, size_t n, int n_w, const int* __restrict__ list) {
@@ -42,28 +73,29 @@ __global__ void __launch_bounds__(256) ip_trial_kernel(IpState S, IpWork W, size
     W.wt32[(size_t)c * S.ld + q] = (float)(S.w[(size_t)c * S.ld + p] + a * W.dw[(size_t)c * S.ld + p]);
 }
 // problems whose trial step is refused are appended to `next` (their order does not matter: every problem is independent)
-__global__ void __launch_bounds__(IP_TPB) ip_merit_kernel(IpTables T, IpState S, IpWork W, size_t n, const int* __restrict__ list,
-                                                          int* __restrict__ next) {
-  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= n) return;
-  const size_t p = list ? (size_t)list[q] : q;
-  if (ip_merit_body(T, S, W, p, q)) next[atomicAdd(W.counters + 1, 1)] = (int)p;
+__global__ void __launch_bounds__(32 * IP_TEAM) ip_merit_kernel(IpTables T, IpState S, IpWork W, size_t n, const int* __restrict__ list,
+                                                                int* __restrict__ next) {
+  IP_TEAM_SETUP(n);
+  const size_t p = list ? (size_t)list[qc_] : qc_;
+  const int rej = ip_merit_body(T, S, W, p, qc_, red);
+  if (threadIdx.y == 0 && red.act && rej) next[atomicAdd(W.counters + 1, 1)] = (int)p;
 }
-__global__ void __launch_bounds__(IP_TPB) ip_update_kernel(IpTables T, IpState S, IpWork W, size_t P) {
-  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < P) ip_update_body(T, S, W, p);
+__global__ void __launch_bounds__(32 * IP_TEAM) ip_update_kernel(IpTables T, IpState S, IpWork W, size_t P) {
+  IP_TEAM_SETUP(P);
+  ip_update_body(T, S, W, qc_, red);
 }
-__global__ void __launch_bounds__(IP_TPB) ip_lsq_prep_kernel(IpTables T, IpState S, IpWork W, size_t P) {
-  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < P) ip_lsq_prep_body(T, S, W, p);
+__global__ void __launch_bounds__(32 * IP_TEAM) ip_lsq_prep_kernel(IpTables T, IpState S, IpWork W, size_t P) {
+  IP_TEAM_SETUP(P);
+  ip_lsq_prep_body(T, S, W, qc_, red);
 }
-__global__ void __launch_bounds__(IP_TPB) ip_lsq_choose_kernel(IpTables T, IpState S, IpWork W, size_t P) {
-  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < P) ip_lsq_choose_body(T, S, W, p);
+__global__ void __launch_bounds__(32 * IP_TEAM) ip_lsq_choose_kernel(IpTables T, IpState S, IpWork W, size_t P) {
+  IP_TEAM_SETUP(P);
+  ip_lsq_choose_body(T, S, W, qc_, red);
 }
-__global__ void __launch_bounds__(IP_TPB) ip_flush_kernel(IpTables T, IpState S, IpWork W, IpOut O, size_t P, int only_done) {
-  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < P && (!only_done || S.done[p])) ip_flush_body(T, S, W, O, p);
+__global__ void __launch_bounds__(32 * IP_TEAM) ip_flush_kernel(IpTables T, IpState S, IpWork W, IpOut O, size_t P, int only_done) {
+  IP_TEAM_SETUP(P);
+  if (only_done && !S.done[qc_]) red.act = false;      // (per lane; the lane still reaches the team's barriers)
+  ip_flush_body(T, S, W, O, qc_, red);
 }
 __global__ void __launch_bounds__(256) ip_w32_kernel(IpState S, IpWork W, size_t P, int n_w) {
   const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -138,7 +170,7 @@ __global__ void __launch_bounds__(BT_TPB) bt_spd_kernel(BtTables B, const double
 template <int NS, int NXR>
 int launch_bt_kkt(const BtTables& B, const double* K, double* Lf, const double* rhs, double* dw, double* dw_alt, size_t P, size_t ld,
                   int n_unknown, const double* delta_in, const int* skip, double* dwt_out, int device, cudaStream_t st) {
-  constexpr size_t smem = (size_t)(NXR * NS + NS * (NS + 1) / 2) * BT_TPB * sizeof(double);
+  constexpr size_t smem = (size_t)(2 * (NXR * NS + NS * (NS + 1) / 2) + NS) * BT_TPB * sizeof(double);
   static bool attr[64] = {false};
   if (!attr[device & 63]) {
     NLO_CUDA(cudaFuncSetAttribute(bt_kkt_kernel<NS, NXR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -151,7 +183,7 @@ int launch_bt_kkt(const BtTables& B, const double* K, double* Lf, const double* 
 template <int NS, int NXR>
 int launch_bt_spd(const BtTables& B, const double* K, double* Lf, const double* rhs, double* x, size_t P, size_t ld, int n_unknown,
                   const double* shift, const double* fallback, int device, cudaStream_t st) {
-  constexpr size_t smem = (size_t)(NXR * NS + NS * (NS + 1) / 2) * BT_TPB * sizeof(double);
+  constexpr size_t smem = (size_t)(2 * (NXR * NS + NS * (NS + 1) / 2) + NS) * BT_TPB * sizeof(double);
   static bool attr[64] = {false};
   if (!attr[device & 63]) {
     NLO_CUDA(cudaFuncSetAttribute(bt_spd_kernel<NS, NXR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -219,7 +251,8 @@ int upload(V** dst, const std::vector<V>& v) {
 struct GpuBackend {
   nlo_ip* s;
   cudaStream_t st;
-  dim3 g1(size_t P) const { return dim3((unsigned)((P + IP_TPB - 1) / IP_TPB)); }
+  dim3 g1(size_t P) const { return dim3((unsigned)((P + 31) / 32)); }
+  dim3 b1() const { return dim3(32, IP_TEAM); }
 
   int read_counter(int which, size_t* out) {
     NLO_CUDA(cudaMemcpyAsync(s->h_pin, s->W.counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -231,13 +264,13 @@ struct GpuBackend {
     return nlo_nlp_eval(s->nlp, s->W.w32, P, s->cap, s->W.g, s->W.jac, s->W.f, s->W.grad, st);
   }
   int init(size_t P, double mu0, int max_iter) {
-    ip_init_kernel<<<g1(P), IP_TPB, 0, st>>>(s->T, s->S, s->W, P, mu0, max_iter);
+    ip_init_kernel<<<g1(P), b1(), 0, st>>>(s->T, s->S, s->W, P, mu0, max_iter);
     NLO_CHECK_LAUNCH();
     return 0;
   }
   int residual(size_t P, int it, double tol, size_t* n_done) {
     NLO_CUDA(cudaMemsetAsync(s->W.counters, 0, 2 * sizeof(int), st));
-    ip_residual_kernel<<<g1(P), IP_TPB, 0, st>>>(s->T, s->S, s->W, P, it, tol);
+    ip_residual_kernel<<<g1(P), b1(), 0, st>>>(s->T, s->S, s->W, P, it, tol);
     NLO_CHECK_LAUNCH();
     return read_counter(0, n_done);
   }
@@ -259,7 +292,7 @@ struct GpuBackend {
     return nlo_fail("interior point: no factorisation kernel for stage blocks of %d unknowns (%d states)", s->KB.NS, s->KB.NXR);
   }
   int step(size_t P) {
-    ip_step_kernel<<<g1(P), IP_TPB, 0, st>>>(s->T, s->S, s->W, P);
+    ip_step_kernel<<<g1(P), b1(), 0, st>>>(s->T, s->S, s->W, P);
     NLO_CHECK_LAUNCH();
     return 0;
   }
@@ -269,18 +302,18 @@ struct GpuBackend {
     NLO_CHECK_LAUNCH();
     if (nlo_nlp_eval(s->nlp, s->W.wt32, n, s->cap, s->W.gt, nullptr, s->W.ft, nullptr, st)) return 1;
     NLO_CUDA(cudaMemsetAsync(s->W.counters + 1, 0, sizeof(int), st));
-    ip_merit_kernel<<<g1(n), IP_TPB, 0, st>>>(s->T, s->S, s->W, n, list, s->W.ls_list[ls & 1]);
+    ip_merit_kernel<<<g1(n), b1(), 0, st>>>(s->T, s->S, s->W, n, list, s->W.ls_list[ls & 1]);
     NLO_CHECK_LAUNCH();
     return read_counter(1, rejected);
   }
   int update(size_t P) {
-    ip_update_kernel<<<g1(P), IP_TPB, 0, st>>>(s->T, s->S, s->W, P);
+    ip_update_kernel<<<g1(P), b1(), 0, st>>>(s->T, s->S, s->W, P);
     NLO_CHECK_LAUNCH();
     return 0;
   }
   int lsq_multipliers(size_t P) {
     if (s->T.nE == 0) return 0;
-    ip_lsq_prep_kernel<<<g1(P), IP_TPB, 0, st>>>(s->T, s->S, s->W, P);
+    ip_lsq_prep_kernel<<<g1(P), b1(), 0, st>>>(s->T, s->S, s->W, P);
     NLO_CHECK_LAUNCH();
     if (assemble(s->LB, P)) return 1;
     int rc = -1;
@@ -291,12 +324,12 @@ struct GpuBackend {
 #undef IP_CASE
     if (rc < 0) return nlo_fail("interior point: no multiplier kernel for %d states", s->LB.NS);
     if (rc) return rc;
-    ip_lsq_choose_kernel<<<g1(P), IP_TPB, 0, st>>>(s->T, s->S, s->W, P);
+    ip_lsq_choose_kernel<<<g1(P), b1(), 0, st>>>(s->T, s->S, s->W, P);
     NLO_CHECK_LAUNCH();
     return 0;
   }
   int flush(size_t P, int only_done) {
-    ip_flush_kernel<<<g1(P), IP_TPB, 0, st>>>(s->T, s->S, s->W, s->O, P, only_done);
+    ip_flush_kernel<<<g1(P), b1(), 0, st>>>(s->T, s->S, s->W, s->O, P, only_done);
     NLO_CHECK_LAUNCH();
     return 0;
   }

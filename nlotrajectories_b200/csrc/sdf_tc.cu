@@ -77,21 +77,6 @@ struct TcCfg {
   }
 };
 
-template <int N> struct TmemIO;
-template <> struct TmemIO<16> {
-  __device__ static __forceinline__ void ld(uint32_t a, uint32_t (&v)[16]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                 : "r"(a) : "memory");
-  }
-  __device__ static __forceinline__ void st(uint32_t a, const uint32_t (&v)[16]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};"
-                 ::"r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
-                   "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(a) : "memory");
-  }
-};
-
 struct TileCtx {
   uint32_t tmem_base, lane_base, sB_hi, sB_lo, sV_hi, sV_lo, mbar_addr, bar_id;
   int* lock;
@@ -104,15 +89,6 @@ struct TileCtx {
   long long* dbg;          // optional phase timeline (NLO_B200_TC_TIMELINE): clock stamps per tile of CTA 0, groups 0 / 1
 };
 
-// named barrier of one tile group
-template <int NT>
-__device__ __forceinline__ void group_bar(uint32_t id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NT) : "memory"); }
-
-__device__ __forceinline__ bool elect_one(uint32_t mask) {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, %1;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred) : "r"(mask));
-  return pred != 0;
-}
 template <int H, bool RELU_BWD>
 __device__ __forceinline__ void issue_mmas(const TileCtx& c, bool fwd) {
   constexpr uint32_t COL_AHI = 0, COL_ALO = H / 2, COL_D = H;
@@ -159,18 +135,6 @@ __device__ __forceinline__ void issue_gemm(const TileCtx& c, bool fwd, long long
   // next tile of this group: the atomic's latency hides behind the GEMM that was just issued
   if (fwd && c.ctr) *c.next_slot = atomicAdd(c.ctr, 1u) + c.ctr_bias;
 }
-__device__ __forceinline__ void mbar_wait_addr(uint32_t a, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ uint32_t pack_f16(float v0, float v1) {
-  const __half2 p = __floats2half2_rn(v0, v1);
-  return *reinterpret_cast<const uint32_t*>(&p);
-}
-
 // One tile (128 points) of one group.  SPLIT = 2: two threads own a point - HALF 0 the low half of the neurons / D
 // columns, HALF 1 the high half; they meet only to add three partial sums per point through shared memory.
 // Deliberately NOT inlined into the persistent loop: the constants are loop-invariant, and an inlined body makes

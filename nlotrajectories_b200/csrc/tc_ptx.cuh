@@ -89,6 +89,42 @@ __device__ __forceinline__ void row_scale(float bound, float& sc, float& inv) {
   inv = __uint_as_float((uint32_t)(127 - e) << 23);
 }
 
+template <int N> struct TmemIO;
+template <> struct TmemIO<16> {
+  __device__ static __forceinline__ void ld(uint32_t a, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(a) : "memory");
+  }
+  __device__ static __forceinline__ void st(uint32_t a, const uint32_t (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};"
+                 ::"r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+                   "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(a) : "memory");
+  }
+};
+
+// named barrier of one tile group
+template <int NT>
+__device__ __forceinline__ void group_bar(uint32_t id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NT) : "memory"); }
+
+__device__ __forceinline__ bool elect_one(uint32_t mask) {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, %1;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred) : "r"(mask));
+  return pred != 0;
+}
+__device__ __forceinline__ void mbar_wait_addr(uint32_t a, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ uint32_t pack_f16(float v0, float v1) {
+  const __half2 p = __floats2half2_rn(v0, v1);
+  return *reinterpret_cast<const uint32_t*>(&p);
+}
+
 template <int A>
 __device__ __forceinline__ void act_vd(float a, int rt, float prm, float& v, float& d) {
   if (A >= 0) nlo_phi_d_tc(a, A, prm, v, d); else nlo_phi_d_tc(a, rt, prm, v, d);

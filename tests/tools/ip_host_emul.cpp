@@ -45,7 +45,7 @@ void bind_bt(BtTables& B, const BtHost& h) {
 
 template <int NS, int NXR>
 void kkt_all(Emul& e, size_t P, const double* delta_in, const int* skip, double* dwt_out) {
-  double sc[NXR * NS + NS * (NS + 1) / 2];
+  double sc[2 * (NXR * NS + NS * (NS + 1) / 2) + NS];
   for (size_t p = 0; p < P; ++p) {
     double dwt;
     bt_kkt_body<NS, NXR>(e.KB, e.K.data(), e.L.data(), e.W.rhs, e.W.dw, e.W.dw_alt, e.ld, p, e.T.n_w, delta_in[p], skip ? skip[p] : 0, &dwt, sc, 1);
@@ -54,7 +54,7 @@ void kkt_all(Emul& e, size_t P, const double* delta_in, const int* skip, double*
 }
 template <int NS, int NXR>
 void spd_all(Emul& e, size_t P) {
-  double sc[NXR * NS + NS * (NS + 1) / 2];
+  double sc[2 * (NXR * NS + NS * (NS + 1) / 2) + NS];
   for (size_t p = 0; p < P; ++p)
     if (!bt_solve_attempt<NS, NXR>(e.LB, e.K.data(), e.L.data(), e.W.v, e.W.lam_ls, e.ld, p, e.W.eps_ls[p], HUGE_VAL, sc, 1))
       for (int q = 0; q < e.T.nE; ++q) e.W.lam_ls[(size_t)q * e.ld + p] = e.S.lamE[(size_t)q * e.ld + p];
@@ -66,11 +66,12 @@ void spd_all(Emul& e, size_t P) {
 struct HostBackend {
   Emul& e;
   int verbose;
+  IpSolo solo;
   int eval_full(size_t P) { return e.eval(e.W.w32, P, e.ld, e.W.g, e.W.jac, e.W.f, e.W.grad); }
-  int init(size_t P, double mu0, int max_iter) { for (size_t p = 0; p < P; ++p) ip_init_body(e.T, e.S, e.W, p, mu0, max_iter); return 0; }
+  int init(size_t P, double mu0, int max_iter) { for (size_t p = 0; p < P; ++p) ip_init_body(e.T, e.S, e.W, p, mu0, max_iter, solo); return 0; }
   int residual(size_t P, int it, double tol, size_t* n_done) {
     size_t n = 0;
-    for (size_t p = 0; p < P; ++p) n += ip_residual_body(e.T, e.S, e.W, p, it, tol);
+    for (size_t p = 0; p < P; ++p) n += ip_residual_body(e.T, e.S, e.W, p, it, tol, solo);
     *n_done = n;
     return 0;
   }
@@ -87,7 +88,7 @@ struct HostBackend {
 #undef IP_CASE
     return 1;
   }
-  int step(size_t P) { for (size_t p = 0; p < P; ++p) ip_step_body(e.T, e.S, e.W, p); return 0; }
+  int step(size_t P) { for (size_t p = 0; p < P; ++p) ip_step_body(e.T, e.S, e.W, p, solo); return 0; }
   int trial(size_t n, int ls, size_t* rejected) {
     const int* list = ls > 0 ? e.W.ls_list[(ls + 1) & 1] : nullptr;
     int* next = e.W.ls_list[ls & 1];
@@ -100,28 +101,28 @@ struct HostBackend {
     size_t m = 0;
     for (size_t q = 0; q < n; ++q) {
       const size_t p = list ? (size_t)list[q] : q;
-      if (ip_merit_body(e.T, e.S, e.W, p, q)) next[m++] = (int)p;
+      if (ip_merit_body(e.T, e.S, e.W, p, q, solo)) next[m++] = (int)p;
     }
     *rejected = m;
     return 0;
   }
-  int update(size_t P) { for (size_t p = 0; p < P; ++p) ip_update_body(e.T, e.S, e.W, p); return 0; }
+  int update(size_t P) { for (size_t p = 0; p < P; ++p) ip_update_body(e.T, e.S, e.W, p, solo); return 0; }
   int lsq_multipliers(size_t P) {
     if (e.T.nE == 0) return 0;
-    for (size_t p = 0; p < P; ++p) ip_lsq_prep_body(e.T, e.S, e.W, p);
+    for (size_t p = 0; p < P; ++p) ip_lsq_prep_body(e.T, e.S, e.W, p, solo);
     assemble(e.LB, P);
     bool hit = false;
 #define IP_CASE(NS_, NXR_) if (!hit && e.LB.NS == NS_) { spd_all<NS_, NXR_>(e, P); hit = true; }
     IP_LSQ_SIZES(IP_CASE)
 #undef IP_CASE
     if (!hit) return 1;
-    for (size_t p = 0; p < P; ++p) ip_lsq_choose_body(e.T, e.S, e.W, p);
+    for (size_t p = 0; p < P; ++p) ip_lsq_choose_body(e.T, e.S, e.W, p, solo);
     return 0;
   }
-  int flush_all(size_t P) { for (size_t p = 0; p < P; ++p) ip_flush_body(e.T, e.S, e.W, e.O, p); return 0; }
+  int flush_all(size_t P) { for (size_t p = 0; p < P; ++p) ip_flush_body(e.T, e.S, e.W, e.O, p, solo); return 0; }
   int compact(size_t P, size_t* newP) {
     std::vector<int> keep;
-    for (size_t p = 0; p < P; ++p) { if (e.S.done[p]) ip_flush_body(e.T, e.S, e.W, e.O, p); else keep.push_back((int)p); }
+    for (size_t p = 0; p < P; ++p) { if (e.S.done[p]) ip_flush_body(e.T, e.S, e.W, e.O, p, solo); else keep.push_back((int)p); }
     *newP = keep.size();
     if (keep.empty()) return 0;
     const int other = 1 - e.cur;
