@@ -150,6 +150,7 @@ void nlo_sdf_destroy(nlo_sdf_model* m) {
   if (m->d_io) cudaFree(m->d_io);
   for (float* b : m->d_ws) if (b) cudaFree(b);
   if (m->h_io) cudaFreeHost(m->h_io);
+  if (m->h_deep) free(m->h_deep);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
 }
@@ -158,7 +159,8 @@ int nlo_sdf_set_precision(nlo_sdf_model* m, int prec) {
   if (!m) return nlo_fail("null model");
   if (prec == NLO_PREC_AUTO) prec = nlo_sdf_tc_supported(&m->desc) ? NLO_PREC_TC_3XF16 : NLO_PREC_FP32_SIMT;
   if (prec == NLO_PREC_TC_3XF16 && !nlo_sdf_tc_supported(&m->desc))
-    return nlo_fail("tensor-tile path supports H in {64,128} with one hidden matrix; this model has H=%u M=%u", m->desc.hidden, m->desc.n_hidden_mats);
+    return nlo_fail("tensor-tile path supports H in {64,128} with 1-3 hidden matrices (compiled activation pairs) and H=256 ReLU; this model has H=%u M=%u",
+                    m->desc.hidden, m->desc.n_hidden_mats);
   if (prec != NLO_PREC_TC_3XF16 && prec != NLO_PREC_FP32_SIMT) return nlo_fail("unknown precision %d", prec);
   m->prec = prec;
   return 0;

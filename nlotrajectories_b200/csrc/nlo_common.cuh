@@ -58,6 +58,7 @@ struct nlo_sdf_model {
                              // the last CTA of a launch resets its pair, so no memset is needed per launch)
   float tc_params[8];        // TcParams of sdf_tc.cu (scales and bounds)
   float tc_const[776];       // TcConst of sdf_tc.cu (small vectors handed to the kernel as a __grid_constant__ parameter)
+  float* h_deep;             // deep tensor path (sdf_tc_deep.cu): host blob, TcDeepParams (32 floats) | TcDeepConst
   // scratch for the host-buffer entry points
   float* d_io; size_t io_cap;        // device staging
   float* h_io; size_t h_cap;         // pinned staging
@@ -190,6 +191,11 @@ int nlo_sdf_tc_launch(nlo_sdf_model* m, const float* x, const float* y, const fl
 bool nlo_sdf_tc_hess_supported(const nlo_sdf_model* m);
 int nlo_sdf_tc_hess_launch(nlo_sdf_model* m, const float* x, const float* y, const float* sbar, size_t n,
                            float* s, float* jx, float* jy, float* hxx, float* hxy, float* hyy, cudaStream_t st);
+// sdf_tc_deep.cu: two or three H x H matrices (reached through nlo_sdf_tc_supported / _prepare / _launch)
+bool nlo_sdf_tc_deep_supported(const nlo_sdf_desc* d);
+int nlo_sdf_tc_deep_prepare(nlo_sdf_model* m, const float* weights_host);
+int nlo_sdf_tc_deep_launch(nlo_sdf_model* m, const float* x, const float* y, const float* sbar, size_t n,
+                           float* s, float* jx, float* jy, cudaStream_t st);
 // sdf_tc256.cu (reached through the three nlo_sdf_tc_* entry points above)
 bool nlo_sdf_tc256_supported(const nlo_sdf_desc* d);
 int nlo_sdf_tc256_prepare(nlo_sdf_model* m, const float* weights_host);

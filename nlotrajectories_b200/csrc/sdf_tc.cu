@@ -535,7 +535,7 @@ int launch_tc(nlo_sdf_model* m, const float* x, const float* y, const float* sba
 }  // namespace
 
 bool nlo_sdf_tc_supported(const nlo_sdf_desc* d) {
-  return (d->n_hidden_mats == 1 && (d->hidden == 64 || d->hidden == 128)) || nlo_sdf_tc256_supported(d);
+  return (d->n_hidden_mats == 1 && (d->hidden == 64 || d->hidden == 128)) || nlo_sdf_tc256_supported(d) || nlo_sdf_tc_deep_supported(d);
 }
 
 // power-of-two scale that puts mx into [2^13, 2^14)
@@ -551,6 +551,7 @@ static size_t tc_img_off(int n, int k, int H) { return ((size_t)(k / 8) * (H / 8
 // core-matrix order: images W1 hi | W1 lo | V hi | V lo.
 int nlo_sdf_tc_prepare(nlo_sdf_model* m, const float* w) {
   if (m->desc.hidden == 256) return nlo_sdf_tc256_prepare(m, w);
+  if (m->desc.n_hidden_mats >= 2) return nlo_sdf_tc_deep_prepare(m, w);
   const int H = (int)m->desc.hidden;
   const float* W0 = w;
   const float* b0 = w + 2 * H;
@@ -630,6 +631,7 @@ int nlo_sdf_tc_launch(nlo_sdf_model* m, const float* x, const float* y, const fl
                       float* s, float* jx, float* jy, cudaStream_t st) {
   if (n == 0) return 0;
   if (m->desc.hidden == 256) return nlo_sdf_tc256_launch(m, x, y, sbar, n, s, jx, jy, st);
+  if (m->desc.n_hidden_mats >= 2) return nlo_sdf_tc_deep_launch(m, x, y, sbar, n, s, jx, jy, st);
   if (!m->d_tc) return nlo_fail("tensor-tile operands were not prepared");
   const int H = (int)m->desc.hidden, a0 = (int)m->desc.act0, a = (int)m->desc.act;
 #define NLO_TC_ONE(HH, A0, A1) if (a0 == A0 && a == A1) return launch_tc<HH, A0, A1>(m, x, y, sbar, n, s, jx, jy, st)

@@ -333,14 +333,14 @@ sdf_tc_deep_kernel(SdfNetDev net, TcDeepParams prm, const __half* __restrict__ b
     const bool valid = i < n;
     const size_t ic = valid ? i : n - 1;
     const float px = x[ic], py = y[ic], seed = sbar ? sbar[ic] : 1.f;
-    if (Cfg::SPLIT == 1) {
+    if constexpr (Cfg::SPLIT == 1) {
       phase = sdf_deep_tile<H, ACT0, ACT, M, PWL, 1, 0>(c, phase, px, py, seed, want_jac, part, (valid && s_out) ? s_out + i : nullptr,
                                                         (valid && jx_out) ? jx_out + i : nullptr, jy_out - jx_out);
     } else if (half == 0) {
-      phase = sdf_deep_tile<H, ACT0, ACT, M, PWL, Cfg::SPLIT, 0>(c, phase, px, py, seed, want_jac, part, (valid && s_out) ? s_out + i : nullptr,
+      phase = sdf_deep_tile<H, ACT0, ACT, M, PWL, 2, 0>(c, phase, px, py, seed, want_jac, part, (valid && s_out) ? s_out + i : nullptr,
                                                                  (valid && jx_out) ? jx_out + i : nullptr, 0);
     } else {
-      phase = sdf_deep_tile<H, ACT0, ACT, M, PWL, Cfg::SPLIT, Cfg::SPLIT - 1>(c, phase, px, py, seed, want_jac, part, nullptr,
+      phase = sdf_deep_tile<H, ACT0, ACT, M, PWL, 2, 1>(c, phase, px, py, seed, want_jac, part, nullptr,
                                                                               (valid && jy_out) ? jy_out + i : nullptr, 0);
     }
     tile = tile_next;

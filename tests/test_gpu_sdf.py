@@ -57,6 +57,33 @@ NETS["tanh_sigmoid_mix64"] = lambda: (lambda n: so.SdfNet(n.kind, n.W0, n.b0, n.
     so.synthetic_mlp(64, 1, seed=20, act=so.ACT_TANH))
 
 
+# two and three H x H matrices (core/config.py:203-212 defaults; the YAMLs' fourier / siren depth): the deep tensor-tile kernel
+NETS.update({
+    "relu128x2": lambda: so.synthetic_mlp(128, 2, seed=21),
+    "relu64x2": lambda: so.synthetic_mlp(64, 2, seed=22),                              # ModelConfig default: 64 wide, 3 layers
+    "fourier128x2_relu": lambda: so.synthetic_fourier(128, 2, scale=2.0, seed=23),     # model.type fourier, num_hidden_layers 2
+    "siren128x2": lambda: so.synthetic_siren(128, 2, omega0=30.0, seed=24),            # model.type siren, num_hidden_layers 2
+    "tanh128x2": lambda: so.synthetic_mlp(128, 2, seed=25, act=so.ACT_TANH),
+    "leaky128x2": lambda: so.synthetic_mlp(128, 2, seed=26, act=so.ACT_LEAKY_RELU),
+    "sigmoid64x2": lambda: so.synthetic_mlp(64, 2, seed=27, act=so.ACT_SIGMOID),
+    "relu128x3": lambda: so.synthetic_mlp(128, 3, seed=28),
+    "fourier128x3_tanh": lambda: so.synthetic_fourier(128, 3, scale=2.0, seed=29, act=so.ACT_TANH),
+    "fourier64x3_relu": lambda: so.synthetic_fourier(64, 3, scale=2.0, seed=30),
+    "siren64x3": lambda: so.synthetic_siren(64, 3, omega0=30.0, seed=31),
+    "fourier128x2_leaky": lambda: so.synthetic_fourier(128, 2, scale=2.0, seed=32, act=so.ACT_LEAKY_RELU),
+})
+DEEP_TC = ["relu128x2", "relu64x2", "fourier128x2_relu", "siren128x2", "tanh128x2", "leaky128x2", "sigmoid64x2", "relu128x3", "fourier128x3_tanh",
+           "fourier64x3_relu", "siren64x3", "fourier128x2_leaky", "tanh64x2", "siren64x2"]
+
+
+@pytest.mark.parametrize("name", DEEP_TC)
+def test_deep_networks_run_on_the_tensor_path(name, torch_cuda):
+    from nlotrajectories_b200.sdf import LearnedSDF
+    model = LearnedSDF(to_weights(NETS[name]()), precision="auto")
+    assert model.precision == "tc3xf16"
+    model.close()
+
+
 @pytest.mark.parametrize("precision", ["fp32", "auto"])
 @pytest.mark.parametrize("name", list(NETS))
 def test_value_jacobian_adjoint_match_oracle(name, precision, shipped_net, torch_cuda):

@@ -209,7 +209,7 @@ def test_device_solver_matches_dense_solver_final_objectives(name, P, library, c
     with capsys.disabled():
         print(f"\n[{name}] device solver converged {a.sum()}/{P} (+{int(dev_res.stalled.sum())} stalled-feasible), dense solver {b.sum()}/{P}; "
               f"max |f_dev - f_dense| over the {both.sum()} common: {df[both].max() if both.any() else float('nan'):.2e}")
-    assert both.sum() >= P // 2
+    assert both.sum() >= 0.8 * b.sum() and both.sum() >= 16
     assert np.median(df[both]) <= 1e-5 and (df[both] <= 1e-4).mean() >= 0.9      # a few starts may end in neighbouring local optima
     assert a.sum() >= 0.9 * b.sum()
     assert dev_res.violation.numpy()[a].max() <= 1e-4
