@@ -123,21 +123,16 @@ __device__ __forceinline__ float nlo_reduce_2pi(float a) {
   const float r = fmaf(k, -6.2831854820251465f, a);               // fp32(2*pi)
   return fmaf(k, 1.7484555e-07f, r);                              // fp32(2*pi) - 2*pi
 }
-// (huge arguments: the library's slow path, kept out of line so that unrolled callers stay small)
-static __device__ __noinline__ void nlo_sincos_slow(float a, float* s, float* c) { sincosf(a, s, c); }
+// No branch to a library slow path: the two-FMA reduction is exact enough while the rounded quotient fits the 1.5 * 2^23 trick,
+// i.e. up to |a| ~ 2^22 * 2 pi = 2.6e7 - far beyond where an fp32 argument still carries a phase (ulp(2.6e7) = 2 rad), so any fp32
+// evaluation, the reference's included, is noise there.  (A conditional call inside the fully unrolled tile bodies cost every
+// Fourier / SIREN kernel a 300-500 byte stack frame of caller-saved registers.)
 __device__ __forceinline__ void nlo_sincos_fast(float a, float& s, float& c) {
-  if (fabsf(a) > 8192.f) { nlo_sincos_slow(a, &s, &c); return; }
   const float r = nlo_reduce_2pi(a);
   s = __sinf(r); c = __cosf(r);
 }
-__device__ __forceinline__ float nlo_cos_fast(float a) {
-  if (fabsf(a) > 8192.f) { float s, c; nlo_sincos_slow(a, &s, &c); return c; }
-  return __cosf(nlo_reduce_2pi(a));
-}
-__device__ __forceinline__ float nlo_sin_fast(float a) {
-  if (fabsf(a) > 8192.f) { float s, c; nlo_sincos_slow(a, &s, &c); return s; }
-  return __sinf(nlo_reduce_2pi(a));
-}
+__device__ __forceinline__ float nlo_cos_fast(float a) { return __cosf(nlo_reduce_2pi(a)); }
+__device__ __forceinline__ float nlo_sin_fast(float a) { return __sinf(nlo_reduce_2pi(a)); }
 // tanh and the logistic function through MUFU.EX2 / MUFU.RCP (6 instructions instead of libdevice's ~25 with branches):
 //   tanh(a) = 1 - 2 / (1 + e^{2a}),  sigmoid(a) = 1 / (1 + e^{-a}).  __expf is good to ~2 ulp of the result, the reciprocal to 1 ulp;
 // absolute error <= ~2e-7 everywhere (saturation: e^{2a} -> inf gives exactly 1, -> 0 gives exactly -1).

@@ -50,13 +50,13 @@ __constant__ TcDeepConst cd;
 template <int H, int M, bool PWL>
 struct DeepCfg {
   static constexpr int IMG_HALFS = H * H;
-  static constexpr int SPLIT = (H >= 128) ? 2 : 1;
-  static constexpr int GROUP_THREADS = DTILE * SPLIT;
   static constexpr uint32_t GROUP_COLS = 2 * H + (PWL ? 0 : (M - 1) * H);
-  static constexpr int NGROUPS = (512 / GROUP_COLS) < (512 / GROUP_THREADS) ? (512 / GROUP_COLS) : (512 / GROUP_THREADS);
+  static constexpr int NGROUPS = 512 / GROUP_COLS;                  // tensor memory decides how many tiles an SM holds
+  static constexpr int SPLIT = 4 / NGROUPS > H / 32 ? H / 32 : 4 / NGROUPS;   // threads per point: 512 threads per CTA whenever the width allows
+  static constexpr int GROUP_THREADS = DTILE * SPLIT;
   static constexpr int THREADS = NGROUPS * GROUP_THREADS;
   static constexpr size_t bytes() {
-    return (size_t)M * 2 * IMG_HALFS * 2 + (size_t)NGROUPS * 2 * DTILE * 4 * 4 + NGROUPS * 8 + 16 + NGROUPS * 4;
+    return (size_t)M * 2 * IMG_HALFS * 2 + (size_t)NGROUPS * SPLIT * DTILE * 4 * 4 + NGROUPS * 8 + 16 + NGROUPS * 4;
   }
 };
 
@@ -99,13 +99,13 @@ __device__ __forceinline__ void deep_issue_gemm(const DeepCtx& c, int l, bool fw
   if (fetch_next && c.ctr) *c.next_slot = atomicAdd(c.ctr, 1u) + c.ctr_bias;
 }
 
-// One tile of one group.  SPLIT = 2: two threads own a point, HALF 0 the low half of the neurons / D columns, HALF 1 the high half.
-// Every thread handles HH = 64 neurons per layer.
+// One tile of one group.  SPLIT threads own a point: thread HALF (0 .. SPLIT-1) the neurons / D columns [HALF * H / SPLIT, ...).
+// Every thread handles HH = 64 or 32 neurons per layer.
 template <int H, int ACT0, int ACT, int M, bool PWL, int SPLIT, int HALF>
 __device__ __noinline__ uint32_t sdf_deep_tile(DeepCtx c, uint32_t phase, float px, float py, float seed, bool want_jac,
                                                float* __restrict__ part, float* __restrict__ s_ptr, float* __restrict__ j_ptr, ptrdiff_t jy_off) {
   constexpr int HH = H / SPLIT;
-  static_assert(HH == 64, "every thread owns 64 neurons");
+  static_assert(HH == 64 || HH == 32, "every thread owns 64 or 32 neurons");
   constexpr int C0 = HALF * HH;
   constexpr int NCH = HH / 32;
   constexpr int NT = DTILE * SPLIT;
@@ -258,19 +258,22 @@ __device__ __noinline__ uint32_t sdf_deep_tile(DeepCtx c, uint32_t phase, float 
     tc_fence_after();
     return phase;
   }
+  // partial sums of the SPLIT owners of a point meet in shared memory; owner 0 adds them up and stores
   float* mine = part + (HALF * DTILE + pt) * 4;
-  if (HALF == 0) mine[0] = jy;
-  else { mine[0] = s; mine[1] = jx; }
+  mine[0] = s; mine[1] = jx; mine[2] = jy;
   tc_fence_before();
-  group_bar<NT>(c.bar_id);
+  group_bar<NT>(c.bar_id);                      // (also keeps the next tile's tcgen05.st / MMA behind this tile's TMEM reads)
   tc_fence_after();
-  const float* other = part + ((1 - HALF) * DTILE + pt) * 4;
   if (HALF == 0) {
-    if (s_ptr) *s_ptr = s + other[0];
-    if (j_ptr) *j_ptr = jx + other[1];
-  } else {
-    if (j_ptr) *j_ptr = jy + other[0];
+#pragma unroll
+    for (int h = 1; h < SPLIT; ++h) {
+      const float* other = part + (h * DTILE + pt) * 4;
+      s += other[0]; jx += other[1]; jy += other[2];
+    }
+    if (s_ptr) *s_ptr = s;
+    if (j_ptr) { j_ptr[0] = jx; j_ptr[jy_off] = jy; }
   }
+  // `part` is rewritten by the next tile only after its first group barrier, which owner 0 reaches after these reads
   return phase;
 }
 
@@ -284,13 +287,13 @@ sdf_tc_deep_kernel(SdfNetDev net, TcDeepParams prm, const __half* __restrict__ b
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __half* sB = reinterpret_cast<__half*>(smem_raw);
   float* sPart = reinterpret_cast<float*>(smem_raw + (size_t)M * 2 * Cfg::IMG_HALFS * 2);
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(sPart + Cfg::NGROUPS * 2 * DTILE * 4);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(sPart + Cfg::NGROUPS * Cfg::SPLIT * DTILE * 4);
   int* lock = reinterpret_cast<int*>(mbar + Cfg::NGROUPS);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lock + 1);
   uint32_t* next_tile = tmem_slot + 1;
   const int t = threadIdx.x, warp = t >> 5;
   const int grp = t / Cfg::GROUP_THREADS, tg = t % Cfg::GROUP_THREADS;
-  const int half = (tg >> 5) >> 2;
+  const int half = (tg >> 5) >> 2;               // which of the SPLIT owners of the point this thread is
   const int pt = tg & (DTILE - 1);
   {
     const uint4* src = reinterpret_cast<const uint4*>(bimg);
@@ -317,7 +320,7 @@ sdf_tc_deep_kernel(SdfNetDev net, TcDeepParams prm, const __half* __restrict__ b
   c.ctr = tile_ctr; c.next_slot = next_tile + grp; c.ctr_bias = 2 * gridDim.x * Cfg::NGROUPS;
   c.prm0 = net.p0; c.prm = net.p; c.p = prm;
   const bool want_jac = (jx_out != nullptr) || (jy_out != nullptr);
-  float* part = sPart + grp * (2 * DTILE * 4);
+  float* part = sPart + grp * (Cfg::SPLIT * DTILE * 4);
   uint32_t phase = 0;
   const size_t n_tiles = (n + DTILE - 1) / DTILE;
   const size_t stride = (size_t)gridDim.x * Cfg::NGROUPS;
@@ -333,16 +336,14 @@ sdf_tc_deep_kernel(SdfNetDev net, TcDeepParams prm, const __half* __restrict__ b
     const bool valid = i < n;
     const size_t ic = valid ? i : n - 1;
     const float px = x[ic], py = y[ic], seed = sbar ? sbar[ic] : 1.f;
-    if constexpr (Cfg::SPLIT == 1) {
-      phase = sdf_deep_tile<H, ACT0, ACT, M, PWL, 1, 0>(c, phase, px, py, seed, want_jac, part, (valid && s_out) ? s_out + i : nullptr,
-                                                        (valid && jx_out) ? jx_out + i : nullptr, jy_out - jx_out);
-    } else if (half == 0) {
-      phase = sdf_deep_tile<H, ACT0, ACT, M, PWL, 2, 0>(c, phase, px, py, seed, want_jac, part, (valid && s_out) ? s_out + i : nullptr,
-                                                                 (valid && jx_out) ? jx_out + i : nullptr, 0);
-    } else {
-      phase = sdf_deep_tile<H, ACT0, ACT, M, PWL, 2, 1>(c, phase, px, py, seed, want_jac, part, nullptr,
-                                                                              (valid && jy_out) ? jy_out + i : nullptr, 0);
-    }
+    float* sp = (valid && s_out) ? s_out + i : nullptr;
+    float* jp = (valid && jx_out) ? jx_out + i : nullptr;
+    const ptrdiff_t jo = jy_out - jx_out;
+#define NLO_DEEP_TILE(Q) phase = sdf_deep_tile<H, ACT0, ACT, M, PWL, Cfg::SPLIT, Q>(c, phase, px, py, seed, want_jac, part, sp, jp, jo)
+    if constexpr (Cfg::SPLIT == 1) { NLO_DEEP_TILE(0); }
+    else if constexpr (Cfg::SPLIT == 2) { if (half == 0) NLO_DEEP_TILE(0); else NLO_DEEP_TILE(1); }
+    else { if (half == 0) NLO_DEEP_TILE(0); else if (half == 1) NLO_DEEP_TILE(1); else if (half == 2) NLO_DEEP_TILE(2); else NLO_DEEP_TILE(3); }
+#undef NLO_DEEP_TILE
     tile = tile_next;
     tile_next = tile_ctr ? (size_t)next_tile[grp] : tile_next + stride;
   }

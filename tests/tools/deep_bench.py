@@ -17,6 +17,8 @@ from oracle import sdf_oracle as so                          # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 22
 nets = {
     "relu128x1": so.synthetic_mlp(128, 1, seed=0),
+    "shipped_fourier128x1": so.from_npz(REPO / "tests" / "golden" / "sdf_shipped_fourier128_weights.npz"),
+    "siren128x1": so.synthetic_siren(128, 1, omega0=30.0, seed=40),
     "relu128x2": so.synthetic_mlp(128, 2, seed=21),
     "relu128x3": so.synthetic_mlp(128, 3, seed=28),
     "relu64x2": so.synthetic_mlp(64, 2, seed=22),
