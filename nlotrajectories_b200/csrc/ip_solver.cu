@@ -8,6 +8,7 @@
 #include "ip_core.cuh"
 #include "ip_tables.hpp"
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -194,6 +195,257 @@ int launch_bt_spd(const BtTables& B, const double* K, double* Lf, const double* 
   return 0;
 }
 
+// ---- the same factor + solve with a TEAM per 32 problems ------------------------------------------------------------------------
+// lanes = 32 consecutive problems (coalesced global access), warps = the NS rows of a block + one warp for the right-hand side.
+// The blocks live in shared memory ([slot][lane]); a Cholesky column costs two block barriers, the triangular solves of the
+// sub-diagonal rows and of the right-hand side are row-local, and the Schur update of the next diagonal block is one row per warp.
+// One thread per problem (bt_kkt_kernel above) walks the 81 stages alone - ~1 ms per attempt however few problems there are; a team
+// shares each stage among NS + 1 warps.
+template <int NS, int NXR>
+struct BtTeam {
+  static constexpr int ND = NS * (NS + 1) / 2, NO = NXR * NS, SLK = ND + NO, SLL = ND + NO + NS;
+  static constexpr int S = 0, LD = S + ND, LO = LD + NS, Y = LO + NO, TOTAL = Y + NS;      // shared-memory slots
+  static constexpr int NW = NS + 1;
+  static constexpr size_t smem_bytes = (size_t)TOTAL * 32 * sizeof(double);
+};
+
+// One attempt for the 32 problems of the block with `delta` on the diagonal; lanes with store == false run along without writing.
+// Returns (to every thread of a lane) whether the factorisation succeeded and the solution is finite with max |x| < xmax.
+template <int NS, int NXR>
+__device__ __forceinline__ bool bt_team_attempt(const BtTables& B, const double* __restrict__ K, double* __restrict__ Lf,
+                                                const double* __restrict__ rhs, double* __restrict__ x, size_t ld, size_t p, double delta,
+                                                double xmax, bool store, double* sm, int* s_flag) {
+  using T = BtTeam<NS, NXR>;
+  constexpr int ND = T::ND, NO = T::NO, SLK = T::SLK, SLL = T::SLL;
+  const int lane = threadIdx.x, w = threadIdx.y;
+#define SM(slot) sm[(slot) * 32 + lane]
+  const int nb = B.nb;
+  bool ok = true;
+  double dinv[NS], b[NS], y[NS], lo[NS];
+#pragma unroll
+  for (int i = 0; i < NS; ++i) { b[i] = 0.0; y[i] = 0.0; lo[i] = 0.0; }
+  __syncthreads();                                           // the previous attempt's readers are done with shared memory
+  if (w < NS) {
+    const bool real = B.var[w] >= 0;
+#pragma unroll
+    for (int j = 0; j < NS; ++j)
+      if (j <= w) SM(T::S + BT_LI(w, j)) = K[(size_t)BT_LI(w, j) * ld + p] + ((j == w && real) ? delta : 0.0);
+  } else {
+#pragma unroll
+    for (int i = 0; i < NS; ++i) { const int u = B.var[i]; b[i] = u >= 0 ? rhs[(size_t)u * ld + p] : 0.0; }
+  }
+  for (int k = 0; k < nb; ++k) {
+    // rows of the next stage travel while this block is factorised
+    double dn[NS], on[NS], bn[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) { dn[i] = 0.0; on[i] = 0.0; bn[i] = 0.0; }
+    if (k < nb - 1) {
+      const double* Kn = K + (size_t)(k + 1) * SLK * ld + p;
+      const double* Ok = K + ((size_t)k * SLK + ND) * ld + p;
+      if (w < NS) {
+#pragma unroll
+        for (int j = 0; j < NS; ++j) if (j <= w) dn[j] = Kn[(size_t)BT_LI(w, j) * ld];
+        if (w < NXR) {
+#pragma unroll
+          for (int j = 0; j < NS; ++j) on[j] = Ok[(size_t)(w * NS + j) * ld];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) { const int u = B.var[(k + 1) * NS + i]; bn[i] = u >= 0 ? rhs[(size_t)u * ld + p] : 0.0; }
+      }
+    }
+    // Cholesky, column by column: every thread of the lane follows the pivots (so `ok` and 1 / pivot are known to all rows)
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      __syncthreads();
+      double d = SM(T::S + BT_LI(j, j));
+      if (!(d > 0.0) || !ip_finite(d)) { ok = false; d = 1.0; }
+      const double sd = sqrt(d);
+      dinv[j] = 1.0 / sd;
+      double lwj = 0.0;
+      if (w == j) SM(T::LD + j) = sd;
+      if (w > j && w < NS) { lwj = SM(T::S + BT_LI(w, j)) * dinv[j]; SM(T::S + BT_LI(w, j)) = lwj; }
+      __syncthreads();
+      if (w > j && w < NS) {
+#pragma unroll
+        for (int m = j + 1; m < NS; ++m) if (m <= w) SM(T::S + BT_LI(w, m)) -= lwj * SM(T::S + BT_LI(m, j));
+      }
+    }
+    __syncthreads();
+    const bool st = store && ok;
+    double* Lk = Lf + (size_t)k * SLL * ld + p;
+    if (w < NS) {
+      if (k < nb - 1 && w < NXR) {                           // row w of L_{k+1,k} = O_k L_kk^-T
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+          double v = on[j];
+#pragma unroll
+          for (int m = 0; m < NS; ++m) if (m < j) v -= lo[m] * SM(T::S + BT_LI(j, m));
+          lo[j] = v * dinv[j];
+        }
+#pragma unroll
+        for (int j = 0; j < NS; ++j) { SM(T::LO + w * NS + j) = lo[j]; if (st) Lk[(size_t)(ND + w * NS + j) * ld] = lo[j]; }
+      }
+      if (st) {                                              // row w of L_kk
+#pragma unroll
+        for (int j = 0; j < NS; ++j) if (j < w) Lk[(size_t)BT_LI(w, j) * ld] = SM(T::S + BT_LI(w, j));
+        Lk[(size_t)BT_LI(w, w) * ld] = SM(T::LD + w);
+      }
+    } else {                                                 // y = L^-1 b
+#pragma unroll
+      for (int i = 0; i < NS; ++i) {
+        double v = b[i];
+#pragma unroll
+        for (int m = 0; m < NS; ++m) if (m < i) v -= SM(T::S + BT_LI(i, m)) * y[m];
+        y[i] = v * dinv[i];
+      }
+#pragma unroll
+      for (int i = 0; i < NS; ++i) { SM(T::Y + i) = y[i]; if (st) Lk[(size_t)(ND + NO + i) * ld] = y[i]; }
+    }
+    __syncthreads();
+    if (k == nb - 1) break;
+    if (w < NS) {                                            // row w of the next diagonal block's Schur complement
+      const bool real = B.var[(k + 1) * NS + w] >= 0;
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        if (j > w) continue;
+        double v = dn[j];
+        if (w < NXR) {
+#pragma unroll
+          for (int m = 0; m < NS; ++m) v -= lo[m] * SM(T::LO + j * NS + m);
+        }
+        if (j == w && real) v += delta;
+        SM(T::S + BT_LI(w, j)) = v;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NS; ++i) {
+        double v = bn[i];
+        if (i < NXR) {
+#pragma unroll
+          for (int m = 0; m < NS; ++m) v -= SM(T::LO + i * NS + m) * y[m];
+        }
+        b[i] = v;
+      }
+    }
+  }
+  // backward pass: the factor blocks of stage k come back into shared memory row by row, the right-hand-side warp substitutes
+  double xp[NS];
+  double amax = 0.0;
+  bool fin = true;
+#pragma unroll
+  for (int i = 0; i < NS; ++i) xp[i] = 0.0;
+  for (int k = nb - 1; k >= 0; --k) {
+    const double* Lk = Lf + (size_t)k * SLL * ld + p;
+    double t[NS];
+    if (w < NS) {
+#pragma unroll
+      for (int j = 0; j < NS; ++j) if (j < w) SM(T::S + BT_LI(w, j)) = Lk[(size_t)BT_LI(w, j) * ld];
+      SM(T::LD + w) = Lk[(size_t)BT_LI(w, w) * ld];
+      if (k < nb - 1 && w < NXR) {
+#pragma unroll
+        for (int j = 0; j < NS; ++j) SM(T::LO + w * NS + j) = Lk[(size_t)(ND + w * NS + j) * ld];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NS; ++i) t[i] = Lk[(size_t)(ND + NO + i) * ld];
+    }
+    __syncthreads();
+    if (w == NS) {
+      if (k < nb - 1) {
+#pragma unroll
+        for (int i = 0; i < NXR; ++i)
+#pragma unroll
+          for (int j = 0; j < NS; ++j) t[j] -= SM(T::LO + i * NS + j) * xp[i];
+      }
+#pragma unroll
+      for (int i = NS - 1; i >= 0; --i) {
+        double v = t[i];
+#pragma unroll
+        for (int m = 0; m < NS; ++m) if (m > i) v -= SM(T::S + BT_LI(m, i)) * xp[m];
+        xp[i] = v / SM(T::LD + i);
+      }
+#pragma unroll
+      for (int i = 0; i < NS; ++i) {
+        const int u = B.var[k * NS + i];
+        if (u >= 0) {
+          if (store && ok) x[(size_t)u * ld + p] = xp[i];
+          if (!ip_finite(xp[i])) fin = false;
+          amax = ip_max(amax, fabs(xp[i]));
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (w == NS) s_flag[lane] = (ok && fin && amax < xmax) ? 1 : 0;
+  __syncthreads();
+  return s_flag[lane] != 0;
+#undef SM
+}
+
+// KKT mode: max_attempts 16, bump 1, xmax 1e3, fallback NULL (zero step on failure), delta_out written.
+// SPD mode (least-squares multipliers): one attempt with the given shift, no bump, fallback = the vector kept on failure.
+template <int NS, int NXR>
+__global__ void __launch_bounds__(32 * (NS + 1)) bt_team_kernel(BtTables B, const double* __restrict__ K, double* __restrict__ Lf,
+                                                                const double* __restrict__ rhs, double* __restrict__ x, double* __restrict__ x_alt,
+                                                                size_t P, size_t ld, int n_unknown, const double* __restrict__ delta_in,
+                                                                const int* __restrict__ skip, double* __restrict__ delta_out, int max_attempts,
+                                                                int bump, double xmax, const double* __restrict__ fallback) {
+  using T = BtTeam<NS, NXR>;
+  extern __shared__ double bt_team_smem[];
+  __shared__ int s_flag[32];
+  const int lane = threadIdx.x, w = threadIdx.y;
+  const size_t p_raw = (size_t)blockIdx.x * 32 + lane;
+  const bool in_range = p_raw < P;
+  const size_t p = in_range ? p_raw : P - 1;                 // lanes beyond the batch shadow the last problem and store nothing
+  const bool skipped = in_range && skip && skip[p];
+  const double d0 = delta_in[p];
+  double dwt = d0;
+  int state = (in_range && !skipped) ? 0 : 2;                // 0 to solve, 1 solved, 2 not taking part
+  if (skipped)
+    for (int c = w; c < n_unknown; c += T::NW) x[(size_t)c * ld + p] = 0.0;
+  for (int attempt = 0; attempt < max_attempts; ++attempt) {
+    const bool active = state == 0;
+    if (!__syncthreads_or(active)) break;
+    const bool good = bt_team_attempt<NS, NXR>(B, K, Lf, rhs, x_alt, ld, p, dwt, xmax, active, bt_team_smem, s_flag);
+    if (active) {
+      if (good) { state = 1; for (int c = w; c < n_unknown; c += T::NW) x[(size_t)c * ld + p] = x_alt[(size_t)c * ld + p]; }
+      else dwt = ip_min(ip_max(dwt * 8.0, 1e-4), 1e8);
+    }
+  }
+  if (state == 0)                                            // every attempt failed
+    for (int c = w; c < n_unknown; c += T::NW) x[(size_t)c * ld + p] = fallback ? fallback[(size_t)c * ld + p] : 0.0;
+  if (bump) {
+    // a problem that needed more regularisation than last time is solved once more with twice the value that first passed
+    const bool again = in_range && !skipped && dwt > d0;
+    if (__syncthreads_or(again)) {
+      const bool good = bt_team_attempt<NS, NXR>(B, K, Lf, rhs, x_alt, ld, p, 2.0 * dwt, xmax, again, bt_team_smem, s_flag);
+      if (again && good) {
+        for (int c = w; c < n_unknown; c += T::NW) x[(size_t)c * ld + p] = x_alt[(size_t)c * ld + p];
+        dwt = 2.0 * dwt;
+      }
+    }
+  }
+  if (delta_out && w == 0 && in_range) delta_out[p] = dwt;
+}
+
+template <int NS, int NXR>
+int launch_bt_team(const BtTables& B, const double* K, double* Lf, const double* rhs, double* x, double* x_alt, size_t P, size_t ld,
+                   int n_unknown, const double* delta_in, const int* skip, double* delta_out, int max_attempts, int bump, double xmax,
+                   const double* fallback, int device, cudaStream_t st) {
+  using T = BtTeam<NS, NXR>;
+  static bool attr[64] = {false};
+  if (!attr[device & 63]) {
+    NLO_CUDA(cudaFuncSetAttribute(bt_team_kernel<NS, NXR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::smem_bytes));
+    attr[device & 63] = true;
+  }
+  bt_team_kernel<NS, NXR><<<(unsigned)((P + 31) / 32), dim3(32, T::NW), T::smem_bytes, st>>>(B, K, Lf, rhs, x, x_alt, P, ld, n_unknown, delta_in, skip,
+                                                                                          delta_out, max_attempts, bump, xmax, fallback);
+  NLO_CHECK_LAUNCH();
+  return 0;
+}
+inline bool ip_thread_kkt() { static const bool v = getenv("NLO_B200_IP_THREAD_KKT") != nullptr; return v; }   // A / B switch: one thread per problem
+
 // block sizes of the six dynamics models (core/dynamics.py:151-158) with and without slack: NS = nx + nu + slack, NXR = nx
 #define IP_KKT_SIZES(X) X(5, 3) X(6, 3) X(6, 4) X(7, 4) X(7, 5) X(8, 5) X(9, 7) X(10, 7)
 #define IP_LSQ_SIZES(X) X(3, 3) X(4, 4) X(5, 5) X(7, 7)
@@ -285,8 +537,10 @@ struct GpuBackend {
     if (assemble(s->KB, P)) return 1;
 #define IP_CASE(NS_, NXR_)                                                                                                      \
     if (s->KB.NS == NS_ && s->KB.NXR == NXR_)                                                                                   \
-      return launch_bt_kkt<NS_, NXR_>(s->KB, s->d_K, s->d_L, s->W.rhs, s->W.dw, s->W.dw_alt, P, s->cap, s->T.n_w, s->S.delta_w, s->S.done, \
-                                      s->W.dwt, s->device, st);
+      return ip_thread_kkt() ? launch_bt_kkt<NS_, NXR_>(s->KB, s->d_K, s->d_L, s->W.rhs, s->W.dw, s->W.dw_alt, P, s->cap, s->T.n_w, s->S.delta_w,   \
+                                                        s->S.done, s->W.dwt, s->device, st)                                     \
+                             : launch_bt_team<NS_, NXR_>(s->KB, s->d_K, s->d_L, s->W.rhs, s->W.dw, s->W.dw_alt, P, s->cap, s->T.n_w, s->S.delta_w,  \
+                                                         s->S.done, s->W.dwt, 16, 1, 1e3, nullptr, s->device, st);
     IP_KKT_SIZES(IP_CASE)
 #undef IP_CASE
     return nlo_fail("interior point: no factorisation kernel for stage blocks of %d unknowns (%d states)", s->KB.NS, s->KB.NXR);
@@ -319,7 +573,9 @@ struct GpuBackend {
     int rc = -1;
 #define IP_CASE(NS_, NXR_)                                                                                                      \
     if (rc < 0 && s->LB.NS == NS_)                                                                                              \
-      rc = launch_bt_spd<NS_, NXR_>(s->LB, s->d_K, s->d_L, s->W.v, s->W.lam_ls, P, s->cap, s->T.nE, s->W.eps_ls, s->S.lamE, s->device, st);
+      rc = ip_thread_kkt() ? launch_bt_spd<NS_, NXR_>(s->LB, s->d_K, s->d_L, s->W.v, s->W.lam_ls, P, s->cap, s->T.nE, s->W.eps_ls, s->S.lamE, s->device, st) \
+                           : launch_bt_team<NS_, NXR_>(s->LB, s->d_K, s->d_L, s->W.v, s->W.lam_ls, s->W.dw_alt, P, s->cap, s->T.nE, s->W.eps_ls, nullptr,  \
+                                                       nullptr, 1, 0, HUGE_VAL, s->S.lamE, s->device, st);
     IP_LSQ_SIZES(IP_CASE)
 #undef IP_CASE
     if (rc < 0) return nlo_fail("interior point: no multiplier kernel for %d states", s->LB.NS);
@@ -533,7 +789,9 @@ int nlo_ip_kkt_step(nlo_ip* s, const float* jac, const float* hess, const double
   NLO_CHECK_LAUNCH();
 #define IP_CASE(NS_, NXR_)                                                                                                      \
   if (B.NS == NS_ && B.NXR == NXR_)                                                                                             \
-    return launch_bt_kkt<NS_, NXR_>(B, s->d_K, s->d_L, rhs, dw, s->W.dw_alt, P, ld, s->T.n_w, delta_in, nullptr, delta_out, s->device, st);
+    return ip_thread_kkt() ? launch_bt_kkt<NS_, NXR_>(B, s->d_K, s->d_L, rhs, dw, s->W.dw_alt, P, ld, s->T.n_w, delta_in, nullptr, delta_out, s->device, st) \
+                           : launch_bt_team<NS_, NXR_>(B, s->d_K, s->d_L, rhs, dw, s->W.dw_alt, P, ld, s->T.n_w, delta_in, nullptr, delta_out, 16, 1, 1e3,  \
+                                                       nullptr, s->device, st);
   IP_KKT_SIZES(IP_CASE)
 #undef IP_CASE
   return nlo_fail("interior point: no factorisation kernel for stage blocks of %d unknowns (%d states)", B.NS, B.NXR);
