@@ -287,6 +287,8 @@ typedef struct nlo_ip_options {
 typedef struct nlo_ip_stats {
   int iterations, evaluations, hessians, trials, compactions;   /* batched calls of each kind                              */
   long long trial_problems;                                     /* problems evaluated by the line-search trials, in total   */
+  double phase_ms[9];   /* device time per phase (CUDA events): evaluation, residuals + barrier update, Hessian, KKT assembly +
+                           factorisation, step, line search, update, least-squares multipliers, compaction / output            */
 } nlo_ip_stats;
 /* lbg, ubg: fp64[n_g] bounds of g in Opti's canonical form (+-INFINITY for one-sided rows; rows with lbg == ubg are equalities).
  * max_problems: batch size the device buffers are sized for.  The solver keeps a pointer to `p` (not owned).              */

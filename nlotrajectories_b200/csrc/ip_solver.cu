@@ -452,6 +452,27 @@ inline bool ip_thread_kkt() { static const bool v = getenv("NLO_B200_IP_THREAD_K
 
 }  // namespace
 
+namespace {
+// Where a solve spends its time: a CUDA event at the start of every phase, read back at the loop's own synchronisation points
+// (no extra synchronisation); the interval between two marks is charged to the phase of the first.
+enum { PH_EVAL = 0, PH_RESIDUAL, PH_HESSIAN, PH_KKT, PH_STEP, PH_LINESEARCH, PH_UPDATE, PH_MULTIPLIERS, PH_COMPACT, PH_COUNT };
+struct PhaseTimer {
+  static constexpr int CAP = 96;
+  cudaEvent_t ev[CAP]; int id[CAP]; int n = 0; bool ready = false;
+  double ms[PH_COUNT] = {0};
+  int init() { for (auto& e : ev) NLO_CUDA(cudaEventCreate(&e)); ready = true; return 0; }
+  void destroy() { if (ready) for (auto& e : ev) cudaEventDestroy(e); ready = false; }
+  void reset() { n = 0; for (double& m : ms) m = 0.0; }
+  void mark(int phase, cudaStream_t st) { if (ready && n < CAP) { cudaEventRecord(ev[n], st); id[n++] = phase; } }
+  void collect() {                                         // call right after a stream synchronisation that follows the last mark
+    if (!ready || n < 2) return;
+    for (int i = 0; i + 1 < n; ++i) { float t = 0.f; if (cudaEventElapsedTime(&t, ev[i], ev[i + 1]) == cudaSuccess) ms[id[i]] += t; }
+    std::swap(ev[0], ev[n - 1]); id[0] = id[n - 1]; n = 1;
+  }
+};
+
+}  // namespace
+
 // ---- the solver object ----------------------------------------------------------------------------------------------------
 struct nlo_ip {
   nlo_nlp* nlp;
@@ -471,6 +492,7 @@ struct nlo_ip {
   int* h_pin;                        // pinned: counters[2] + done flags
   IpState S; IpWork W; IpOut O;
   IpOptions opt;
+  PhaseTimer timer;
 };
 
 namespace {
@@ -503,6 +525,7 @@ int upload(V** dst, const std::vector<V>& v) {
 struct GpuBackend {
   nlo_ip* s;
   cudaStream_t st;
+  PhaseTimer* tm;
   dim3 g1(size_t P) const { return dim3((unsigned)((P + 31) / 32)); }
   dim3 b1() const { return dim3(32, IP_TEAM); }
 
@@ -513,6 +536,7 @@ struct GpuBackend {
     return 0;
   }
   int eval_full(size_t P) {
+    tm->mark(PH_EVAL, st);
     return nlo_nlp_eval(s->nlp, s->W.w32, P, s->cap, s->W.g, s->W.jac, s->W.f, s->W.grad, st);
   }
   int init(size_t P, double mu0, int max_iter) {
@@ -521,12 +545,16 @@ struct GpuBackend {
     return 0;
   }
   int residual(size_t P, int it, double tol, size_t* n_done) {
+    tm->mark(PH_RESIDUAL, st);
     NLO_CUDA(cudaMemsetAsync(s->W.counters, 0, 2 * sizeof(int), st));
     ip_residual_kernel<<<g1(P), b1(), 0, st>>>(s->T, s->S, s->W, P, it, tol);
     NLO_CHECK_LAUNCH();
-    return read_counter(0, n_done);
+    tm->mark(PH_HESSIAN, st);                              // (closes the residual interval; the Hessian is what follows)
+    if (read_counter(0, n_done)) return 1;
+    tm->collect();
+    return 0;
   }
-  int hessian(size_t P) { return nlo_nlp_hess(s->nlp, s->W.w32, nullptr, s->W.lam32, P, s->cap, s->W.hess, st); }
+  int hessian(size_t P) { tm->mark(PH_HESSIAN, st); return nlo_nlp_hess(s->nlp, s->W.w32, nullptr, s->W.lam32, P, s->cap, s->W.hess, st); }
   int assemble(const BtTables& B, size_t P) {
     const int n_slots = B.nb * B.SLK;
     bt_assemble_kernel<<<dim3((unsigned)((P + 255) / 256), (unsigned)std::min(n_slots, 65535)), 256, 0, st>>>(B, s->W.jac, s->W.hess, s->W.omega, s->d_K, P, s->cap);
@@ -534,6 +562,7 @@ struct GpuBackend {
     return 0;
   }
   int kkt_solve(size_t P) {
+    tm->mark(PH_KKT, st);
     if (assemble(s->KB, P)) return 1;
 #define IP_CASE(NS_, NXR_)                                                                                                      \
     if (s->KB.NS == NS_ && s->KB.NXR == NXR_)                                                                                   \
@@ -546,11 +575,13 @@ struct GpuBackend {
     return nlo_fail("interior point: no factorisation kernel for stage blocks of %d unknowns (%d states)", s->KB.NS, s->KB.NXR);
   }
   int step(size_t P) {
+    tm->mark(PH_STEP, st);
     ip_step_kernel<<<g1(P), b1(), 0, st>>>(s->T, s->S, s->W, P);
     NLO_CHECK_LAUNCH();
     return 0;
   }
   int trial(size_t n, int ls, size_t* rejected) {
+    tm->mark(PH_LINESEARCH, st);
     const int* list = ls > 0 ? s->W.ls_list[(ls + 1) & 1] : nullptr;
     ip_trial_kernel<<<dim3((unsigned)((n + 255) / 256), 32), 256, 0, st>>>(s->S, s->W, n, s->T.n_w, list);
     NLO_CHECK_LAUNCH();
@@ -561,12 +592,14 @@ struct GpuBackend {
     return read_counter(1, rejected);
   }
   int update(size_t P) {
+    tm->mark(PH_UPDATE, st);
     ip_update_kernel<<<g1(P), b1(), 0, st>>>(s->T, s->S, s->W, P);
     NLO_CHECK_LAUNCH();
     return 0;
   }
   int lsq_multipliers(size_t P) {
     if (s->T.nE == 0) return 0;
+    tm->mark(PH_MULTIPLIERS, st);
     ip_lsq_prep_kernel<<<g1(P), b1(), 0, st>>>(s->T, s->S, s->W, P);
     NLO_CHECK_LAUNCH();
     if (assemble(s->LB, P)) return 1;
@@ -591,6 +624,7 @@ struct GpuBackend {
   }
   int flush_all(size_t P) { return flush(P, 0); }
   int compact(size_t P, size_t* newP) {
+    tm->mark(PH_COMPACT, st);
     if (flush(P, 1)) return 1;
     int* h_done = s->h_pin + 2;
     NLO_CUDA(cudaMemcpyAsync(h_done, s->S.done, P * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -627,6 +661,7 @@ void nlo_ip_destroy(nlo_ip* s) {
                   s->d_K, s->d_L, s->d_out, s->d_iout, s->d_keep};
   for (void* b : bufs) if (b) cudaFree(b);
   if (s->h_pin) cudaFreeHost(s->h_pin);
+  s->timer.destroy();
   if (s->st) cudaStreamDestroy(s->st);
   delete s;
 }
@@ -747,9 +782,14 @@ int nlo_ip_solve(nlo_ip* s, const double* w0_host, size_t P, const nlo_ip_option
     NLO_CUDA(cudaMemcpyAsync(s->S.orig, orig.data(), P * sizeof(int), cudaMemcpyHostToDevice, st));
     NLO_CUDA(cudaStreamSynchronize(st));
   }
-  GpuBackend x{s, st};
+  if (!s->timer.ready && s->timer.init()) return 1;
+  s->timer.reset();
+  GpuBackend x{s, st, &s->timer};
   IpStats stats;
   if (ip_solve_loop(x, P, opt, &stats)) return 1;
+  s->timer.mark(PH_COMPACT, st);
+  NLO_CUDA(cudaStreamSynchronize(st));
+  s->timer.collect();
   // results: variable-major on the device -> problem-major on the host (staged through the K buffer)
   auto download = [&](const double* soa, int rows, double* host) -> int {
     if (!host) return 0;
@@ -770,6 +810,7 @@ int nlo_ip_solve(nlo_ip* s, const double* w0_host, size_t P, const nlo_ip_option
   if (stats_out) {
     stats_out->iterations = stats.iterations; stats_out->evaluations = stats.evaluations; stats_out->hessians = stats.hessians;
     stats_out->trials = stats.trials; stats_out->compactions = stats.compactions; stats_out->trial_problems = stats.trial_problems;
+    for (int i = 0; i < PH_COUNT; ++i) stats_out->phase_ms[i] = s->timer.ms[i];
   }
   return 0;
 }

@@ -455,6 +455,8 @@ class DeviceIPSolver:
         _lib.check(self._L.nlo_ip_solve(self._h, w0.ctypes.data, P, C.byref(self.opt), w.ctypes.data, f.ctypes.data, viol.ctypes.data,
                                         err.ctypes.data, iters.ctypes.data, status.ctypes.data, lam.ctypes.data, C.byref(st)))
         self.stats = {k: int(getattr(st, k)) for k in ("iterations", "evaluations", "hessians", "trials", "compactions", "trial_problems")}
+        self.stats["phase_ms"] = dict(zip(("evaluation", "residual", "hessian", "kkt", "step", "line_search", "update", "multipliers", "compaction_output"),
+                                          (round(float(v), 2) for v in st.phase_ms)))
         t = torch.from_numpy
         return IPResult(w=t(w), f=t(f), violation=t(viol), kkt_error=t(err), iterations=t(iters.astype(np.int64)), converged=t(status == 1),
                         lam=t(lam), stalled=t(status == 2))
