@@ -275,16 +275,15 @@ IP_HD void ip_step_body(const IpTables& T, const IpState& S, const IpWork& W, si
   W.accepted[p] = done;
 }
 
-// ---- line search: merit at the trial point; returns 1 if the problem is still not accepted --------------------------------------
-// The trial batch holds only the problems still searching: column q of the trial evaluation (wt32, gt, ft) belongs to problem p.
-// Worker 0 updates accepted / alpha; every worker returns the same verdict.
+// ---- line search ------------------------------------------------------------------------------------------------------------------
+// Armijo test of the l1 merit function at the trial point w + a dw, s + a ds, evaluated in column q_col of the trial batch
+// (wt32 -> gt, ft).  Collective over the team; every worker gets the verdict.  `skip`: nothing to test (the loops are skipped).
 template <class R>
-IP_HD int ip_merit_body(const IpTables& T, const IpState& S, const IpWork& W, size_t p, size_t q_col, R& red) {
-  const int was_accepted = W.accepted[p];
+IP_HD bool ip_merit_ok(const IpTables& T, const IpState& S, const IpWork& W, size_t p, size_t q_col, double a, bool skip, R& red) {
   const size_t ld = S.ld;
-  const double mu = S.mu[p], a = W.alpha[p];
+  const double mu = S.mu[p];
   double c1 = 0.0, bar = 0.0;
-  if (!was_accepted)
+  if (!skip)
     for (int r = red.part(); r < T.n_g; r += red.nparts()) {
       const double gr = (double)W.gt[(size_t)r * ld + q_col];
       if (T.rkind[r] == 0) { c1 += fabs(gr - T.lb[r]); continue; }
@@ -294,15 +293,26 @@ IP_HD int ip_merit_body(const IpTables& T, const IpState& S, const IpWork& W, si
       if (ip_finite(T.lb[r])) bar -= mu * log(ip_max(st - T.lb[r], 1e-300));
       if (ip_finite(T.ub[r])) bar -= mu * log(ip_max(T.ub[r] - st, 1e-300));
     }
-  c1 = red.sum(c1); bar = red.sum(bar);                  // (collectives: reached by every worker of every team, accepted or not)
+  c1 = red.sum(c1); bar = red.sum(bar);                  // (collectives: reached by every worker of every team, tested or not)
   const double phi = (double)W.ft[q_col] + bar + S.nu[p] * c1;
   const double phi0 = W.phi0[p];
-  const bool ok = ip_finite(phi) && phi <= phi0 + 1e-4 * a * ip_min(W.dphi[p], 0.0) + 1e-12 * fabs(phi0);
+  return ip_finite(phi) && phi <= phi0 + 1e-4 * a * ip_min(W.dphi[p], 0.0) + 1e-12 * fabs(phi0);
+}
+
+// One backtracking trial: returns 1 if the problem is still not accepted (its step length is halved for the next trial).
+// The trial batch holds only the problems still searching: column q_col belongs to problem p.  Worker 0 updates accepted / alpha.
+template <class R>
+IP_HD int ip_merit_body(const IpTables& T, const IpState& S, const IpWork& W, size_t p, size_t q_col, R& red) {
+  const int was_accepted = W.accepted[p];
+  const double a = W.alpha[p];
+  const bool ok = ip_merit_ok(T, S, W, p, q_col, a, was_accepted != 0, red);
   red.sync();                                            // every worker has read accepted / alpha
   if (was_accepted) return 0;
   if (red.part() == 0) { if (ok) W.accepted[p] = 1; else W.alpha[p] = 0.5 * a; }
   return ok ? 0 : 1;
 }
+
+#define IP_LS_TRIALS 14       // backtracking trials per iteration (the first at the fraction-to-the-boundary step)
 
 // ---- take the step ------------------------------------------------------------------------------------------------------------
 template <class R>
@@ -465,8 +475,12 @@ struct BtStage {
 // 2 * (NXR * NS + ND) + NS doubles with element stride ss (shared memory on the device).  Writes x (indexed by unknown).  Returns true
 // when every pivot was positive and the solution is finite with max |x| < xmax.
 template <int NS, int NXR>
-IP_HD bool bt_solve_attempt(const BtTables& B, const double* __restrict__ K, double* __restrict__ Lf, const double* __restrict__ rhs,
-                            double* __restrict__ x, size_t ld, size_t p, double delta, double xmax, double* sc, int ss) {
+IP_HD bool bt_solve_attempt(const BtTables& B, const double* __restrict__ Ksrc, double* __restrict__ Lf, const double* __restrict__ rhs_src,
+                            double* __restrict__ x, size_t ld, size_t p_src, size_t p, double delta, double xmax, double* sc, int ss) {
+  // the matrix and the right-hand side are read from column p_src, the factor and the solution are written to column p (several
+  // attempts at one problem with different delta run side by side, each in its own column)
+  const double* K = Ksrc + p_src - p;          // so that K[... * ld + p] addresses column p_src
+  const double* rhs = rhs_src + p_src - p;
   constexpr int ND = NS * (NS + 1) / 2, NO = NXR * NS, SLK = ND + NO, SLL = ND + NO + NS;
   double* sLo = sc;                      // L_{k+1,k} rows
   double* sSn = sc + (size_t)NO * ss;    // Schur complement of the next diagonal block
@@ -600,6 +614,13 @@ IP_HD bool bt_solve_attempt(const BtTables& B, const double* __restrict__ K, dou
   return ok && fin && amax < xmax;
 }
 
+// delta of attempt a (0 = the value that worked last time) of the regularisation search below
+IP_HD double bt_ladder_delta(double delta0, int a) {
+  double d = delta0;
+  for (int i = 0; i < a; ++i) d = ip_min(ip_max(d * 8.0, 1e-4), 1e8);
+  return d;
+}
+
 // Newton step of the condensed KKT system with the inertia-correcting regularisation of the reference solver:
 // delta starts at the value that worked last time, grows x8 (from 1e-4) until the factorisation succeeds (<= 16 attempts), and a
 // problem that needed more than last time is solved once more with twice the value that first passed.
@@ -614,7 +635,7 @@ IP_HD void bt_kkt_body(const BtTables& B, const double* K, double* Lf, const dou
   double dwt = delta0;
   bool good = false;
   for (int attempt = 0; attempt < 16; ++attempt) {
-    good = bt_solve_attempt<NS, NXR>(B, K, Lf, rhs, dw, ld, p, dwt, 1e3, sc, ss);
+    good = bt_solve_attempt<NS, NXR>(B, K, Lf, rhs, dw, ld, p, p, dwt, 1e3, sc, ss);
     if (good) break;
     dwt = ip_min(ip_max(dwt * 8.0, 1e-4), 1e8);
   }
@@ -622,7 +643,7 @@ IP_HD void bt_kkt_body(const BtTables& B, const double* K, double* Lf, const dou
     for (int c = 0; c < n_unknown; ++c) dw[(size_t)c * ld + p] = 0.0;
   if (dwt > delta0) {
     const double d2 = 2.0 * dwt;
-    if (bt_solve_attempt<NS, NXR>(B, K, Lf, rhs, dw_alt, ld, p, d2, 1e3, sc, ss)) {
+    if (bt_solve_attempt<NS, NXR>(B, K, Lf, rhs, dw_alt, ld, p, p, d2, 1e3, sc, ss)) {
       for (int c = 0; c < n_unknown; ++c) dw[(size_t)c * ld + p] = dw_alt[(size_t)c * ld + p];
       dwt = d2;
     }
@@ -635,6 +656,21 @@ IP_HD void bt_kkt_body(const BtTables& B, const double* K, double* Lf, const dou
 // =====================================================================================================================
 struct IpOptions { double tol; int max_iter; double mu0; int ls_multipliers; int compact; int verbose; };
 struct IpStats { int iterations, evaluations, hessians, trials, compactions; long long trial_problems; };
+
+// Backtracking line search, one trial after the other: after the first trial only the problems whose step was refused are evaluated
+// again.  (The CUDA backend evaluates all remaining step lengths of the refused problems in ONE batch instead - same verdicts.)
+template <class X>
+int ip_line_search_sequential(X& x, size_t P, IpStats* st) {
+  size_t n_ls = P;
+  for (int ls = 0; ls < IP_LS_TRIALS; ++ls) {
+    size_t rejected = 0;
+    if (x.trial(n_ls, ls, &rejected)) return 1;
+    ++st->trials; st->trial_problems += (long long)n_ls;
+    if (rejected == 0) break;
+    n_ls = rejected;
+  }
+  return 0;
+}
 
 template <class X>
 int ip_solve_loop(X& x, size_t P0, const IpOptions& opt, IpStats* stats) {
@@ -662,15 +698,7 @@ int ip_solve_loop(X& x, size_t P0, const IpOptions& opt, IpStats* stats) {
     ++st.hessians;
     if (x.kkt_solve(P)) return 1;
     if (x.step(P)) return 1;
-    // backtracking line search: after the first trial only the problems whose step was refused are evaluated again
-    size_t n_ls = P;
-    for (int ls = 0; ls < 14; ++ls) {
-      size_t rejected = 0;
-      if (x.trial(n_ls, ls, &rejected)) return 1;
-      ++st.trials; st.trial_problems += (long long)n_ls;
-      if (rejected == 0) break;
-      n_ls = rejected;
-    }
+    if (x.line_search(P, &st)) return 1;
     if (x.update(P)) return 1;
     if (x.eval_full(P)) return 1;
     ++st.evaluations;

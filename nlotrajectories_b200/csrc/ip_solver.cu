@@ -81,6 +81,35 @@ __global__ void __launch_bounds__(32 * IP_TEAM) ip_merit_kernel(IpTables T, IpSt
   const int rej = ip_merit_body(T, S, W, p, qc_, red);
   if (threadIdx.y == 0 && red.act && rej) next[atomicAdd(W.counters + 1, 1)] = (int)p;
 }
+// ---- the remaining trials of the line search at once: for every refused problem the 13 step lengths a, a/2, ... a/2^12 (a = the
+// halved step the sequential search would try next) are 13 columns of one trial batch; ip_ls_select_kernel takes the first accepted.
+#define IP_LS_LADDER (IP_LS_TRIALS - 1)
+__global__ void __launch_bounds__(256) ip_trial_ladder_kernel(IpState S, IpWork W, size_t n, int n_w, const int* __restrict__ list) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n * IP_LS_LADDER) return;
+  const size_t p = (size_t)list[q / IP_LS_LADDER];
+  const double a = ldexp(W.alpha[p], -(int)(q % IP_LS_LADDER));
+  for (int c = blockIdx.y; c < n_w; c += gridDim.y)
+    W.wt32[(size_t)c * S.ld + q] = (float)(S.w[(size_t)c * S.ld + p] + a * W.dw[(size_t)c * S.ld + p]);
+}
+__global__ void __launch_bounds__(32 * IP_TEAM) ip_merit_ladder_kernel(IpTables T, IpState S, IpWork W, size_t n, const int* __restrict__ list,
+                                                                       int* __restrict__ flags) {
+  IP_TEAM_SETUP(n * IP_LS_LADDER);
+  const size_t p = (size_t)list[qc_ / IP_LS_LADDER];
+  const double a = ldexp(W.alpha[p], -(int)(qc_ % IP_LS_LADDER));
+  const bool ok = ip_merit_ok(T, S, W, p, qc_, a, false, red);
+  if (threadIdx.y == 0 && red.act) flags[qc_] = ok ? 1 : 0;
+}
+__global__ void __launch_bounds__(256) ip_ls_select_kernel(IpWork W, size_t n, const int* __restrict__ list, const int* __restrict__ flags) {
+  const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const size_t p = (size_t)list[r];
+  const double a = W.alpha[p];
+  int j = 0;
+  while (j < IP_LS_LADDER && !flags[r * IP_LS_LADDER + j]) ++j;
+  if (j < IP_LS_LADDER) { W.accepted[p] = 1; W.alpha[p] = ldexp(a, -j); }
+  else W.alpha[p] = ldexp(a, -IP_LS_LADDER);               // refused to the end: the (tiny) last step is taken, as in the sequential search
+}
 __global__ void __launch_bounds__(32 * IP_TEAM) ip_update_kernel(IpTables T, IpState S, IpWork W, size_t P) {
   IP_TEAM_SETUP(P);
   ip_update_body(T, S, W, qc_, red);
@@ -164,7 +193,7 @@ __global__ void __launch_bounds__(BT_TPB) bt_spd_kernel(BtTables B, const double
   extern __shared__ double bt_smem[];
   const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
-  if (!bt_solve_attempt<NS, NXR>(B, K, Lf, rhs, x, ld, p, shift[p], HUGE_VAL, bt_smem + threadIdx.x, BT_TPB))
+  if (!bt_solve_attempt<NS, NXR>(B, K, Lf, rhs, x, ld, p, p, shift[p], HUGE_VAL, bt_smem + threadIdx.x, BT_TPB))
     for (int e = 0; e < n_unknown; ++e) x[(size_t)e * ld + p] = fallback[(size_t)e * ld + p];
 }
 
@@ -390,7 +419,8 @@ __global__ void __launch_bounds__(32 * (NS + 1)) bt_team_kernel(BtTables B, cons
                                                                 const double* __restrict__ rhs, double* __restrict__ x, double* __restrict__ x_alt,
                                                                 size_t P, size_t ld, int n_unknown, const double* __restrict__ delta_in,
                                                                 const int* __restrict__ skip, double* __restrict__ delta_out, int max_attempts,
-                                                                int bump, double xmax, const double* __restrict__ fallback) {
+                                                                int bump, double xmax, const double* __restrict__ fallback,
+                                                                int* __restrict__ fail_list, int* __restrict__ fail_count) {
   using T = BtTeam<NS, NXR>;
   extern __shared__ double bt_team_smem[];
   __shared__ int s_flag[32];
@@ -413,8 +443,10 @@ __global__ void __launch_bounds__(32 * (NS + 1)) bt_team_kernel(BtTables B, cons
       else dwt = ip_min(ip_max(dwt * 8.0, 1e-4), 1e8);
     }
   }
-  if (state == 0)                                            // every attempt failed
+  if (state == 0) {                                          // every attempt failed
     for (int c = w; c < n_unknown; c += T::NW) x[(size_t)c * ld + p] = fallback ? fallback[(size_t)c * ld + p] : 0.0;
+    if (fail_list && w == 0) fail_list[atomicAdd(fail_count, 1)] = (int)p;
+  }
   if (bump) {
     // a problem that needed more regularisation than last time is solved once more with twice the value that first passed
     const bool again = in_range && !skipped && dwt > d0;
@@ -432,7 +464,7 @@ __global__ void __launch_bounds__(32 * (NS + 1)) bt_team_kernel(BtTables B, cons
 template <int NS, int NXR>
 int launch_bt_team(const BtTables& B, const double* K, double* Lf, const double* rhs, double* x, double* x_alt, size_t P, size_t ld,
                    int n_unknown, const double* delta_in, const int* skip, double* delta_out, int max_attempts, int bump, double xmax,
-                   const double* fallback, int device, cudaStream_t st) {
+                   const double* fallback, int device, cudaStream_t st, int* fail_list = nullptr, int* fail_count = nullptr) {
   using T = BtTeam<NS, NXR>;
   static bool attr[64] = {false};
   if (!attr[device & 63]) {
@@ -440,11 +472,67 @@ int launch_bt_team(const BtTables& B, const double* K, double* Lf, const double*
     attr[device & 63] = true;
   }
   bt_team_kernel<NS, NXR><<<(unsigned)((P + 31) / 32), dim3(32, T::NW), T::smem_bytes, st>>>(B, K, Lf, rhs, x, x_alt, P, ld, n_unknown, delta_in, skip,
-                                                                                          delta_out, max_attempts, bump, xmax, fallback);
+                                                                                          delta_out, max_attempts, bump, xmax, fallback, fail_list, fail_count);
   NLO_CHECK_LAUNCH();
   return 0;
 }
-inline bool ip_thread_kkt() { static const bool v = getenv("NLO_B200_IP_THREAD_KKT") != nullptr; return v; }   // A / B switch: one thread per problem
+
+// ---- the regularisation search for the problems whose first factorisation failed: all remaining attempts AT ONCE -------------------
+// The search of bt_kkt_body is sequential per problem (delta x8 until the Cholesky succeeds, then once more with twice that value),
+// and in a batch of thousands some problem needs ten or more attempts in almost every iteration: with the attempts inside one kernel
+// the whole batch waited ~1 ms per attempt of its slowest member (72 % of a benchmark_6 x 8,192 solve).  Here every failed problem gets
+// 32 lanes: lane a - 1 (a = 1..15) factorises with the delta of attempt a, lane 16 + a - 1 with twice that; bt_select_kernel then takes
+// the first success in the order of the sequential search, so the result is the same and the cost is one more attempt, not fifteen.
+template <int NS, int NXR>
+__global__ void __launch_bounds__(BT_TPB) bt_ladder_kernel(BtTables B, const double* __restrict__ K, double* __restrict__ Lf,
+                                                           const double* __restrict__ rhs, double* __restrict__ xbuf, size_t ld,
+                                                           const int* __restrict__ list, size_t n_list, const double* __restrict__ delta_in,
+                                                           int* __restrict__ flags) {
+  extern __shared__ double bt_smem[];
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_list * 32) return;
+  const size_t prob = (size_t)list[q >> 5];
+  const int i = (int)(q & 31), a = (i & 15) + 1;
+  if (a > 15) { flags[q] = 0; return; }
+  const double d = bt_ladder_delta(delta_in[prob], a) * (i >= 16 ? 2.0 : 1.0);
+  flags[q] = bt_solve_attempt<NS, NXR>(B, K, Lf, rhs, xbuf, ld, prob, q, d, 1e3, bt_smem + threadIdx.x, BT_TPB) ? 1 : 0;
+}
+// one warp per failed problem: the first successful attempt (and its doubled twin when that succeeded too) -> dw, delta
+__global__ void __launch_bounds__(256) bt_select_kernel(const int* __restrict__ list, size_t n_list, const int* __restrict__ flags,
+                                                        const double* __restrict__ xbuf, double* __restrict__ dw, size_t ld, int n_unknown,
+                                                        const double* __restrict__ delta_in, double* __restrict__ delta_out) {
+  const size_t wq = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wq >= n_list) return;
+  const size_t prob = (size_t)list[wq], q0 = wq * 32;
+  const unsigned m = __ballot_sync(0xffffffffu, flags[q0 + lane] != 0);
+  const unsigned first = m & 0x7fffu;
+  const double d0 = delta_in[prob];
+  if (!first) {                                              // all sixteen attempts failed: no step, delta as the sequential search leaves it
+    for (int c = lane; c < n_unknown; c += 32) dw[(size_t)c * ld + prob] = 0.0;
+    if (lane == 0) delta_out[prob] = bt_ladder_delta(d0, 16);
+    return;
+  }
+  const int i = __ffs(first) - 1;
+  const bool twice = (m >> (16 + i)) & 1u;
+  const size_t src = q0 + (twice ? 16 + i : i);
+  for (int c = lane; c < n_unknown; c += 32) dw[(size_t)c * ld + prob] = xbuf[(size_t)c * ld + src];
+  if (lane == 0) delta_out[prob] = bt_ladder_delta(d0, i + 1) * (twice ? 2.0 : 1.0);
+}
+template <int NS, int NXR>
+int launch_bt_ladder(const BtTables& B, const double* K, double* Lf, const double* rhs, double* xbuf, size_t ld, const int* list, size_t n_list,
+                     const double* delta_in, int* flags, int device, cudaStream_t st) {
+  constexpr size_t smem = (size_t)(2 * (NXR * NS + NS * (NS + 1) / 2) + NS) * BT_TPB * sizeof(double);
+  static bool attr[64] = {false};
+  if (!attr[device & 63]) {
+    NLO_CUDA(cudaFuncSetAttribute(bt_ladder_kernel<NS, NXR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr[device & 63] = true;
+  }
+  bt_ladder_kernel<NS, NXR><<<(unsigned)((n_list * 32 + BT_TPB - 1) / BT_TPB), BT_TPB, smem, st>>>(B, K, Lf, rhs, xbuf, ld, list, n_list, delta_in, flags);
+  NLO_CHECK_LAUNCH();
+  return 0;
+}
+inline bool ip_thread_kkt() { static const bool v = [] { const char* e = getenv("NLO_B200_IP_THREAD_KKT"); return e && *e && *e != '0'; }(); return v; }   // A / B switch: one thread per problem
 
 // block sizes of the six dynamics models (core/dynamics.py:151-158) with and without slack: NS = nx + nu + slack, NXR = nx
 #define IP_KKT_SIZES(X) X(5, 3) X(6, 3) X(6, 4) X(7, 4) X(7, 5) X(8, 5) X(9, 7) X(10, 7)
@@ -521,6 +609,33 @@ int upload(V** dst, const std::vector<V>& v) {
   return 0;
 }
 
+// Regularised Newton step for P problems whose matrix blocks are assembled in s->d_K: one attempt for everybody (team kernel), then
+// every remaining attempt of the failed ones side by side (ladder + select kernels).  NLO_B200_IP_THREAD_KKT=1 selects the sequential
+// search inside one kernel (one thread per problem) instead - same results, for A / B timing.
+template <int NS, int NXR>
+int ip_kkt_device(nlo_ip* s, const double* rhs, double* dw, size_t P, size_t ld, const double* delta_in, const int* skip, double* delta_out,
+                  cudaStream_t st) {
+  const BtTables& B = s->KB;
+  if (ip_thread_kkt() || ld < 32)
+    return launch_bt_kkt<NS, NXR>(B, s->d_K, s->d_L, rhs, dw, s->W.dw_alt, P, ld, s->T.n_w, delta_in, skip, delta_out, s->device, st);
+  int* fail_count = s->W.counters + 2;
+  int* fail_list = s->W.ls_list[0];
+  int* flags = s->W.ls_list[1];
+  NLO_CUDA(cudaMemsetAsync(fail_count, 0, sizeof(int), st));
+  if (launch_bt_team<NS, NXR>(B, s->d_K, s->d_L, rhs, dw, s->W.dw_alt, P, ld, s->T.n_w, delta_in, skip, delta_out, 1, 0, 1e3, nullptr, s->device, st,
+                              fail_list, fail_count)) return 1;
+  NLO_CUDA(cudaMemcpyAsync(s->h_pin, s->W.counters, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  NLO_CUDA(cudaStreamSynchronize(st));
+  const size_t n_fail = (size_t)s->h_pin[2], chunk = ld / 32;
+  for (size_t off = 0; off < n_fail; off += chunk) {
+    const size_t n = std::min(chunk, n_fail - off);
+    if (launch_bt_ladder<NS, NXR>(B, s->d_K, s->d_L, rhs, s->W.dw_alt, ld, fail_list + off, n, delta_in, flags, s->device, st)) return 1;
+    bt_select_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(fail_list + off, n, flags, s->W.dw_alt, dw, ld, s->T.n_w, delta_in, delta_out);
+    NLO_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
 // the backend ip_solve_loop drives: every method enqueues kernels on the solver's stream; the few that return a count synchronise
 struct GpuBackend {
   nlo_ip* s;
@@ -566,10 +681,7 @@ struct GpuBackend {
     if (assemble(s->KB, P)) return 1;
 #define IP_CASE(NS_, NXR_)                                                                                                      \
     if (s->KB.NS == NS_ && s->KB.NXR == NXR_)                                                                                   \
-      return ip_thread_kkt() ? launch_bt_kkt<NS_, NXR_>(s->KB, s->d_K, s->d_L, s->W.rhs, s->W.dw, s->W.dw_alt, P, s->cap, s->T.n_w, s->S.delta_w,   \
-                                                        s->S.done, s->W.dwt, s->device, st)                                     \
-                             : launch_bt_team<NS_, NXR_>(s->KB, s->d_K, s->d_L, s->W.rhs, s->W.dw, s->W.dw_alt, P, s->cap, s->T.n_w, s->S.delta_w,  \
-                                                         s->S.done, s->W.dwt, 16, 1, 1e3, nullptr, s->device, st);
+      return ip_kkt_device<NS_, NXR_>(s, s->W.rhs, s->W.dw, P, s->cap, s->S.delta_w, s->S.done, s->W.dwt, st);
     IP_KKT_SIZES(IP_CASE)
 #undef IP_CASE
     return nlo_fail("interior point: no factorisation kernel for stage blocks of %d unknowns (%d states)", s->KB.NS, s->KB.NXR);
@@ -590,6 +702,29 @@ struct GpuBackend {
     ip_merit_kernel<<<g1(n), b1(), 0, st>>>(s->T, s->S, s->W, n, list, s->W.ls_list[ls & 1]);
     NLO_CHECK_LAUNCH();
     return read_counter(1, rejected);
+  }
+  int line_search(size_t P, IpStats* stats) {
+    static const bool sequential = [] { const char* e = getenv("NLO_B200_IP_SEQ_LS"); return e && *e && *e != '0'; }();
+    if (sequential || s->cap < 2 * IP_LS_LADDER) return ip_line_search_sequential(*this, P, stats);
+    size_t rejected = 0;
+    if (trial(P, 0, &rejected)) return 1;                    // refused problems: ls_list[0], step length already halved
+    ++stats->trials; stats->trial_problems += (long long)P;
+    const int* list = s->W.ls_list[0];
+    int* flags = s->W.ls_list[1];
+    const size_t chunk = s->cap / IP_LS_LADDER;
+    for (size_t off = 0; off < rejected; off += chunk) {
+      const size_t n = std::min(chunk, rejected - off), cols = n * IP_LS_LADDER;
+      tm->mark(PH_LINESEARCH, st);
+      ip_trial_ladder_kernel<<<dim3((unsigned)((cols + 255) / 256), 32), 256, 0, st>>>(s->S, s->W, n, s->T.n_w, list + off);
+      NLO_CHECK_LAUNCH();
+      if (nlo_nlp_eval(s->nlp, s->W.wt32, cols, s->cap, s->W.gt, nullptr, s->W.ft, nullptr, st)) return 1;
+      ip_merit_ladder_kernel<<<g1(cols), b1(), 0, st>>>(s->T, s->S, s->W, n, list + off, flags);
+      NLO_CHECK_LAUNCH();
+      ip_ls_select_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s->W, n, list + off, flags);
+      NLO_CHECK_LAUNCH();
+      ++stats->trials; stats->trial_problems += (long long)cols;
+    }
+    return 0;
   }
   int update(size_t P) {
     tm->mark(PH_UPDATE, st);
@@ -829,10 +964,7 @@ int nlo_ip_kkt_step(nlo_ip* s, const float* jac, const float* hess, const double
   bt_assemble_kernel<<<dim3((unsigned)((P + 255) / 256), (unsigned)std::min(n_slots, 65535)), 256, 0, st>>>(B, jac, hess, omega, s->d_K, P, ld);
   NLO_CHECK_LAUNCH();
 #define IP_CASE(NS_, NXR_)                                                                                                      \
-  if (B.NS == NS_ && B.NXR == NXR_)                                                                                             \
-    return ip_thread_kkt() ? launch_bt_kkt<NS_, NXR_>(B, s->d_K, s->d_L, rhs, dw, s->W.dw_alt, P, ld, s->T.n_w, delta_in, nullptr, delta_out, s->device, st) \
-                           : launch_bt_team<NS_, NXR_>(B, s->d_K, s->d_L, rhs, dw, s->W.dw_alt, P, ld, s->T.n_w, delta_in, nullptr, delta_out, 16, 1, 1e3,  \
-                                                       nullptr, s->device, st);
+  if (B.NS == NS_ && B.NXR == NXR_) return ip_kkt_device<NS_, NXR_>(s, rhs, dw, P, ld, delta_in, nullptr, delta_out, st);
   IP_KKT_SIZES(IP_CASE)
 #undef IP_CASE
   return nlo_fail("interior point: no factorisation kernel for stage blocks of %d unknowns (%d states)", B.NS, B.NXR);

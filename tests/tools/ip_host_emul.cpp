@@ -56,7 +56,7 @@ template <int NS, int NXR>
 void spd_all(Emul& e, size_t P) {
   double sc[2 * (NXR * NS + NS * (NS + 1) / 2) + NS];
   for (size_t p = 0; p < P; ++p)
-    if (!bt_solve_attempt<NS, NXR>(e.LB, e.K.data(), e.L.data(), e.W.v, e.W.lam_ls, e.ld, p, e.W.eps_ls[p], HUGE_VAL, sc, 1))
+    if (!bt_solve_attempt<NS, NXR>(e.LB, e.K.data(), e.L.data(), e.W.v, e.W.lam_ls, e.ld, p, p, e.W.eps_ls[p], HUGE_VAL, sc, 1))
       for (int q = 0; q < e.T.nE; ++q) e.W.lam_ls[(size_t)q * e.ld + p] = e.S.lamE[(size_t)q * e.ld + p];
 }
 
@@ -106,6 +106,7 @@ struct HostBackend {
     *rejected = m;
     return 0;
   }
+  int line_search(size_t P, IpStats* st) { return ip_line_search_sequential(*this, P, st); }
   int update(size_t P) { for (size_t p = 0; p < P; ++p) ip_update_body(e.T, e.S, e.W, p, solo); return 0; }
   int lsq_multipliers(size_t P) {
     if (e.T.nE == 0) return 0;
