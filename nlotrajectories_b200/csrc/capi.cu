@@ -594,7 +594,7 @@ static int ensure_scratch(const nlo_nlp* p, NlpScratch& sc, size_t P) {
 
 static int nlp_eval_on(nlo_nlp* p, NlpScratch& sc, const float* w, size_t P, size_t ld, float* g, float* jac, float* f, float* grad_f,
                        cudaStream_t st) {
-  if ((g || jac) && ensure_scratch(p, sc, P)) return 1;
+  if ((g || jac) && p->L.sdf_mode == NLO_SDF_LEARNED && ensure_scratch(p, sc, P)) return 1;   // (analytic obstacles need no scratch)
   if (nlo_nlp_launch_assembly(p, sc, w, P, ld, g, jac, f, grad_f, st, 0)) return 1;
   if (g || jac) {
     if (p->L.sdf_mode == NLO_SDF_LEARNED) {

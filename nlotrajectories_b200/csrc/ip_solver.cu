@@ -250,37 +250,38 @@ __device__ __forceinline__ bool bt_team_attempt(const BtTables& B, const double*
 #define SM(slot) sm[(slot) * 32 + lane]
   const int nb = B.nb;
   bool ok = true;
-  double dinv[NS], b[NS], y[NS], lo[NS];
+  // Three register rows per thread, named by the role of its warp (a union: the row warps never touch the right-hand side's values):
+  //   row warp w < NS:        r1 = next diagonal block's row (dn)   r2 = sub-diagonal block's row (on)   r3 = its row of L_{k+1,k} (lo)
+  //   right-hand-side warp:   r1 = next block's right-hand side (bn) r2 = current right-hand side (b)     r3 = y_k
+  double dinv[NS], r1[NS], r2[NS], r3[NS];
+  const bool rhs_warp = (w == NS);
 #pragma unroll
-  for (int i = 0; i < NS; ++i) { b[i] = 0.0; y[i] = 0.0; lo[i] = 0.0; }
+  for (int i = 0; i < NS; ++i) { r1[i] = 0.0; r2[i] = 0.0; r3[i] = 0.0; }
   __syncthreads();                                           // the previous attempt's readers are done with shared memory
-  if (w < NS) {
+  if (!rhs_warp) {
     const bool real = B.var[w] >= 0;
 #pragma unroll
     for (int j = 0; j < NS; ++j)
       if (j <= w) SM(T::S + BT_LI(w, j)) = K[(size_t)BT_LI(w, j) * ld + p] + ((j == w && real) ? delta : 0.0);
   } else {
 #pragma unroll
-    for (int i = 0; i < NS; ++i) { const int u = B.var[i]; b[i] = u >= 0 ? rhs[(size_t)u * ld + p] : 0.0; }
+    for (int i = 0; i < NS; ++i) { const int u = B.var[i]; r2[i] = u >= 0 ? rhs[(size_t)u * ld + p] : 0.0; }
   }
   for (int k = 0; k < nb; ++k) {
     // rows of the next stage travel while this block is factorised
-    double dn[NS], on[NS], bn[NS];
-#pragma unroll
-    for (int i = 0; i < NS; ++i) { dn[i] = 0.0; on[i] = 0.0; bn[i] = 0.0; }
     if (k < nb - 1) {
       const double* Kn = K + (size_t)(k + 1) * SLK * ld + p;
       const double* Ok = K + ((size_t)k * SLK + ND) * ld + p;
-      if (w < NS) {
+      if (!rhs_warp) {
 #pragma unroll
-        for (int j = 0; j < NS; ++j) if (j <= w) dn[j] = Kn[(size_t)BT_LI(w, j) * ld];
+        for (int j = 0; j < NS; ++j) if (j <= w) r1[j] = Kn[(size_t)BT_LI(w, j) * ld];
         if (w < NXR) {
 #pragma unroll
-          for (int j = 0; j < NS; ++j) on[j] = Ok[(size_t)(w * NS + j) * ld];
+          for (int j = 0; j < NS; ++j) r2[j] = Ok[(size_t)(w * NS + j) * ld];
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < NS; ++i) { const int u = B.var[(k + 1) * NS + i]; bn[i] = u >= 0 ? rhs[(size_t)u * ld + p] : 0.0; }
+        for (int i = 0; i < NS; ++i) { const int u = B.var[(k + 1) * NS + i]; r1[i] = u >= 0 ? rhs[(size_t)u * ld + p] : 0.0; }
       }
     }
     // Cholesky, column by column: every thread of the lane follows the pivots (so `ok` and 1 / pivot are known to all rows)
@@ -289,10 +290,9 @@ __device__ __forceinline__ bool bt_team_attempt(const BtTables& B, const double*
       __syncthreads();
       double d = SM(T::S + BT_LI(j, j));
       if (!(d > 0.0) || !ip_finite(d)) { ok = false; d = 1.0; }
-      const double sd = sqrt(d);
-      dinv[j] = 1.0 / sd;
+      dinv[j] = rsqrt(d);                                  // one dependent sequence instead of sqrt + divide
       double lwj = 0.0;
-      if (w == j) SM(T::LD + j) = sd;
+      if (w == j) SM(T::LD + j) = d * dinv[j];
       if (w > j && w < NS) { lwj = SM(T::S + BT_LI(w, j)) * dinv[j]; SM(T::S + BT_LI(w, j)) = lwj; }
       __syncthreads();
       if (w > j && w < NS) {
@@ -303,17 +303,17 @@ __device__ __forceinline__ bool bt_team_attempt(const BtTables& B, const double*
     __syncthreads();
     const bool st = store && ok;
     double* Lk = Lf + (size_t)k * SLL * ld + p;
-    if (w < NS) {
+    if (!rhs_warp) {
       if (k < nb - 1 && w < NXR) {                           // row w of L_{k+1,k} = O_k L_kk^-T
 #pragma unroll
         for (int j = 0; j < NS; ++j) {
-          double v = on[j];
+          double v = r2[j];
 #pragma unroll
-          for (int m = 0; m < NS; ++m) if (m < j) v -= lo[m] * SM(T::S + BT_LI(j, m));
-          lo[j] = v * dinv[j];
+          for (int m = 0; m < NS; ++m) if (m < j) v -= r3[m] * SM(T::S + BT_LI(j, m));
+          r3[j] = v * dinv[j];
         }
 #pragma unroll
-        for (int j = 0; j < NS; ++j) { SM(T::LO + w * NS + j) = lo[j]; if (st) Lk[(size_t)(ND + w * NS + j) * ld] = lo[j]; }
+        for (int j = 0; j < NS; ++j) { SM(T::LO + w * NS + j) = r3[j]; if (st) Lk[(size_t)(ND + w * NS + j) * ld] = r3[j]; }
       }
       if (st) {                                              // row w of L_kk
 #pragma unroll
@@ -323,25 +323,25 @@ __device__ __forceinline__ bool bt_team_attempt(const BtTables& B, const double*
     } else {                                                 // y = L^-1 b
 #pragma unroll
       for (int i = 0; i < NS; ++i) {
-        double v = b[i];
+        double v = r2[i];
 #pragma unroll
-        for (int m = 0; m < NS; ++m) if (m < i) v -= SM(T::S + BT_LI(i, m)) * y[m];
-        y[i] = v * dinv[i];
+        for (int m = 0; m < NS; ++m) if (m < i) v -= SM(T::S + BT_LI(i, m)) * r3[m];
+        r3[i] = v * dinv[i];
       }
 #pragma unroll
-      for (int i = 0; i < NS; ++i) { SM(T::Y + i) = y[i]; if (st) Lk[(size_t)(ND + NO + i) * ld] = y[i]; }
+      for (int i = 0; i < NS; ++i) { SM(T::Y + i) = r3[i]; if (st) Lk[(size_t)(ND + NO + i) * ld] = r3[i]; }
     }
     __syncthreads();
     if (k == nb - 1) break;
-    if (w < NS) {                                            // row w of the next diagonal block's Schur complement
+    if (!rhs_warp) {                                         // row w of the next diagonal block's Schur complement
       const bool real = B.var[(k + 1) * NS + w] >= 0;
 #pragma unroll
       for (int j = 0; j < NS; ++j) {
         if (j > w) continue;
-        double v = dn[j];
+        double v = r1[j];
         if (w < NXR) {
 #pragma unroll
-          for (int m = 0; m < NS; ++m) v -= lo[m] * SM(T::LO + j * NS + m);
+          for (int m = 0; m < NS; ++m) v -= r3[m] * SM(T::LO + j * NS + m);
         }
         if (j == w && real) v += delta;
         SM(T::S + BT_LI(w, j)) = v;
@@ -349,25 +349,24 @@ __device__ __forceinline__ bool bt_team_attempt(const BtTables& B, const double*
     } else {
 #pragma unroll
       for (int i = 0; i < NS; ++i) {
-        double v = bn[i];
+        double v = r1[i];
         if (i < NXR) {
 #pragma unroll
-          for (int m = 0; m < NS; ++m) v -= SM(T::LO + i * NS + m) * y[m];
+          for (int m = 0; m < NS; ++m) v -= SM(T::LO + i * NS + m) * r3[m];
         }
-        b[i] = v;
+        r2[i] = v;
       }
     }
   }
   // backward pass: the factor blocks of stage k come back into shared memory row by row, the right-hand-side warp substitutes
-  double xp[NS];
+  // (r1 = y_k - L_{k+1,k}^T x_{k+1}, r2 = x_{k+1} then x_k)
   double amax = 0.0;
   bool fin = true;
 #pragma unroll
-  for (int i = 0; i < NS; ++i) xp[i] = 0.0;
+  for (int i = 0; i < NS; ++i) r2[i] = 0.0;
   for (int k = nb - 1; k >= 0; --k) {
     const double* Lk = Lf + (size_t)k * SLL * ld + p;
-    double t[NS];
-    if (w < NS) {
+    if (!rhs_warp) {
 #pragma unroll
       for (int j = 0; j < NS; ++j) if (j < w) SM(T::S + BT_LI(w, j)) = Lk[(size_t)BT_LI(w, j) * ld];
       SM(T::LD + w) = Lk[(size_t)BT_LI(w, w) * ld];
@@ -377,30 +376,30 @@ __device__ __forceinline__ bool bt_team_attempt(const BtTables& B, const double*
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < NS; ++i) t[i] = Lk[(size_t)(ND + NO + i) * ld];
+      for (int i = 0; i < NS; ++i) r1[i] = Lk[(size_t)(ND + NO + i) * ld];
     }
     __syncthreads();
-    if (w == NS) {
+    if (rhs_warp) {
       if (k < nb - 1) {
 #pragma unroll
         for (int i = 0; i < NXR; ++i)
 #pragma unroll
-          for (int j = 0; j < NS; ++j) t[j] -= SM(T::LO + i * NS + j) * xp[i];
+          for (int j = 0; j < NS; ++j) r1[j] -= SM(T::LO + i * NS + j) * r2[i];
       }
 #pragma unroll
       for (int i = NS - 1; i >= 0; --i) {
-        double v = t[i];
+        double v = r1[i];
 #pragma unroll
-        for (int m = 0; m < NS; ++m) if (m > i) v -= SM(T::S + BT_LI(m, i)) * xp[m];
-        xp[i] = v / SM(T::LD + i);
+        for (int m = 0; m < NS; ++m) if (m > i) v -= SM(T::S + BT_LI(m, i)) * r2[m];
+        r2[i] = v / SM(T::LD + i);
       }
 #pragma unroll
       for (int i = 0; i < NS; ++i) {
         const int u = B.var[k * NS + i];
         if (u >= 0) {
-          if (store && ok) x[(size_t)u * ld + p] = xp[i];
-          if (!ip_finite(xp[i])) fin = false;
-          amax = ip_max(amax, fabs(xp[i]));
+          if (store && ok) x[(size_t)u * ld + p] = r2[i];
+          if (!ip_finite(r2[i])) fin = false;
+          amax = ip_max(amax, fabs(r2[i]));
         }
       }
     }
@@ -415,7 +414,7 @@ __device__ __forceinline__ bool bt_team_attempt(const BtTables& B, const double*
 // KKT mode: max_attempts 16, bump 1, xmax 1e3, fallback NULL (zero step on failure), delta_out written.
 // SPD mode (least-squares multipliers): one attempt with the given shift, no bump, fallback = the vector kept on failure.
 template <int NS, int NXR>
-__global__ void __launch_bounds__(32 * (NS + 1)) bt_team_kernel(BtTables B, const double* __restrict__ K, double* __restrict__ Lf,
+__global__ void __launch_bounds__(32 * (NS + 1), 2) bt_team_kernel(BtTables B, const double* __restrict__ K, double* __restrict__ Lf,
                                                                 const double* __restrict__ rhs, double* __restrict__ x, double* __restrict__ x_alt,
                                                                 size_t P, size_t ld, int n_unknown, const double* __restrict__ delta_in,
                                                                 const int* __restrict__ skip, double* __restrict__ delta_out, int max_attempts,

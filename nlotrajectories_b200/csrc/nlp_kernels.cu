@@ -221,57 +221,75 @@ __device__ __forceinline__ void nlp_points_body(const NlpDev& L, const float* __
   }
 }
 
-// ---- K5: analytic circles / squares + soft-min union (core/sdf/casadi.py:33-41, 69-115, 385-386) ----------------
-__global__ void __launch_bounds__(256) nlp_circles_kernel(NlpDev L, const float* __restrict__ px, const float* __restrict__ py, size_t n,
-                                                          float* __restrict__ s, float* __restrict__ jx, float* __restrict__ jy) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const NloJet u = nlo_union_jet(L.n_circles, L.okind, L.circles, px[i], py[i]);
-    s[i] = u.v; jx[i] = u.dx; jy[i] = u.dy;
+// ---- K3b: SDF constraint rows + chain rule to the pose (core/geometry.py:63-67, 107-117) --------------------
+// rows of knot k of problem p from the SDF values / gradients of its footprint points (sv, gx, gy; sn, cs = sin / cos of the heading)
+__device__ __forceinline__ void nlp_rows_emit(const NlpDev& L, const float* __restrict__ w, size_t P, size_t ld, float* __restrict__ g,
+                                              float* __restrict__ jac, const int k, const size_t p, const float sn, const float cs,
+                                              const float* sv, const float* gx, const float* gy) {
+  const int* __restrict__ nz = L.nzmap + L.e_off_sdf + k * L.rows_per_knot * L.nnz_sdf_row;
+  if (L.shape == NLO_SHAPE_DOT) {
+    if (g) g[(size_t)(L.g_off_sdf + k) * ld + p] = sv[0];
+    if (jac) { jac[(size_t)nz[0] * ld + p] = gx[0]; jac[(size_t)nz[1] * ld + p] = gy[0]; }
+    return;
+  }
+  float gt[4];
+  for (int b = 0; b < L.nb; ++b) {
+    const float dpx = -sn * L.bx[b] - cs * L.by[b], dpy = cs * L.bx[b] - sn * L.by[b];
+    gt[b] = gx[b] * dpx + gy[b] * dpy;
+  }
+  if (L.use_slack) {
+    // soft_min + slack (core/utils.py:28-31: un-stabilised)
+    float e[4], sum = 0.f;
+    for (int b = 0; b < L.nb; ++b) { e[b] = expf(-NLO_ALPHA * sv[b]); sum += e[b]; }
+    const float inv = 1.f / sum;
+    float rx = 0.f, ry = 0.f, rt = 0.f;
+    for (int b = 0; b < L.nb; ++b) { const float om = e[b] * inv; rx += om * gx[b]; ry += om * gy[b]; rt += om * gt[b]; }
+    if (g) g[(size_t)(L.g_off_sdf + k) * ld + p] = -logf(sum) / NLO_ALPHA + w[(size_t)(L.n_X + L.n_U + k) * ld + p];
+    if (jac) {
+      jac[(size_t)nz[0] * ld + p] = rx; jac[(size_t)nz[1] * ld + p] = ry; jac[(size_t)nz[2] * ld + p] = rt;
+      jac[(size_t)nz[3] * ld + p] = 1.f;
+    }
+  } else {
+    for (int b = 0; b < L.nb; ++b) {
+      if (g) g[(size_t)(L.g_off_sdf + k * L.nb + b) * ld + p] = sv[b];
+      if (jac) {
+        jac[(size_t)nz[3 * b + 0] * ld + p] = gx[b]; jac[(size_t)nz[3 * b + 1] * ld + p] = gy[b];
+        jac[(size_t)nz[3 * b + 2] * ld + p] = gt[b];
+      }
+    }
   }
 }
 
-// ---- K3b: SDF constraint rows + chain rule to the pose (core/geometry.py:63-67, 107-117) --------------------
 __global__ void __launch_bounds__(256) nlp_sdf_rows_kernel(NlpDev L, const float* __restrict__ w, size_t P, size_t ld,
                                                            const float* __restrict__ s, const float* __restrict__ jx,
                                                            const float* __restrict__ jy, float* __restrict__ g, float* __restrict__ jac) {
   const int k = blockIdx.y;
   for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (size_t)gridDim.x * blockDim.x) {
-    const int* __restrict__ nz = L.nzmap + L.e_off_sdf + k * L.rows_per_knot * L.nnz_sdf_row;
-    if (L.shape == NLO_SHAPE_DOT) {
-      const size_t q = (size_t)k * P + p;
-      if (g) g[(size_t)(L.g_off_sdf + k) * ld + p] = s[q];
-      if (jac) { jac[(size_t)nz[0] * ld + p] = jx[q]; jac[(size_t)nz[1] * ld + p] = jy[q]; }
-      continue;
-    }
-    float sn, cs; sincosf(w[(size_t)(k * L.nx + 2) * ld + p], &sn, &cs);
-    float sv[4], gx[4], gy[4], gt[4];
+    float sn = 0.f, cs = 1.f, sv[4], gx[4], gy[4];
+    if (L.shape != NLO_SHAPE_DOT) sincosf(w[(size_t)(k * L.nx + 2) * ld + p], &sn, &cs);
     for (int b = 0; b < L.nb; ++b) {
       const size_t q = (size_t)(k * L.nb + b) * P + p;
       sv[b] = s[q]; gx[b] = jx[q]; gy[b] = jy[q];
-      const float dpx = -sn * L.bx[b] - cs * L.by[b], dpy = cs * L.bx[b] - sn * L.by[b];
-      gt[b] = gx[b] * dpx + gy[b] * dpy;
     }
-    if (L.use_slack) {
-      // soft_min + slack (core/utils.py:28-31: un-stabilised)
-      float e[4], sum = 0.f;
-      for (int b = 0; b < L.nb; ++b) { e[b] = expf(-NLO_ALPHA * sv[b]); sum += e[b]; }
-      const float inv = 1.f / sum;
-      float rx = 0.f, ry = 0.f, rt = 0.f;
-      for (int b = 0; b < L.nb; ++b) { const float om = e[b] * inv; rx += om * gx[b]; ry += om * gy[b]; rt += om * gt[b]; }
-      if (g) g[(size_t)(L.g_off_sdf + k) * ld + p] = -logf(sum) / NLO_ALPHA + w[(size_t)(L.n_X + L.n_U + k) * ld + p];
-      if (jac) {
-        jac[(size_t)nz[0] * ld + p] = rx; jac[(size_t)nz[1] * ld + p] = ry; jac[(size_t)nz[2] * ld + p] = rt;
-        jac[(size_t)nz[3] * ld + p] = 1.f;
-      }
-    } else {
-      for (int b = 0; b < L.nb; ++b) {
-        if (g) g[(size_t)(L.g_off_sdf + k * L.nb + b) * ld + p] = sv[b];
-        if (jac) {
-          jac[(size_t)nz[3 * b + 0] * ld + p] = gx[b]; jac[(size_t)nz[3 * b + 1] * ld + p] = gy[b];
-          jac[(size_t)nz[3 * b + 2] * ld + p] = gt[b];
-        }
-      }
+    nlp_rows_emit(L, w, P, ld, g, jac, k, p, sn, cs, sv, gx, gy);
+  }
+}
+
+// ---- K3 + K5 in one pass for the analytic obstacles (solver.mode casadi): footprint points, soft-min union of circles / squares and
+// the constraint rows of knot k, without any scratch between them (benchmarks 1, 2, 5) -----------------------------------------------
+__device__ __forceinline__ void nlp_analytic_rows_body(const NlpDev& L, const float* __restrict__ w, size_t P, size_t ld,
+                                                       float* __restrict__ g, float* __restrict__ jac, const int k) {
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (size_t)gridDim.x * blockDim.x) {
+    const float x = w[(size_t)(k * L.nx + 0) * ld + p], y = w[(size_t)(k * L.nx + 1) * ld + p];
+    float sn = 0.f, cs = 1.f, sv[4], gx[4], gy[4];
+    if (L.shape != NLO_SHAPE_DOT) sincosf(w[(size_t)(k * L.nx + 2) * ld + p], &sn, &cs);
+    for (int b = 0; b < L.nb; ++b) {
+      const float px = L.shape == NLO_SHAPE_DOT ? x : x + cs * L.bx[b] - sn * L.by[b];
+      const float py = L.shape == NLO_SHAPE_DOT ? y : y + sn * L.bx[b] + cs * L.by[b];
+      const NloJet u = nlo_union_jet(L.n_circles, L.okind, L.circles, px, py);
+      sv[b] = u.v; gx[b] = u.dx; gy[b] = u.dy;
     }
+    nlp_rows_emit(L, w, P, ld, g, jac, k, p, sn, cs, sv, gx, gy);
   }
 }
 
@@ -357,8 +375,10 @@ __device__ __forceinline__ void nlp_grad_body(const NlpDev& L, const float* __re
 }
 
 // ---- everything that precedes the SDF evaluation, in ONE launch: blockIdx.y selects the role and its row -----------------
-template <int DYN>
-__global__ void __launch_bounds__(256, 8) nlp_phase0_kernel(NlpDev L, const float* __restrict__ w, size_t P, size_t ld, float* __restrict__ g,
+// ANALYTIC (solver.mode casadi): the footprint role evaluates the obstacles and writes the SDF rows itself; the jets of the square
+// obstacles need more than the 32 registers the light roles are held to.
+template <int DYN, bool ANALYTIC>
+__global__ void __launch_bounds__(256, ANALYTIC ? 3 : 8) nlp_phase0_kernel(NlpDev L, const float* __restrict__ w, size_t P, size_t ld, float* __restrict__ g,
                                                          float* __restrict__ jac, float* __restrict__ px, float* __restrict__ py,
                                                          float* __restrict__ f, float* __restrict__ grad, int n_dyn, int n_copy, int n_pts,
                                                          int n_grad) {
@@ -367,7 +387,11 @@ __global__ void __launch_bounds__(256, 8) nlp_phase0_kernel(NlpDev L, const floa
   r -= n_dyn;
   if (r < n_copy) { nlp_copy_rows_body(L, w, P, ld, g, jac, r); return; }
   r -= n_copy;
-  if (r < n_pts) { nlp_points_body(L, w, P, ld, px, py, r); return; }
+  if (r < n_pts) {
+    if (ANALYTIC) nlp_analytic_rows_body(L, w, P, ld, g, jac, r);   // analytic obstacles: rows at once, no scratch
+    else nlp_points_body(L, w, P, ld, px, py, r);
+    return;
+  }
   r -= n_pts;
   if (r < n_grad) { nlp_grad_body(L, w, P, ld, grad, r); return; }
   nlp_obj_body(L, w, P, ld, f);
@@ -466,20 +490,18 @@ int nlo_nlp_launch_assembly(nlo_nlp* p, const NlpScratch& sc, const float* w, si
     if (rows) {
       const dim3 grid((unsigned)std::min<size_t>((P + 255) / 256, 4096), rows);
       switch (L.dyn) {
-#define NLO_CASE(D) case D: nlp_phase0_kernel<D><<<grid, 256, 0, st>>>(L, w, P, ld, g, jac, sc.px, sc.py, f, grad_f, n_dyn, n_copy, n_pts, n_grad); break;
+#define NLO_CASE(D) case D:                                                                                                         \
+          if (L.sdf_mode == NLO_SDF_CIRCLES) nlp_phase0_kernel<D, true><<<grid, 256, 0, st>>>(L, w, P, ld, g, jac, sc.px, sc.py, f, grad_f, n_dyn, n_copy, n_pts, n_grad); \
+          else nlp_phase0_kernel<D, false><<<grid, 256, 0, st>>>(L, w, P, ld, g, jac, sc.px, sc.py, f, grad_f, n_dyn, n_copy, n_pts, n_grad);               \
+          break;
         NLO_CASE(NLO_DYN_POINT_1ST) NLO_CASE(NLO_DYN_POINT_2ND) NLO_CASE(NLO_DYN_UNICYCLE)
         NLO_CASE(NLO_DYN_UNICYCLE_2ND) NLO_CASE(NLO_DYN_ACKERMANN) NLO_CASE(NLO_DYN_ACKERMANN_2ND)
 #undef NLO_CASE
       }
       NLO_CHECK_LAUNCH();
     }
-    if (gj && L.sdf_mode == NLO_SDF_CIRCLES) {
-      const size_t n = (size_t)(L.N + 1) * L.nb * P;
-      nlp_circles_kernel<<<grid_for(n, 256, sm), 256, 0, st>>>(L, sc.px, sc.py, n, sc.s, sc.jx, sc.jy);
-      NLO_CHECK_LAUNCH();
-    }
   } else {
-    if (g || jac) {
+    if ((g || jac) && L.sdf_mode != NLO_SDF_CIRCLES) {       // (analytic obstacles: phase 0 wrote the rows already)
       nlp_sdf_rows_kernel<<<dim3((unsigned)std::min<size_t>((P + 255) / 256, 4096), (unsigned)(L.N + 1)), 256, 0, st>>>(L, w, P, ld, sc.s, sc.jx, sc.jy, g, jac);
       NLO_CHECK_LAUNCH();
     }
@@ -491,7 +513,7 @@ int nlo_nlp_launch_assembly(nlo_nlp* p, const NlpScratch& sc, const float* w, si
 int nlo_nlp_launch_dynamics(const NlpDev& L, const float* w, size_t P, size_t ld, float* g, float* jac, cudaStream_t st) {
   const dim3 grid((unsigned)std::min<size_t>((P + 255) / 256, 4096), (unsigned)L.N);
   switch (L.dyn) {
-#define NLO_CASE(D) case D: nlp_phase0_kernel<D><<<grid, 256, 0, st>>>(L, w, P, ld, g, jac, nullptr, nullptr, nullptr, nullptr, L.N, 0, 0, 0); break;
+#define NLO_CASE(D) case D: nlp_phase0_kernel<D, false><<<grid, 256, 0, st>>>(L, w, P, ld, g, jac, nullptr, nullptr, nullptr, nullptr, L.N, 0, 0, 0); break;
     NLO_CASE(NLO_DYN_POINT_1ST) NLO_CASE(NLO_DYN_POINT_2ND) NLO_CASE(NLO_DYN_UNICYCLE)
     NLO_CASE(NLO_DYN_UNICYCLE_2ND) NLO_CASE(NLO_DYN_ACKERMANN) NLO_CASE(NLO_DYN_ACKERMANN_2ND)
 #undef NLO_CASE
