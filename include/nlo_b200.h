@@ -289,6 +289,8 @@ typedef struct nlo_ip_stats {
   long long trial_problems;                                     /* problems evaluated by the line-search trials, in total   */
   double phase_ms[9];   /* device time per phase (CUDA events): evaluation, residuals + barrier update, Hessian, KKT assembly +
                            factorisation, step, line search, update, least-squares multipliers, compaction / output            */
+  long long kkt_problems, kkt_retries;   /* Newton systems solved / of those, how many failed the inertia test at their first delta      */
+  long long kkt_retry_hist[16];          /* of the retries: how many succeeded at attempt 1..15 of the search (slot 15: none)            */
 } nlo_ip_stats;
 /* lbg, ubg: fp64[n_g] bounds of g in Opti's canonical form (+-INFINITY for one-sided rows; rows with lbg == ubg are equalities).
  * max_problems: batch size the device buffers are sized for.  The solver keeps a pointer to `p` (not owned).              */

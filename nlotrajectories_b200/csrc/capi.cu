@@ -198,6 +198,8 @@ int nlo_sdf_hess(nlo_sdf_model* m, const float* x, const float* y, const float* 
   }
   if (m->prec == NLO_PREC_TC_3XF16 && hxx && hxy && hyy && nlo_sdf_tc_hess_supported(m))
     return nlo_sdf_tc_hess_launch(m, x, y, sbar, n, nullptr, nullptr, nullptr, hxx, hxy, hyy, (cudaStream_t)stream);
+  if (m->prec == NLO_PREC_TC_3XF16 && hxx && hxy && hyy && nlo_sdf_tc_hess_gemm_supported(m))
+    return nlo_sdf_tc_hess_gemm_launch(m, x, y, sbar, n, nullptr, nullptr, nullptr, hxx, hxy, hyy, (cudaStream_t)stream);
   return nlo_sdf_simt_hess_launch(m, x, y, sbar, n, hxx, hxy, hyy, (cudaStream_t)stream);
 }
 
@@ -659,9 +661,11 @@ int nlo_nlp_hess(nlo_nlp* p, const float* w, const float* sigma, const float* la
   if (p->L.sdf_mode == NLO_SDF_CIRCLES) {
     if (nlo_nlp_launch_circles_hess(p->L, sc.px, sc.py, n, sc.s, sc.jx, sc.jy, p->d_hs[0], p->d_hs[1], p->d_hs[2], p->sm_count, st)) return 1;
   } else {
-    if (p->model->prec == NLO_PREC_TC_3XF16 && nlo_sdf_tc_hess_supported(p->model)) {
+    if (p->model->prec == NLO_PREC_TC_3XF16 && (nlo_sdf_tc_hess_supported(p->model) || nlo_sdf_tc_hess_gemm_supported(p->model))) {
       // one fused launch: value, Jacobian and Hessian of every footprint point
-      if (nlo_sdf_tc_hess_launch(p->model, sc.px, sc.py, nullptr, n, sc.s, sc.jx, sc.jy, p->d_hs[0], p->d_hs[1], p->d_hs[2], st)) return 1;
+      if (nlo_sdf_tc_hess_supported(p->model)
+              ? nlo_sdf_tc_hess_launch(p->model, sc.px, sc.py, nullptr, n, sc.s, sc.jx, sc.jy, p->d_hs[0], p->d_hs[1], p->d_hs[2], st)
+              : nlo_sdf_tc_hess_gemm_launch(p->model, sc.px, sc.py, nullptr, n, sc.s, sc.jx, sc.jy, p->d_hs[0], p->d_hs[1], p->d_hs[2], st)) return 1;
       return nlo_nlp_launch_hess(p->L, p->d_hmap, w, sigma, lam, P, ld, sc.s, sc.jx, sc.jy, p->d_hs[0], p->d_hs[1], p->d_hs[2], hess, st);
     }
     if (nlo_sdf_eval(p->model, sc.px, sc.py, nullptr, n, sc.s, sc.jx, sc.jy, st)) return 1;

@@ -499,7 +499,8 @@ __global__ void __launch_bounds__(BT_TPB) bt_ladder_kernel(BtTables B, const dou
 // one warp per failed problem: the first successful attempt (and its doubled twin when that succeeded too) -> dw, delta
 __global__ void __launch_bounds__(256) bt_select_kernel(const int* __restrict__ list, size_t n_list, const int* __restrict__ flags,
                                                         const double* __restrict__ xbuf, double* __restrict__ dw, size_t ld, int n_unknown,
-                                                        const double* __restrict__ delta_in, double* __restrict__ delta_out) {
+                                                        const double* __restrict__ delta_in, double* __restrict__ delta_out,
+                                                        unsigned long long* __restrict__ hist) {
   const size_t wq = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (wq >= n_list) return;
@@ -509,10 +510,11 @@ __global__ void __launch_bounds__(256) bt_select_kernel(const int* __restrict__ 
   const double d0 = delta_in[prob];
   if (!first) {                                              // all sixteen attempts failed: no step, delta as the sequential search leaves it
     for (int c = lane; c < n_unknown; c += 32) dw[(size_t)c * ld + prob] = 0.0;
-    if (lane == 0) delta_out[prob] = bt_ladder_delta(d0, 16);
+    if (lane == 0) { delta_out[prob] = bt_ladder_delta(d0, 16); atomicAdd(hist + 15, 1ull); }
     return;
   }
   const int i = __ffs(first) - 1;
+  if (lane == 0) atomicAdd(hist + i, 1ull);
   const bool twice = (m >> (16 + i)) & 1u;
   const size_t src = q0 + (twice ? 16 + i : i);
   for (int c = lane; c < n_unknown; c += 32) dw[(size_t)c * ld + prob] = xbuf[(size_t)c * ld + src];
@@ -580,6 +582,8 @@ struct nlo_ip {
   IpState S; IpWork W; IpOut O;
   IpOptions opt;
   PhaseTimer timer;
+  unsigned long long* d_hist;        // [16] how many regularisation searches ended at attempt 1..15 (slot 15: none succeeded)
+  long long kkt_problems, kkt_retries;
 };
 
 namespace {
@@ -626,10 +630,11 @@ int ip_kkt_device(nlo_ip* s, const double* rhs, double* dw, size_t P, size_t ld,
   NLO_CUDA(cudaMemcpyAsync(s->h_pin, s->W.counters, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
   NLO_CUDA(cudaStreamSynchronize(st));
   const size_t n_fail = (size_t)s->h_pin[2], chunk = ld / 32;
+  s->kkt_problems += (long long)P; s->kkt_retries += (long long)n_fail;
   for (size_t off = 0; off < n_fail; off += chunk) {
     const size_t n = std::min(chunk, n_fail - off);
     if (launch_bt_ladder<NS, NXR>(B, s->d_K, s->d_L, rhs, s->W.dw_alt, ld, fail_list + off, n, delta_in, flags, s->device, st)) return 1;
-    bt_select_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(fail_list + off, n, flags, s->W.dw_alt, dw, ld, s->T.n_w, delta_in, delta_out);
+    bt_select_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(fail_list + off, n, flags, s->W.dw_alt, dw, ld, s->T.n_w, delta_in, delta_out, s->d_hist);
     NLO_CHECK_LAUNCH();
   }
   return 0;
@@ -792,7 +797,7 @@ void nlo_ip_destroy(nlo_ip* s) {
   if (!s) return;
   cudaSetDevice(s->device);
   void* bufs[] = {s->d_itab, s->d_dtab, s->d_state[0], s->d_state[1], s->d_istate[0], s->d_istate[1], s->d_f32, s->d_f64, s->d_i32,
-                  s->d_K, s->d_L, s->d_out, s->d_iout, s->d_keep};
+                  s->d_K, s->d_L, s->d_out, s->d_iout, s->d_keep, s->d_hist};
   for (void* b : bufs) if (b) cudaFree(b);
   if (s->h_pin) cudaFreeHost(s->h_pin);
   s->timer.destroy();
@@ -811,7 +816,7 @@ int nlo_ip_create(nlo_nlp* p, const double* lbg, const double* ubg, size_t max_p
   s->nlp = p; s->device = p->device; s->cap = (max_problems + 31) / 32 * 32;
   s->d_itab = nullptr; s->d_dtab = nullptr; s->d_state[0] = s->d_state[1] = nullptr; s->d_istate[0] = s->d_istate[1] = nullptr;
   s->d_f32 = nullptr; s->d_f64 = nullptr; s->d_i32 = nullptr; s->d_K = s->d_L = nullptr; s->d_out = nullptr; s->d_iout = nullptr;
-  s->d_keep = nullptr; s->h_pin = nullptr; s->st = nullptr;
+  s->d_keep = nullptr; s->h_pin = nullptr; s->st = nullptr; s->d_hist = nullptr; s->kkt_problems = s->kkt_retries = 0;
   const NlpDev& L = p->L;
   {
     std::vector<int> jc(L.n_w + 1, 0), hc(L.n_w + 1, 0);
@@ -859,7 +864,7 @@ int nlo_ip_create(nlo_nlp* p, const double* lbg, const double* ubg, size_t max_p
        cudaMalloc(&s->d_i32, (3 * ld + 8) * sizeof(int)) == cudaSuccess && cudaMalloc(&s->d_K, k_slots * ld * sizeof(double)) == cudaSuccess &&
        cudaMalloc(&s->d_L, l_slots * ld * sizeof(double)) == cudaSuccess &&
        cudaMalloc(&s->d_out, ((size_t)T.n_w + T.n_g + 3) * ld * sizeof(double)) == cudaSuccess && cudaMalloc(&s->d_iout, 2 * ld * sizeof(int)) == cudaSuccess &&
-       cudaMalloc(&s->d_keep, ld * sizeof(int)) == cudaSuccess && cudaHostAlloc(&s->h_pin, (ld + 2) * sizeof(int), cudaHostAllocDefault) == cudaSuccess &&
+       cudaMalloc(&s->d_keep, ld * sizeof(int)) == cudaSuccess && cudaMalloc(&s->d_hist, 16 * sizeof(unsigned long long)) == cudaSuccess && cudaHostAlloc(&s->h_pin, (ld + 2) * sizeof(int), cudaHostAllocDefault) == cudaSuccess &&
        cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking) == cudaSuccess;
   if (!ok) {
     const double gb = ((2 * s->state_rows + f64_rows + k_slots + l_slots + T.n_w + T.n_g + 3) * 8.0 + f32_rows * 4.0) * ld / 1e9;
@@ -918,6 +923,8 @@ int nlo_ip_solve(nlo_ip* s, const double* w0_host, size_t P, const nlo_ip_option
   }
   if (!s->timer.ready && s->timer.init()) return 1;
   s->timer.reset();
+  s->kkt_problems = s->kkt_retries = 0;
+  NLO_CUDA(cudaMemsetAsync(s->d_hist, 0, 16 * sizeof(unsigned long long), st));
   GpuBackend x{s, st, &s->timer};
   IpStats stats;
   if (ip_solve_loop(x, P, opt, &stats)) return 1;
@@ -945,6 +952,10 @@ int nlo_ip_solve(nlo_ip* s, const double* w0_host, size_t P, const nlo_ip_option
     stats_out->iterations = stats.iterations; stats_out->evaluations = stats.evaluations; stats_out->hessians = stats.hessians;
     stats_out->trials = stats.trials; stats_out->compactions = stats.compactions; stats_out->trial_problems = stats.trial_problems;
     for (int i = 0; i < PH_COUNT; ++i) stats_out->phase_ms[i] = s->timer.ms[i];
+    stats_out->kkt_problems = s->kkt_problems; stats_out->kkt_retries = s->kkt_retries;
+    unsigned long long hist[16];
+    NLO_CUDA(cudaMemcpy(hist, s->d_hist, sizeof(hist), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 16; ++i) stats_out->kkt_retry_hist[i] = (long long)hist[i];
   }
   return 0;
 }

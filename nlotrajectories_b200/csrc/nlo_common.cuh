@@ -186,6 +186,10 @@ int nlo_sdf_tc_launch(nlo_sdf_model* m, const float* x, const float* y, const fl
 bool nlo_sdf_tc_hess_supported(const nlo_sdf_model* m);
 int nlo_sdf_tc_hess_launch(nlo_sdf_model* m, const float* x, const float* y, const float* sbar, size_t n,
                            float* s, float* jx, float* jy, float* hxx, float* hxy, float* hyy, cudaStream_t st);
+// sdf_tc_hess.cu: value + Jacobian + Hessian of one-hidden-matrix networks with a smooth hidden activation, as GEMMs
+bool nlo_sdf_tc_hess_gemm_supported(const nlo_sdf_model* m);
+int nlo_sdf_tc_hess_gemm_launch(nlo_sdf_model* m, const float* x, const float* y, const float* sbar, size_t n, float* s, float* jx, float* jy,
+                                float* hxx, float* hxy, float* hyy, cudaStream_t st);
 // sdf_tc_deep.cu: two or three H x H matrices (reached through nlo_sdf_tc_supported / _prepare / _launch)
 bool nlo_sdf_tc_deep_supported(const nlo_sdf_desc* d);
 int nlo_sdf_tc_deep_prepare(nlo_sdf_model* m, const float* weights_host);

@@ -44,20 +44,6 @@ namespace {
 
 constexpr int TILE = 128;          // points per tile == TMEM lanes
 
-struct TcParams {          // built by nlo_sdf_tc_prepare
-  float inv_sw;            // 1 / (power-of-two scale applied to W1 in its fp16 images)
-  float inv_sv;            // 1 / (power-of-two scale applied to V = diag(w2) W1 in its fp16 images)
-  float inv_sc1;           // 1 / (power-of-two scale folded into w2s, the generic reverse-pass seed vector)
-  float max_w0x, max_w0y, max_b0;
-};
-// Small vectors of the network live in __constant__ memory: with fully unrolled loops every use is an FFMA/FMUL
-// with a constant-bank operand (c[3][imm]) - no load instruction and no shared-memory bandwidth (which the tensor
-// core needs for its B-operand fetches).  One copy per device context; nlo_sdf_tc_launch re-uploads it (after a
-// device-wide sync) whenever a different model is evaluated.
-struct TcConst {
-  float w0x[128], w0y[128], b0[128], b1[128], w2[128], w2s[128];
-  float bout;
-};
 __constant__ TcConst cst;
 
 // One persistent CTA of 512 threads per SM.  Its threads form NGROUPS independent tile groups (H = 128: two groups of

@@ -89,6 +89,20 @@ __device__ __forceinline__ void row_scale(float bound, float& sc, float& inv) {
   inv = __uint_as_float((uint32_t)(127 - e) << 23);
 }
 
+struct TcParams {          // built by nlo_sdf_tc_prepare
+  float inv_sw;            // 1 / (power-of-two scale applied to W1 in its fp16 images)
+  float inv_sv;            // 1 / (power-of-two scale applied to V = diag(w2) W1 in its fp16 images)
+  float inv_sc1;           // 1 / (power-of-two scale folded into w2s, the generic reverse-pass seed vector)
+  float max_w0x, max_w0y, max_b0;
+};
+// Small vectors of the network live in __constant__ memory: with fully unrolled loops every use is an FFMA/FMUL
+// with a constant-bank operand (c[3][imm]) - no load instruction and no shared-memory bandwidth (which the tensor
+// core needs for its B-operand fetches).  One copy per device context; nlo_sdf_tc_launch re-uploads it (after a
+// device-wide sync) whenever a different model is evaluated.
+struct TcConst {
+  float w0x[128], w0y[128], b0[128], b1[128], w2[128], w2s[128];
+  float bout;
+};
 template <int N> struct TmemIO;
 template <> struct TmemIO<16> {
   __device__ static __forceinline__ void ld(uint32_t a, uint32_t (&v)[16]) {

@@ -39,7 +39,8 @@ class IpOptions(C.Structure):
 
 
 class IpStats(C.Structure):
-    _fields_ = [(n, C.c_int) for n in ("iterations", "evaluations", "hessians", "trials", "compactions")] + [("trial_problems", C.c_longlong), ("phase_ms", C.c_double * 9)]
+    _fields_ = [(n, C.c_int) for n in ("iterations", "evaluations", "hessians", "trials", "compactions")] + [("trial_problems", C.c_longlong), ("phase_ms", C.c_double * 9), ("kkt_problems", C.c_longlong),
+                                                                                                               ("kkt_retries", C.c_longlong), ("kkt_retry_hist", C.c_longlong * 16)]
 
 
 _P = C.c_void_p

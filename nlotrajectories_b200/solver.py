@@ -455,6 +455,7 @@ class DeviceIPSolver:
         _lib.check(self._L.nlo_ip_solve(self._h, w0.ctypes.data, P, C.byref(self.opt), w.ctypes.data, f.ctypes.data, viol.ctypes.data,
                                         err.ctypes.data, iters.ctypes.data, status.ctypes.data, lam.ctypes.data, C.byref(st)))
         self.stats = {k: int(getattr(st, k)) for k in ("iterations", "evaluations", "hessians", "trials", "compactions", "trial_problems")}
+        self.stats.update(kkt_problems=int(st.kkt_problems), kkt_retries=int(st.kkt_retries), kkt_retry_hist=[int(v) for v in st.kkt_retry_hist])
         self.stats["phase_ms"] = dict(zip(("evaluation", "residual", "hessian", "kkt", "step", "line_search", "update", "multipliers", "compaction_output"),
                                           (round(float(v), 2) for v in st.phase_ms)))
         t = torch.from_numpy

@@ -326,11 +326,12 @@ def test_hessian_golden_from_reference_expressions(name, shipped_net, library):
 
 
 @pytest.mark.parametrize("name", ["benchmark_1", "benchmark_3", "benchmark_6"])
-@pytest.mark.parametrize("netname", ["fourier64_tanh", "relu128"])
+@pytest.mark.parametrize("netname", ["fourier64_tanh", "relu128", "tanh128"])
 def test_hessian_batch_matches_oracle(name, netname, library):
     """Ragged batch against the fp64 oracle: a smooth network (FP32 general path + K1b Hessian kernel) and the
     benchmark-shaped ReLU network (tensor path; its second derivatives vanish identically)."""
-    net = so.synthetic_fourier(64, 1, scale=3.0, seed=8, act=so.ACT_TANH) if netname == "fourier64_tanh" else so.synthetic_mlp(128, 1, seed=0)
+    net = (so.synthetic_fourier(64, 1, scale=3.0, seed=8, act=so.ACT_TANH) if netname == "fourier64_tanh"
+           else so.synthetic_mlp(128, 1, seed=13, act=so.ACT_TANH) if netname == "tanh128" else so.synthetic_mlp(128, 1, seed=0))
     cfg, model, prob = make_problem(name, net)
     spec = no.NlpSpec.from_yaml_dict(yaml.safe_load(open(bench_yaml(name))))
     P = 77

@@ -127,7 +127,8 @@ def test_golden_vectors_from_reference_torchscript(shipped_net, torch_cuda):
         model.close()
 
 
-@pytest.mark.parametrize("name", ["tanh64x2", "siren64x2", "fourier64_tanh", "sigmoid48", "relu128"])
+@pytest.mark.parametrize("name", ["tanh64x2", "siren64x2", "fourier64_tanh", "sigmoid48", "relu128",
+                                  "tanh128", "sigmoid128", "siren64x1", "fourier128_sigmoid"])     # the last four: Hessian as GEMMs (sdf_tc_hess.cu)
 def test_hessian_matches_oracle(name, torch_cuda):
     from nlotrajectories_b200.sdf import LearnedSDF
     net = NETS[name]()

@@ -24,14 +24,17 @@ def timed(fn, reps):
 
 
 nets = {"relu128": so.synthetic_mlp(128, 1, seed=0), "shipped_fourier128": so.from_npz(REPO / "tests/golden/sdf_shipped_fourier128_weights.npz"),
-        "tanh128": so.synthetic_mlp(128, 1, seed=13, act=so.ACT_TANH)}
+        "tanh128": so.synthetic_mlp(128, 1, seed=13, act=so.ACT_TANH), "sigmoid128": so.synthetic_mlp(128, 1, seed=15, act=so.ACT_SIGMOID),
+        "siren64": so.synthetic_siren(64, 1, omega0=30.0, seed=17), "siren128": so.synthetic_siren(128, 1, omega0=30.0, seed=40),
+        "tanh64x2_fp32_general": so.synthetic_mlp(64, 2, seed=4, act=so.ACT_TANH)}
 for netname, net in nets.items():
     model = LearnedSDF(to_weights(net))
-    n = 1 << (22 if netname != "tanh128" else 18)
+    slow = netname.endswith("fp32_general")            # FP32 warp-per-point kernel (sdf_simt.cu): no tensor-tile Hessian for this shape
+    n = 1 << (18 if slow else 22)
     x = torch.rand(n, device="cuda") * 2 - 0.5; y = torch.rand(n, device="cuda") * 2 - 0.5
     ms = timed(lambda: model.hess(x, y), 5)
     print(json.dumps({"row": "sdf_hess", "net": netname, "precision": model.precision, "points": n, "Gpts_s": n / ms / 1e6}), flush=True)
-    for name, P in (("benchmark_6", 65536 if netname != "tanh128" else 2048), ("benchmark_4", 4096 if netname != "tanh128" else 512)):
+    for name, P in (("benchmark_6", 2048 if slow else 65536), ("benchmark_4", 512 if slow else 4096)):
         cfg = Config.load(next((REPO / "nlotrajectories_b200/benchmarks").glob(name + "*.yaml")))
         prob = NlpProblem.from_config(cfg, model)
         w = torch.from_numpy(prob.multistart_guess(P)).cuda().T.contiguous()
