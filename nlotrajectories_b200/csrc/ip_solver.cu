@@ -81,34 +81,36 @@ __global__ void __launch_bounds__(32 * IP_TEAM) ip_merit_kernel(IpTables T, IpSt
   const int rej = ip_merit_body(T, S, W, p, qc_, red);
   if (threadIdx.y == 0 && red.act && rej) next[atomicAdd(W.counters + 1, 1)] = (int)p;
 }
-// ---- the remaining trials of the line search at once: for every refused problem the 13 step lengths a, a/2, ... a/2^12 (a = the
-// halved step the sequential search would try next) are 13 columns of one trial batch; ip_ls_select_kernel takes the first accepted.
+// ---- the remaining trials of the line search side by side: for every refused problem, nj of the 13 step lengths a, a/2, ... a/2^12
+// (a = the halved step the sequential search would try next) are nj columns of one trial batch; ip_ls_select_kernel takes the first
+// accepted one.  Two stages: the three largest step lengths first, the other ten only for the problems that refuse all three.
 #define IP_LS_LADDER (IP_LS_TRIALS - 1)
-__global__ void __launch_bounds__(256) ip_trial_ladder_kernel(IpState S, IpWork W, size_t n, int n_w, const int* __restrict__ list) {
+__global__ void __launch_bounds__(256) ip_trial_ladder_kernel(IpState S, IpWork W, size_t n, int n_w, const int* __restrict__ list, int j0, int nj) {
   const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= n * IP_LS_LADDER) return;
-  const size_t p = (size_t)list[q / IP_LS_LADDER];
-  const double a = ldexp(W.alpha[p], -(int)(q % IP_LS_LADDER));
+  if (q >= n * nj) return;
+  const size_t p = (size_t)list[q / nj];
+  const double a = ldexp(W.alpha[p], -(j0 + (int)(q % nj)));
   for (int c = blockIdx.y; c < n_w; c += gridDim.y)
     W.wt32[(size_t)c * S.ld + q] = (float)(S.w[(size_t)c * S.ld + p] + a * W.dw[(size_t)c * S.ld + p]);
 }
 __global__ void __launch_bounds__(32 * IP_TEAM) ip_merit_ladder_kernel(IpTables T, IpState S, IpWork W, size_t n, const int* __restrict__ list,
-                                                                       int* __restrict__ flags) {
-  IP_TEAM_SETUP(n * IP_LS_LADDER);
-  const size_t p = (size_t)list[qc_ / IP_LS_LADDER];
-  const double a = ldexp(W.alpha[p], -(int)(qc_ % IP_LS_LADDER));
+                                                                       int* __restrict__ flags, int j0, int nj) {
+  IP_TEAM_SETUP(n * nj);
+  const size_t p = (size_t)list[qc_ / nj];
+  const double a = ldexp(W.alpha[p], -(j0 + (int)(qc_ % nj)));
   const bool ok = ip_merit_ok(T, S, W, p, qc_, a, false, red);
   if (threadIdx.y == 0 && red.act) flags[qc_] = ok ? 1 : 0;
 }
-__global__ void __launch_bounds__(256) ip_ls_select_kernel(IpWork W, size_t n, const int* __restrict__ list, const int* __restrict__ flags) {
+__global__ void __launch_bounds__(256) ip_ls_select_kernel(IpWork W, size_t n, const int* __restrict__ list, const int* __restrict__ flags, int j0,
+                                                           int nj, int* __restrict__ next, int* __restrict__ next_count) {
   const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   const size_t p = (size_t)list[r];
-  const double a = W.alpha[p];
   int j = 0;
-  while (j < IP_LS_LADDER && !flags[r * IP_LS_LADDER + j]) ++j;
-  if (j < IP_LS_LADDER) { W.accepted[p] = 1; W.alpha[p] = ldexp(a, -j); }
-  else W.alpha[p] = ldexp(a, -IP_LS_LADDER);               // refused to the end: the (tiny) last step is taken, as in the sequential search
+  while (j < nj && !flags[r * nj + j]) ++j;
+  if (j < nj) { W.accepted[p] = 1; W.alpha[p] = ldexp(W.alpha[p], -(j0 + j)); }
+  else if (next) next[atomicAdd(next_count, 1)] = (int)p;
+  else W.alpha[p] = ldexp(W.alpha[p], -IP_LS_LADDER);      // refused to the end: the (tiny) last step is taken, as in the sequential search
 }
 __global__ void __launch_bounds__(32 * IP_TEAM) ip_update_kernel(IpTables T, IpState S, IpWork W, size_t P) {
   IP_TEAM_SETUP(P);
@@ -482,54 +484,64 @@ int launch_bt_team(const BtTables& B, const double* K, double* Lf, const double*
 // the whole batch waited ~1 ms per attempt of its slowest member (72 % of a benchmark_6 x 8,192 solve).  Here every failed problem gets
 // 32 lanes: lane a - 1 (a = 1..15) factorises with the delta of attempt a, lane 16 + a - 1 with twice that; bt_select_kernel then takes
 // the first success in the order of the sequential search, so the result is the same and the cost is one more attempt, not fifteen.
+// A stage of the search covers attempts a0 .. a0 + n_att - 1: 2^lanes_log2 lanes per problem, the first half factorises with the
+// delta of those attempts, the second half with twice that.  Most searches end at the first step of the ladder (benchmark_6 x
+// 65,536: 76 % at attempt 1, 18 % at 2..5), so stage A tries attempts 1 and 2 with 4 lanes per problem and only what is left gets
+// the 32 lanes of stage B (attempts 3..15).
 template <int NS, int NXR>
 __global__ void __launch_bounds__(BT_TPB) bt_ladder_kernel(BtTables B, const double* __restrict__ K, double* __restrict__ Lf,
                                                            const double* __restrict__ rhs, double* __restrict__ xbuf, size_t ld,
                                                            const int* __restrict__ list, size_t n_list, const double* __restrict__ delta_in,
-                                                           int* __restrict__ flags) {
+                                                           int* __restrict__ flags, int lanes_log2, int a0, int n_att) {
   extern __shared__ double bt_smem[];
   const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= n_list * 32) return;
-  const size_t prob = (size_t)list[q >> 5];
-  const int i = (int)(q & 31), a = (i & 15) + 1;
-  if (a > 15) { flags[q] = 0; return; }
-  const double d = bt_ladder_delta(delta_in[prob], a) * (i >= 16 ? 2.0 : 1.0);
+  if (q >= (n_list << lanes_log2)) return;
+  const size_t prob = (size_t)list[q >> lanes_log2];
+  const int half = 1 << (lanes_log2 - 1), i = (int)(q & ((1u << lanes_log2) - 1)), k = i & (half - 1);
+  if (k >= n_att) { flags[q] = 0; return; }
+  const double d = bt_ladder_delta(delta_in[prob], a0 + k) * (i >= half ? 2.0 : 1.0);
   flags[q] = bt_solve_attempt<NS, NXR>(B, K, Lf, rhs, xbuf, ld, prob, q, d, 1e3, bt_smem + threadIdx.x, BT_TPB) ? 1 : 0;
 }
-// one warp per failed problem: the first successful attempt (and its doubled twin when that succeeded too) -> dw, delta
+// one warp per problem of the stage: the first successful attempt (and its doubled twin when that succeeded too) -> dw, delta;
+// problems without a success go to `next` (the following stage) or, at the last stage, get a zero step
 __global__ void __launch_bounds__(256) bt_select_kernel(const int* __restrict__ list, size_t n_list, const int* __restrict__ flags,
                                                         const double* __restrict__ xbuf, double* __restrict__ dw, size_t ld, int n_unknown,
                                                         const double* __restrict__ delta_in, double* __restrict__ delta_out,
-                                                        unsigned long long* __restrict__ hist) {
+                                                        unsigned long long* __restrict__ hist, int lanes_log2, int a0,
+                                                        int* __restrict__ next, int* __restrict__ next_count) {
   const size_t wq = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (wq >= n_list) return;
-  const size_t prob = (size_t)list[wq], q0 = wq * 32;
-  const unsigned m = __ballot_sync(0xffffffffu, flags[q0 + lane] != 0);
-  const unsigned first = m & 0x7fffu;
+  const int LP = 1 << lanes_log2, half = LP >> 1;
+  const size_t prob = (size_t)list[wq], q0 = wq << lanes_log2;
+  const unsigned m = __ballot_sync(0xffffffffu, lane < LP && flags[q0 + lane] != 0);
+  const unsigned first = m & ((1u << half) - 1u);
   const double d0 = delta_in[prob];
-  if (!first) {                                              // all sixteen attempts failed: no step, delta as the sequential search leaves it
+  if (!first) {
+    if (next) { if (lane == 0) next[atomicAdd(next_count, 1)] = (int)prob; return; }
+    // all sixteen attempts failed: no step, delta as the sequential search leaves it
     for (int c = lane; c < n_unknown; c += 32) dw[(size_t)c * ld + prob] = 0.0;
     if (lane == 0) { delta_out[prob] = bt_ladder_delta(d0, 16); atomicAdd(hist + 15, 1ull); }
     return;
   }
   const int i = __ffs(first) - 1;
-  if (lane == 0) atomicAdd(hist + i, 1ull);
-  const bool twice = (m >> (16 + i)) & 1u;
-  const size_t src = q0 + (twice ? 16 + i : i);
+  if (lane == 0) atomicAdd(hist + (a0 - 1 + i), 1ull);
+  const bool twice = (m >> (half + i)) & 1u;
+  const size_t src = q0 + (twice ? half + i : i);
   for (int c = lane; c < n_unknown; c += 32) dw[(size_t)c * ld + prob] = xbuf[(size_t)c * ld + src];
-  if (lane == 0) delta_out[prob] = bt_ladder_delta(d0, i + 1) * (twice ? 2.0 : 1.0);
+  if (lane == 0) delta_out[prob] = bt_ladder_delta(d0, a0 + i) * (twice ? 2.0 : 1.0);
 }
 template <int NS, int NXR>
 int launch_bt_ladder(const BtTables& B, const double* K, double* Lf, const double* rhs, double* xbuf, size_t ld, const int* list, size_t n_list,
-                     const double* delta_in, int* flags, int device, cudaStream_t st) {
+                     const double* delta_in, int* flags, int lanes_log2, int a0, int n_att, int device, cudaStream_t st) {
   constexpr size_t smem = (size_t)(2 * (NXR * NS + NS * (NS + 1) / 2) + NS) * BT_TPB * sizeof(double);
   static bool attr[64] = {false};
   if (!attr[device & 63]) {
     NLO_CUDA(cudaFuncSetAttribute(bt_ladder_kernel<NS, NXR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr[device & 63] = true;
   }
-  bt_ladder_kernel<NS, NXR><<<(unsigned)((n_list * 32 + BT_TPB - 1) / BT_TPB), BT_TPB, smem, st>>>(B, K, Lf, rhs, xbuf, ld, list, n_list, delta_in, flags);
+  bt_ladder_kernel<NS, NXR><<<(unsigned)(((n_list << lanes_log2) + BT_TPB - 1) / BT_TPB), BT_TPB, smem, st>>>(B, K, Lf, rhs, xbuf, ld, list, n_list,
+                                                                                                         delta_in, flags, lanes_log2, a0, n_att);
   NLO_CHECK_LAUNCH();
   return 0;
 }
@@ -629,12 +641,29 @@ int ip_kkt_device(nlo_ip* s, const double* rhs, double* dw, size_t P, size_t ld,
                               fail_list, fail_count)) return 1;
   NLO_CUDA(cudaMemcpyAsync(s->h_pin, s->W.counters, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
   NLO_CUDA(cudaStreamSynchronize(st));
-  const size_t n_fail = (size_t)s->h_pin[2], chunk = ld / 32;
+  const size_t n_fail = (size_t)s->h_pin[2];
   s->kkt_problems += (long long)P; s->kkt_retries += (long long)n_fail;
-  for (size_t off = 0; off < n_fail; off += chunk) {
+  if (n_fail == 0) return 0;
+  // stage A: attempts 1 and 2 (+ their doubled twins), 4 lanes per problem; what is left goes to the list of stage B
+  int* list_b = s->d_keep;                                   // (the compaction's index buffer is free during an iteration)
+  int* count_b = s->W.counters + 3;
+  NLO_CUDA(cudaMemsetAsync(count_b, 0, sizeof(int), st));
+  for (size_t off = 0, chunk = ld / 4; off < n_fail; off += chunk) {
     const size_t n = std::min(chunk, n_fail - off);
-    if (launch_bt_ladder<NS, NXR>(B, s->d_K, s->d_L, rhs, s->W.dw_alt, ld, fail_list + off, n, delta_in, flags, s->device, st)) return 1;
-    bt_select_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(fail_list + off, n, flags, s->W.dw_alt, dw, ld, s->T.n_w, delta_in, delta_out, s->d_hist);
+    if (launch_bt_ladder<NS, NXR>(B, s->d_K, s->d_L, rhs, s->W.dw_alt, ld, fail_list + off, n, delta_in, flags, 2, 1, 2, s->device, st)) return 1;
+    bt_select_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(fail_list + off, n, flags, s->W.dw_alt, dw, ld, s->T.n_w, delta_in, delta_out,
+                                                                       s->d_hist, 2, 1, list_b, count_b);
+    NLO_CHECK_LAUNCH();
+  }
+  NLO_CUDA(cudaMemcpyAsync(s->h_pin, s->W.counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  NLO_CUDA(cudaStreamSynchronize(st));
+  const size_t n_b = (size_t)s->h_pin[3];
+  // stage B: attempts 3..15, 32 lanes per problem
+  for (size_t off = 0, chunk = ld / 32; off < n_b; off += chunk) {
+    const size_t n = std::min(chunk, n_b - off);
+    if (launch_bt_ladder<NS, NXR>(B, s->d_K, s->d_L, rhs, s->W.dw_alt, ld, list_b + off, n, delta_in, flags, 5, 3, 13, s->device, st)) return 1;
+    bt_select_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(list_b + off, n, flags, s->W.dw_alt, dw, ld, s->T.n_w, delta_in, delta_out,
+                                                                       s->d_hist, 5, 3, nullptr, nullptr);
     NLO_CHECK_LAUNCH();
   }
   return 0;
@@ -713,20 +742,34 @@ struct GpuBackend {
     size_t rejected = 0;
     if (trial(P, 0, &rejected)) return 1;                    // refused problems: ls_list[0], step length already halved
     ++stats->trials; stats->trial_problems += (long long)P;
-    const int* list = s->W.ls_list[0];
+    if (rejected == 0) return 0;
     int* flags = s->W.ls_list[1];
-    const size_t chunk = s->cap / IP_LS_LADDER;
-    for (size_t off = 0; off < rejected; off += chunk) {
-      const size_t n = std::min(chunk, rejected - off), cols = n * IP_LS_LADDER;
-      tm->mark(PH_LINESEARCH, st);
-      ip_trial_ladder_kernel<<<dim3((unsigned)((cols + 255) / 256), 32), 256, 0, st>>>(s->S, s->W, n, s->T.n_w, list + off);
-      NLO_CHECK_LAUNCH();
-      if (nlo_nlp_eval(s->nlp, s->W.wt32, cols, s->cap, s->W.gt, nullptr, s->W.ft, nullptr, st)) return 1;
-      ip_merit_ladder_kernel<<<g1(cols), b1(), 0, st>>>(s->T, s->S, s->W, n, list + off, flags);
-      NLO_CHECK_LAUNCH();
-      ip_ls_select_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s->W, n, list + off, flags);
-      NLO_CHECK_LAUNCH();
-      ++stats->trials; stats->trial_problems += (long long)cols;
+    int* count_b = s->W.counters + 3;
+    const int* list = s->W.ls_list[0];
+    size_t n_list = rejected;
+    const int stage_j0[2] = {0, 3}, stage_nj[2] = {3, IP_LS_LADDER - 3};
+    for (int stage = 0; stage < 2 && n_list > 0; ++stage) {
+      const int j0 = stage_j0[stage], nj = stage_nj[stage];
+      int* next = stage == 0 ? s->d_keep : nullptr;           // (the compaction's index buffer is free during an iteration)
+      if (next) NLO_CUDA(cudaMemsetAsync(count_b, 0, sizeof(int), st));
+      const size_t chunk = s->cap / nj;
+      for (size_t off = 0; off < n_list; off += chunk) {
+        const size_t n = std::min(chunk, n_list - off), cols = n * nj;
+        tm->mark(PH_LINESEARCH, st);
+        ip_trial_ladder_kernel<<<dim3((unsigned)((cols + 255) / 256), 32), 256, 0, st>>>(s->S, s->W, n, s->T.n_w, list + off, j0, nj);
+        NLO_CHECK_LAUNCH();
+        if (nlo_nlp_eval(s->nlp, s->W.wt32, cols, s->cap, s->W.gt, nullptr, s->W.ft, nullptr, st)) return 1;
+        ip_merit_ladder_kernel<<<g1(cols), b1(), 0, st>>>(s->T, s->S, s->W, n, list + off, flags, j0, nj);
+        NLO_CHECK_LAUNCH();
+        ip_ls_select_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s->W, n, list + off, flags, j0, nj, next, count_b);
+        NLO_CHECK_LAUNCH();
+        ++stats->trials; stats->trial_problems += (long long)cols;
+      }
+      if (!next) break;
+      NLO_CUDA(cudaMemcpyAsync(s->h_pin, s->W.counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+      NLO_CUDA(cudaStreamSynchronize(st));
+      n_list = (size_t)s->h_pin[3];
+      list = s->d_keep;
     }
     return 0;
   }
