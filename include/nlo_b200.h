@@ -311,6 +311,25 @@ NLO_API int    nlo_ip_solve(nlo_ip* s, const double* w0_host, size_t P, const nl
 NLO_API int    nlo_ip_kkt_step(nlo_ip* s, const float* jac, const float* hess, const double* omega, const double* rhs,
                                const double* delta_in, size_t P, size_t ld, double* dw, double* delta_out, void* stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* initial guesses: batched RRT against the exact obstacle SDF (core/trajectory_initialization.py:175-216) */
+/* ------------------------------------------------------------------------------------------ */
+enum { NLO_RRT_CIRCLE = 0, NLO_RRT_SQUARE = 1, NLO_RRT_POLYGON = 2 };
+typedef struct nlo_rrt_obstacle {
+  uint32_t kind;                      /* NLO_RRT_*  (trapezoids and elliptical half-rings are polygons: core/sdf/casadi.py:135-148,218-246) */
+  uint32_t first_vertex, n_vertices;  /* polygon: range in the vertex array                                                              */
+  uint32_t pad;
+  double cx, cy, size, margin;        /* circle: centre, radius; square: centre, side length; every kind: margin                         */
+} nlo_rrt_obstacle;
+/* P planners, one per seed, each from start[2] towards goal[2] inside the box [lo, hi]: one warp per planner runs its whole search
+ * (sample / nearest / steer by step_size / keep `inflation` of clearance at both ends and the midpoint of the new edge / stop within
+ * step_size of the goal) in one kernel.  path_host[P][max_path][2] receives every path root first, path_len_host[P] its number of
+ * nodes (-1: no path within max_iter iterations, -2: longer than max_path).  Synchronous.                                            */
+NLO_API int nlo_rrt_paths(const nlo_rrt_obstacle* obstacles, int n_obstacles, const double* vertices, int n_vertices,
+                          const double* start, const double* goal, const double* lo, const double* hi, const long long* seeds, size_t P,
+                          double step_size, int max_iter, double inflation, double goal_sample_rate, int max_path, int device,
+                          double* path_host, int* path_len_host);
+
 /* layout helpers on device: [rows][ld] variable-major <-> [P][rows] problem-major              */
 NLO_API int nlo_transpose_to_soa(const float* aos, float* soa, size_t P, size_t rows, size_t ld, void* stream);
 NLO_API int nlo_transpose_to_aos(const float* soa, float* aos, size_t P, size_t rows, size_t ld, void* stream);

@@ -16,7 +16,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OBJ = PKG / "csrc" / "_obj"
 LIB = PKG / "libnlo_b200.so"
-SOURCES = ["capi.cu", "sdf_simt.cu", "sdf_tc.cu", "sdf_tc256.cu", "nlp_kernels.cu", "nlp_hess.cu", "ip_solver.cu",
+SOURCES = ["capi.cu", "sdf_simt.cu", "sdf_tc.cu", "sdf_tc256.cu", "nlp_kernels.cu", "nlp_hess.cu", "ip_solver.cu", "rrt_kernels.cu",
            "sdf_tc_hess.cu", "sdf_tc_deep.cu", "sdf_tc_deep_h128m2.cu", "sdf_tc_deep_h128m3.cu", "sdf_tc_deep_h64m2.cu", "sdf_tc_deep_h64m3.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -33,6 +33,11 @@ class CompactCounts(C.Structure):
     _fields_ = [(n, C.c_longlong) for n in ("n_g_var", "n_g_copy", "n_jac_var", "n_jac_const", "n_grad_var", "n_grad_lin")]
 
 
+class RrtObstacle(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("first_vertex", C.c_uint32), ("n_vertices", C.c_uint32), ("pad", C.c_uint32),
+                ("cx", C.c_double), ("cy", C.c_double), ("size", C.c_double), ("margin", C.c_double)]
+
+
 class IpOptions(C.Structure):
     _fields_ = [("tol", C.c_double), ("max_iter", C.c_int), ("mu0", C.c_double), ("ls_multipliers", C.c_int), ("compact", C.c_int),
                 ("verbose", C.c_int)]
@@ -94,6 +99,8 @@ SIGNATURES = {
     "nlo_ip_capacity": (_SZ, [_P]),
     "nlo_ip_solve": (C.c_int, [_P, _F, _SZ, C.POINTER(IpOptions), _F, _F, _F, _F, _F, _F, _F, C.POINTER(IpStats)]),
     "nlo_ip_kkt_step": (C.c_int, [_P, _F, _F, _F, _F, _F, _SZ, _SZ, _F, _F, _P]),
+    "nlo_rrt_paths": (C.c_int, [C.POINTER(RrtObstacle), C.c_int, _F, C.c_int, _F, _F, _F, _F, _F, _SZ, C.c_double, C.c_int, C.c_double, C.c_double,
+                                C.c_int, C.c_int, _F, _F]),
     "nlo_transpose_to_soa": (C.c_int, [_F, _F, _SZ, _SZ, _SZ, _P]),
     "nlo_transpose_to_aos": (C.c_int, [_F, _F, _SZ, _SZ, _SZ, _P]),
 }

@@ -1,7 +1,9 @@
-"""Batched RRT on the device: the tree search of ``core/trajectory_initialization.py:175-216`` for P planners in
-lock step as torch tensor operations - one sampled point, one nearest-node search, one steer and one collision check per planner per
-iteration, all planners at once.  The exact obstacle SDF (circles, squares, polygons, elliptical half-rings) is evaluated on the
-same device.  Path post-processing (shortcut, corner splitting, cubic spline, optional lifting) stays with ``initializer.py`` on
+"""Batched RRT on the device: the tree search of ``core/trajectory_initialization.py:175-216`` for P planners at
+once.  On a CUDA device the search is ONE kernel of the library (``csrc/rrt_kernels.cu``, C ABI ``nlo_rrt_paths``): a warp per
+planner runs its whole tree search against the exact obstacle SDF and extracts its path.  ``batched_rrt_trees`` is the same algorithm,
+draw for draw, as lock-step torch tensor operations - one sampled point, one nearest-node search, one steer and one collision check
+per planner per iteration: the readable form, the CPU test double, and what the kernel is checked against.  The exact obstacle SDF
+(circles, squares, polygons, elliptical half-rings) is evaluated on the same device.  Path post-processing (shortcut, corner splitting, cubic spline, optional lifting) stays with ``initializer.py`` on
 the host, where it is a few milliseconds per path.
 
 The host planners of ``initializer.rrt_multistart`` (a pool of forked processes) are the better tool for tens of starts; this one
@@ -130,6 +132,53 @@ def batched_rrt_trees(sdf, start, goal, bounds, P: int, seeds, step_size: float,
     return pos.cpu().numpy(), parent.cpu().numpy(), final.cpu().numpy()
 
 
+def scene_obstacles(cfg):
+    """The YAML's obstacle list as the ``nlo_rrt_obstacle`` records + vertex array of ``nlo_rrt_paths``."""
+    from . import lib as _lib
+    from .train import elliptic_ring_points
+    obs, verts = [], []
+    for ob in cfg.obstacles:
+        p = ob.params
+        m = float(p.get("margin", 0.0))
+        if ob.type == "circle":
+            obs.append((0, 0, 0, p["center"][0], p["center"][1], float(p["radius"]), m))
+        elif ob.type == "square":
+            obs.append((1, 0, 0, p["center"][0], p["center"][1], float(p["size"]), m))
+        elif ob.type in ("polygon", "trapezoid", "elliptical_ring"):
+            pts = (elliptic_ring_points(p["center"], p["semi_axes"], p["width"], p.get("angle", np.pi), p.get("num_arc_points", 15),
+                                        p.get("rotation", 0.0)) if ob.type == "elliptical_ring" else p["points"])
+            obs.append((2, len(verts), len(pts), 0.0, 0.0, 0.0, m))
+            verts.extend([(float(x), float(y)) for x, y in pts])
+        else:
+            raise NotImplementedError(f"exact SDF of obstacle type {ob.type!r}")
+    arr = (_lib.RrtObstacle * len(obs))()
+    for i, (kind, first, n, cx, cy, size, m) in enumerate(obs):
+        arr[i] = _lib.RrtObstacle(kind, first, n, 0, float(cx), float(cy), float(size), float(m))
+    return arr, np.ascontiguousarray(np.asarray(verts, np.float64).reshape(-1, 2))
+
+
+def cuda_rrt_paths(cfg, seeds, start, goal, bounds, step_size: float, max_iter: int, inflation: float, goal_sample_rate: float = 0.05,
+                   device_index: int = 0, max_path: int = 512):
+    """The tree search as one CUDA kernel (``nlo_rrt_paths``).  Returns a list of (n_i, 2) fp64 paths root first (None where the planner
+    ran out of iterations)."""
+    import ctypes as C
+    from . import lib as _lib
+    L = _lib.load()
+    _lib.require_gpu()
+    obs, verts = scene_obstacles(cfg)
+    seeds = np.ascontiguousarray(seeds, np.int64)
+    P = len(seeds)
+    f2 = lambda v: np.ascontiguousarray(np.asarray(v, np.float64)[:2])
+    s2, g2, lo, hi = f2(start), f2(goal), f2(np.asarray(bounds, float)[0]), f2(np.asarray(bounds, float)[1])
+    path = np.empty((P, max_path, 2)); plen = np.empty(P, np.int32)
+    _lib.check(L.nlo_rrt_paths(obs, len(obs), verts.ctypes.data if len(verts) else None, len(verts), s2.ctypes.data, g2.ctypes.data,
+                               lo.ctypes.data, hi.ctypes.data, seeds.ctypes.data, P, float(step_size), int(max_iter), float(inflation),
+                               float(goal_sample_rate), int(max_path), int(device_index), path.ctypes.data, plen.ctypes.data))
+    if (plen == -2).any():
+        raise RuntimeError(f"RRT path longer than {max_path} nodes")
+    return [path[i, :plen[i]].copy() if plen[i] > 0 else None for i in range(P)]
+
+
 _POST_STATE = None      # (host planner, cfg, lift, nx, nu): set before the post-processing pool forks
 
 
@@ -201,17 +250,22 @@ def rrt_multistart_device(cfg, P: int, first: int = 0, seed0: int = 1234, lift: 
     may_fork = pool is None and not torch.cuda.is_initialized()      # decided before the trees run on the device
     host, bounds = _host_planner(cfg)
     seeds = [seed0 + first + i for i in range(P)]
-    pos, parent, final = batched_rrt_trees(torch_scene_sdf(cfg, device), b.start_state, b.goal_state, bounds, P, seeds, ini.step_size,
-                                           ini.max_iter, host.inflation, device=device)
-    paths = []
-    for i in range(P):
-        if final[i] < 0:
-            paths.append(None)
-            continue
-        idx, node = [], int(final[i])
-        while node >= 0:
-            idx.append(node); node = int(parent[i, node])
-        paths.append(pos[i, idx[::-1]])
+    if torch.device(device).type == "cuda":                   # the search as one kernel of the library: a warp per planner
+        dev_index = torch.device(device).index
+        paths = cuda_rrt_paths(cfg, seeds, b.start_state, b.goal_state, bounds, ini.step_size, ini.max_iter, host.inflation,
+                               device_index=dev_index if dev_index is not None else torch.cuda.current_device())
+    else:
+        pos, parent, final = batched_rrt_trees(torch_scene_sdf(cfg, device), b.start_state, b.goal_state, bounds, P, seeds, ini.step_size,
+                                               ini.max_iter, host.inflation, device=device)
+        paths = []
+        for i in range(P):
+            if final[i] < 0:
+                paths.append(None)
+                continue
+            idx, node = [], int(final[i])
+            while node >= 0:
+                idx.append(node); node = int(parent[i, node])
+            paths.append(pos[i, idx[::-1]])
     if workers is None:
         workers = min(32, os.cpu_count() or 1)
     workers = min(workers, P)

@@ -63,6 +63,51 @@ def test_multistart_guesses_have_the_reference_shape_and_clear_the_obstacles():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name", ["benchmark_3", "benchmark_4", "benchmark_5", "benchmark_6"])
+def test_cuda_rrt_kernel_plans_the_same_paths_as_the_tensor_program(name, library):
+    """nlo_rrt_paths (one warp per planner, csrc/rrt_kernels.cu) against the lock-step torch program on the CPU: same seeds, same
+    draws, same trees - the extracted paths agree node for node (fp64 on both sides)."""
+    from nlotrajectories_b200.rrt_device import _host_planner, cuda_rrt_paths
+    cfg = Config.load(bench_yaml(name))
+    ini, b = cfg.solver.initializer, cfg.body
+    host, bounds = _host_planner(cfg)
+    seeds = [2000 + i for i in range(24)]
+    got = cuda_rrt_paths(cfg, seeds, b.start_state, b.goal_state, bounds, ini.step_size, ini.max_iter, host.inflation)
+    pos, parent, final = batched_rrt_trees(torch_scene_sdf(cfg, CPU), b.start_state, b.goal_state, bounds, len(seeds), seeds, ini.step_size,
+                                           ini.max_iter, host.inflation, device=CPU)
+    same = 0
+    for i in range(len(seeds)):
+        if final[i] < 0:
+            assert got[i] is None
+            continue
+        idx, node = [], int(final[i])
+        while node >= 0:
+            idx.append(node); node = int(parent[i, node])
+        want = pos[i, idx[::-1]]
+        assert got[i] is not None and got[i].shape == want.shape, (i, None if got[i] is None else got[i].shape, want.shape)
+        np.testing.assert_allclose(got[i], want, atol=1e-9)
+        same += 1
+    assert same >= len(seeds) // 2
+
+
+@pytest.mark.gpu
+def test_cuda_rrt_4096_benchmark_6_plans(library, capsys):
+    """4,096 benchmark_6 starts planned on the GPU (tree search: one kernel) and post-processed on the host cores."""
+    import time
+    cfg = Config.load(bench_yaml("benchmark_6"))
+    t0 = time.time()
+    w0 = rrt_multistart_device(cfg, 4096, device=torch.device("cuda"))
+    dt = time.time() - t0
+    N, nx = cfg.solver.N, 7
+    X = w0[:, :nx * (N + 1)].reshape(4096, N + 1, nx).astype(float)
+    clear = scene_sdf(cfg)(X[..., 0], X[..., 1]).min(axis=1)
+    with capsys.disabled():
+        print(f"\n[rrt] 4,096 benchmark_6 plans in {dt:.2f} s (kernel + host post-processing); {(clear > 0).mean() * 100:.1f} % of the splines clear the obstacles")
+    assert (clear > 0).mean() > 0.95
+    assert len({tuple(np.round(x[::8, :2].ravel(), 5)) for x in X}) > 4000
+
+
+@pytest.mark.gpu
 def test_trees_on_the_gpu_are_valid_and_feed_the_solver(library):
     """The same tensor program on CUDA: every start of benchmark_3 finds a path whose spline clears the obstacles, and the guesses
     go straight into the batched interior point."""
