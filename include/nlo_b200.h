@@ -323,12 +323,14 @@ typedef struct nlo_rrt_obstacle {
 } nlo_rrt_obstacle;
 /* P planners, one per seed, each from start[2] towards goal[2] inside the box [lo, hi]: one warp per planner runs its whole search
  * (sample / nearest / steer by step_size / keep `inflation` of clearance at both ends and the midpoint of the new edge / stop within
- * step_size of the goal) in one kernel.  path_host[P][max_path][2] receives every path root first, path_len_host[P] its number of
- * nodes (-1: no path within max_iter iterations, -2: longer than max_path).  Synchronous.                                            */
+ * step_size of the goal) in one kernel.  postprocess != 0: the same warp then inserts a midpoint before every corner sharper than
+ * 60 degrees and shortcuts the path greedily through collision-free straight segments (the reference's insert_intermediate_points /
+ * _shortcut_path, core/trajectory_initialization.py:222-224).  path_host[P][max_path][2] receives every path root first,
+ * path_len_host[P] its number of nodes (-1: no path within max_iter iterations, -2: longer than max_path).  Synchronous.            */
 NLO_API int nlo_rrt_paths(const nlo_rrt_obstacle* obstacles, int n_obstacles, const double* vertices, int n_vertices,
                           const double* start, const double* goal, const double* lo, const double* hi, const long long* seeds, size_t P,
-                          double step_size, int max_iter, double inflation, double goal_sample_rate, int max_path, int device,
-                          double* path_host, int* path_len_host);
+                          double step_size, int max_iter, double inflation, double goal_sample_rate, int max_path, int postprocess,
+                          int device, double* path_host, int* path_len_host);
 
 /* layout helpers on device: [rows][ld] variable-major <-> [P][rows] problem-major              */
 NLO_API int nlo_transpose_to_soa(const float* aos, float* soa, size_t P, size_t rows, size_t ld, void* stream);

@@ -22,7 +22,7 @@ struct RrtScene {                  // passed by value
   const double* verts;             // device: [n][2]
   int n_obs;
   double sx, sy, gx, gy, lox, loy, hix, hiy, step, inflation, goal_rate;
-  int max_iter, M, max_path;
+  int max_iter, M, max_path, post;
 };
 
 __device__ __forceinline__ double rrt_uniform(long long seed, long long it, long long k) {
@@ -87,6 +87,19 @@ __device__ double rrt_scene_sdf(const RrtScene& S, double px, double py, int lan
   return best;
 }
 
+// every ~step along the segment p1 -> p2 the scene keeps `inflation` of clearance (trajectory_initialization.py:_collision_free);
+// evaluated by the whole warp, every lane returns the verdict
+__device__ bool rrt_segment_free(const RrtScene& S, double x1, double y1, double x2, double y2, int lane) {
+  const double dx = x2 - x1, dy = y2 - y1;
+  int n = (int)ceil(sqrt(dx * dx + dy * dy) / S.step);
+  if (n < 1) n = 1;
+  for (int q = 0; q <= n; ++q) {
+    const double t = (double)q / (double)n;
+    if (!(rrt_scene_sdf(S, x1 + dx * t, y1 + dy * t, lane) >= S.inflation)) return false;
+  }
+  return true;
+}
+
 __global__ void __launch_bounds__(128) rrt_trees_kernel(RrtScene S, const long long* __restrict__ seeds, size_t P, double* __restrict__ pos,
                                                         int* __restrict__ parent, double* __restrict__ path, int* __restrict__ path_len) {
   const size_t wid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -138,27 +151,60 @@ __global__ void __launch_bounds__(128) rrt_trees_kernel(RrtScene S, const long l
     }
   }
   // path: walk the parents from the goal node to the root, then store it root first
-  if (lane == 0) {
-    int len = -1;
-    if (final_node >= 0) {
-      len = 0;
-      for (int node = final_node; node >= 0; node = Pa[node]) ++len;
-      if (len > S.max_path) len = -2;                            // longer than the caller's buffer
-      else {
-        double* out = path + wid * (size_t)S.max_path * 2;
-        int k = len - 1;
-        for (int node = final_node; node >= 0; node = Pa[node], --k) { out[2 * k] = X[2 * node]; out[2 * k + 1] = X[2 * node + 1]; }
-      }
+  double* out = path + wid * (size_t)S.max_path * 2;
+  int len = -1;
+  if (final_node >= 0) {
+    len = 0;
+    for (int node = final_node; node >= 0; node = Pa[node]) ++len;
+    if (len > S.max_path) len = -2;                              // longer than the caller's buffer
+    else if (lane == 0) {
+      int k = len - 1;
+      for (int node = final_node; node >= 0; node = Pa[node], --k) { out[2 * k] = X[2 * node]; out[2 * k + 1] = X[2 * node + 1]; }
     }
-    path_len[wid] = len;
   }
+  __syncwarp();
+  if (S.post && len > 2) {
+    // (1) a midpoint before every corner sharper than 60 degrees (insert_intermediate_points), into the tree array as scratch
+    double* T = X;
+    int m = 0;
+    if (2 * len > S.M) len = -2;
+    else {
+      if (lane == 0) {
+        T[0] = out[0]; T[1] = out[1]; m = 1;
+        for (int i = 1; i < len - 1; ++i) {
+          const double v1x = out[2 * i] - out[2 * i - 2], v1y = out[2 * i + 1] - out[2 * i - 1];
+          const double v2x = out[2 * i + 2] - out[2 * i], v2y = out[2 * i + 3] - out[2 * i + 1];
+          double c = (v1x * v2x + v1y * v2y) / (sqrt(v1x * v1x + v1y * v1y) * sqrt(v2x * v2x + v2y * v2y));
+          c = c < -1.0 ? -1.0 : (c > 1.0 ? 1.0 : c);
+          if (acos(c) * 57.29577951308232 > 60.0) { T[2 * m] = (out[2 * i] + out[2 * i - 2]) / 2; T[2 * m + 1] = (out[2 * i + 1] + out[2 * i - 1]) / 2; ++m; }
+          T[2 * m] = out[2 * i]; T[2 * m + 1] = out[2 * i + 1]; ++m;
+        }
+        T[2 * m] = out[2 * len - 2]; T[2 * m + 1] = out[2 * len - 1]; ++m;
+      }
+      m = __shfl_sync(0xffffffffu, m, 0);
+      __syncwarp();
+      // (2) greedy shortcut: from node i jump to the farthest node the straight segment to which is collision free (_shortcut)
+      int n_out = 1, i = 0;                                     // out[0] is the start already
+      while (i < m - 1) {
+        int j = m - 1;
+        while (j > i + 1 && !rrt_segment_free(S, T[2 * i], T[2 * i + 1], T[2 * j], T[2 * j + 1], lane)) --j;
+        if (n_out >= S.max_path) { n_out = -2; break; }          // longer than the caller's buffer
+        if (lane == 0) { out[2 * n_out] = T[2 * j]; out[2 * n_out + 1] = T[2 * j + 1]; }
+        ++n_out;
+        i = j;
+      }
+      len = n_out;
+    }
+  }
+  if (lane == 0) path_len[wid] = len;
 }
 
 }  // namespace
 
 extern "C" int nlo_rrt_paths(const nlo_rrt_obstacle* obs, int n_obs, const double* vertices, int n_vertices, const double* start, const double* goal,
                              const double* lo, const double* hi, const long long* seeds, size_t P, double step_size, int max_iter,
-                             double inflation, double goal_sample_rate, int max_path, int device, double* path_host, int* path_len_host) {
+                             double inflation, double goal_sample_rate, int max_path, int postprocess, int device, double* path_host,
+                             int* path_len_host) {
   if (!obs || n_obs < 1 || !start || !goal || !lo || !hi || !seeds || !path_host || !path_len_host) return nlo_fail("null argument");
   if (P == 0) return 0;
   if (max_iter < 1 || max_path < 2 || !(step_size > 0.0)) return nlo_fail("rrt: bad parameters");
@@ -173,7 +219,7 @@ extern "C" int nlo_rrt_paths(const nlo_rrt_obstacle* obs, int n_obs, const doubl
   NLO_CUDA(cudaSetDevice(device));
   RrtScene S;
   S.n_obs = n_obs; S.sx = start[0]; S.sy = start[1]; S.gx = goal[0]; S.gy = goal[1]; S.lox = lo[0]; S.loy = lo[1]; S.hix = hi[0]; S.hiy = hi[1];
-  S.step = step_size; S.inflation = inflation; S.goal_rate = goal_sample_rate; S.max_iter = max_iter; S.M = max_iter + 3; S.max_path = max_path;
+  S.step = step_size; S.inflation = inflation; S.goal_rate = goal_sample_rate; S.max_iter = max_iter; S.M = max_iter + 3; S.max_path = max_path; S.post = postprocess;
   nlo_rrt_obstacle* d_obs = nullptr; double* d_verts = nullptr; long long* d_seeds = nullptr; double* d_pos = nullptr; int* d_parent = nullptr;
   double* d_path = nullptr; int* d_len = nullptr;
   auto cleanup = [&]() { for (void* b : {(void*)d_obs, (void*)d_verts, (void*)d_seeds, (void*)d_pos, (void*)d_parent, (void*)d_path, (void*)d_len}) if (b) cudaFree(b); };

@@ -100,7 +100,7 @@ SIGNATURES = {
     "nlo_ip_solve": (C.c_int, [_P, _F, _SZ, C.POINTER(IpOptions), _F, _F, _F, _F, _F, _F, _F, C.POINTER(IpStats)]),
     "nlo_ip_kkt_step": (C.c_int, [_P, _F, _F, _F, _F, _F, _SZ, _SZ, _F, _F, _P]),
     "nlo_rrt_paths": (C.c_int, [C.POINTER(RrtObstacle), C.c_int, _F, C.c_int, _F, _F, _F, _F, _F, _SZ, C.c_double, C.c_int, C.c_double, C.c_double,
-                                C.c_int, C.c_int, _F, _F]),
+                                C.c_int, C.c_int, C.c_int, _F, _F]),
     "nlo_transpose_to_soa": (C.c_int, [_F, _F, _SZ, _SZ, _SZ, _P]),
     "nlo_transpose_to_aos": (C.c_int, [_F, _F, _SZ, _SZ, _SZ, _P]),
 }

@@ -158,9 +158,10 @@ def scene_obstacles(cfg):
 
 
 def cuda_rrt_paths(cfg, seeds, start, goal, bounds, step_size: float, max_iter: int, inflation: float, goal_sample_rate: float = 0.05,
-                   device_index: int = 0, max_path: int = 512):
+                   device_index: int = 0, max_path: int = 512, postprocess: bool = False):
     """The tree search as one CUDA kernel (``nlo_rrt_paths``).  Returns a list of (n_i, 2) fp64 paths root first (None where the planner
-    ran out of iterations)."""
+    ran out of iterations).  ``postprocess``: the kernel also inserts the corner midpoints and shortcuts the path (what
+    ``RRTInitializer._shortcut(_insert_intermediate_points(path))`` does on the host)."""
     import ctypes as C
     from . import lib as _lib
     L = _lib.load()
@@ -173,7 +174,8 @@ def cuda_rrt_paths(cfg, seeds, start, goal, bounds, step_size: float, max_iter: 
     path = np.empty((P, max_path, 2)); plen = np.empty(P, np.int32)
     _lib.check(L.nlo_rrt_paths(obs, len(obs), verts.ctypes.data if len(verts) else None, len(verts), s2.ctypes.data, g2.ctypes.data,
                                lo.ctypes.data, hi.ctypes.data, seeds.ctypes.data, P, float(step_size), int(max_iter), float(inflation),
-                               float(goal_sample_rate), int(max_path), int(device_index), path.ctypes.data, plen.ctypes.data))
+                               float(goal_sample_rate), int(max_path), int(bool(postprocess)), int(device_index), path.ctypes.data,
+                               plen.ctypes.data))
     if (plen == -2).any():
         raise RuntimeError(f"RRT path longer than {max_path} nodes")
     return [path[i, :plen[i]].copy() if plen[i] > 0 else None for i in range(P)]
@@ -182,8 +184,9 @@ def cuda_rrt_paths(cfg, seeds, start, goal, bounds, step_size: float, max_iter: 
 _POST_STATE = None      # (host planner, cfg, lift, nx, nu): set before the post-processing pool forks
 
 
-def _post_one(path):
-    """Raw tree path (or None: planner failed) -> (X, U) like initializer._plan_one."""
+def _post_one(arg):
+    """(tree path or None when the planner failed, whether it is shortcut already) -> (X, U) like initializer._plan_one."""
+    path, shortcut_done = arg
     from .initializer import lift_path
     host, cfg, lift, nx, nu = _POST_STATE
     b, s = cfg.body, cfg.solver
@@ -191,7 +194,8 @@ def _post_one(path):
     if path is None:
         X = np.linspace(np.asarray(b.start_state, float), np.asarray(b.goal_state, float), N + 1)
     else:
-        path = host._shortcut(host._insert_intermediate_points(path))
+        if not shortcut_done:
+            path = host._shortcut(host._insert_intermediate_points(path))
         X = np.zeros((N + 1, nx))
         X[:, 0:2] = host._spline(path, N + 1)
     U = np.zeros((N, nu))
@@ -250,10 +254,12 @@ def rrt_multistart_device(cfg, P: int, first: int = 0, seed0: int = 1234, lift: 
     may_fork = pool is None and not torch.cuda.is_initialized()      # decided before the trees run on the device
     host, bounds = _host_planner(cfg)
     seeds = [seed0 + first + i for i in range(P)]
+    shortcut_done = False
     if torch.device(device).type == "cuda":                   # the search as one kernel of the library: a warp per planner
         dev_index = torch.device(device).index
         paths = cuda_rrt_paths(cfg, seeds, b.start_state, b.goal_state, bounds, ini.step_size, ini.max_iter, host.inflation,
-                               device_index=dev_index if dev_index is not None else torch.cuda.current_device())
+                               device_index=dev_index if dev_index is not None else torch.cuda.current_device(), postprocess=True)
+        shortcut_done = True
     else:
         pos, parent, final = batched_rrt_trees(torch_scene_sdf(cfg, device), b.start_state, b.goal_state, bounds, P, seeds, ini.step_size,
                                                ini.max_iter, host.inflation, device=device)
@@ -270,15 +276,15 @@ def rrt_multistart_device(cfg, P: int, first: int = 0, seed0: int = 1234, lift: 
         workers = min(32, os.cpu_count() or 1)
     workers = min(workers, P)
     if pool is not None:
-        plans = pool.map(_post_one, paths, chunksize=max(1, P // (4 * workers)))
+        plans = pool.map(_post_one, [(pth, shortcut_done) for pth in paths], chunksize=max(1, P // (4 * workers)))
     elif may_fork and str(device) == "cpu" and workers > 1 and P >= 8:
         import multiprocessing as mp
         _POST_STATE = (host, cfg, lift, nx, nu)
         with mp.get_context("fork").Pool(workers) as own:
-            plans = own.map(_post_one, paths, chunksize=max(1, P // (4 * workers)))
+            plans = own.map(_post_one, [(pth, shortcut_done) for pth in paths], chunksize=max(1, P // (4 * workers)))
     else:
         _POST_STATE = (host, cfg, lift, nx, nu)
-        plans = [_post_one(pth) for pth in paths]
+        plans = [_post_one((pth, shortcut_done)) for pth in paths]
     w = np.zeros((P, n_w), np.float32)
     for i, (X, U) in enumerate(plans):
         w[i, :n_X] = X.reshape(-1)

@@ -91,6 +91,31 @@ def test_cuda_rrt_kernel_plans_the_same_paths_as_the_tensor_program(name, librar
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name", ["benchmark_4", "benchmark_6"])
+def test_cuda_rrt_kernel_shortcuts_like_the_host_planner(name, library):
+    """postprocess=1: corner midpoints + greedy shortcut inside the kernel against RRTInitializer's numpy versions on the same raw
+    paths (decisions are comparisons of exact SDF values: a rare near-tie may differ, most paths must agree node for node)."""
+    from nlotrajectories_b200.rrt_device import _host_planner, cuda_rrt_paths
+    cfg = Config.load(bench_yaml(name))
+    ini, b = cfg.solver.initializer, cfg.body
+    host, bounds = _host_planner(cfg)
+    seeds = [3000 + i for i in range(48)]
+    args = (cfg, seeds, b.start_state, b.goal_state, bounds, ini.step_size, ini.max_iter, host.inflation)
+    raw = cuda_rrt_paths(*args)
+    post = cuda_rrt_paths(*args, postprocess=True)
+    same = total = 0
+    for r, p in zip(raw, post):
+        if r is None:
+            assert p is None
+            continue
+        want = host._shortcut(host._insert_intermediate_points(r))
+        total += 1
+        np.testing.assert_allclose(p[0], want[0]); np.testing.assert_allclose(p[-1], want[-1])
+        same += int(p.shape == want.shape and np.allclose(p, want, atol=1e-9))
+    assert total >= 24 and same >= 0.9 * total, (same, total)
+
+
+@pytest.mark.gpu
 def test_cuda_rrt_4096_benchmark_6_plans(library, capsys):
     """4,096 benchmark_6 starts planned on the GPU (tree search: one kernel) and post-processed on the host cores."""
     import time
