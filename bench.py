@@ -218,17 +218,17 @@ def run_reference(args):
 # CUDA arm
 # ---------------------------------------------------------------------------------------------------------
 def plan_solver_starts(args):
-    """Seeded RRT plans for the solve block, made on forked host processes BEFORE this process creates its CUDA context or NCCL
-    threads (a process that holds either must not fork).  Every rank plans the same `--solve-plans` seeds; they are tiled over the
-    batch with a small seeded jitter so that every start is distinct (tests/tools/ip_device_check.py does the same)."""
+    """The solve block plans one seeded RRT guess per start ON THE DEVICE (nlo_rrt_paths: tree search, corner midpoints and shortcut in
+    one kernel, a warp per planner); only the cubic spline and the lifting of each path run on host processes, which are forked here,
+    BEFORE this process creates its CUDA context or NCCL threads (a process that holds either must not fork)."""
     if args.solve_problems <= 0:
         return None
     from nlotrajectories_b200.config import Config
-    from nlotrajectories_b200.initializer import rrt_multistart
+    from nlotrajectories_b200.rrt_device import make_post_pool
     cfg = Config.load(REPO / "nlotrajectories_b200" / "benchmarks" / YAML)
-    t0 = time.perf_counter()
-    plans = rrt_multistart(cfg, args.solve_plans, lift=True).astype(np.float64)
-    return {"plans": plans, "seconds": time.perf_counter() - t0}
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    workers = max(1, min(32, (os.cpu_count() or 1) // world))
+    return {"cfg": cfg, "pool": make_post_pool(cfg, lift=True, workers=workers), "workers": workers}
 
 
 def run_solver(args, planned, rank, local_rank, world, dev):
@@ -249,13 +249,11 @@ def run_solver(args, planned, rank, local_rank, world, dev):
     total = args.solve_problems
     lo, hi = shard_range(total, rank, world)
     P = hi - lo
-    plans = planned["plans"]
-    idx = np.arange(lo, hi)
-    w0 = plans[idx % len(plans)].copy()
-    jitter = np.stack([np.random.default_rng(7_000_000 + int(i)).normal(0.0, 0.005, (prob.N + 1, 2)) for i in idx]) if P else np.zeros((0, prob.N + 1, 2))
-    jitter[:, 0] = 0.0; jitter[:, -1] = 0.0
-    jitter[idx < len(plans)] = 0.0                                        # the plans themselves stay as planned
-    w0[:, :prob.n_X].reshape(P, prob.N + 1, prob.nx)[:, :, :2] += jitter
+    from nlotrajectories_b200.rrt_device import rrt_multistart_device
+    t0 = time.perf_counter()
+    w0 = rrt_multistart_device(planned["cfg"], P, first=lo, lift=True, device=dev, pool=planned["pool"], workers=planned["workers"]).astype(np.float64)
+    plan_s = time.perf_counter() - t0
+    planned["pool"].close(); planned["pool"].join()
     solver = DeviceIPSolver(prob, max_problems=max(P, 1), max_iter=args.solve_max_iter)
     if world > 1:
         dist.barrier()
@@ -273,11 +271,12 @@ def run_solver(args, planned, rank, local_rank, world, dev):
     score = torch.from_numpy(np.where(usable, f, f + 1e3 * (1.0 + v))).float().to(dev)
     best_val, best_idx, _ = select_best(score, res.w.float().T.contiguous().to(dev), lo, prob.n_w)
     n_ok, n_st, n_all = (float(c) for c in counts.tolist())
-    return {"workload": f"{YAML} x {total} starts sharded over {world} GPU(s): {len(plans)} seeded RRT plans (lifted), tiled with N(0, 0.005) path jitter",
+    return {"workload": f"{YAML} x {total} starts sharded over {world} GPU(s): one seeded RRT plan per start (device tree search + shortcut, nlo_rrt_paths; "
+                        "spline and lifting on host processes)",
             "sdf_model": "tests/golden/sdf_benchmark_6_relu128.npz (ReLU 2-128-128-1 trained on the YAML's scene)",
             "solver": "device interior point, tol 1e-4, exact Hessian, block-tridiagonal KKT kernels (nlo_ip_solve)", "max_iter": args.solve_max_iter,
             "solve_s": float(t.item()), "solves_per_s": n_all / float(t.item()), "converged_frac": n_ok / max(n_all, 1.0),
-            "stalled_feasible_frac": n_st / max(n_all, 1.0), "stats_rank0": solver.stats, "rrt_plan_s": planned["seconds"],
+            "stalled_feasible_frac": n_st / max(n_all, 1.0), "stats_rank0": solver.stats, "rrt_plan_s_rank0": plan_s,
             "best_of_batch": {"objective": best_val, "global_index": best_idx, "selection": "all-gather of (objective, index) + broadcast of the winner over the SOLVED starts"}}
 
 
@@ -527,7 +526,6 @@ def main():
     ap.add_argument("--cpu-problems", type=int, default=8192, help="problems per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--solve-problems", type=int, default=16384, help="starts solved by the device interior point after the timed evaluation (0: skip)")
-    ap.add_argument("--solve-plans", type=int, default=256, help="seeded RRT plans the solved starts are tiled from")
     ap.add_argument("--solve-max-iter", type=int, default=300)
     args = ap.parse_args()
     if args.impl == "reference":
