@@ -375,10 +375,8 @@ __device__ __forceinline__ void nlp_grad_body(const NlpDev& L, const float* __re
 }
 
 // ---- everything that precedes the SDF evaluation, in ONE launch: blockIdx.y selects the role and its row -----------------
-// ANALYTIC (solver.mode casadi): the footprint role evaluates the obstacles and writes the SDF rows itself; the jets of the square
-// obstacles need more than the 32 registers the light roles are held to.
-template <int DYN, bool ANALYTIC>
-__global__ void __launch_bounds__(256, ANALYTIC ? 3 : 8) nlp_phase0_kernel(NlpDev L, const float* __restrict__ w, size_t P, size_t ld, float* __restrict__ g,
+template <int DYN>
+__global__ void __launch_bounds__(256, 8) nlp_phase0_kernel(NlpDev L, const float* __restrict__ w, size_t P, size_t ld, float* __restrict__ g,
                                                          float* __restrict__ jac, float* __restrict__ px, float* __restrict__ py,
                                                          float* __restrict__ f, float* __restrict__ grad, int n_dyn, int n_copy, int n_pts,
                                                          int n_grad) {
@@ -387,14 +385,17 @@ __global__ void __launch_bounds__(256, ANALYTIC ? 3 : 8) nlp_phase0_kernel(NlpDe
   r -= n_dyn;
   if (r < n_copy) { nlp_copy_rows_body(L, w, P, ld, g, jac, r); return; }
   r -= n_copy;
-  if (r < n_pts) {
-    if (ANALYTIC) nlp_analytic_rows_body(L, w, P, ld, g, jac, r);   // analytic obstacles: rows at once, no scratch
-    else nlp_points_body(L, w, P, ld, px, py, r);
-    return;
-  }
+  if (r < n_pts) { nlp_points_body(L, w, P, ld, px, py, r); return; }
   r -= n_pts;
   if (r < n_grad) { nlp_grad_body(L, w, P, ld, grad, r); return; }
   nlp_obj_body(L, w, P, ld, f);
+}
+// analytic obstacles (solver.mode casadi): footprint points, union SDF and constraint rows of one knot per block row - its own launch,
+// because the jets of the square obstacles need far more than the 32 registers the light roles of the phase-0 launch are held to
+// (inside that launch they cost every role its occupancy: benchmark_1 x 65,536 went from 0.18 to 0.25 ms)
+__global__ void __launch_bounds__(256) nlp_analytic_rows_kernel(NlpDev L, const float* __restrict__ w, size_t P, size_t ld,
+                                                                float* __restrict__ g, float* __restrict__ jac) {
+  nlp_analytic_rows_body(L, w, P, ld, g, jac, blockIdx.y);
 }
 __global__ void __launch_bounds__(256) nlp_points_kernel(NlpDev L, const float* __restrict__ w, size_t P, size_t ld,
                                                          float* __restrict__ px, float* __restrict__ py) {
@@ -485,23 +486,25 @@ int nlo_nlp_launch_assembly(nlo_nlp* p, const NlpScratch& sc, const float* w, si
   const int sm = p->sm_count;
   if (phase == 0) {
     const bool gj = g || jac;
-    const int n_dyn = gj ? L.N : 0, n_copy = gj ? L.n_copy : 0, n_pts = gj ? L.N + 1 : 0, n_grad = grad_f ? L.N + 1 : 0, n_obj = f ? 1 : 0;
+    const bool analytic = L.sdf_mode == NLO_SDF_CIRCLES;
+    const int n_dyn = gj ? L.N : 0, n_copy = gj ? L.n_copy : 0, n_pts = (gj && !analytic) ? L.N + 1 : 0, n_grad = grad_f ? L.N + 1 : 0, n_obj = f ? 1 : 0;
     const unsigned rows = (unsigned)(n_dyn + n_copy + n_pts + n_grad + n_obj);
     if (rows) {
       const dim3 grid((unsigned)std::min<size_t>((P + 255) / 256, 4096), rows);
       switch (L.dyn) {
-#define NLO_CASE(D) case D:                                                                                                         \
-          if (L.sdf_mode == NLO_SDF_CIRCLES) nlp_phase0_kernel<D, true><<<grid, 256, 0, st>>>(L, w, P, ld, g, jac, sc.px, sc.py, f, grad_f, n_dyn, n_copy, n_pts, n_grad); \
-          else nlp_phase0_kernel<D, false><<<grid, 256, 0, st>>>(L, w, P, ld, g, jac, sc.px, sc.py, f, grad_f, n_dyn, n_copy, n_pts, n_grad);               \
-          break;
+#define NLO_CASE(D) case D: nlp_phase0_kernel<D><<<grid, 256, 0, st>>>(L, w, P, ld, g, jac, sc.px, sc.py, f, grad_f, n_dyn, n_copy, n_pts, n_grad); break;
         NLO_CASE(NLO_DYN_POINT_1ST) NLO_CASE(NLO_DYN_POINT_2ND) NLO_CASE(NLO_DYN_UNICYCLE)
         NLO_CASE(NLO_DYN_UNICYCLE_2ND) NLO_CASE(NLO_DYN_ACKERMANN) NLO_CASE(NLO_DYN_ACKERMANN_2ND)
 #undef NLO_CASE
       }
       NLO_CHECK_LAUNCH();
     }
+    if (gj && analytic) {                                    // footprint + union SDF + rows in one pass, no scratch
+      nlp_analytic_rows_kernel<<<dim3((unsigned)std::min<size_t>((P + 255) / 256, 4096), (unsigned)(L.N + 1)), 256, 0, st>>>(L, w, P, ld, g, jac);
+      NLO_CHECK_LAUNCH();
+    }
   } else {
-    if ((g || jac) && L.sdf_mode != NLO_SDF_CIRCLES) {       // (analytic obstacles: phase 0 wrote the rows already)
+    if ((g || jac) && L.sdf_mode != NLO_SDF_CIRCLES) {       // (analytic obstacles: nlp_analytic_rows_kernel wrote the rows in phase 0)
       nlp_sdf_rows_kernel<<<dim3((unsigned)std::min<size_t>((P + 255) / 256, 4096), (unsigned)(L.N + 1)), 256, 0, st>>>(L, w, P, ld, sc.s, sc.jx, sc.jy, g, jac);
       NLO_CHECK_LAUNCH();
     }
@@ -513,7 +516,7 @@ int nlo_nlp_launch_assembly(nlo_nlp* p, const NlpScratch& sc, const float* w, si
 int nlo_nlp_launch_dynamics(const NlpDev& L, const float* w, size_t P, size_t ld, float* g, float* jac, cudaStream_t st) {
   const dim3 grid((unsigned)std::min<size_t>((P + 255) / 256, 4096), (unsigned)L.N);
   switch (L.dyn) {
-#define NLO_CASE(D) case D: nlp_phase0_kernel<D, false><<<grid, 256, 0, st>>>(L, w, P, ld, g, jac, nullptr, nullptr, nullptr, nullptr, L.N, 0, 0, 0); break;
+#define NLO_CASE(D) case D: nlp_phase0_kernel<D><<<grid, 256, 0, st>>>(L, w, P, ld, g, jac, nullptr, nullptr, nullptr, nullptr, L.N, 0, 0, 0); break;
     NLO_CASE(NLO_DYN_POINT_1ST) NLO_CASE(NLO_DYN_POINT_2ND) NLO_CASE(NLO_DYN_UNICYCLE)
     NLO_CASE(NLO_DYN_UNICYCLE_2ND) NLO_CASE(NLO_DYN_ACKERMANN) NLO_CASE(NLO_DYN_ACKERMANN_2ND)
 #undef NLO_CASE
