@@ -59,7 +59,8 @@ struct TcCfg {
   static constexpr int NGROUPS = 512 / TMEM_COLS;
   static constexpr int THREADS = NGROUPS * GROUP_THREADS;           // 512
   static constexpr size_t bytes(bool relu_hidden) {
-    return (size_t)(relu_hidden ? 4 : 2) * IMG_HALFS * 2 + (size_t)NGROUPS * 2 * TILE * 4 * 4 + NGROUPS * 8 + 16 + NGROUPS * 4;
+    return (size_t)(relu_hidden ? 4 : 2) * IMG_HALFS * 2 + (size_t)NGROUPS * 2 * TILE * 4 * 4 + NGROUPS * 8 + 16 + NGROUPS * 4 +
+           (size_t)NGROUPS * 2 * 3 * TILE * 4;      // + the coordinate staging of the next tile, double-buffered per group
   }
 };
 
@@ -76,11 +77,12 @@ struct TileCtx {
 };
 
 template <int H, bool RELU_BWD>
-__device__ __forceinline__ void issue_mmas(const TileCtx& c, bool fwd) {
+__device__ __forceinline__ void issue_mmas(const TileCtx& c, bool fwd, long long* dbg = nullptr) {
   constexpr uint32_t COL_AHI = 0, COL_ALO = H / 2, COL_D = H;
   constexpr uint32_t IDESC_K = umma_idesc_f16(TILE, H, 0), IDESC_MN = umma_idesc_f16(TILE, H, 1);
   if (!fwd && RELU_BWD) {
 #pragma unroll
+    if (dbg) dbg[30] = clock64();
     for (int pass = 0; pass < 2; ++pass) {               // smaller term first: mask.lo, mask.hi
       const uint32_t b_base = (pass == 0) ? c.sV_lo : c.sV_hi;
 #pragma unroll
@@ -88,11 +90,13 @@ __device__ __forceinline__ void issue_mmas(const TileCtx& c, bool fwd) {
         tc_mma_f16_ts(c.tmem_base + COL_D, c.tmem_base + COL_AHI + ks * 8, umma_desc(b_base + ks * 32u * H, 16u * H, 128u), IDESC_K,
                       (pass | ks) != 0);
     }
+    if (dbg) dbg[31] = clock64();
   } else {
     const uint32_t lbo = fwd ? 16u * H : 128u, sbo = fwd ? 128u : 16u * H;
     const uint32_t kstep_bytes = fwd ? 32u * H : 256u;     // 16 k: two K-adjacent core matrices
     const uint32_t idesc = fwd ? IDESC_K : IDESC_MN;
 #pragma unroll
+    if (dbg && fwd) dbg[13] = clock64();
     for (int pass = 0; pass < 3; ++pass) {               // smallest terms first: lo.hi, hi.lo, hi.hi
       const uint32_t a_col = (pass == 0) ? COL_ALO : COL_AHI;
       const uint32_t b_base = (pass == 1) ? c.sB_lo : c.sB_hi;
@@ -100,8 +104,13 @@ __device__ __forceinline__ void issue_mmas(const TileCtx& c, bool fwd) {
       for (int ks = 0; ks < H / 16; ++ks)
         tc_mma_f16_ts(c.tmem_base + COL_D, c.tmem_base + a_col + ks * 8, umma_desc(b_base + ks * kstep_bytes, lbo, sbo), idesc,
                       (pass | ks) != 0);
+      if (dbg && fwd) dbg[pass == 0 ? 14 : pass == 1 ? 15 : 29] = clock64();
     }
   }
+  // The lock goes back right behind the last MMA, ahead of the commit, with a plain store: it only shapes the order in which the groups'
+  // GEMMs enter the tensor queue.  (With commit + __threadfence_block() + atomicExch in front of the release the lock stayed taken for
+  // 300 - 600 cycles after the last MMA - NLO_B200_TC_TIMELINE - while the other group's issuer waited for it with the queue draining.)
+  *reinterpret_cast<volatile int*>(c.lock) = 0;
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(c.mbar_addr) : "memory");
 }
 // Lane 0 of the group issues the MMAs of a GEMM and commits them to the group's mbarrier.  The CTA-wide lock makes the
@@ -111,15 +120,14 @@ __device__ __forceinline__ void issue_mmas(const TileCtx& c, bool fwd) {
 // MMA, instead of wrapping each one in a ~16-instruction R2UR waterfall loop.  Measured on B200 (G points/s, ReLU
 // H=128 / H=64): this form 6.39 / 15.97; plain single lane 6.02 / 12.54; whole warp converged + elect 5.54 / 15.15.
 template <int H, bool RELU_BWD>
-__device__ __forceinline__ void issue_gemm(const TileCtx& c, bool fwd, long long* dbg) {
+__device__ __forceinline__ uint32_t issue_gemm(const TileCtx& c, bool fwd, long long* dbg) {
   tc_fence_after();
   while (atomicCAS(c.lock, 0, 1) != 0) { }
   if (dbg) dbg[fwd ? 10 : 11] = clock64();
-  if (elect_one(1u)) issue_mmas<H, RELU_BWD>(c, fwd);
-  __threadfence_block();
-  atomicExch(c.lock, 0);
-  // next tile of this group: the atomic's latency hides behind the GEMM that was just issued
-  if (fwd && c.ctr) *c.next_slot = atomicAdd(c.ctr, 1u) + c.ctr_bias;
+  if (elect_one(1u)) issue_mmas<H, RELU_BWD>(c, fwd, dbg);
+  // next tile of this group: requested here, consumed (stored to next_slot) at the end of the tile - the round trip to the one hot
+  // counter is longer than the GEMM, and with the store right here the issuing thread sat it out while its group waited for it
+  return (fwd && c.ctr) ? atomicAdd(c.ctr, 1u) : 0u;      // (the bias is added where the value is consumed, not here)
 }
 // One tile (128 points) of one group.  SPLIT = 2: two threads own a point - HALF 0 the low half of the neurons / D
 // columns, HALF 1 the high half; they meet only to add three partial sums per point through shared memory.
@@ -144,6 +152,7 @@ __device__ __noinline__ uint32_t sdf_tc_tile(TileCtx c, uint32_t phase, float px
 #define TC_STAMP(i) do { if (dbg) dbg[i] = clock64(); } while (0)
   TC_STAMP(0);
   if (dbg) { unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); dbg[12] = (long long)gt; }
+  uint32_t next_tile_idx = 0u;
   // ---- layer 0 -> A operand (row-scaled fp16 hi/lo) ------------------------------------------------------------
   float sc0, inv0;
   row_scale(act_bound(c.act0, c.prm0, fmaf(fabsf(px), c.max_w0x, fmaf(fabsf(py), c.max_w0y, c.max_b0))) + 1e-30f, sc0, inv0);
@@ -175,7 +184,7 @@ __device__ __noinline__ uint32_t sdf_tc_tile(TileCtx c, uint32_t phase, float px
   tc_fence_before();
   group_bar<NT>(c.bar_id);
   TC_STAMP(8);
-  if (tg == 0) issue_gemm<H, RH>(c, true, dbg);
+  if (tg == 0) next_tile_idx = issue_gemm<H, RH>(c, true, dbg);
   TC_STAMP(2);
   mbar_wait_addr(c.mbar_addr, phase); phase ^= 1;
   tc_fence_after();
@@ -308,6 +317,8 @@ __device__ __noinline__ uint32_t sdf_tc_tile(TileCtx c, uint32_t phase, float px
     if (s_ptr) *s_ptr = s;
     if (j_ptr) { j_ptr[0] = jx; j_ptr[jy_off] = jy; }
     if (HESS && h_ptr) { h_ptr[0] = hxx; h_ptr[c.hxy_off] = hxy; h_ptr[c.hyy_off] = hyy; }
+    if (HALF == 0 && tg == 0 && c.ctr) *c.next_slot = next_tile_idx + c.ctr_bias;
+    asm volatile("cp.async.wait_all;" ::: "memory");       // the next tile's coordinates (staged by the persistent loop) have landed
     // the next tile's tcgen05.st / MMA must not overtake this tile's TMEM reads
     tc_fence_before();
     group_bar<NT>(c.bar_id);
@@ -318,6 +329,8 @@ __device__ __noinline__ uint32_t sdf_tc_tile(TileCtx c, uint32_t phase, float px
   float* mine = part + (HALF * TILE + pt) * 4;
   if (HALF == 0) { mine[0] = jy; if (HESS) mine[1] = hyy; }
   else { mine[0] = s; mine[1] = jx; if (HESS) { mine[2] = hxx; mine[3] = hxy; } }
+  if (HALF == 0 && tg == 0 && c.ctr) *c.next_slot = next_tile_idx + c.ctr_bias;
+  asm volatile("cp.async.wait_all;" ::: "memory");         // the next tile's coordinates (staged by the persistent loop) have landed
   // (this barrier also keeps the next tile's tcgen05.st / MMA from overtaking this tile's TMEM reads)
   tc_fence_before();
   group_bar<NT>(c.bar_id);
@@ -332,6 +345,7 @@ __device__ __noinline__ uint32_t sdf_tc_tile(TileCtx c, uint32_t phase, float px
     if (HESS && h_ptr) h_ptr[c.hyy_off] = hyy + other[1];
   }
   // `part` is rewritten by the next tile only after its first group barrier, which every thread reaches after these reads
+  if (HALF == 0) TC_STAMP(27);
   return phase;
 }
 
@@ -351,6 +365,7 @@ sdf_tc_kernel(SdfNetDev net, TcParams prm_tc, const __half* __restrict__ bimg, c
   int* lock = reinterpret_cast<int*>(mbar + Cfg::NGROUPS);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lock + 1);
   uint32_t* next_tile = tmem_slot + 1;                                                      // [NGROUPS]
+  float* sCoord = reinterpret_cast<float*>(next_tile + Cfg::NGROUPS);                       // [NGROUPS][2][3][TILE]: x | y | seed of the next tile
   const int t = threadIdx.x, warp = t >> 5;
   const int grp = t / Cfg::GROUP_THREADS, tg = t % Cfg::GROUP_THREADS;
   const int half = (tg >> 5) >> 2;
@@ -399,19 +414,32 @@ sdf_tc_kernel(SdfNetDev net, TcParams prm_tc, const __half* __restrict__ bimg, c
   // can be pulled towards the SM while this tile computes (the loads at the top of a tile are otherwise an exposed DRAM latency).
   const size_t stride = (size_t)gridDim.x * Cfg::NGROUPS;
   size_t tile_next = (size_t)blockIdx.x * Cfg::NGROUPS + grp + stride;
+  // The coordinates of the group's NEXT tile travel global -> shared memory with cp.async while this tile computes (its index is known
+  // a tile ahead, see above), double-buffered per group; the tile body waits for the copies just before its final barrier.  Loading them
+  // at the top of their own tile left 400 - 800 cycles of L2 / DRAM latency exposed in front of every tile's layer 0 (a prefetch.global.L1
+  // a tile ahead did not survive in the 28 KB of L1 that the operand images leave).
+  float* coord = sCoord + grp * (2 * 3 * TILE);
   for (size_t tile = (size_t)blockIdx.x * Cfg::NGROUPS + grp; tile < n_tiles; ++it) {
     if (tile_next < n_tiles && half == 0) {
       const size_t in = min(tile_next * TILE + pt, n - 1);
-      asm volatile("prefetch.global.L1 [%0];" :: "l"(x + in));
-      asm volatile("prefetch.global.L1 [%0];" :: "l"(y + in));
-      if (sbar) asm volatile("prefetch.global.L1 [%0];" :: "l"(sbar + in));
+      float* dst = coord + ((it + 1) & 1) * (3 * TILE) + pt;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(dst)), "l"(x + in) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(dst + TILE)), "l"(y + in) : "memory");
+      if (sbar) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(dst + 2 * TILE)), "l"(sbar + in) : "memory");
     }
     // timeline: groups 0 and 1 of CTA 0, first 64 tiles
     c.dbg = (dbg && (it & 15) == 0 && (it >> 4) < 64 && blockIdx.x == 0 && grp < 2) ? dbg + (grp * 64 + (it >> 4)) * 32 : nullptr;
+    if (c.dbg && tg == 0) c.dbg[26] = clock64();
     const size_t i = tile * TILE + pt;
     const bool valid = i < n;
-    const size_t ic = valid ? i : n - 1;
-    const float px = x[ic], py = y[ic], seed = sbar ? sbar[ic] : 1.f;
+    float px, py, seed;
+    if (it == 0) {
+      const size_t ic = valid ? i : n - 1;
+      px = x[ic]; py = y[ic]; seed = sbar ? sbar[ic] : 1.f;
+    } else {
+      const float* src = coord + (it & 1) * (3 * TILE) + pt;
+      px = src[0]; py = src[TILE]; seed = sbar ? src[2 * TILE] : 1.f;
+    }
     if (Cfg::SPLIT == 1) {
       // jx and jy are both written by the one owner of the point (both non-null whenever a Jacobian is requested through this path)
       phase = sdf_tc_tile<H, ACT0, ACT, FULL, 1, 0, HESS>(c, phase, px, py, seed, want_jac, part, (valid && s_out) ? s_out + i : nullptr,
@@ -512,6 +540,10 @@ int launch_tc(nlo_sdf_model* m, const float* x, const float* y, const float* sba
         fprintf(stderr, "[tc timeline] group%d tile%2d half0: L0 %5lld bar %5lld lock %5lld issue %5lld mma1 %5lld E1 %5lld bar %5lld lock %5lld issue %5lld mma2 %5lld E2 %5lld | start-to-start %6lld | half1 L0 %5lld E1 %5lld E2 %5lld\n",
                 g, it, r[1] - r[0], r[8] - r[1], r[10] - r[8], r[2] - r[10], r[3] - r[2], r[4] - r[3], r[9] - r[4], r[11] - r[9], r[5] - r[11], r[6] - r[5], r[7] - r[6],
                 0LL, r[17] - r[16], r[20] - r[19], r[23] - r[22]);
+        fprintf(stderr, "[tc timeline]   loop top -> tile body %5lld | E2 end -> tile end (exchange, barrier, stores) %5lld | whole tile incl. loads %6lld\n",
+                r[0] - r[26], r[27] - r[7], r[27] - r[26]);
+        fprintf(stderr, "[tc timeline]   GEMM 1 issue: lock -> first MMA %5lld, pass 0 %5lld, pass 1 %5lld, pass 2 %5lld, -> returned %5lld | GEMM 2: lock -> first %5lld, MMAs %5lld, -> returned %5lld\n",
+                r[13] - r[10], r[14] - r[13], r[15] - r[14], r[29] - r[15], r[2] - r[29], r[30] - r[11], r[31] - r[30], r[5] - r[31]);
       }
   }
   NLO_CHECK_LAUNCH();

@@ -87,16 +87,17 @@ __device__ __forceinline__ void deep_issue_mmas(const DeepCtx& c, int l, bool fw
     for (int ks = 0; ks < H / 16; ++ks)
       tc_mma_f16_ts(c.tmem_base + COL_D, c.tmem_base + a_col + ks * 8, umma_desc(b_base + ks * kstep_bytes, lbo, sbo), idesc, (pass | ks) != 0);
   }
+  *reinterpret_cast<volatile int*>(c.lock) = 0;          // the lock goes back right behind the last MMA, ahead of the commit (sdf_tc.cu)
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(c.mbar_addr) : "memory");
 }
 template <int H>
-__device__ __forceinline__ void deep_issue_gemm(const DeepCtx& c, int l, bool fwd, bool fetch_next) {
+__device__ __forceinline__ uint32_t deep_issue_gemm(const DeepCtx& c, int l, bool fwd, bool fetch_next) {
   tc_fence_after();
   while (atomicCAS(c.lock, 0, 1) != 0) { }
   if (elect_one(1u)) deep_issue_mmas<H>(c, l, fwd);
-  __threadfence_block();
-  atomicExch(c.lock, 0);
-  if (fetch_next && c.ctr) *c.next_slot = atomicAdd(c.ctr, 1u) + c.ctr_bias;
+  // next tile of this group: requested here, stored to next_slot at the end of the tile (sdf_tc.cu: the issuing thread must not
+  // sit out the counter's round trip in front of its epilogue)
+  return (fetch_next && c.ctr) ? atomicAdd(c.ctr, 1u) : 0u;      // (the bias is added where the value is consumed)
 }
 
 // One tile of one group.  SPLIT threads own a point: thread HALF (0 .. SPLIT-1) the neurons / D columns [HALF * H / SPLIT, ...).
@@ -112,6 +113,7 @@ __device__ __noinline__ uint32_t sdf_deep_tile(DeepCtx c, uint32_t phase, float 
   constexpr uint32_t COL_AHI = HALF * (HH / 2), COL_ALO = H / 2 + HALF * (HH / 2), COL_D = H + C0;
   const int tg = threadIdx.x % NT;
   const int pt = tg & (DTILE - 1);
+  uint32_t next_tile_idx = 0u;
   // ---- layer 0 -> A ---------------------------------------------------------------------------------------------------------
   float bound = act_bound(ACT0, c.prm0, fmaf(fabsf(px), c.p.max_w0x, fmaf(fabsf(py), c.p.max_w0y, c.p.max_b0))) + 1e-30f;
   float sc, inv;
@@ -140,7 +142,7 @@ __device__ __noinline__ uint32_t sdf_deep_tile(DeepCtx c, uint32_t phase, float 
     tc_wait_st();
     tc_fence_before();
     group_bar<NT>(c.bar_id);
-    if (tg == 0) deep_issue_gemm<H>(c, l, true, l == 1);
+    if (tg == 0) { const uint32_t nx = deep_issue_gemm<H>(c, l, true, l == 1); if (l == 1) next_tile_idx = nx; }
     mbar_wait_addr(c.mbar_addr, phase); phase ^= 1;
     tc_fence_after();
     const float unscale = inv * c.p.inv_sw[l - 1];
@@ -253,6 +255,7 @@ __device__ __noinline__ uint32_t sdf_deep_tile(DeepCtx c, uint32_t phase, float 
   if (SPLIT == 1) {
     if (s_ptr) *s_ptr = s;
     if (j_ptr) { j_ptr[0] = jx; j_ptr[jy_off] = jy; }
+    if (HALF == 0 && tg == 0 && c.ctr) *c.next_slot = next_tile_idx + c.ctr_bias;
     tc_fence_before();
     group_bar<NT>(c.bar_id);                    // the next tile's tcgen05.st / MMA must not overtake this tile's TMEM reads
     tc_fence_after();
@@ -261,6 +264,7 @@ __device__ __noinline__ uint32_t sdf_deep_tile(DeepCtx c, uint32_t phase, float 
   // partial sums of the SPLIT owners of a point meet in shared memory; owner 0 adds them up and stores
   float* mine = part + (HALF * DTILE + pt) * 4;
   mine[0] = s; mine[1] = jx; mine[2] = jy;
+  if (HALF == 0 && tg == 0 && c.ctr) *c.next_slot = next_tile_idx + c.ctr_bias;
   tc_fence_before();
   group_bar<NT>(c.bar_id);                      // (also keeps the next tile's tcgen05.st / MMA behind this tile's TMEM reads)
   tc_fence_after();

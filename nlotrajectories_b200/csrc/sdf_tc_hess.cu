@@ -60,10 +60,9 @@ __device__ __forceinline__ void hess_issue_gemm(const HessCtx& c, uint32_t d_col
       for (int ks = 0; ks < H / 16; ++ks)
         tc_mma_f16_ts(c.tmem_base + d_col, c.tmem_base + a_col + ks * 8, umma_desc(b_base + ks * kstep_bytes, lbo, sbo), idesc, (pass | ks) != 0);
     }
+    *reinterpret_cast<volatile int*>(c.lock) = 0;        // the lock goes back right behind the last MMA, ahead of the commit (sdf_tc.cu)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(c.mbar_addr) : "memory");
   }
-  __threadfence_block();
-  atomicExch(c.lock, 0);
 }
 
 // value, first and second derivative of the compile-time activation
