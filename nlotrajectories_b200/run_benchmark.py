@@ -156,7 +156,7 @@ def main():
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tc3xf16"])
     ap.add_argument("--solve", action="store_true", help="solve every start (batched interior point) instead of evaluating the initial guesses")
     ap.add_argument("--lift", action="store_true", help="--solve: fill heading / speed / steering of the RRT guesses from the planned path")
-    ap.add_argument("--device-rrt", action="store_true", help="--solve: grow the RRT trees of all starts in lock step on the GPU instead of on host processes")
+    ap.add_argument("--device-rrt", action="store_true", help="--solve: plan the RRT paths of all starts with the CUDA planner (one warp per start) instead of on host processes")
     ap.add_argument("--elastic", type=float, default=None, metavar="PENALTY", help="--solve: elastic mode (exact l1 penalty) on the inequality rows")
     ap.add_argument("--dense", action="store_true", help="--solve: the dense torch solver instead of the device solver (at most 512 starts)")
     ap.add_argument("--max-iter", type=int, default=300, help="--solve: iteration limit")
