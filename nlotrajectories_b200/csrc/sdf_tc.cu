@@ -81,8 +81,8 @@ __device__ __forceinline__ void issue_mmas(const TileCtx& c, bool fwd, long long
   constexpr uint32_t COL_AHI = 0, COL_ALO = H / 2, COL_D = H;
   constexpr uint32_t IDESC_K = umma_idesc_f16(TILE, H, 0), IDESC_MN = umma_idesc_f16(TILE, H, 1);
   if (!fwd && RELU_BWD) {
-#pragma unroll
     if (dbg) dbg[30] = clock64();
+#pragma unroll
     for (int pass = 0; pass < 2; ++pass) {               // smaller term first: mask.lo, mask.hi
       const uint32_t b_base = (pass == 0) ? c.sV_lo : c.sV_hi;
 #pragma unroll
@@ -95,8 +95,8 @@ __device__ __forceinline__ void issue_mmas(const TileCtx& c, bool fwd, long long
     const uint32_t lbo = fwd ? 16u * H : 128u, sbo = fwd ? 128u : 16u * H;
     const uint32_t kstep_bytes = fwd ? 32u * H : 256u;     // 16 k: two K-adjacent core matrices
     const uint32_t idesc = fwd ? IDESC_K : IDESC_MN;
-#pragma unroll
     if (dbg && fwd) dbg[13] = clock64();
+#pragma unroll
     for (int pass = 0; pass < 3; ++pass) {               // smallest terms first: lo.hi, hi.lo, hi.hi
       const uint32_t a_col = (pass == 0) ? COL_ALO : COL_AHI;
       const uint32_t b_base = (pass == 1) ? c.sB_lo : c.sB_hi;
