@@ -91,6 +91,45 @@ __device__ __forceinline__ NloJet nlo_obstacle_jet(int kind, const float* c, flo
   const NloJet xo = smax(d_x, zero), yo = smax(d_y, zero);
   return nlo_jsqrt(xo * xo + yo * yo) + smin(smax(d_x, d_y), zero);
 }
+// First-order twin of the jet above (value and gradient only) for the constraint rows: the compiler does not drop the second-order
+// fields of NloJet from the smooth square's chain of products and square roots, and they are three quarters of its arithmetic
+// (the benchmark_5 rows kernel - 4 footprint points x 3 obstacles per thread - was bound by exactly that arithmetic).
+struct NloJet1 {
+  float v, dx, dy;
+  __device__ __forceinline__ static NloJet1 cst(float c) { return {c, 0.f, 0.f}; }
+};
+__device__ __forceinline__ NloJet1 operator+(const NloJet1& a, const NloJet1& b) { return {a.v + b.v, a.dx + b.dx, a.dy + b.dy}; }
+__device__ __forceinline__ NloJet1 operator-(const NloJet1& a, const NloJet1& b) { return {a.v - b.v, a.dx - b.dx, a.dy - b.dy}; }
+__device__ __forceinline__ NloJet1 operator*(const NloJet1& a, float c) { return {a.v * c, a.dx * c, a.dy * c}; }
+__device__ __forceinline__ NloJet1 operator*(const NloJet1& a, const NloJet1& b) { return {a.v * b.v, a.dx * b.v + a.v * b.dx, a.dy * b.v + a.v * b.dy}; }
+__device__ __forceinline__ NloJet1 nlo_jsqrt(const NloJet1& a) {
+  const float ir = rsqrtf(a.v), f1 = 0.5f * ir;       // one MUFU instead of an IEEE square root and an IEEE division (2 ulp; a.v >= eps > 0)
+  return {a.v * ir, f1 * a.dx, f1 * a.dy};
+}
+__device__ __forceinline__ NloJet1 nlo_obstacle_jet1(int kind, const float* c, float x, float y) {
+  if (kind == NLO_OBST_CIRCLE) {
+    const float dx = x - c[0], dy = y - c[1], q = dx * dx + dy * dy, id = rsqrtf(q);
+    return {q * id - (c[2] + c[3]), dx * id, dy * id};
+  }
+  const NloJet1 X{x - c[0], 1.f, 0.f}, Y{y - c[1], 0.f, 1.f};
+  const NloJet1 eps = NloJet1::cst(1e-6f), half = NloJet1::cst(0.5f * c[2] + c[3]), zero = NloJet1::cst(0.f);
+  const NloJet1 d_x = nlo_jsqrt(X * X + eps) - half, d_y = nlo_jsqrt(Y * Y + eps) - half;
+  auto smax = [&](const NloJet1& a, const NloJet1& b) { return (a + b + nlo_jsqrt((a - b) * (a - b) + eps)) * 0.5f; };
+  auto smin = [&](const NloJet1& a, const NloJet1& b) { return (a + b - nlo_jsqrt((a - b) * (a - b) + eps)) * 0.5f; };
+  const NloJet1 xo = smax(d_x, zero), yo = smax(d_y, zero);
+  return nlo_jsqrt(xo * xo + yo * yo) + smin(smax(d_x, d_y), zero);
+}
+__device__ __forceinline__ NloJet1 nlo_union_jet1(int n, const int* kinds, const float (*circles)[4], float x, float y) {
+  float sum = 0.f, gx = 0.f, gy = 0.f;
+  for (int q = 0; q < n; ++q) {
+    const NloJet1 j = nlo_obstacle_jet1(kinds[q], circles[q], x, y);
+    const float e = expf(-NLO_ALPHA * j.v);
+    sum += e; gx += e * j.dx; gy += e * j.dy;
+  }
+  const float inv = 1.f / sum;
+  return {-logf(sum) / NLO_ALPHA, gx * inv, gy * inv};
+}
+
 // soft-min union (core/sdf/casadi.py:385-386, core/utils.py:28-31) of the obstacles' jets
 __device__ __forceinline__ NloJet nlo_union_jet(int n, const int* kinds, const float (*circles)[4], float x, float y) {
   float sum = 0.f, gx = 0.f, gy = 0.f, a = 0.f, b = 0.f, c = 0.f;

@@ -222,39 +222,52 @@ __device__ __forceinline__ void nlp_points_body(const NlpDev& L, const float* __
 }
 
 // ---- K3b: SDF constraint rows + chain rule to the pose (core/geometry.py:63-67, 107-117) --------------------
-// rows of knot k of problem p from the SDF values / gradients of its footprint points (sv, gx, gy; sn, cs = sin / cos of the heading)
+// Rows of knot k of problem p.  point(b, sv, gx, gy) delivers the SDF value / gradient of footprint point b (from the scratch of the
+// learned SDF, or computed on the spot for analytic obstacles); sn, cs = sin / cos of the heading.  The footprint loop is unrolled to
+// its bound of four with the soft-min accumulated on the fly: with run-time trip counts the per-point arrays lived in local memory
+// (96 B of stack per thread; the benchmark_5 rows kernel took 276 us for 41 MB of traffic).
+template <typename F>
 __device__ __forceinline__ void nlp_rows_emit(const NlpDev& L, const float* __restrict__ w, size_t P, size_t ld, float* __restrict__ g,
-                                              float* __restrict__ jac, const int k, const size_t p, const float sn, const float cs,
-                                              const float* sv, const float* gx, const float* gy) {
+                                              float* __restrict__ jac, const int k, const size_t p, const float sn, const float cs, F&& point) {
   const int* __restrict__ nz = L.nzmap + L.e_off_sdf + k * L.rows_per_knot * L.nnz_sdf_row;
   if (L.shape == NLO_SHAPE_DOT) {
-    if (g) g[(size_t)(L.g_off_sdf + k) * ld + p] = sv[0];
-    if (jac) { jac[(size_t)nz[0] * ld + p] = gx[0]; jac[(size_t)nz[1] * ld + p] = gy[0]; }
+    float sv, gx, gy;
+    point(0, sv, gx, gy);
+    if (g) g[(size_t)(L.g_off_sdf + k) * ld + p] = sv;
+    if (jac) { jac[(size_t)nz[0] * ld + p] = gx; jac[(size_t)nz[1] * ld + p] = gy; }
     return;
-  }
-  float gt[4];
-  for (int b = 0; b < L.nb; ++b) {
-    const float dpx = -sn * L.bx[b] - cs * L.by[b], dpy = cs * L.bx[b] - sn * L.by[b];
-    gt[b] = gx[b] * dpx + gy[b] * dpy;
   }
   if (L.use_slack) {
     // soft_min + slack (core/utils.py:28-31: un-stabilised)
-    float e[4], sum = 0.f;
-    for (int b = 0; b < L.nb; ++b) { e[b] = expf(-NLO_ALPHA * sv[b]); sum += e[b]; }
+    float sum = 0.f, rx = 0.f, ry = 0.f, rt = 0.f;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      if (b < L.nb) {
+        float sv, gx, gy;
+        point(b, sv, gx, gy);
+        const float dpx = -sn * L.bx[b] - cs * L.by[b], dpy = cs * L.bx[b] - sn * L.by[b];
+        const float e = expf(-NLO_ALPHA * sv);
+        sum += e; rx += e * gx; ry += e * gy; rt += e * (gx * dpx + gy * dpy);
+      }
+    }
     const float inv = 1.f / sum;
-    float rx = 0.f, ry = 0.f, rt = 0.f;
-    for (int b = 0; b < L.nb; ++b) { const float om = e[b] * inv; rx += om * gx[b]; ry += om * gy[b]; rt += om * gt[b]; }
     if (g) g[(size_t)(L.g_off_sdf + k) * ld + p] = -logf(sum) / NLO_ALPHA + w[(size_t)(L.n_X + L.n_U + k) * ld + p];
     if (jac) {
-      jac[(size_t)nz[0] * ld + p] = rx; jac[(size_t)nz[1] * ld + p] = ry; jac[(size_t)nz[2] * ld + p] = rt;
+      jac[(size_t)nz[0] * ld + p] = rx * inv; jac[(size_t)nz[1] * ld + p] = ry * inv; jac[(size_t)nz[2] * ld + p] = rt * inv;
       jac[(size_t)nz[3] * ld + p] = 1.f;
     }
   } else {
-    for (int b = 0; b < L.nb; ++b) {
-      if (g) g[(size_t)(L.g_off_sdf + k * L.nb + b) * ld + p] = sv[b];
-      if (jac) {
-        jac[(size_t)nz[3 * b + 0] * ld + p] = gx[b]; jac[(size_t)nz[3 * b + 1] * ld + p] = gy[b];
-        jac[(size_t)nz[3 * b + 2] * ld + p] = gt[b];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      if (b < L.nb) {
+        float sv, gx, gy;
+        point(b, sv, gx, gy);
+        const float dpx = -sn * L.bx[b] - cs * L.by[b], dpy = cs * L.bx[b] - sn * L.by[b];
+        if (g) g[(size_t)(L.g_off_sdf + k * L.nb + b) * ld + p] = sv;
+        if (jac) {
+          jac[(size_t)nz[3 * b + 0] * ld + p] = gx; jac[(size_t)nz[3 * b + 1] * ld + p] = gy;
+          jac[(size_t)nz[3 * b + 2] * ld + p] = gx * dpx + gy * dpy;
+        }
       }
     }
   }
@@ -265,13 +278,12 @@ __global__ void __launch_bounds__(256) nlp_sdf_rows_kernel(NlpDev L, const float
                                                            const float* __restrict__ jy, float* __restrict__ g, float* __restrict__ jac) {
   const int k = blockIdx.y;
   for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (size_t)gridDim.x * blockDim.x) {
-    float sn = 0.f, cs = 1.f, sv[4], gx[4], gy[4];
+    float sn = 0.f, cs = 1.f;
     if (L.shape != NLO_SHAPE_DOT) sincosf(w[(size_t)(k * L.nx + 2) * ld + p], &sn, &cs);
-    for (int b = 0; b < L.nb; ++b) {
+    nlp_rows_emit(L, w, P, ld, g, jac, k, p, sn, cs, [&](int b, float& sv, float& gx, float& gy) {
       const size_t q = (size_t)(k * L.nb + b) * P + p;
-      sv[b] = s[q]; gx[b] = jx[q]; gy[b] = jy[q];
-    }
-    nlp_rows_emit(L, w, P, ld, g, jac, k, p, sn, cs, sv, gx, gy);
+      sv = s[q]; gx = jx[q]; gy = jy[q];
+    });
   }
 }
 
@@ -281,15 +293,14 @@ __device__ __forceinline__ void nlp_analytic_rows_body(const NlpDev& L, const fl
                                                        float* __restrict__ g, float* __restrict__ jac, const int k) {
   for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (size_t)gridDim.x * blockDim.x) {
     const float x = w[(size_t)(k * L.nx + 0) * ld + p], y = w[(size_t)(k * L.nx + 1) * ld + p];
-    float sn = 0.f, cs = 1.f, sv[4], gx[4], gy[4];
+    float sn = 0.f, cs = 1.f;
     if (L.shape != NLO_SHAPE_DOT) sincosf(w[(size_t)(k * L.nx + 2) * ld + p], &sn, &cs);
-    for (int b = 0; b < L.nb; ++b) {
+    nlp_rows_emit(L, w, P, ld, g, jac, k, p, sn, cs, [&](int b, float& sv, float& gx, float& gy) {
       const float px = L.shape == NLO_SHAPE_DOT ? x : x + cs * L.bx[b] - sn * L.by[b];
       const float py = L.shape == NLO_SHAPE_DOT ? y : y + sn * L.bx[b] + cs * L.by[b];
-      const NloJet u = nlo_union_jet(L.n_circles, L.okind, L.circles, px, py);
-      sv[b] = u.v; gx[b] = u.dx; gy[b] = u.dy;
-    }
-    nlp_rows_emit(L, w, P, ld, g, jac, k, p, sn, cs, sv, gx, gy);
+      const NloJet1 u = nlo_union_jet1(L.n_circles, L.okind, L.circles, px, py);
+      sv = u.v; gx = u.dx; gy = u.dy;
+    });
   }
 }
 
