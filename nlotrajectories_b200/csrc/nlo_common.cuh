@@ -56,7 +56,7 @@ struct nlo_sdf_model {
   void* d_tc;                // W1 split into fp16 hi | lo images in UMMA core-matrix order
   size_t tc_bytes;           // bytes of the images; NLO_STREAM_SLOTS x {tile counter, finished-CTA counter} follow them (zeroed once;
                              // the last CTA of a launch resets its pair, so no memset is needed per launch)
-  float tc_params[8];        // TcParams of sdf_tc.cu (scales and bounds)
+  float tc_params[12];       // TcParams of sdf_tc.cu (scales and bounds)
   float tc_const[776];       // TcConst of sdf_tc.cu (small vectors handed to the kernel as a __grid_constant__ parameter)
   float* h_deep;             // deep tensor path (sdf_tc_deep.cu): host blob, TcDeepParams (32 floats) | TcDeepConst
   // scratch for the host-buffer entry points

@@ -550,6 +550,375 @@ int launch_tc(nlo_sdf_model* m, const float* x, const float* y, const float* sba
   return 0;
 }
 
+
+// =====================================================================================================================
+// ReLU first layer + ReLU hidden layer, H = 128, value + Jacobian (the benchmark shape, scripts/run_benchmark.py:65):
+// LAYER 0 ON THE TENSOR CORE.  The tile bodies above are bound by their SIMT instructions (ncu: issue slots 61 %, ALU pipe 40 %,
+// tensor pipe 51 %), and a third of those instructions evaluate a0 = W0 p + b0 - twice: in layer 0 and again in epilogue 2 for
+// the sign of a0.  Here a0 is one more MMA per tile:
+//   D0[128 points x 128 neurons] = P[128 x 16] . B0[16 x 128]
+// where a row of P holds the point in fp16 pieces (px = h + m + l, py likewise, and a power of two for the bias) and B0 the
+// matching pieces of W0 and b0 (two pieces of W0, three of b0), arranged so that the 13 used K slots are exactly the products that
+// matter: h.H, h.L, m.H, m.L, l.H per coordinate and c.b0{H,M,L}.  Every product is exact in the FP32 accumulator; the sum carries a0
+// to 2^-22 relative (the two-piece W0), like the GEMMs behind it.  The row scale of the A operand of GEMM 1 is folded into P
+// (P = p . sc0 / s_W0), so D0 = sc0 . a0 arrives ready to split:
+//   layer 0   tcgen05.ld D0;  hi = truncate(D0) to fp16's 11 bits (one LOP3), lo = D0 - hi >= 0 (one FADD); ReLU is the .relu of the
+//             two packed conversions (a negative D0 has a negative hi AND a negative remainder)          3 instructions / neuron (was 9)
+//   epilogue 1  as above; the 0/1 mask goes to the A-lo columns (dead after GEMM 1), so that h0's hi image SURVIVES in the A-hi columns
+//   epilogue 2  phi0'(a0) = [hi(h0) != 0] read back from the A-hi columns: a bit test instead of re-evaluating a0
+//                                                                                                          3.5 instructions / neuron (was 6)
+// The layer-0 MMA of the group's NEXT tile is issued from epilogue 2, as soon as every thread holds its G0 columns (the D columns
+// are free from then on, and the 8 A columns it reads sit in the dead A-lo range): its latency hides behind epilogue 2 and the
+// loop top, and the tile body starts by waiting on its mbarrier.  41 MMAs per tile instead of 40.
+// =====================================================================================================================
+constexpr int RR_H = 128;
+constexpr int RR_B0_HALFS = 16 * RR_H;      // layer-0 operand image: 16 K slots x 128 neurons, K-major core-matrix order
+
+struct RrCtx {
+  uint32_t tmem_base, lane_base, sB_hi, sB_lo, sV_hi, sV_lo, sB0, mbar_addr, mbar2_addr, bar_id;
+  int* lock;
+  unsigned int* ctr;
+  uint32_t* next_slot;
+  uint32_t ctr_bias;
+  float inv_sw, unscale2, max_w0x, max_w0y, max_b0, spx_mul, spy_mul, cb_mul;
+};
+
+__device__ __forceinline__ float rr_bound(const RrCtx& c, float px, float py) {
+  return fmaf(fabsf(px), c.max_w0x, fmaf(fabsf(py), c.max_w0y, c.max_b0)) + 1e-30f;
+}
+// v = h + m + l with every part an fp16 value (33 significant bits together; the parts are returned as floats)
+__device__ __forceinline__ void rr_split3(float v, float& h, float& m, float& l) {
+  h = __half2float(__float2half_rn(v));
+  const float r = v - h;
+  m = __half2float(__float2half_rn(r));
+  l = __half2float(__float2half_rn(r - m));
+}
+// One row of the layer-0 A operand (16 fp16 values = 8 tensor-memory columns):
+//   slot  0   1   2   3   4   5   6   7   8   9   10  11  12  13..15
+//   A     xh  xh  xm  xm  xl  yh  yh  ym  ym  yl  c   c   c   0          x = px sc0 / s_W0x, y = py sc0 / s_W0y, c = sc0 / s_b0
+//   B0    XH  XL  XH  XL  XH  YH  YL  YH  YL  YH  bH  bM  bL  0          X = W0[:,0] s_W0x = XH + XL, b = b0 s_b0 = bH + bM + bL
+// |x| <= 2^14 / (max|W0x| s_W0x) <= 2^10 and c <= 4 by the choice of the scales (nlo_sdf_tc_prepare); the clamps only keep
+// degenerate rows (a zero weight column, bound underflow) free of inf . 0.
+__device__ __forceinline__ void rr_point_row(const RrCtx& c, float px, float py, uint32_t (&w)[8]) {
+  float sc0, inv0;
+  row_scale(rr_bound(c, px, py), sc0, inv0);
+  const float lim = 60000.f;
+  float xh, xm, xl, yh, ym, yl;
+  rr_split3(fminf(fmaxf(px * (sc0 * c.spx_mul), -lim), lim), xh, xm, xl);
+  rr_split3(fminf(fmaxf(py * (sc0 * c.spy_mul), -lim), lim), yh, ym, yl);
+  const float cb = fminf(sc0 * c.cb_mul, 32768.f);
+  w[0] = pack_f16(xh, xh); w[1] = pack_f16(xm, xm); w[2] = pack_f16(xl, yh); w[3] = pack_f16(yh, ym);
+  w[4] = pack_f16(ym, yl); w[5] = pack_f16(cb, cb); w[6] = pack_f16(cb, 0.f); w[7] = 0u;
+}
+
+constexpr uint32_t RR_COL_AHI = 0, RR_COL_ALO = RR_H / 2, RR_COL_D = RR_H, RR_COL_P = RR_H / 2;   // P: the first 8 A-lo columns
+
+// the layer-0 MMA of one tile: D0 = P . B0.  No lock: one MMA slipping into the other group's GEMM is harmless (other D columns).
+__device__ __forceinline__ void rr_issue_l0(const RrCtx& c) {
+  tc_fence_after();
+  if (elect_one(1u)) {
+    tc_mma_f16_ts(c.tmem_base + RR_COL_D, c.tmem_base + RR_COL_P, umma_desc(c.sB0, 16u * RR_H, 128u), umma_idesc_f16(TILE, RR_H, 0), 0u);
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(c.mbar2_addr) : "memory");
+  }
+}
+__device__ __forceinline__ uint32_t rr_issue_gemm(const RrCtx& c, bool fwd) {
+  constexpr uint32_t H = RR_H, IDESC_K = umma_idesc_f16(TILE, RR_H, 0);
+  tc_fence_after();
+  while (atomicCAS(c.lock, 0, 1) != 0) { }
+  if (elect_one(1u)) {
+    if (!fwd) {
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {               // smaller term first: mask.lo, mask.hi; the mask sits in the A-lo columns
+        const uint32_t b_base = (pass == 0) ? c.sV_lo : c.sV_hi;
+#pragma unroll
+        for (int ks = 0; ks < (int)H / 16; ++ks)
+          tc_mma_f16_ts(c.tmem_base + RR_COL_D, c.tmem_base + RR_COL_ALO + ks * 8, umma_desc(b_base + ks * 32u * H, 16u * H, 128u), IDESC_K,
+                        (pass | ks) != 0);
+      }
+    } else {
+#pragma unroll
+      for (int pass = 0; pass < 3; ++pass) {               // smallest terms first: lo.hi, hi.lo, hi.hi
+        const uint32_t a_col = (pass == 0) ? RR_COL_ALO : RR_COL_AHI;
+        const uint32_t b_base = (pass == 1) ? c.sB_lo : c.sB_hi;
+#pragma unroll
+        for (int ks = 0; ks < (int)H / 16; ++ks)
+          tc_mma_f16_ts(c.tmem_base + RR_COL_D, c.tmem_base + a_col + ks * 8, umma_desc(b_base + ks * 32u * H, 16u * H, 128u), IDESC_K,
+                        (pass | ks) != 0);
+      }
+    }
+    *reinterpret_cast<volatile int*>(c.lock) = 0;          // right behind the last MMA (see issue_mmas)
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(c.mbar_addr) : "memory");
+  }
+  return (fwd && c.ctr) ? atomicAdd(c.ctr, 1u) : 0u;
+}
+
+// One tile of one group; two threads per point (HALF 0: neurons / D columns 0..63, stores s and jx; HALF 1: 64..127, stores jy).
+// `phases`: bit 0 = parity of the GEMM mbarrier, bit 1 = parity of the layer-0 mbarrier.  next_xy: the staged coordinates of the
+// group's next tile (x at [pt], y at [TILE + pt]) or nullptr after the last tile.
+template <int HALF>
+__device__ __noinline__ uint32_t sdf_rr_tile(RrCtx c, uint32_t phases, float px, float py, float seed, const float* next_xy,
+                                             float* __restrict__ part, float* __restrict__ s_ptr, float* __restrict__ j_ptr) {
+  constexpr int HH = RR_H / 2, C0 = HALF * HH, NCH = HH / 32, NT = 2 * TILE;
+  constexpr uint32_t COL_AHI = RR_COL_AHI + HALF * (HH / 2), COL_ALO = RR_COL_ALO + HALF * (HH / 2), COL_D = RR_COL_D + C0;
+  const int tg = threadIdx.x % NT;
+  const int pt = tg & (TILE - 1);
+  uint32_t ph = phases & 1u, ph2 = (phases >> 1) & 1u;
+  float sc0, inv0;
+  row_scale(rr_bound(c, px, py), sc0, inv0);
+  // ---- layer 0: D0 = sc0 . a0 from the tensor core -> ReLU, fp16 hi / lo -> A operand ----------------------------------
+  mbar_wait_addr(c.mbar2_addr, ph2); ph2 ^= 1u;
+  tc_fence_after();
+  {
+    uint32_t d[NCH][32];
+#pragma unroll
+    for (int cc = 0; cc < NCH; ++cc) tmem_ld32(c.lane_base + COL_D + cc * 32, d[cc]);
+    tc_wait_ld();
+#pragma unroll
+    for (int cc = 0; cc < NCH; ++cc) {
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const uint32_t u0 = d[cc][2 * q], u1 = d[cc][2 * q + 1];
+        const float h0 = __uint_as_float(u0 & 0xFFFFE000u), h1 = __uint_as_float(u1 & 0xFFFFE000u);   // 11 significant bits: exact in fp16
+        hi[q] = pack_relu_f16(h0, h1);
+        lo[q] = pack_relu_f16(__uint_as_float(u0) - h0, __uint_as_float(u1) - h1);
+      }
+      TmemIO<16>::st(c.lane_base + COL_AHI + cc * 16, hi);
+      TmemIO<16>::st(c.lane_base + COL_ALO + cc * 16, lo);
+    }
+  }
+  tc_wait_st();
+  tc_fence_before();
+  group_bar<NT>(c.bar_id);
+  uint32_t next_tile_idx = 0u;
+  if (tg == 0) next_tile_idx = rr_issue_gemm(c, true);
+  mbar_wait_addr(c.mbar_addr, ph); ph ^= 1u;
+  tc_fence_after();
+  // ---- epilogue 1: value; the 0 / 1 mask of the hidden layer -> A-lo columns --------------------------------------------
+  float s = HALF == 0 ? cst.bout : 0.f;
+  {
+    const float unscale1 = inv0 * c.inv_sw;
+    uint32_t z[NCH][32];
+#pragma unroll
+    for (int cc = 0; cc < NCH; ++cc) tmem_ld32(c.lane_base + COL_D + cc * 32, z[cc]);
+    tc_wait_ld();
+#pragma unroll
+    for (int cc = 0; cc < NCH; ++cc) {
+      uint32_t mk[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        uint32_t mask = 0u;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = C0 + cc * 32 + 2 * q + e;
+          const float zz = fmaf(__uint_as_float(z[cc][2 * q + e]), unscale1, cst.b1[j]);
+          if (zz > 0.f) { s = fmaf(cst.w2[j], zz, s); mask |= (e == 0 ? 0x3C00u : 0x3C000000u); }
+        }
+        mk[q] = mask;
+      }
+      TmemIO<16>::st(c.lane_base + COL_ALO + cc * 16, mk);
+    }
+  }
+  tc_wait_st();
+  tc_fence_before();
+  group_bar<NT>(c.bar_id);
+  if (tg == 0) rr_issue_gemm(c, false);
+  mbar_wait_addr(c.mbar_addr, ph); ph ^= 1u;
+  tc_fence_after();
+  // ---- epilogue 2: through layer 0 to the Jacobian; the next tile's layer-0 MMA goes out as soon as D is free -----------
+  float jx = 0.f, jy = 0.f;
+  {
+    uint32_t gz[NCH][32];
+#pragma unroll
+    for (int cc = 0; cc < NCH; ++cc) tmem_ld32(c.lane_base + COL_D + cc * 32, gz[cc]);
+    if (HALF == 0 && next_xy) {
+      asm volatile("cp.async.wait_all;" ::: "memory");     // this thread staged the point itself (persistent loop)
+      uint32_t w[8];
+      rr_point_row(c, next_xy[pt], next_xy[TILE + pt], w);
+      TmemIO<8>::st(c.lane_base + RR_COL_P, w);
+      tc_wait_st();
+    }
+    tc_wait_ld();
+    tc_fence_before();
+    group_bar<NT>(c.bar_id);
+    if (tg == 0 && next_xy) rr_issue_l0(c);
+#pragma unroll
+    for (int cc = 0; cc < NCH; ++cc) {
+      uint32_t hw[16];
+      TmemIO<16>::ld(c.lane_base + COL_AHI + cc * 16, hw);
+      tc_wait_ld();
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int k = C0 + cc * 32 + 2 * q + e;
+          // select, then two unconditional FFMAs: under a per-thread predicate the constants would arrive one LDC each
+          // instead of four per LDCU.128
+          const float g = (hw[q] & (e == 0 ? 0x00007FFFu : 0x7FFF0000u)) ? __uint_as_float(gz[cc][2 * q + e]) : 0.f;
+          jx = fmaf(g, cst.w0x[k], jx);
+          jy = fmaf(g, cst.w0y[k], jy);
+        }
+      }
+    }
+    const float unscale2 = seed * c.unscale2;
+    jx *= unscale2; jy *= unscale2;
+  }
+  // ---- hand the other half what it stores: HALF 0 writes s, jx; HALF 1 writes jy -------------------------------------------
+  float* mine = part + (HALF * TILE + pt) * 4;
+  if (HALF == 0) mine[0] = jy; else { mine[0] = s; mine[1] = jx; }
+  if (HALF == 0 && tg == 0 && c.ctr) *c.next_slot = next_tile_idx + c.ctr_bias;
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  tc_fence_before();
+  group_bar<NT>(c.bar_id);          // also: the next tile's tcgen05.st must not overtake this tile's TMEM reads
+  tc_fence_after();
+  const float* other = part + ((1 - HALF) * TILE + pt) * 4;
+  if (HALF == 0) {
+    if (s_ptr) *s_ptr = s + other[0];
+    if (j_ptr) *j_ptr = jx + other[1];
+  } else {
+    if (j_ptr) *j_ptr = jy + other[0];
+  }
+  return ph | (ph2 << 1);
+}
+
+constexpr size_t rr_smem_bytes() {
+  return (size_t)4 * RR_H * RR_H * 2 + (size_t)RR_B0_HALFS * 2 + (size_t)2 * 2 * TILE * 4 * 4 + 4 * 8 + 32 + 2 * 4 + (size_t)2 * 2 * 3 * TILE * 4;
+}
+
+__global__ void __launch_bounds__(512, 1)
+sdf_tc_rr_kernel(TcParams prm_tc, const __half* __restrict__ bimg, const float* __restrict__ x, const float* __restrict__ y,
+                 const float* __restrict__ sbar, size_t n, float* __restrict__ s_out, float* __restrict__ jx_out, float* __restrict__ jy_out,
+                 unsigned int* __restrict__ tile_ctr) {
+  constexpr int H = RR_H, NG = 2, GT = 2 * TILE, IMG = H * H;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __half* sB = reinterpret_cast<__half*>(smem_raw);                       // W1 hi | W1 lo | V hi | V lo | B0
+  float* sPart = reinterpret_cast<float*>(smem_raw + ((size_t)4 * IMG + RR_B0_HALFS) * 2);   // [NG][2][TILE][4]
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(sPart + NG * 2 * TILE * 4);                  // [NG] GEMMs | [NG] layer 0
+  int* lock = reinterpret_cast<int*>(mbar + 2 * NG);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lock + 1);
+  uint32_t* next_tile = tmem_slot + 1;                                                       // [NG]
+  float* sCoord = reinterpret_cast<float*>(next_tile + NG + 1);                              // [NG][2][3][TILE]
+  const int t = threadIdx.x, warp = t >> 5;
+  const int grp = t / GT, tg = t % GT;
+  const int half = (tg >> 5) >> 2;
+  const int pt = tg & (TILE - 1);
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(bimg);
+    uint4* dst = reinterpret_cast<uint4*>(sB);
+    for (int i = t; i < (4 * IMG + RR_B0_HALFS) / 8; i += 512) dst[i] = src[i];
+    if (t == 0) {
+      for (int g = 0; g < 2 * NG; ++g) mbar_init(mbar + g, 1);
+      *lock = 0;
+    }
+    fence_async_smem();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  RrCtx c;
+  const uint32_t tmem_all = *tmem_slot;
+  c.tmem_base = tmem_all + (uint32_t)grp * (2 * H);
+  c.lane_base = c.tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+  c.sB_hi = smem_u32(sB); c.sB_lo = smem_u32(sB + IMG);
+  c.sV_hi = smem_u32(sB + 2 * IMG); c.sV_lo = smem_u32(sB + 3 * IMG);
+  c.sB0 = smem_u32(sB + 4 * IMG);
+  c.mbar_addr = smem_u32(mbar + grp); c.mbar2_addr = smem_u32(mbar + NG + grp);
+  c.bar_id = 1 + grp;
+  c.lock = lock;
+  c.ctr = tile_ctr; c.next_slot = next_tile + grp; c.ctr_bias = 2 * gridDim.x * NG;
+  c.inv_sw = prm_tc.inv_sw; c.unscale2 = prm_tc.inv_sv;
+  c.max_w0x = prm_tc.max_w0x; c.max_w0y = prm_tc.max_w0y; c.max_b0 = prm_tc.max_b0;
+  c.spx_mul = prm_tc.spx_mul; c.spy_mul = prm_tc.spy_mul; c.cb_mul = prm_tc.cb_mul;
+  float* part = sPart + grp * (2 * TILE * 4);
+  uint32_t phases = 0;
+  const size_t n_tiles = (n + TILE - 1) / TILE;
+  const size_t stride = (size_t)gridDim.x * NG;
+  size_t tile = (size_t)blockIdx.x * NG + grp;
+  size_t tile_next = tile + stride;
+  float* coord = sCoord + grp * (2 * 3 * TILE);
+  float px = 0.f, py = 0.f, seed = 1.f;
+  if (tile < n_tiles) {                       // (group-uniform) the first tile: coordinates from global memory, its layer-0 MMA up front
+    const size_t ic = min(tile * TILE + pt, n - 1);
+    px = x[ic]; py = y[ic]; seed = sbar ? sbar[ic] : 1.f;
+    if (half == 0) {
+      uint32_t w[8];
+      rr_point_row(c, px, py, w);
+      TmemIO<8>::st(c.lane_base + RR_COL_P, w);
+      tc_wait_st();
+    }
+    tc_fence_before();
+    group_bar<GT>(c.bar_id);
+    if (tg == 0) rr_issue_l0(c);
+  }
+  for (int it = 0; tile < n_tiles; ++it) {
+    const bool has_next = tile_next < n_tiles;
+    if (has_next && half == 0) {
+      const size_t in = min(tile_next * TILE + pt, n - 1);
+      float* dst = coord + ((it + 1) & 1) * (3 * TILE) + pt;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(dst)), "l"(x + in) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(dst + TILE)), "l"(y + in) : "memory");
+      if (sbar) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(dst + 2 * TILE)), "l"(sbar + in) : "memory");
+    }
+    const size_t i = tile * TILE + pt;
+    const bool valid = i < n;
+    if (it > 0) {
+      const float* src = coord + (it & 1) * (3 * TILE) + pt;
+      px = src[0]; py = src[TILE]; seed = sbar ? src[2 * TILE] : 1.f;
+    }
+    const float* nxy = has_next ? coord + ((it + 1) & 1) * (3 * TILE) : nullptr;
+    if (half == 0)
+      phases = sdf_rr_tile<0>(c, phases, px, py, seed, nxy, part, (valid && s_out) ? s_out + i : nullptr, valid ? jx_out + i : nullptr);
+    else
+      phases = sdf_rr_tile<1>(c, phases, px, py, seed, nxy, part, nullptr, valid ? jy_out + i : nullptr);
+    tile = tile_next;
+    tile_next = tile_ctr ? (size_t)next_tile[grp] : tile_next + stride;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tile_ctr && t == 0) {
+    __threadfence();
+    if (atomicAdd(tile_ctr + 1, 1u) == gridDim.x - 1) { tile_ctr[0] = 0u; tile_ctr[1] = 0u; __threadfence(); }
+  }
+  if (warp == 0) tmem_dealloc(tmem_all, 512);
+}
+
+// NLO_B200_TC_L0=0 keeps the SIMT layer 0 (the A / B switch of this form)
+bool rr_enabled() {
+  static const int on = [] { const char* e = getenv("NLO_B200_TC_L0"); return (e && e[0] == '0') ? 0 : 1; }();
+  return on != 0;
+}
+
+int launch_tc_rr(nlo_sdf_model* m, const float* x, const float* y, const float* sbar, size_t n, float* s, float* jx, float* jy, cudaStream_t st) {
+  auto kfn = sdf_tc_rr_kernel;
+  const size_t smem = rr_smem_bytes();
+  static bool attr_set[64] = {false};
+  if (!attr_set[m->device & 63]) {
+    NLO_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set[m->device & 63] = true;
+  }
+  const size_t tiles = (n + TILE - 1) / TILE;
+  const size_t want = (tiles + 1) / 2;
+  const int grid = (int)(want < (size_t)m->sm_count ? want : (size_t)m->sm_count);
+  TcParams prm;
+  memcpy(&prm, m->tc_params, sizeof(prm));
+  std::lock_guard<std::mutex> lk(g_const_mu);
+  if (g_const_owner[m->device] != m->uid) {
+    NLO_CUDA(cudaDeviceSynchronize());
+    NLO_CUDA(cudaMemcpyToSymbol(cst, m->tc_const, sizeof(TcConst), 0, cudaMemcpyHostToDevice));
+    g_const_owner[m->device] = m->uid;
+  }
+  unsigned int* ctr = nullptr;
+  if (tiles > (size_t)grid * 2) {
+    const int slot = nlo_model_stream_slot(m, st);
+    if (slot < 0) return 1;
+    ctr = reinterpret_cast<unsigned int*>(static_cast<char*>(m->d_tc) + m->tc_bytes) + 2 * slot;
+  }
+  kfn<<<grid, 512, smem, st>>>(prm, reinterpret_cast<const __half*>(m->d_tc), x, y, sbar, n, s, jx, jy, ctr);
+  NLO_CHECK_LAUNCH();
+  return 0;
+}
+
 }  // namespace
 
 bool nlo_sdf_tc_supported(const nlo_sdf_desc* d) {
@@ -595,6 +964,11 @@ int nlo_sdf_tc_prepare(nlo_sdf_model* m, const float* w) {
     prm.max_w0x = fmaxf(prm.max_w0x, fabsf(W0[2 * k])); prm.max_w0y = fmaxf(prm.max_w0y, fabsf(W0[2 * k + 1]));
     prm.max_b0 = fmaxf(prm.max_b0, fabsf(b0[k]));
   }
+  // layer 0 on the tensor core (ReLU / ReLU form): W0 columns scaled into [2^4, 2^5), b0 into [2^12, 2^13) - see rr_point_row
+  float mb0 = 0.f;
+  for (int k = 0; k < H; ++k) mb0 = fmaxf(mb0, fabsf(b0[k]));
+  const float s_w0x = tc_pow2_scale(prm.max_w0x) / 512.f, s_w0y = tc_pow2_scale(prm.max_w0y) / 512.f, s_b0 = tc_pow2_scale(mb0) / 2.f;
+  prm.spx_mul = 1.f / s_w0x; prm.spy_mul = 1.f / s_w0y; prm.cb_mul = 1.f / s_b0;
   static_assert(sizeof(TcParams) <= sizeof(m->tc_params), "tc_params too small");
   memcpy(m->tc_params, &prm, sizeof(prm));
   static_assert(sizeof(TcConst) <= sizeof(m->tc_const), "tc_const too small");
@@ -606,7 +980,21 @@ int nlo_sdf_tc_prepare(nlo_sdf_model* m, const float* w) {
   }
   cst->bout = w2[H];
   const size_t HH = (size_t)H * H;
-  std::vector<__half> img(4 * HH);
+  std::vector<__half> img(4 * HH + (H == RR_H ? RR_B0_HALFS : 0), __float2half_rn(0.f));
+  if (H == RR_H) {
+    // B0: the layer-0 operand, 16 K slots x H neurons, same core-matrix order as one k-step of the W1 image (slots: rr_point_row)
+    __half* b0img = img.data() + 4 * HH;
+    for (int nn = 0; nn < H; ++nn) {
+      const float xv = W0[2 * nn] * s_w0x, yv = W0[2 * nn + 1] * s_w0y, bv = b0[nn] * s_b0;
+      const __half xH = __float2half_rn(xv), xL = __float2half_rn(xv - __half2float(xH));
+      const __half yH = __float2half_rn(yv), yL = __float2half_rn(yv - __half2float(yH));
+      const __half bH = __float2half_rn(bv);
+      const float br = bv - __half2float(bH);
+      const __half bM = __float2half_rn(br), bL = __float2half_rn(br - __half2float(bM));
+      const __half rows[16] = {xH, xL, xH, xL, xH, yH, yL, yH, yL, yH, bH, bM, bL, __float2half_rn(0.f), __float2half_rn(0.f), __float2half_rn(0.f)};
+      for (int k = 0; k < 16; ++k) b0img[tc_img_off(nn, k, H)] = rows[k];
+    }
+  }
   for (int nn = 0; nn < H; ++nn)
     for (int k = 0; k < H; ++k) {
       // forward / generic reverse operand: B(n, k) = W1[n][k]
@@ -652,6 +1040,7 @@ int nlo_sdf_tc_launch(nlo_sdf_model* m, const float* x, const float* y, const fl
   if (m->desc.n_hidden_mats >= 2) return nlo_sdf_tc_deep_launch(m, x, y, sbar, n, s, jx, jy, st);
   if (!m->d_tc) return nlo_fail("tensor-tile operands were not prepared");
   const int H = (int)m->desc.hidden, a0 = (int)m->desc.act0, a = (int)m->desc.act;
+  if (H == RR_H && a0 == NLO_ACT_RELU && a == NLO_ACT_RELU && jx && jy && rr_enabled()) return launch_tc_rr(m, x, y, sbar, n, s, jx, jy, st);
 #define NLO_TC_ONE(HH, A0, A1) if (a0 == A0 && a == A1) return launch_tc<HH, A0, A1>(m, x, y, sbar, n, s, jx, jy, st)
   // compile-time activation pairs of the layer zoo (core/nn_architectures.py:42-100, l4casadi's naive MLP): unrolled tile bodies with
   // constant-bank operands; anything else runs the generic instantiation (run-time activation switch, ~10x slower)

@@ -94,6 +94,8 @@ struct TcParams {          // built by nlo_sdf_tc_prepare
   float inv_sv;            // 1 / (power-of-two scale applied to V = diag(w2) W1 in its fp16 images)
   float inv_sc1;           // 1 / (power-of-two scale folded into w2s, the generic reverse-pass seed vector)
   float max_w0x, max_w0y, max_b0;
+  // layer 0 on the tensor core (sdf_tc.cu, ReLU / ReLU form): 1 / (power-of-two scales of the W0 columns and of b0 in their fp16 pieces)
+  float spx_mul, spy_mul, cb_mul;
 };
 // Small vectors of the network live in __constant__ memory: with fully unrolled loops every use is an FFMA/FMUL
 // with a constant-bank operand (c[3][imm]) - no load instruction and no shared-memory bandwidth (which the tensor
@@ -117,6 +119,19 @@ template <> struct TmemIO<16> {
                    "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(a) : "memory");
   }
 };
+
+template <> struct TmemIO<8> {
+  __device__ static __forceinline__ void st(uint32_t a, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};"
+                 ::"r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(a) : "memory");
+  }
+};
+// {fp16(max(v0, 0)) in the low half, fp16(max(v1, 0)) in the high half}: ReLU folded into the packed conversion
+__device__ __forceinline__ uint32_t pack_relu_f16(float v0, float v1) {
+  uint32_t d;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(v1), "f"(v0));
+  return d;
+}
 
 // named barrier of one tile group
 template <int NT>
