@@ -655,7 +655,9 @@ __device__ __forceinline__ uint32_t rr_issue_gemm(const RrCtx& c, bool fwd) {
 // One tile of one group; two threads per point (HALF 0: neurons / D columns 0..63, stores s and jx; HALF 1: 64..127, stores jy).
 // `phases`: bit 0 = parity of the GEMM mbarrier, bit 1 = parity of the layer-0 mbarrier.  next_xy: the staged coordinates of the
 // group's next tile (x at [pt], y at [TILE + pt]) or nullptr after the last tile.
-template <int HALF>
+// JAC = false (value only): no mask, no reverse GEMM; the next tile's layer-0 MMA goes out from epilogue 1 instead.  The value is computed by
+// the same instruction sequence in both forms, so a value-only evaluation (a line-search trial) reproduces the value of a full one bit for bit.
+template <int HALF, bool JAC>
 __device__ __noinline__ uint32_t sdf_rr_tile(RrCtx c, uint32_t phases, float px, float py, float seed, const float* next_xy,
                                              float* __restrict__ part, float* __restrict__ s_ptr, float* __restrict__ j_ptr) {
   constexpr int HH = RR_H / 2, C0 = HALF * HH, NCH = HH / 32, NT = 2 * TILE;
@@ -701,7 +703,21 @@ __device__ __noinline__ uint32_t sdf_rr_tile(RrCtx c, uint32_t phases, float px,
     uint32_t z[NCH][32];
 #pragma unroll
     for (int cc = 0; cc < NCH; ++cc) tmem_ld32(c.lane_base + COL_D + cc * 32, z[cc]);
-    tc_wait_ld();
+    if (!JAC) {                       // D is free once every thread holds its columns: the next tile's layer-0 MMA
+      if (HALF == 0 && next_xy) {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        uint32_t w[8];
+        rr_point_row(c, next_xy[pt], next_xy[TILE + pt], w);
+        TmemIO<8>::st(c.lane_base + RR_COL_P, w);
+        tc_wait_st();
+      }
+      tc_wait_ld();
+      tc_fence_before();
+      group_bar<NT>(c.bar_id);
+      if (tg == 0 && next_xy) rr_issue_l0(c);
+    } else {
+      tc_wait_ld();
+    }
 #pragma unroll
     for (int cc = 0; cc < NCH; ++cc) {
       uint32_t mk[16];
@@ -716,9 +732,11 @@ __device__ __noinline__ uint32_t sdf_rr_tile(RrCtx c, uint32_t phases, float px,
         }
         mk[q] = mask;
       }
-      TmemIO<16>::st(c.lane_base + COL_ALO + cc * 16, mk);
+      if (JAC) TmemIO<16>::st(c.lane_base + COL_ALO + cc * 16, mk);
     }
   }
+  float jx = 0.f, jy = 0.f;
+  if (JAC) {
   tc_wait_st();
   tc_fence_before();
   group_bar<NT>(c.bar_id);
@@ -726,7 +744,6 @@ __device__ __noinline__ uint32_t sdf_rr_tile(RrCtx c, uint32_t phases, float px,
   mbar_wait_addr(c.mbar_addr, ph); ph ^= 1u;
   tc_fence_after();
   // ---- epilogue 2: through layer 0 to the Jacobian; the next tile's layer-0 MMA goes out as soon as D is free -----------
-  float jx = 0.f, jy = 0.f;
   {
     uint32_t gz[NCH][32];
 #pragma unroll
@@ -763,6 +780,7 @@ __device__ __noinline__ uint32_t sdf_rr_tile(RrCtx c, uint32_t phases, float px,
     const float unscale2 = seed * c.unscale2;
     jx *= unscale2; jy *= unscale2;
   }
+  }
   // ---- hand the other half what it stores: HALF 0 writes s, jx; HALF 1 writes jy -------------------------------------------
   float* mine = part + (HALF * TILE + pt) * 4;
   if (HALF == 0) mine[0] = jy; else { mine[0] = s; mine[1] = jx; }
@@ -785,6 +803,7 @@ constexpr size_t rr_smem_bytes() {
   return (size_t)4 * RR_H * RR_H * 2 + (size_t)RR_B0_HALFS * 2 + (size_t)2 * 2 * TILE * 4 * 4 + 4 * 8 + 32 + 2 * 4 + (size_t)2 * 2 * 3 * TILE * 4;
 }
 
+template <bool JAC>
 __global__ void __launch_bounds__(512, 1)
 sdf_tc_rr_kernel(TcParams prm_tc, const __half* __restrict__ bimg, const float* __restrict__ x, const float* __restrict__ y,
                  const float* __restrict__ sbar, size_t n, float* __restrict__ s_out, float* __restrict__ jx_out, float* __restrict__ jy_out,
@@ -868,9 +887,9 @@ sdf_tc_rr_kernel(TcParams prm_tc, const __half* __restrict__ bimg, const float* 
     }
     const float* nxy = has_next ? coord + ((it + 1) & 1) * (3 * TILE) : nullptr;
     if (half == 0)
-      phases = sdf_rr_tile<0>(c, phases, px, py, seed, nxy, part, (valid && s_out) ? s_out + i : nullptr, valid ? jx_out + i : nullptr);
+      phases = sdf_rr_tile<0, JAC>(c, phases, px, py, seed, nxy, part, (valid && s_out) ? s_out + i : nullptr, (JAC && valid) ? jx_out + i : nullptr);
     else
-      phases = sdf_rr_tile<1>(c, phases, px, py, seed, nxy, part, nullptr, valid ? jy_out + i : nullptr);
+      phases = sdf_rr_tile<1, JAC>(c, phases, px, py, seed, nxy, part, nullptr, (JAC && valid) ? jy_out + i : nullptr);
     tile = tile_next;
     tile_next = tile_ctr ? (size_t)next_tile[grp] : tile_next + stride;
   }
@@ -889,8 +908,9 @@ bool rr_enabled() {
   return on != 0;
 }
 
+template <bool JAC>
 int launch_tc_rr(nlo_sdf_model* m, const float* x, const float* y, const float* sbar, size_t n, float* s, float* jx, float* jy, cudaStream_t st) {
-  auto kfn = sdf_tc_rr_kernel;
+  auto kfn = sdf_tc_rr_kernel<JAC>;
   const size_t smem = rr_smem_bytes();
   static bool attr_set[64] = {false};
   if (!attr_set[m->device & 63]) {
@@ -1040,7 +1060,10 @@ int nlo_sdf_tc_launch(nlo_sdf_model* m, const float* x, const float* y, const fl
   if (m->desc.n_hidden_mats >= 2) return nlo_sdf_tc_deep_launch(m, x, y, sbar, n, s, jx, jy, st);
   if (!m->d_tc) return nlo_fail("tensor-tile operands were not prepared");
   const int H = (int)m->desc.hidden, a0 = (int)m->desc.act0, a = (int)m->desc.act;
-  if (H == RR_H && a0 == NLO_ACT_RELU && a == NLO_ACT_RELU && jx && jy && rr_enabled()) return launch_tc_rr(m, x, y, sbar, n, s, jx, jy, st);
+  if (H == RR_H && a0 == NLO_ACT_RELU && a == NLO_ACT_RELU && rr_enabled()) {
+    if (jx && jy) return launch_tc_rr<true>(m, x, y, sbar, n, s, jx, jy, st);
+    if (!jx && !jy) return launch_tc_rr<false>(m, x, y, sbar, n, s, nullptr, nullptr, st);
+  }
 #define NLO_TC_ONE(HH, A0, A1) if (a0 == A0 && a == A1) return launch_tc<HH, A0, A1>(m, x, y, sbar, n, s, jx, jy, st)
   // compile-time activation pairs of the layer zoo (core/nn_architectures.py:42-100, l4casadi's naive MLP): unrolled tile bodies with
   // constant-bank operands; anything else runs the generic instantiation (run-time activation switch, ~10x slower)
