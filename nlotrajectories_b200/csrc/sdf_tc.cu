@@ -574,12 +574,22 @@ int launch_tc(nlo_sdf_model* m, const float* x, const float* y, const float* sba
 constexpr int RR_H = 128;
 constexpr int RR_B0_HALFS = 16 * RR_H;      // layer-0 operand image: 16 K slots x 128 neurons, K-major core-matrix order
 
+// What a tile body needs: the hot words by value (registers), the launch-wide pointers behind one shared-memory pointer.
+struct RrGlobal {
+  const float* x; const float* y; const float* sbar;
+  float* s_out; float* jx_out; float* jy_out;
+  unsigned int* ctr;
+  long long* dbg;
+  uint32_t n, n_tiles, ctr_bias, pad;
+  long long ret_clock[2];  // timeline only: when thread 0 of each group last returned from a tile body
+};
 struct RrCtx {
   uint32_t tmem_base, lane_base, sB_hi, sB_lo, sV_hi, sV_lo, sB0, mbar_addr, mbar2_addr, bar_id;
   int* lock;
-  unsigned int* ctr;
-  uint32_t* next_slot;
-  uint32_t ctr_bias;
+  const RrGlobal* g;       // shared memory
+  uint32_t* next_slot;     // the group's next-but-one tile index
+  float* coord;            // the group's coordinate staging: [2][3][TILE]  (x | y | seed) of this tile and of the next one
+  float* part;             // the group's exchange buffer [2][TILE][4]
   float inv_sw, unscale2, max_w0x, max_w0y, max_b0, spx_mul, spy_mul, cb_mul;
 };
 
@@ -621,7 +631,7 @@ __device__ __forceinline__ void rr_issue_l0(const RrCtx& c) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(c.mbar2_addr) : "memory");
   }
 }
-__device__ __forceinline__ uint32_t rr_issue_gemm(const RrCtx& c, bool fwd) {
+__device__ __forceinline__ void rr_issue_gemm(const RrCtx& c, bool fwd) {
   constexpr uint32_t H = RR_H, IDESC_K = umma_idesc_f16(TILE, RR_H, 0);
   tc_fence_after();
   while (atomicCAS(c.lock, 0, 1) != 0) { }
@@ -649,27 +659,46 @@ __device__ __forceinline__ uint32_t rr_issue_gemm(const RrCtx& c, bool fwd) {
     *reinterpret_cast<volatile int*>(c.lock) = 0;          // right behind the last MMA (see issue_mmas)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(c.mbar_addr) : "memory");
   }
-  return (fwd && c.ctr) ? atomicAdd(c.ctr, 1u) : 0u;
 }
 
 // One tile of one group; two threads per point (HALF 0: neurons / D columns 0..63, stores s and jx; HALF 1: 64..127, stores jy).
-// `phases`: bit 0 = parity of the GEMM mbarrier, bit 1 = parity of the layer-0 mbarrier.  next_xy: the staged coordinates of the
-// group's next tile (x at [pt], y at [TILE + pt]) or nullptr after the last tile.
-// JAC = false (value only): no mask, no reverse GEMM; the next tile's layer-0 MMA goes out from epilogue 1 instead.  The value is computed by
-// the same instruction sequence in both forms, so a value-only evaluation (a line-search trial) reproduces the value of a full one bit for bit.
+// `state`: bit 0 = parity of the GEMM mbarrier, bit 1 = parity of the layer-0 mbarrier, bit 2 = which half of the coordinate
+// staging holds THIS tile.  Everything the persistent loop used to do around the call - staging the next tile's coordinates,
+// fetching this tile's, forming the output addresses - happens in here, in the shadow of the GEMM waits: with it in the loop
+// (64-bit index arithmetic, S2R, a dozen pointer arguments) 800 of a tile's 8,900 cycles went by between two calls.
+// JAC = false (value only): no mask, no reverse GEMM; the next tile's layer-0 MMA goes out from epilogue 1 instead.  The value is
+// computed by the same instruction sequence in both forms, so a value-only evaluation (a line-search trial) reproduces the value
+// of a full one bit for bit.
+struct RrTile {            // what a tile carries from its front half (layer 0, GEMM 1 issued) to its back half
+  uint32_t ph, ph2, buf, tile, tile_next, next_tile_idx;
+  float inv0;
+  long long* dbg;
+};
+#define RR_STAMP(i) do { if (t.dbg) t.dbg[i] = clock64(); } while (0)
+#define RR_TILE_CONSTS                                                                                                     \
+  constexpr int HH = RR_H / 2, C0 = HALF * HH, NCH = HH / 32, NT = 2 * TILE;                                               \
+  constexpr uint32_t COL_AHI = RR_COL_AHI + HALF * (HH / 2), COL_ALO = RR_COL_ALO + HALF * (HH / 2), COL_D = RR_COL_D + C0; \
+  const int tg = threadIdx.x % NT;                                                                                         \
+  const int pt = tg & (TILE - 1);                                                                                          \
+  const float* cur = c.coord + t.buf * (3 * TILE) + pt;                                                                    \
+  float* nxt = c.coord + (t.buf ^ 1u) * (3 * TILE) + pt;                                                                   \
+  const bool has_next = t.tile_next < c.g->n_tiles;                                                                        \
+  (void)COL_AHI; (void)COL_ALO; (void)COL_D; (void)C0; (void)NCH; (void)cur; (void)nxt; (void)has_next; (void)tg
+
+// front half of a tile: layer 0 from the tensor core's D0, GEMM 1 issued, the next tile's coordinates on their way
 template <int HALF, bool JAC>
-__device__ __noinline__ uint32_t sdf_rr_tile(RrCtx c, uint32_t phases, float px, float py, float seed, const float* next_xy,
-                                             float* __restrict__ part, float* __restrict__ s_ptr, float* __restrict__ j_ptr) {
-  constexpr int HH = RR_H / 2, C0 = HALF * HH, NCH = HH / 32, NT = 2 * TILE;
-  constexpr uint32_t COL_AHI = RR_COL_AHI + HALF * (HH / 2), COL_ALO = RR_COL_ALO + HALF * (HH / 2), COL_D = RR_COL_D + C0;
-  const int tg = threadIdx.x % NT;
-  const int pt = tg & (TILE - 1);
-  uint32_t ph = phases & 1u, ph2 = (phases >> 1) & 1u;
-  float sc0, inv0;
-  row_scale(rr_bound(c, px, py), sc0, inv0);
+__device__ __forceinline__ void rr_front(const RrCtx& c, RrTile& t) {
+  RR_TILE_CONSTS;
+  t.dbg = (HALF == 0 && tg == 0 && c.g->dbg && blockIdx.x == 0 && t.tile >= 32u * 2u * gridDim.x && t.tile < 40u * 2u * gridDim.x)
+              ? c.g->dbg + ((threadIdx.x / NT) * 8 + (t.tile / (2u * gridDim.x) - 32u)) * 16 : nullptr;
+  RR_STAMP(0);
+  if (t.dbg) t.dbg[14] = c.g->ret_clock[threadIdx.x / NT];
+  float sc0;
+  row_scale(rr_bound(c, cur[0], cur[TILE]), sc0, t.inv0);
   // ---- layer 0: D0 = sc0 . a0 from the tensor core -> ReLU, fp16 hi / lo -> A operand ----------------------------------
-  mbar_wait_addr(c.mbar2_addr, ph2); ph2 ^= 1u;
+  mbar_wait_addr(c.mbar2_addr, t.ph2); t.ph2 ^= 1u;
   tc_fence_after();
+  RR_STAMP(1);
   {
     uint32_t d[NCH][32];
 #pragma unroll
@@ -689,32 +718,56 @@ __device__ __noinline__ uint32_t sdf_rr_tile(RrCtx c, uint32_t phases, float px,
       TmemIO<16>::st(c.lane_base + COL_ALO + cc * 16, lo);
     }
   }
+  RR_STAMP(2);
   tc_wait_st();
   tc_fence_before();
   group_bar<NT>(c.bar_id);
-  uint32_t next_tile_idx = 0u;
-  if (tg == 0) next_tile_idx = rr_issue_gemm(c, true);
-  mbar_wait_addr(c.mbar_addr, ph); ph ^= 1u;
+  RR_STAMP(3);
+  t.next_tile_idx = 0u;
+  if (tg == 0) {
+    rr_issue_gemm(c, true);
+    // the tile after the next one: requested here, stored at the end of the tile (the round trip to the one hot counter is long)
+    if (c.g->ctr) t.next_tile_idx = atomicAdd(c.g->ctr, 1u);
+  }
+  RR_STAMP(4);
+  // while GEMM 1 runs: the next tile's coordinates start their way global -> shared memory (consumed in epilogue 2 and by the next tile)
+  if (HALF == 0 && has_next) {
+    const RrGlobal* g = c.g;
+    const uint32_t in = min(t.tile_next * (uint32_t)TILE + (uint32_t)pt, g->n - 1u);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(nxt)), "l"(g->x + in) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(nxt + TILE)), "l"(g->y + in) : "memory");
+    if (g->sbar) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(nxt + 2 * TILE)), "l"(g->sbar + in) : "memory");
+  }
+}
+
+// back half of a tile: GEMM 1 done -> epilogue 1 -> (GEMM 2 -> epilogue 2) -> stores.  The loop's backward branch sits between the
+// front half and this wait: a far branch costs ~700 cycles of instruction fetch (measured with the timeline stamps - whether the tile body
+// was a function called per tile or a loop), and here that latency runs under GEMM 1 instead of between two tiles.
+template <int HALF, bool JAC>
+__device__ __forceinline__ void rr_back(const RrCtx& c, RrTile& t) {
+  RR_TILE_CONSTS;
+  mbar_wait_addr(c.mbar_addr, t.ph); t.ph ^= 1u;
   tc_fence_after();
+  RR_STAMP(5);
   // ---- epilogue 1: value; the 0 / 1 mask of the hidden layer -> A-lo columns --------------------------------------------
   float s = HALF == 0 ? cst.bout : 0.f;
+  uint32_t wrow[8];
   {
-    const float unscale1 = inv0 * c.inv_sw;
+    const float unscale1 = t.inv0 * c.inv_sw;
     uint32_t z[NCH][32];
 #pragma unroll
     for (int cc = 0; cc < NCH; ++cc) tmem_ld32(c.lane_base + COL_D + cc * 32, z[cc]);
     if (!JAC) {                       // D is free once every thread holds its columns: the next tile's layer-0 MMA
-      if (HALF == 0 && next_xy) {
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        uint32_t w[8];
-        rr_point_row(c, next_xy[pt], next_xy[TILE + pt], w);
-        TmemIO<8>::st(c.lane_base + RR_COL_P, w);
+      if (HALF == 0 && has_next) {
+        asm volatile("cp.async.wait_all;" ::: "memory");     // this thread staged the point itself
+        rr_point_row(c, nxt[0], nxt[TILE], wrow);
+        TmemIO<8>::st(c.lane_base + RR_COL_P, wrow);
         tc_wait_st();
       }
       tc_wait_ld();
       tc_fence_before();
       group_bar<NT>(c.bar_id);
-      if (tg == 0 && next_xy) rr_issue_l0(c);
+      if (tg == 0 && has_next) rr_issue_l0(c);
     } else {
       tc_wait_ld();
     }
@@ -737,32 +790,39 @@ __device__ __noinline__ uint32_t sdf_rr_tile(RrCtx c, uint32_t phases, float px,
   }
   float jx = 0.f, jy = 0.f;
   if (JAC) {
-  tc_wait_st();
-  tc_fence_before();
-  group_bar<NT>(c.bar_id);
-  if (tg == 0) rr_issue_gemm(c, false);
-  mbar_wait_addr(c.mbar_addr, ph); ph ^= 1u;
-  tc_fence_after();
-  // ---- epilogue 2: through layer 0 to the Jacobian; the next tile's layer-0 MMA goes out as soon as D is free -----------
-  {
+    RR_STAMP(6);
+    tc_wait_st();
+    tc_fence_before();
+    group_bar<NT>(c.bar_id);
+    RR_STAMP(7);
+    if (tg == 0) rr_issue_gemm(c, false);
+    RR_STAMP(8);
+    // while GEMM 2 runs: the next tile's layer-0 A row (its coordinates were staged during GEMM 1)
+    if (HALF == 0 && has_next) {
+      asm volatile("cp.async.wait_all;" ::: "memory");       // this thread staged the point itself
+      rr_point_row(c, nxt[0], nxt[TILE], wrow);
+    }
+    mbar_wait_addr(c.mbar_addr, t.ph); t.ph ^= 1u;
+    tc_fence_after();
+    RR_STAMP(9);
+    // ---- epilogue 2: through layer 0 to the Jacobian; the next tile's layer-0 MMA goes out as soon as D is free ---------
     uint32_t gz[NCH][32];
 #pragma unroll
     for (int cc = 0; cc < NCH; ++cc) tmem_ld32(c.lane_base + COL_D + cc * 32, gz[cc]);
-    if (HALF == 0 && next_xy) {
-      asm volatile("cp.async.wait_all;" ::: "memory");     // this thread staged the point itself (persistent loop)
-      uint32_t w[8];
-      rr_point_row(c, next_xy[pt], next_xy[TILE + pt], w);
-      TmemIO<8>::st(c.lane_base + RR_COL_P, w);
+    if (HALF == 0 && has_next) {
+      TmemIO<8>::st(c.lane_base + RR_COL_P, wrow);           // the A-lo columns are dead once GEMM 2 has completed
       tc_wait_st();
     }
     tc_wait_ld();
     tc_fence_before();
     group_bar<NT>(c.bar_id);
-    if (tg == 0 && next_xy) rr_issue_l0(c);
+    RR_STAMP(10);
+    if (tg == 0 && has_next) rr_issue_l0(c);
+    RR_STAMP(11);
 #pragma unroll
     for (int cc = 0; cc < NCH; ++cc) {
       uint32_t hw[16];
-      TmemIO<16>::ld(c.lane_base + COL_AHI + cc * 16, hw);
+      TmemIO<16>::ld(c.lane_base + COL_AHI + cc * 16, hw);   // hi(h0) of THIS tile: nonzero exactly where a0 > 0
       tc_wait_ld();
 #pragma unroll
       for (int q = 0; q < 16; ++q) {
@@ -777,46 +837,73 @@ __device__ __noinline__ uint32_t sdf_rr_tile(RrCtx c, uint32_t phases, float px,
         }
       }
     }
-    const float unscale2 = seed * c.unscale2;
+    const float unscale2 = (c.g->sbar ? cur[2 * TILE] : 1.f) * c.unscale2;
     jx *= unscale2; jy *= unscale2;
   }
-  }
+  RR_STAMP(12);
   // ---- hand the other half what it stores: HALF 0 writes s, jx; HALF 1 writes jy -------------------------------------------
-  float* mine = part + (HALF * TILE + pt) * 4;
+  float* mine = c.part + (HALF * TILE + pt) * 4;
   if (HALF == 0) mine[0] = jy; else { mine[0] = s; mine[1] = jx; }
-  if (HALF == 0 && tg == 0 && c.ctr) *c.next_slot = next_tile_idx + c.ctr_bias;
+  if (HALF == 0 && tg == 0 && c.g->ctr) *c.next_slot = t.next_tile_idx + c.g->ctr_bias;
   asm volatile("cp.async.wait_all;" ::: "memory");
   tc_fence_before();
   group_bar<NT>(c.bar_id);          // also: the next tile's tcgen05.st must not overtake this tile's TMEM reads
   tc_fence_after();
-  const float* other = part + ((1 - HALF) * TILE + pt) * 4;
-  if (HALF == 0) {
-    if (s_ptr) *s_ptr = s + other[0];
-    if (j_ptr) *j_ptr = jx + other[1];
-  } else {
-    if (j_ptr) *j_ptr = jy + other[0];
+  {
+    const RrGlobal* g = c.g;
+    const uint32_t i = t.tile * (uint32_t)TILE + (uint32_t)pt;
+    const float* other = c.part + ((1 - HALF) * TILE + pt) * 4;
+    if (i < g->n) {
+      if (HALF == 0) {
+        if (g->s_out) g->s_out[i] = s + other[0];
+        if (JAC) g->jx_out[i] = jx + other[1];
+      } else {
+        if (JAC) g->jy_out[i] = jy + other[0];
+      }
+    }
   }
-  return ph | (ph2 << 1);
+  RR_STAMP(13);
+  t.buf ^= 1u;
+}
+#undef RR_STAMP
+#undef RR_TILE_CONSTS
+
+// All tiles of one group half.  The loop is rotated: its backward branch follows the issue of GEMM 1 (see rr_back).
+template <int HALF, bool JAC>
+__device__ __noinline__ void sdf_rr_group(RrCtx c, uint32_t tile, uint32_t tile_next, uint32_t stride) {
+  RrTile t;
+  t.ph = t.ph2 = t.buf = 0u; t.tile = tile; t.tile_next = tile_next; t.next_tile_idx = 0u; t.inv0 = 1.f; t.dbg = nullptr;
+  if (t.tile >= c.g->n_tiles) return;
+  rr_front<HALF, JAC>(c, t);
+#pragma unroll 1
+  for (;;) {
+    rr_back<HALF, JAC>(c, t);
+    if (HALF == 0 && c.g->dbg && threadIdx.x % (2 * TILE) == 0) const_cast<RrGlobal*>(c.g)->ret_clock[threadIdx.x / (2 * TILE)] = clock64();
+    t.tile = t.tile_next;
+    t.tile_next = c.g->ctr ? *c.next_slot : t.tile_next + stride;
+    if (t.tile >= c.g->n_tiles) break;
+    rr_front<HALF, JAC>(c, t);
+  }
 }
 
 constexpr size_t rr_smem_bytes() {
-  return (size_t)4 * RR_H * RR_H * 2 + (size_t)RR_B0_HALFS * 2 + (size_t)2 * 2 * TILE * 4 * 4 + 4 * 8 + 32 + 2 * 4 + (size_t)2 * 2 * 3 * TILE * 4;
+  return (size_t)4 * RR_H * RR_H * 2 + (size_t)RR_B0_HALFS * 2 + (size_t)2 * 2 * TILE * 4 * 4 + 4 * 8 + sizeof(RrGlobal) + 32 +
+         (size_t)2 * 2 * 3 * TILE * 4;
 }
 
 template <bool JAC>
 __global__ void __launch_bounds__(512, 1)
-sdf_tc_rr_kernel(TcParams prm_tc, const __half* __restrict__ bimg, const float* __restrict__ x, const float* __restrict__ y,
-                 const float* __restrict__ sbar, size_t n, float* __restrict__ s_out, float* __restrict__ jx_out, float* __restrict__ jy_out,
-                 unsigned int* __restrict__ tile_ctr) {
+sdf_tc_rr_kernel(TcParams prm_tc, const __half* __restrict__ bimg, RrGlobal gl) {
   constexpr int H = RR_H, NG = 2, GT = 2 * TILE, IMG = H * H;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __half* sB = reinterpret_cast<__half*>(smem_raw);                       // W1 hi | W1 lo | V hi | V lo | B0
   float* sPart = reinterpret_cast<float*>(smem_raw + ((size_t)4 * IMG + RR_B0_HALFS) * 2);   // [NG][2][TILE][4]
   uint64_t* mbar = reinterpret_cast<uint64_t*>(sPart + NG * 2 * TILE * 4);                  // [NG] GEMMs | [NG] layer 0
-  int* lock = reinterpret_cast<int*>(mbar + 2 * NG);
+  RrGlobal* sG = reinterpret_cast<RrGlobal*>(mbar + 2 * NG);
+  int* lock = reinterpret_cast<int*>(sG + 1);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lock + 1);
   uint32_t* next_tile = tmem_slot + 1;                                                       // [NG]
-  float* sCoord = reinterpret_cast<float*>(next_tile + NG + 1);                              // [NG][2][3][TILE]
+  float* sCoord = reinterpret_cast<float*>(next_tile + NG);                                  // [NG][2][3][TILE]
   const int t = threadIdx.x, warp = t >> 5;
   const int grp = t / GT, tg = t % GT;
   const int half = (tg >> 5) >> 2;
@@ -828,6 +915,8 @@ sdf_tc_rr_kernel(TcParams prm_tc, const __half* __restrict__ bimg, const float* 
     if (t == 0) {
       for (int g = 0; g < 2 * NG; ++g) mbar_init(mbar + g, 1);
       *lock = 0;
+      gl.ctr_bias = 2 * gridDim.x * NG;
+      *sG = gl;
     }
     fence_async_smem();
   }
@@ -845,22 +934,22 @@ sdf_tc_rr_kernel(TcParams prm_tc, const __half* __restrict__ bimg, const float* 
   c.mbar_addr = smem_u32(mbar + grp); c.mbar2_addr = smem_u32(mbar + NG + grp);
   c.bar_id = 1 + grp;
   c.lock = lock;
-  c.ctr = tile_ctr; c.next_slot = next_tile + grp; c.ctr_bias = 2 * gridDim.x * NG;
+  c.g = sG;
+  c.next_slot = next_tile + grp;
+  c.coord = sCoord + grp * (2 * 3 * TILE);
+  c.part = sPart + grp * (2 * TILE * 4);
   c.inv_sw = prm_tc.inv_sw; c.unscale2 = prm_tc.inv_sv;
   c.max_w0x = prm_tc.max_w0x; c.max_w0y = prm_tc.max_w0y; c.max_b0 = prm_tc.max_b0;
   c.spx_mul = prm_tc.spx_mul; c.spy_mul = prm_tc.spy_mul; c.cb_mul = prm_tc.cb_mul;
-  float* part = sPart + grp * (2 * TILE * 4);
-  uint32_t phases = 0;
-  const size_t n_tiles = (n + TILE - 1) / TILE;
-  const size_t stride = (size_t)gridDim.x * NG;
-  size_t tile = (size_t)blockIdx.x * NG + grp;
-  size_t tile_next = tile + stride;
-  float* coord = sCoord + grp * (2 * 3 * TILE);
-  float px = 0.f, py = 0.f, seed = 1.f;
-  if (tile < n_tiles) {                       // (group-uniform) the first tile: coordinates from global memory, its layer-0 MMA up front
-    const size_t ic = min(tile * TILE + pt, n - 1);
-    px = x[ic]; py = y[ic]; seed = sbar ? sbar[ic] : 1.f;
+  const uint32_t n_tiles = gl.n_tiles;
+  const uint32_t stride = gridDim.x * NG;
+  uint32_t tile = blockIdx.x * NG + grp;
+  uint32_t tile_next = tile + stride;
+  if (tile < n_tiles) {                       // (group-uniform) the first tile: coordinates and layer-0 MMA up front
     if (half == 0) {
+      const uint32_t ic = min(tile * (uint32_t)TILE + (uint32_t)pt, gl.n - 1u);
+      const float px = gl.x[ic], py = gl.y[ic];
+      c.coord[pt] = px; c.coord[TILE + pt] = py; c.coord[2 * TILE + pt] = gl.sbar ? gl.sbar[ic] : 1.f;
       uint32_t w[8];
       rr_point_row(c, px, py, w);
       TmemIO<8>::st(c.lane_base + RR_COL_P, w);
@@ -870,34 +959,15 @@ sdf_tc_rr_kernel(TcParams prm_tc, const __half* __restrict__ bimg, const float* 
     group_bar<GT>(c.bar_id);
     if (tg == 0) rr_issue_l0(c);
   }
-  for (int it = 0; tile < n_tiles; ++it) {
-    const bool has_next = tile_next < n_tiles;
-    if (has_next && half == 0) {
-      const size_t in = min(tile_next * TILE + pt, n - 1);
-      float* dst = coord + ((it + 1) & 1) * (3 * TILE) + pt;
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(dst)), "l"(x + in) : "memory");
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(dst + TILE)), "l"(y + in) : "memory");
-      if (sbar) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(dst + 2 * TILE)), "l"(sbar + in) : "memory");
-    }
-    const size_t i = tile * TILE + pt;
-    const bool valid = i < n;
-    if (it > 0) {
-      const float* src = coord + (it & 1) * (3 * TILE) + pt;
-      px = src[0]; py = src[TILE]; seed = sbar ? src[2 * TILE] : 1.f;
-    }
-    const float* nxy = has_next ? coord + ((it + 1) & 1) * (3 * TILE) : nullptr;
-    if (half == 0)
-      phases = sdf_rr_tile<0, JAC>(c, phases, px, py, seed, nxy, part, (valid && s_out) ? s_out + i : nullptr, (JAC && valid) ? jx_out + i : nullptr);
-    else
-      phases = sdf_rr_tile<1, JAC>(c, phases, px, py, seed, nxy, part, nullptr, (JAC && valid) ? jy_out + i : nullptr);
-    tile = tile_next;
-    tile_next = tile_ctr ? (size_t)next_tile[grp] : tile_next + stride;
-  }
+  // tiles: the first two by position, the rest from the global counter (the SMs do not all run at the same speed), which the tile
+  // body polls two tiles ahead - or by striding when no counter is given (small launches)
+  if (half == 0) sdf_rr_group<0, JAC>(c, tile, tile_next, stride); else sdf_rr_group<1, JAC>(c, tile, tile_next, stride);
   tc_fence_before();
   __syncthreads();
-  if (tile_ctr && t == 0) {
+  // The last CTA to finish puts the tile counter back to zero for the next launch on this stream
+  if (gl.ctr && t == 0) {
     __threadfence();
-    if (atomicAdd(tile_ctr + 1, 1u) == gridDim.x - 1) { tile_ctr[0] = 0u; tile_ctr[1] = 0u; __threadfence(); }
+    if (atomicAdd(gl.ctr + 1, 1u) == gridDim.x - 1) { gl.ctr[0] = 0u; gl.ctr[1] = 0u; __threadfence(); }
   }
   if (warp == 0) tmem_dealloc(tmem_all, 512);
 }
@@ -928,13 +998,34 @@ int launch_tc_rr(nlo_sdf_model* m, const float* x, const float* y, const float* 
     NLO_CUDA(cudaMemcpyToSymbol(cst, m->tc_const, sizeof(TcConst), 0, cudaMemcpyHostToDevice));
     g_const_owner[m->device] = m->uid;
   }
-  unsigned int* ctr = nullptr;
+  RrGlobal gl;
+  gl.x = x; gl.y = y; gl.sbar = sbar; gl.s_out = s; gl.jx_out = jx; gl.jy_out = jy;
+  gl.ctr = nullptr; gl.dbg = nullptr; gl.n = (uint32_t)n; gl.n_tiles = (uint32_t)tiles; gl.ctr_bias = 0; gl.pad = 0; gl.ret_clock[0] = gl.ret_clock[1] = 0;
   if (tiles > (size_t)grid * 2) {
     const int slot = nlo_model_stream_slot(m, st);
     if (slot < 0) return 1;
-    ctr = reinterpret_cast<unsigned int*>(static_cast<char*>(m->d_tc) + m->tc_bytes) + 2 * slot;
+    gl.ctr = reinterpret_cast<unsigned int*>(static_cast<char*>(m->d_tc) + m->tc_bytes) + 2 * slot;
   }
-  kfn<<<grid, 512, smem, st>>>(prm, reinterpret_cast<const __half*>(m->d_tc), x, y, sbar, n, s, jx, jy, ctr);
+  if (getenv("NLO_B200_TC_TIMELINE")) {             // debugging aid: phase clocks of thread 0 of both groups of CTA 0, its tiles 32..39
+    NLO_CUDA(cudaMalloc(&gl.dbg, 2 * 8 * 16 * sizeof(long long)));
+    NLO_CUDA(cudaMemsetAsync(gl.dbg, 0, 2 * 8 * 16 * sizeof(long long), st));
+  }
+  kfn<<<grid, 512, smem, st>>>(prm, reinterpret_cast<const __half*>(m->d_tc), gl);
+  if (gl.dbg) {
+    long long h[2 * 8 * 16];
+    NLO_CUDA(cudaMemcpyAsync(h, gl.dbg, sizeof(h), cudaMemcpyDeviceToHost, st));
+    NLO_CUDA(cudaStreamSynchronize(st));
+    cudaFree(gl.dbg);
+    for (int g = 0; g < 2; ++g)
+      for (int it = 0; it < 8; ++it) {
+        const long long* r = h + (g * 8 + it) * 16;
+        if (r[0] == 0) continue;
+        fprintf(stderr, "[rr timeline] group%d slot%d: wait L0-MMA %4lld L0 %4lld bar %4lld issue1 %5lld mma1 %4lld | E1 %4lld bar %4lld issue2 %5lld mma2 %4lld | "
+                        "E2: ld+row+bar %4lld issueL0 %4lld compute %4lld | end %4lld | tile body %5lld | return -> next body %5lld\n",
+                g, it, r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[5] - r[4], r[6] - r[5], r[7] - r[6], r[8] - r[7], r[9] - r[8],
+                r[10] - r[9], r[11] - r[10], r[12] - r[11], r[13] - r[12], r[13] - r[0], r[0] - r[14]);
+      }
+  }
   NLO_CHECK_LAUNCH();
   return 0;
 }
@@ -1060,7 +1151,7 @@ int nlo_sdf_tc_launch(nlo_sdf_model* m, const float* x, const float* y, const fl
   if (m->desc.n_hidden_mats >= 2) return nlo_sdf_tc_deep_launch(m, x, y, sbar, n, s, jx, jy, st);
   if (!m->d_tc) return nlo_fail("tensor-tile operands were not prepared");
   const int H = (int)m->desc.hidden, a0 = (int)m->desc.act0, a = (int)m->desc.act;
-  if (H == RR_H && a0 == NLO_ACT_RELU && a == NLO_ACT_RELU && rr_enabled()) {
+  if (H == RR_H && a0 == NLO_ACT_RELU && a == NLO_ACT_RELU && n <= 0x7FFFFF00u && rr_enabled()) {
     if (jx && jy) return launch_tc_rr<true>(m, x, y, sbar, n, s, jx, jy, st);
     if (!jx && !jy) return launch_tc_rr<false>(m, x, y, sbar, n, s, nullptr, nullptr, st);
   }
