@@ -621,6 +621,9 @@ __device__ __forceinline__ void rr_point_row(const RrCtx& c, float px, float py,
   w[4] = pack_f16(ym, yl); w[5] = pack_f16(cb, cb); w[6] = pack_f16(cb, 0.f); w[7] = 0u;
 }
 
+// The thread that issues a group's MMAs sits in the HALF-1 warps: the issuing warp is blocked for most of a GEMM (the tensor queue takes
+// ~9 MMAs), and the HALF-0 warps carry the work that runs in the shadow of the GEMMs (coordinate staging, the next tile's A row)
+constexpr int RR_ISSUER = TILE;
 constexpr uint32_t RR_COL_AHI = 0, RR_COL_ALO = RR_H / 2, RR_COL_D = RR_H, RR_COL_P = RR_H / 2;   // P: the first 8 A-lo columns
 
 // the layer-0 MMA of one tile: D0 = P . B0.  No lock: one MMA slipping into the other group's GEMM is harmless (other D columns).
@@ -670,7 +673,7 @@ __device__ __forceinline__ void rr_issue_gemm(const RrCtx& c, bool fwd) {
 // computed by the same instruction sequence in both forms, so a value-only evaluation (a line-search trial) reproduces the value
 // of a full one bit for bit.
 struct RrTile {            // what a tile carries from its front half (layer 0, GEMM 1 issued) to its back half
-  uint32_t ph, ph2, buf, tile, tile_next, next_tile_idx;
+  uint32_t ph, ph2, buf, tile, tile_next, next_tile_idx, prev_tile, have_prev, stride;
   float inv0;
   long long* dbg;
 };
@@ -682,14 +685,31 @@ struct RrTile {            // what a tile carries from its front half (layer 0, 
   const int pt = tg & (TILE - 1);                                                                                          \
   const float* cur = c.coord + t.buf * (3 * TILE) + pt;                                                                    \
   float* nxt = c.coord + (t.buf ^ 1u) * (3 * TILE) + pt;                                                                   \
-  const bool has_next = t.tile_next < c.g->n_tiles;                                                                        \
-  (void)COL_AHI; (void)COL_ALO; (void)COL_D; (void)C0; (void)NCH; (void)cur; (void)nxt; (void)has_next; (void)tg
+  (void)COL_AHI; (void)COL_ALO; (void)COL_D; (void)C0; (void)NCH; (void)cur; (void)nxt; (void)tg
+
+// The previous tile's results: each half left its partial sums {s, jx, jy} in the exchange buffer; HALF 0 stores s and jx, HALF 1 jy.
+template <int HALF, bool JAC>
+__device__ __forceinline__ void rr_store_prev(const RrCtx& c, const RrTile& t) {
+  const int pt = threadIdx.x & (TILE - 1);
+  const RrGlobal* g = c.g;
+  const uint32_t i = t.prev_tile * (uint32_t)TILE + (uint32_t)pt;
+  if (i < g->n) {
+    const float* pa = c.part + pt * 4;
+    const float* pb = c.part + (TILE + pt) * 4;
+    if (HALF == 0) {
+      if (g->s_out) g->s_out[i] = pa[0] + pb[0];
+      if (JAC) g->jx_out[i] = pa[1] + pb[1];
+    } else {
+      if (JAC) g->jy_out[i] = pb[2] + pa[2];
+    }
+  }
+}
 
 // front half of a tile: layer 0 from the tensor core's D0, GEMM 1 issued, the next tile's coordinates on their way
 template <int HALF, bool JAC>
 __device__ __forceinline__ void rr_front(const RrCtx& c, RrTile& t) {
   RR_TILE_CONSTS;
-  t.dbg = (HALF == 0 && tg == 0 && c.g->dbg && blockIdx.x == 0 && t.tile >= 32u * 2u * gridDim.x && t.tile < 40u * 2u * gridDim.x)
+  t.dbg = (tg == RR_ISSUER && c.g->dbg && blockIdx.x == 0 && t.tile >= 32u * 2u * gridDim.x && t.tile < 40u * 2u * gridDim.x)
               ? c.g->dbg + ((threadIdx.x / NT) * 8 + (t.tile / (2u * gridDim.x) - 32u)) * 16 : nullptr;
   RR_STAMP(0);
   if (t.dbg) t.dbg[14] = c.g->ret_clock[threadIdx.x / NT];
@@ -724,13 +744,21 @@ __device__ __forceinline__ void rr_front(const RrCtx& c, RrTile& t) {
   group_bar<NT>(c.bar_id);
   RR_STAMP(3);
   t.next_tile_idx = 0u;
-  if (tg == 0) {
+  if (tg == RR_ISSUER) {
     rr_issue_gemm(c, true);
     // the tile after the next one: requested here, stored at the end of the tile (the round trip to the one hot counter is long)
     if (c.g->ctr) t.next_tile_idx = atomicAdd(c.g->ctr, 1u);
   }
   RR_STAMP(4);
-  // while GEMM 1 runs: the next tile's coordinates start their way global -> shared memory (consumed in epilogue 2 and by the next tile)
+  // ---- in the shadow of GEMM 1 (everything below used to sit between two tiles, behind a group barrier of its own) ----------
+  // (the barrier in front of GEMM 1 is what orders these shared-memory reads behind the previous tile's writes)
+  if (t.have_prev) {
+    // which tile follows the next one: thread 0 stored it at the end of the previous tile
+    t.tile_next = c.g->ctr ? *c.next_slot : t.tile + t.stride;
+    rr_store_prev<HALF, JAC>(c, t);                     // the previous tile's results: both halves' partial sums -> global memory
+  }
+  const bool has_next = t.tile_next < c.g->n_tiles;
+  // the next tile's coordinates start their way global -> shared memory (consumed in epilogue 2 and by the next tile)
   if (HALF == 0 && has_next) {
     const RrGlobal* g = c.g;
     const uint32_t in = min(t.tile_next * (uint32_t)TILE + (uint32_t)pt, g->n - 1u);
@@ -746,6 +774,7 @@ __device__ __forceinline__ void rr_front(const RrCtx& c, RrTile& t) {
 template <int HALF, bool JAC>
 __device__ __forceinline__ void rr_back(const RrCtx& c, RrTile& t) {
   RR_TILE_CONSTS;
+  const bool has_next = t.tile_next < c.g->n_tiles;
   mbar_wait_addr(c.mbar_addr, t.ph); t.ph ^= 1u;
   tc_fence_after();
   RR_STAMP(5);
@@ -767,7 +796,7 @@ __device__ __forceinline__ void rr_back(const RrCtx& c, RrTile& t) {
       tc_wait_ld();
       tc_fence_before();
       group_bar<NT>(c.bar_id);
-      if (tg == 0 && has_next) rr_issue_l0(c);
+      if (tg == RR_ISSUER && has_next) rr_issue_l0(c);
     } else {
       tc_wait_ld();
     }
@@ -795,7 +824,7 @@ __device__ __forceinline__ void rr_back(const RrCtx& c, RrTile& t) {
     tc_fence_before();
     group_bar<NT>(c.bar_id);
     RR_STAMP(7);
-    if (tg == 0) rr_issue_gemm(c, false);
+    if (tg == RR_ISSUER) rr_issue_gemm(c, false);
     RR_STAMP(8);
     // while GEMM 2 runs: the next tile's layer-0 A row (its coordinates were staged during GEMM 1)
     if (HALF == 0 && has_next) {
@@ -817,7 +846,7 @@ __device__ __forceinline__ void rr_back(const RrCtx& c, RrTile& t) {
     tc_fence_before();
     group_bar<NT>(c.bar_id);
     RR_STAMP(10);
-    if (tg == 0 && has_next) rr_issue_l0(c);
+    if (tg == RR_ISSUER && has_next) rr_issue_l0(c);
     RR_STAMP(11);
 #pragma unroll
     for (int cc = 0; cc < NCH; ++cc) {
@@ -841,27 +870,14 @@ __device__ __forceinline__ void rr_back(const RrCtx& c, RrTile& t) {
     jx *= unscale2; jy *= unscale2;
   }
   RR_STAMP(12);
-  // ---- hand the other half what it stores: HALF 0 writes s, jx; HALF 1 writes jy -------------------------------------------
-  float* mine = c.part + (HALF * TILE + pt) * 4;
-  if (HALF == 0) mine[0] = jy; else { mine[0] = s; mine[1] = jx; }
-  if (HALF == 0 && tg == 0 && c.g->ctr) *c.next_slot = t.next_tile_idx + c.g->ctr_bias;
-  asm volatile("cp.async.wait_all;" ::: "memory");
-  tc_fence_before();
-  group_bar<NT>(c.bar_id);          // also: the next tile's tcgen05.st must not overtake this tile's TMEM reads
-  tc_fence_after();
+  // ---- leave the partial sums for the deferred store (rr_store_prev, in the shadow of the next tile's GEMM 1).  No barrier here: a warp
+  // ---- touches only its own tensor-memory lanes and columns between MMAs, and every MMA is issued behind a group barrier ------------
   {
-    const RrGlobal* g = c.g;
-    const uint32_t i = t.tile * (uint32_t)TILE + (uint32_t)pt;
-    const float* other = c.part + ((1 - HALF) * TILE + pt) * 4;
-    if (i < g->n) {
-      if (HALF == 0) {
-        if (g->s_out) g->s_out[i] = s + other[0];
-        if (JAC) g->jx_out[i] = jx + other[1];
-      } else {
-        if (JAC) g->jy_out[i] = jy + other[0];
-      }
-    }
+    float* mine = c.part + (HALF * TILE + pt) * 4;
+    mine[0] = s; mine[1] = jx; mine[2] = jy;
   }
+  if (tg == RR_ISSUER && c.g->ctr) *c.next_slot = t.next_tile_idx + c.g->ctr_bias;
+  t.prev_tile = t.tile; t.have_prev = 1u;
   RR_STAMP(13);
   t.buf ^= 1u;
 }
@@ -873,17 +889,19 @@ template <int HALF, bool JAC>
 __device__ __noinline__ void sdf_rr_group(RrCtx c, uint32_t tile, uint32_t tile_next, uint32_t stride) {
   RrTile t;
   t.ph = t.ph2 = t.buf = 0u; t.tile = tile; t.tile_next = tile_next; t.next_tile_idx = 0u; t.inv0 = 1.f; t.dbg = nullptr;
+  t.prev_tile = 0u; t.have_prev = 0u; t.stride = stride;
   if (t.tile >= c.g->n_tiles) return;
   rr_front<HALF, JAC>(c, t);
 #pragma unroll 1
   for (;;) {
     rr_back<HALF, JAC>(c, t);
-    if (HALF == 0 && c.g->dbg && threadIdx.x % (2 * TILE) == 0) const_cast<RrGlobal*>(c.g)->ret_clock[threadIdx.x / (2 * TILE)] = clock64();
-    t.tile = t.tile_next;
-    t.tile_next = c.g->ctr ? *c.next_slot : t.tile_next + stride;
+    if (c.g->dbg && threadIdx.x % (2 * TILE) == RR_ISSUER) const_cast<RrGlobal*>(c.g)->ret_clock[threadIdx.x / (2 * TILE)] = clock64();
+    t.tile = t.tile_next;                 // (its successor is read in the front half, behind the barrier that orders it)
     if (t.tile >= c.g->n_tiles) break;
     rr_front<HALF, JAC>(c, t);
   }
+  group_bar<2 * TILE>(c.bar_id);
+  rr_store_prev<HALF, JAC>(c, t);
 }
 
 constexpr size_t rr_smem_bytes() {
