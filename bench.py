@@ -443,7 +443,8 @@ def run_ours(args):
         peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
         bound = "tensor"
         peak_note = (f"{peak_src} cuBLAS bf16 sustained; per point the kernel executes 5 fp16 MMA passes for 2 algorithmic contractions "
-                     "(forward: hi.hi, hi.lo, lo.hi; reverse of the ReLU layer: exact 0/1 mask x hi/lo of diag(w2)W1), so its algorithmic ceiling is peak x 2/5")
+                     "(forward: hi.hi, hi.lo, lo.hi; reverse of the ReLU layer: exact 0/1 mask x hi/lo of diag(w2)W1) plus one K=16 MMA that evaluates "
+                     "layer 0 (sdf_tc_rr_kernel), so its algorithmic ceiling is peak x 2/5.125")
     else:
         sm_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
         peak = model_sm_count(L, local_rank) * 128 * 2 * sm_mhz * 1e6 / 1e12
@@ -473,7 +474,7 @@ def run_ours(args):
                               "h2d_bytes_per_step": e2e_full["h2d"], "d2h_bytes_per_step": e2e_full["d2h"]},
                 "cpu_affinity": (f"rank pinned to the {numa_cpus} CPUs NVML reports local to its GPU" if numa_cpus else "unchanged")},
         "gpu_launches": head["launches"],
-        "roofline": {"kernel": "sdf_tc_kernel" if prec == "tc3xf16" else "sdf_simt_kernel", "bound": bound, "achieved": achieved,
+        "roofline": {"kernel": "sdf_tc_rr_kernel (tcgen05; ReLU / ReLU form of sdf_tc_kernel)" if prec == "tc3xf16" else "sdf_simt_kernel", "bound": bound, "achieved": achieved,
                      "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "traffic": (dram_pp * n_pts if dram_pp is not None else None), "traffic_unit": "bytes per launch (ncu dram read+write)",
                      "traffic_source": (f"profiles/sdf_tc_kernel_dram.json: {dram_src['dram_bytes_read']:.0f} B read + {dram_src['dram_bytes_write']:.0f} B written "
