@@ -482,6 +482,9 @@ def run_ours(args):
                                         if dram_src else None),
                      "algorithmic_bytes_per_launch": 20 * n_pts,
                      "flop_per_point": FLOP_PER_POINT, "points_per_launch": n_pts, "kernel_ms": k_ms, "peak_source": peak_note,
+                     "kernel_note": "timed alone in its plain form (points read from memory, s / jx / jy written); inside the step the same tile "
+                                    "code runs in its rows form (K3 fused: footprint points formed from the poses, results written straight "
+                                    "into g and dg/dw), two launches per evaluation",
                      "kernel_share_of_step": k_ms / ms_per_step,
                      "dynamics_kernel_hbm": {"kernel": "nlp_phase0_kernel (defect rows only)", "algorithmic_bytes_per_launch": DYN_BYTES_PER_PROBLEM * P,
                                              "kernel_ms": dyn_ms, "achieved_gbs": DYN_BYTES_PER_PROBLEM * P / (dyn_ms * 1e-3) / 1e9,

@@ -596,6 +596,16 @@ static int ensure_scratch(const nlo_nlp* p, NlpScratch& sc, size_t P) {
 
 static int nlp_eval_on(nlo_nlp* p, NlpScratch& sc, const float* w, size_t P, size_t ld, float* g, float* jac, float* f, float* grad_f,
                        cudaStream_t st) {
+  // K3 fused into K1: hard SDF rows of a footprint with a heading on the ReLU / ReLU tensor kernel (benchmark_6) - the footprint points are
+  // formed inside the SDF kernel and its results go straight into g and dg/dw: two launches per evaluation, no point / value scratch
+  const NlpDev& L = p->L;
+  const bool fused = (g || jac) && L.sdf_mode == NLO_SDF_LEARNED && !L.use_slack && L.shape != NLO_SHAPE_DOT && L.nnz_sdf_row == 3 &&
+                     L.rows_per_knot == L.nb && nlo_sdf_tc_rows_supported(p->model) && (size_t)(L.N + 1) * L.nb * P <= 0x7FFFFF00u;
+  if (fused) {
+    if (nlo_nlp_launch_assembly(p, sc, w, P, ld, g, jac, f, grad_f, st, 0, true)) return 1;
+    return nlo_sdf_tc_rows_launch(p->model, w, P, ld, L.N + 1, L.nx, L.nb, L.bx, L.by, g ? g + (size_t)L.g_off_sdf * ld : nullptr, jac,
+                                  L.nzmap + L.e_off_sdf, L.rows_per_knot * L.nnz_sdf_row, st);
+  }
   if ((g || jac) && p->L.sdf_mode == NLO_SDF_LEARNED && ensure_scratch(p, sc, P)) return 1;   // (analytic obstacles need no scratch)
   if (nlo_nlp_launch_assembly(p, sc, w, P, ld, g, jac, f, grad_f, st, 0)) return 1;
   if (g || jac) {

@@ -181,6 +181,10 @@ int nlo_sdf_simt_hess_launch(nlo_sdf_model* m, const float* x, const float* y, c
 // sdf_tc.cu
 bool nlo_sdf_tc_supported(const nlo_sdf_desc* d);
 int nlo_sdf_tc_prepare(nlo_sdf_model* m, const float* weights_host);
+// K3 fused into K1 (sdf_tc.cu, ReLU / ReLU H = 128 form): the hard SDF rows of an NLP batch straight from the poses in w
+bool nlo_sdf_tc_rows_supported(const nlo_sdf_model* m);
+int nlo_sdf_tc_rows_launch(nlo_sdf_model* m, const float* w, size_t P, size_t ld, int n_knots, int nx, int nb, const float* bx, const float* by,
+                           float* g_rows, float* jac, const int* nz, int nz_per_knot, cudaStream_t st);
 int nlo_sdf_tc_launch(nlo_sdf_model* m, const float* x, const float* y, const float* sbar, size_t n,
                       float* s, float* jx, float* jy, cudaStream_t st);
 bool nlo_sdf_tc_hess_supported(const nlo_sdf_model* m);

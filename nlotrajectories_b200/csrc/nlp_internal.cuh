@@ -166,7 +166,7 @@ int nlo_launch_pack_rows(const float* in, size_t ld_in, size_t P, const int* idx
 // phase 0: everything before the SDF evaluation (defects, copy rows, footprint points / circles, f, grad f)
 // phase 1: SDF rows (needs p->d_s/d_jx/d_jy)
 int nlo_nlp_launch_assembly(nlo_nlp* p, const NlpScratch& sc, const float* w, size_t P, size_t ld, float* g, float* jac, float* f,
-                            float* grad_f, cudaStream_t st, int phase);
+                            float* grad_f, cudaStream_t st, int phase, bool fused_rows = false);
 int nlo_nlp_build_hess_layout(const NlpDev& L, std::vector<int>* rows, std::vector<int>* cols, std::vector<int>* hmap);
 int nlo_nlp_launch_dynamics(const NlpDev& L, const float* w, size_t P, size_t ld, float* g, float* jac, cudaStream_t st);
 int nlo_nlp_launch_points(const NlpDev& L, const float* w, size_t P, size_t ld, float* px, float* py, cudaStream_t st);

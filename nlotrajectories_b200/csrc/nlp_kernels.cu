@@ -492,13 +492,13 @@ inline int grid_for(size_t total, int threads, int sm_count) {
 }  // namespace
 
 int nlo_nlp_launch_assembly(nlo_nlp* p, const NlpScratch& sc, const float* w, size_t P, size_t ld, float* g, float* jac, float* f,
-                            float* grad_f, cudaStream_t st, int phase) {
+                            float* grad_f, cudaStream_t st, int phase, bool fused_rows) {
   const NlpDev& L = p->L;
   const int sm = p->sm_count;
   if (phase == 0) {
     const bool gj = g || jac;
     const bool analytic = L.sdf_mode == NLO_SDF_CIRCLES;
-    const int n_dyn = gj ? L.N : 0, n_copy = gj ? L.n_copy : 0, n_pts = (gj && !analytic) ? L.N + 1 : 0, n_grad = grad_f ? L.N + 1 : 0, n_obj = f ? 1 : 0;
+    const int n_dyn = gj ? L.N : 0, n_copy = gj ? L.n_copy : 0, n_pts = (gj && !analytic && !fused_rows) ? L.N + 1 : 0, n_grad = grad_f ? L.N + 1 : 0, n_obj = f ? 1 : 0;
     const unsigned rows = (unsigned)(n_dyn + n_copy + n_pts + n_grad + n_obj);
     if (rows) {
       const dim3 grid((unsigned)std::min<size_t>((P + 255) / 256, 4096), rows);

@@ -582,14 +582,21 @@ struct RrGlobal {
   long long* dbg;
   uint32_t n, n_tiles, ctr_bias, pad;
   long long ret_clock[2];  // timeline only: when thread 0 of each group last returned from a tile body
+  // rows mode (K3 fused, nlo_sdf_tc_rows_launch): the points are the footprint points of an NLP batch, formed in the kernel from the
+  // poses in w, and the results go straight to the SDF rows of g and their Jacobian entries (core/geometry.py:78-83, 107-117)
+  const float* w; float* g_rows; float* jac; const int* nz;
+  size_t ld;
+  uint32_t P, nx, nb, nz_per_knot;
+  float bx[4], by[4];
 };
 struct RrCtx {
   uint32_t tmem_base, lane_base, sB_hi, sB_lo, sV_hi, sV_lo, sB0, mbar_addr, mbar2_addr, bar_id;
   int* lock;
   const RrGlobal* g;       // shared memory
   uint32_t* next_slot;     // the group's next-but-one tile index
-  float* coord;            // the group's coordinate staging: [2][3][TILE]  (x | y | seed) of this tile and of the next one
+  float* coord;            // the group's coordinate staging: [2][RR_COORD_SLOTS][TILE]  (x | y | seed | rows mode: (k, b) | dpx | dpy)
   float* part;             // the group's exchange buffer [2][TILE][4]
+  float* rows;             // rows mode: the group's row bookkeeping [3][3][TILE]
   float inv_sw, unscale2, max_w0x, max_w0y, max_b0, spx_mul, spy_mul, cb_mul;
 };
 
@@ -624,6 +631,24 @@ __device__ __forceinline__ void rr_point_row(const RrCtx& c, float px, float py,
 // The thread that issues a group's MMAs sits in the HALF-1 warps: the issuing warp is blocked for most of a GEMM (the tensor queue takes
 // ~9 MMAs), and the HALF-0 warps carry the work that runs in the shadow of the GEMMs (coordinate staging, the next tile's A row)
 constexpr int RR_ISSUER = TILE;
+// Rows mode: point q of the batch is footprint point b of knot k of problem p, q = (k nb + b) P + p.  Its pose (x, y, heading) was
+// staged into slots 0..2 of the tile's coordinate buffer; this forms the point, leaves it in slots 0, 1 (both threads of the point read
+// it for the row scale) and what the deferred store needs in the tile's row-info entry: (k, b), d point / d heading.
+// The row bookkeeping lives in its own three-deep rotation (a tile's entry is written while the tile before it computes and read while the
+// tile after it computes, and in the value-only form no group barrier separates that read from the write two tiles later).
+constexpr int RR_COORD_SLOTS = 3;
+__device__ __forceinline__ void rr_rows_point(const RrGlobal* g, uint32_t q, float* slot, float* rinfo, float x, float y, float th, float& px, float& py) {
+  const uint32_t r = q / g->P, k = r / g->nb, b = r - k * g->nb;
+  float sn, cs;
+  nlo_sincos_fast(th, sn, cs);
+  const float bx = g->bx[b], by = g->by[b];
+  px = x + cs * bx - sn * by;
+  py = y + sn * bx + cs * by;
+  slot[0] = px; slot[TILE] = py;
+  rinfo[0] = __uint_as_float(k * 4u + b);
+  rinfo[TILE] = -sn * bx - cs * by;
+  rinfo[2 * TILE] = cs * bx - sn * by;
+}
 constexpr uint32_t RR_COL_AHI = 0, RR_COL_ALO = RR_H / 2, RR_COL_D = RR_H, RR_COL_P = RR_H / 2;   // P: the first 8 A-lo columns
 
 // the layer-0 MMA of one tile: D0 = P . B0.  No lock: one MMA slipping into the other group's GEMM is harmless (other D columns).
@@ -673,7 +698,7 @@ __device__ __forceinline__ void rr_issue_gemm(const RrCtx& c, bool fwd) {
 // computed by the same instruction sequence in both forms, so a value-only evaluation (a line-search trial) reproduces the value
 // of a full one bit for bit.
 struct RrTile {            // what a tile carries from its front half (layer 0, GEMM 1 issued) to its back half
-  uint32_t ph, ph2, buf, tile, tile_next, next_tile_idx, prev_tile, have_prev, stride;
+  uint32_t ph, ph2, buf, tile, tile_next, next_tile_idx, prev_tile, have_prev, stride, rb;
   float inv0;
   long long* dbg;
 };
@@ -683,12 +708,12 @@ struct RrTile {            // what a tile carries from its front half (layer 0, 
   constexpr uint32_t COL_AHI = RR_COL_AHI + HALF * (HH / 2), COL_ALO = RR_COL_ALO + HALF * (HH / 2), COL_D = RR_COL_D + C0; \
   const int tg = threadIdx.x % NT;                                                                                         \
   const int pt = tg & (TILE - 1);                                                                                          \
-  const float* cur = c.coord + t.buf * (3 * TILE) + pt;                                                                    \
-  float* nxt = c.coord + (t.buf ^ 1u) * (3 * TILE) + pt;                                                                   \
+  const float* cur = c.coord + t.buf * (RR_COORD_SLOTS * TILE) + pt; \
+  float* nxt = c.coord + (t.buf ^ 1u) * (RR_COORD_SLOTS * TILE) + pt; \
   (void)COL_AHI; (void)COL_ALO; (void)COL_D; (void)C0; (void)NCH; (void)cur; (void)nxt; (void)tg
 
 // The previous tile's results: each half left its partial sums {s, jx, jy} in the exchange buffer; HALF 0 stores s and jx, HALF 1 jy.
-template <int HALF, bool JAC>
+template <int HALF, bool JAC, bool ROWS>
 __device__ __forceinline__ void rr_store_prev(const RrCtx& c, const RrTile& t) {
   const int pt = threadIdx.x & (TILE - 1);
   const RrGlobal* g = c.g;
@@ -696,7 +721,22 @@ __device__ __forceinline__ void rr_store_prev(const RrCtx& c, const RrTile& t) {
   if (i < g->n) {
     const float* pa = c.part + pt * 4;
     const float* pb = c.part + (TILE + pt) * 4;
-    if (HALF == 0) {
+    if (ROWS) {
+      // row (k, b) of problem p: g row value, d/dx, d/dy (HALF 0: value and d/dx) and d/dheading through the footprint transform (HALF 1)
+      const float* rinfo = c.rows + ((t.rb + 2u) % 3u) * (3 * TILE) + pt;              // the previous tile's entry
+      const uint32_t kb = __float_as_uint(rinfo[0]), k = kb >> 2, b = kb & 3u;
+      const uint32_t r = k * g->nb + b, p = i - r * g->P;
+      const size_t ld = g->ld;
+      const int* nz = g->nz + k * g->nz_per_knot + 3u * b;
+      if (HALF == 0) {
+        if (g->g_rows) g->g_rows[(size_t)r * ld + p] = pa[0] + pb[0];
+        if (JAC) g->jac[(size_t)nz[0] * ld + p] = pa[1] + pb[1];
+      } else if (JAC) {
+        const float gx = pa[1] + pb[1], gy = pb[2] + pa[2];
+        g->jac[(size_t)nz[1] * ld + p] = gy;
+        g->jac[(size_t)nz[2] * ld + p] = gx * rinfo[TILE] + gy * rinfo[2 * TILE];
+      }
+    } else if (HALF == 0) {
       if (g->s_out) g->s_out[i] = pa[0] + pb[0];
       if (JAC) g->jx_out[i] = pa[1] + pb[1];
     } else {
@@ -706,7 +746,7 @@ __device__ __forceinline__ void rr_store_prev(const RrCtx& c, const RrTile& t) {
 }
 
 // front half of a tile: layer 0 from the tensor core's D0, GEMM 1 issued, the next tile's coordinates on their way
-template <int HALF, bool JAC>
+template <int HALF, bool JAC, bool ROWS>
 __device__ __forceinline__ void rr_front(const RrCtx& c, RrTile& t) {
   RR_TILE_CONSTS;
   t.dbg = (tg == RR_ISSUER && c.g->dbg && blockIdx.x == 0 && t.tile >= 32u * 2u * gridDim.x && t.tile < 40u * 2u * gridDim.x)
@@ -755,23 +795,31 @@ __device__ __forceinline__ void rr_front(const RrCtx& c, RrTile& t) {
   if (t.have_prev) {
     // which tile follows the next one: thread 0 stored it at the end of the previous tile
     t.tile_next = c.g->ctr ? *c.next_slot : t.tile + t.stride;
-    rr_store_prev<HALF, JAC>(c, t);                     // the previous tile's results: both halves' partial sums -> global memory
+    rr_store_prev<HALF, JAC, ROWS>(c, t);                     // the previous tile's results: both halves' partial sums -> global memory
   }
   const bool has_next = t.tile_next < c.g->n_tiles;
   // the next tile's coordinates start their way global -> shared memory (consumed in epilogue 2 and by the next tile)
   if (HALF == 0 && has_next) {
     const RrGlobal* g = c.g;
     const uint32_t in = min(t.tile_next * (uint32_t)TILE + (uint32_t)pt, g->n - 1u);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(nxt)), "l"(g->x + in) : "memory");
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(nxt + TILE)), "l"(g->y + in) : "memory");
-    if (g->sbar) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(nxt + 2 * TILE)), "l"(g->sbar + in) : "memory");
+    if (ROWS) {                        // the pose of the point's knot: x, y, heading
+      const uint32_t r = in / g->P, k = r / g->nb;
+      const float* src = g->w + (size_t)(k * g->nx) * g->ld + (in - r * g->P);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(nxt)), "l"(src) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(nxt + TILE)), "l"(src + g->ld) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(nxt + 2 * TILE)), "l"(src + 2 * g->ld) : "memory");
+    } else {
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(nxt)), "l"(g->x + in) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(nxt + TILE)), "l"(g->y + in) : "memory");
+      if (g->sbar) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(nxt + 2 * TILE)), "l"(g->sbar + in) : "memory");
+    }
   }
 }
 
 // back half of a tile: GEMM 1 done -> epilogue 1 -> (GEMM 2 -> epilogue 2) -> stores.  The loop's backward branch sits between the
 // front half and this wait: a far branch costs ~700 cycles of instruction fetch (measured with the timeline stamps - whether the tile body
 // was a function called per tile or a loop), and here that latency runs under GEMM 1 instead of between two tiles.
-template <int HALF, bool JAC>
+template <int HALF, bool JAC, bool ROWS>
 __device__ __forceinline__ void rr_back(const RrCtx& c, RrTile& t) {
   RR_TILE_CONSTS;
   const bool has_next = t.tile_next < c.g->n_tiles;
@@ -789,7 +837,14 @@ __device__ __forceinline__ void rr_back(const RrCtx& c, RrTile& t) {
     if (!JAC) {                       // D is free once every thread holds its columns: the next tile's layer-0 MMA
       if (HALF == 0 && has_next) {
         asm volatile("cp.async.wait_all;" ::: "memory");     // this thread staged the point itself
-        rr_point_row(c, nxt[0], nxt[TILE], wrow);
+        if (ROWS) {
+          float qx, qy;
+          rr_rows_point(c.g, min(t.tile_next * (uint32_t)TILE + (uint32_t)pt, c.g->n - 1u), nxt, c.rows + ((t.rb + 1u) % 3u) * (3 * TILE) + pt, nxt[0], nxt[TILE],
+                        nxt[2 * TILE], qx, qy);
+          rr_point_row(c, qx, qy, wrow);
+        } else {
+          rr_point_row(c, nxt[0], nxt[TILE], wrow);
+        }
         TmemIO<8>::st(c.lane_base + RR_COL_P, wrow);
         tc_wait_st();
       }
@@ -829,7 +884,14 @@ __device__ __forceinline__ void rr_back(const RrCtx& c, RrTile& t) {
     // while GEMM 2 runs: the next tile's layer-0 A row (its coordinates were staged during GEMM 1)
     if (HALF == 0 && has_next) {
       asm volatile("cp.async.wait_all;" ::: "memory");       // this thread staged the point itself
-      rr_point_row(c, nxt[0], nxt[TILE], wrow);
+      if (ROWS) {
+        float qx, qy;
+        rr_rows_point(c.g, min(t.tile_next * (uint32_t)TILE + (uint32_t)pt, c.g->n - 1u), nxt, c.rows + ((t.rb + 1u) % 3u) * (3 * TILE) + pt, nxt[0], nxt[TILE],
+                        nxt[2 * TILE], qx, qy);
+        rr_point_row(c, qx, qy, wrow);
+      } else {
+        rr_point_row(c, nxt[0], nxt[TILE], wrow);
+      }
     }
     mbar_wait_addr(c.mbar_addr, t.ph); t.ph ^= 1u;
     tc_fence_after();
@@ -866,7 +928,7 @@ __device__ __forceinline__ void rr_back(const RrCtx& c, RrTile& t) {
         }
       }
     }
-    const float unscale2 = (c.g->sbar ? cur[2 * TILE] : 1.f) * c.unscale2;
+    const float unscale2 = ((!ROWS && c.g->sbar) ? cur[2 * TILE] : 1.f) * c.unscale2;
     jx *= unscale2; jy *= unscale2;
   }
   RR_STAMP(12);
@@ -880,36 +942,37 @@ __device__ __forceinline__ void rr_back(const RrCtx& c, RrTile& t) {
   t.prev_tile = t.tile; t.have_prev = 1u;
   RR_STAMP(13);
   t.buf ^= 1u;
+  t.rb = (t.rb + 1u) % 3u;
 }
 #undef RR_STAMP
 #undef RR_TILE_CONSTS
 
 // All tiles of one group half.  The loop is rotated: its backward branch follows the issue of GEMM 1 (see rr_back).
-template <int HALF, bool JAC>
+template <int HALF, bool JAC, bool ROWS>
 __device__ __noinline__ void sdf_rr_group(RrCtx c, uint32_t tile, uint32_t tile_next, uint32_t stride) {
   RrTile t;
   t.ph = t.ph2 = t.buf = 0u; t.tile = tile; t.tile_next = tile_next; t.next_tile_idx = 0u; t.inv0 = 1.f; t.dbg = nullptr;
-  t.prev_tile = 0u; t.have_prev = 0u; t.stride = stride;
+  t.prev_tile = 0u; t.have_prev = 0u; t.stride = stride; t.rb = 0u;
   if (t.tile >= c.g->n_tiles) return;
-  rr_front<HALF, JAC>(c, t);
+  rr_front<HALF, JAC, ROWS>(c, t);
 #pragma unroll 1
   for (;;) {
-    rr_back<HALF, JAC>(c, t);
+    rr_back<HALF, JAC, ROWS>(c, t);
     if (c.g->dbg && threadIdx.x % (2 * TILE) == RR_ISSUER) const_cast<RrGlobal*>(c.g)->ret_clock[threadIdx.x / (2 * TILE)] = clock64();
     t.tile = t.tile_next;                 // (its successor is read in the front half, behind the barrier that orders it)
     if (t.tile >= c.g->n_tiles) break;
-    rr_front<HALF, JAC>(c, t);
+    rr_front<HALF, JAC, ROWS>(c, t);
   }
   group_bar<2 * TILE>(c.bar_id);
-  rr_store_prev<HALF, JAC>(c, t);
+  rr_store_prev<HALF, JAC, ROWS>(c, t);
 }
 
 constexpr size_t rr_smem_bytes() {
   return (size_t)4 * RR_H * RR_H * 2 + (size_t)RR_B0_HALFS * 2 + (size_t)2 * 2 * TILE * 4 * 4 + 4 * 8 + sizeof(RrGlobal) + 32 +
-         (size_t)2 * 2 * 3 * TILE * 4;
+         (size_t)2 * 2 * RR_COORD_SLOTS * TILE * 4 + (size_t)2 * 3 * 3 * TILE * 4;
 }
 
-template <bool JAC>
+template <bool JAC, bool ROWS>
 __global__ void __launch_bounds__(512, 1)
 sdf_tc_rr_kernel(TcParams prm_tc, const __half* __restrict__ bimg, RrGlobal gl) {
   constexpr int H = RR_H, NG = 2, GT = 2 * TILE, IMG = H * H;
@@ -921,7 +984,7 @@ sdf_tc_rr_kernel(TcParams prm_tc, const __half* __restrict__ bimg, RrGlobal gl) 
   int* lock = reinterpret_cast<int*>(sG + 1);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lock + 1);
   uint32_t* next_tile = tmem_slot + 1;                                                       // [NG]
-  float* sCoord = reinterpret_cast<float*>(next_tile + NG);                                  // [NG][2][3][TILE]
+  float* sCoord = reinterpret_cast<float*>(next_tile + NG);                                  // [NG][2][RR_COORD_SLOTS][TILE]
   const int t = threadIdx.x, warp = t >> 5;
   const int grp = t / GT, tg = t % GT;
   const int half = (tg >> 5) >> 2;
@@ -954,7 +1017,8 @@ sdf_tc_rr_kernel(TcParams prm_tc, const __half* __restrict__ bimg, RrGlobal gl) 
   c.lock = lock;
   c.g = sG;
   c.next_slot = next_tile + grp;
-  c.coord = sCoord + grp * (2 * 3 * TILE);
+  c.coord = sCoord + grp * (2 * RR_COORD_SLOTS * TILE);
+  c.rows = sCoord + 2 * (2 * RR_COORD_SLOTS * TILE) + grp * (3 * 3 * TILE);
   c.part = sPart + grp * (2 * TILE * 4);
   c.inv_sw = prm_tc.inv_sw; c.unscale2 = prm_tc.inv_sv;
   c.max_w0x = prm_tc.max_w0x; c.max_w0y = prm_tc.max_w0y; c.max_b0 = prm_tc.max_b0;
@@ -966,8 +1030,15 @@ sdf_tc_rr_kernel(TcParams prm_tc, const __half* __restrict__ bimg, RrGlobal gl) 
   if (tile < n_tiles) {                       // (group-uniform) the first tile: coordinates and layer-0 MMA up front
     if (half == 0) {
       const uint32_t ic = min(tile * (uint32_t)TILE + (uint32_t)pt, gl.n - 1u);
-      const float px = gl.x[ic], py = gl.y[ic];
-      c.coord[pt] = px; c.coord[TILE + pt] = py; c.coord[2 * TILE + pt] = gl.sbar ? gl.sbar[ic] : 1.f;
+      float px, py;
+      if (ROWS) {
+        const uint32_t r = ic / gl.P, k = r / gl.nb;
+        const float* src = gl.w + (size_t)(k * gl.nx) * gl.ld + (ic - r * gl.P);
+        rr_rows_point(sG, ic, c.coord + pt, c.rows + pt, src[0], src[gl.ld], src[2 * gl.ld], px, py);
+      } else {
+        px = gl.x[ic]; py = gl.y[ic];
+        c.coord[pt] = px; c.coord[TILE + pt] = py; c.coord[2 * TILE + pt] = gl.sbar ? gl.sbar[ic] : 1.f;
+      }
       uint32_t w[8];
       rr_point_row(c, px, py, w);
       TmemIO<8>::st(c.lane_base + RR_COL_P, w);
@@ -979,7 +1050,7 @@ sdf_tc_rr_kernel(TcParams prm_tc, const __half* __restrict__ bimg, RrGlobal gl) 
   }
   // tiles: the first two by position, the rest from the global counter (the SMs do not all run at the same speed), which the tile
   // body polls two tiles ahead - or by striding when no counter is given (small launches)
-  if (half == 0) sdf_rr_group<0, JAC>(c, tile, tile_next, stride); else sdf_rr_group<1, JAC>(c, tile, tile_next, stride);
+  if (half == 0) sdf_rr_group<0, JAC, ROWS>(c, tile, tile_next, stride); else sdf_rr_group<1, JAC, ROWS>(c, tile, tile_next, stride);
   tc_fence_before();
   __syncthreads();
   // The last CTA to finish puts the tile counter back to zero for the next launch on this stream
@@ -996,9 +1067,9 @@ bool rr_enabled() {
   return on != 0;
 }
 
-template <bool JAC>
-int launch_tc_rr(nlo_sdf_model* m, const float* x, const float* y, const float* sbar, size_t n, float* s, float* jx, float* jy, cudaStream_t st) {
-  auto kfn = sdf_tc_rr_kernel<JAC>;
+template <bool JAC, bool ROWS>
+int launch_tc_rr_gl(nlo_sdf_model* m, RrGlobal gl, size_t n, cudaStream_t st) {
+  auto kfn = sdf_tc_rr_kernel<JAC, ROWS>;
   const size_t smem = rr_smem_bytes();
   static bool attr_set[64] = {false};
   if (!attr_set[m->device & 63]) {
@@ -1016,8 +1087,6 @@ int launch_tc_rr(nlo_sdf_model* m, const float* x, const float* y, const float* 
     NLO_CUDA(cudaMemcpyToSymbol(cst, m->tc_const, sizeof(TcConst), 0, cudaMemcpyHostToDevice));
     g_const_owner[m->device] = m->uid;
   }
-  RrGlobal gl;
-  gl.x = x; gl.y = y; gl.sbar = sbar; gl.s_out = s; gl.jx_out = jx; gl.jy_out = jy;
   gl.ctr = nullptr; gl.dbg = nullptr; gl.n = (uint32_t)n; gl.n_tiles = (uint32_t)tiles; gl.ctr_bias = 0; gl.pad = 0; gl.ret_clock[0] = gl.ret_clock[1] = 0;
   if (tiles > (size_t)grid * 2) {
     const int slot = nlo_model_stream_slot(m, st);
@@ -1046,6 +1115,14 @@ int launch_tc_rr(nlo_sdf_model* m, const float* x, const float* y, const float* 
   }
   NLO_CHECK_LAUNCH();
   return 0;
+}
+
+template <bool JAC>
+int launch_tc_rr(nlo_sdf_model* m, const float* x, const float* y, const float* sbar, size_t n, float* s, float* jx, float* jy, cudaStream_t st) {
+  RrGlobal gl;
+  memset(&gl, 0, sizeof(gl));
+  gl.x = x; gl.y = y; gl.sbar = sbar; gl.s_out = s; gl.jx_out = jx; gl.jy_out = jy;
+  return launch_tc_rr_gl<JAC, false>(m, gl, n, st);
 }
 
 }  // namespace
@@ -1190,4 +1267,25 @@ int nlo_sdf_tc_launch(nlo_sdf_model* m, const float* x, const float* y, const fl
 #undef NLO_TC
 #undef NLO_TC_ONE
   return nlo_fail("tensor-tile path: unsupported width %d", H);
+}
+
+// K3 fused into K1 (hard SDF rows of a footprint with a heading: benchmark_6): footprint points from the poses in w, results straight into
+// the rows of g (g_rows = g + g_off_sdf * ld; may be NULL) and their Jacobian entries (jac NULL: values only).  nz: the CCS slots of the
+// rows' entries, nz_per_knot apart per knot, three per footprint point (d/dx, d/dy, d/dheading).
+bool nlo_sdf_tc_rows_supported(const nlo_sdf_model* m) {
+  static const int on = [] { const char* e = getenv("NLO_B200_FUSED_ROWS"); return (e && e[0] == '0') ? 0 : 1; }();
+  return on && m->prec == NLO_PREC_TC_3XF16 && m->d_tc && m->desc.n_hidden_mats == 1 && m->desc.hidden == RR_H &&
+         m->desc.act0 == NLO_ACT_RELU && m->desc.act == NLO_ACT_RELU && rr_enabled();
+}
+int nlo_sdf_tc_rows_launch(nlo_sdf_model* m, const float* w, size_t P, size_t ld, int n_knots, int nx, int nb, const float* bx, const float* by,
+                           float* g_rows, float* jac, const int* nz, int nz_per_knot, cudaStream_t st) {
+  const size_t n = (size_t)n_knots * nb * P;
+  if (n == 0) return 0;
+  if (n > 0x7FFFFF00u || nb > 4 || nb < 1) return nlo_fail("fused SDF rows: batch too large or unsupported footprint");
+  RrGlobal gl;
+  memset(&gl, 0, sizeof(gl));
+  gl.w = w; gl.g_rows = g_rows; gl.jac = jac; gl.nz = nz; gl.ld = ld;
+  gl.P = (uint32_t)P; gl.nx = (uint32_t)nx; gl.nb = (uint32_t)nb; gl.nz_per_knot = (uint32_t)nz_per_knot;
+  for (int b = 0; b < nb; ++b) { gl.bx[b] = bx[b]; gl.by[b] = by[b]; }
+  return jac ? launch_tc_rr_gl<true, true>(m, gl, n, st) : launch_tc_rr_gl<false, true>(m, gl, n, st);
 }
