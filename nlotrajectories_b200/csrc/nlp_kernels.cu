@@ -307,10 +307,12 @@ __device__ __forceinline__ void nlp_analytic_rows_body(const NlpDev& L, const fl
 // ---- K4: objective and gradient (core/runner.py:80-98) -----------------------------------------------------
 // Objective: a block is 32 problems x 8 knot ranges (problem index fastest -> every load is one 128-byte line per warp);
 // the 8 partial sums of a problem meet in shared memory.
-__device__ __forceinline__ void nlp_obj_body(const NlpDev& L, const float* __restrict__ w, size_t P, size_t ld, float* __restrict__ f) {
+// `sub` of `n_sub` block rows share the problems: with one row the role was 256 blocks walking 8 problem groups each - the tail of the launch.
+__device__ __forceinline__ void nlp_obj_body(const NlpDev& L, const float* __restrict__ w, size_t P, size_t ld, float* __restrict__ f,
+                                             const int sub, const int n_sub) {
   __shared__ float part[8][33];
   const int tx = threadIdx.x & 31, c = threadIdx.x >> 5;
-  for (size_t p0 = (size_t)blockIdx.x * 32; p0 < P; p0 += (size_t)gridDim.x * 32) {
+  for (size_t p0 = ((size_t)blockIdx.x + (size_t)sub * gridDim.x) * 32; p0 < P; p0 += (size_t)gridDim.x * n_sub * 32) {
     const size_t p = p0 + tx;
     float acc = 0.f;
     if (p < P) {
@@ -390,8 +392,12 @@ template <int DYN>
 __global__ void __launch_bounds__(256, 8) nlp_phase0_kernel(NlpDev L, const float* __restrict__ w, size_t P, size_t ld, float* __restrict__ g,
                                                          float* __restrict__ jac, float* __restrict__ px, float* __restrict__ py,
                                                          float* __restrict__ f, float* __restrict__ grad, int n_dyn, int n_copy, int n_pts,
-                                                         int n_grad) {
+                                                         int n_grad, int n_obj) {
   int r = blockIdx.y;
+  // the objective first (block rows are dispatched in order): its threads walk a tenth of a trajectory each, and as the last rows of the
+  // grid they ran on after everything else had finished
+  if (r < n_obj) { nlp_obj_body(L, w, P, ld, f, r, n_obj); return; }
+  r -= n_obj;
   if (r < n_dyn) { nlp_dyn_body<DYN>(L, w, P, ld, g, jac, r); return; }
   r -= n_dyn;
   if (r < n_copy) { nlp_copy_rows_body(L, w, P, ld, g, jac, r); return; }
@@ -399,7 +405,6 @@ __global__ void __launch_bounds__(256, 8) nlp_phase0_kernel(NlpDev L, const floa
   if (r < n_pts) { nlp_points_body(L, w, P, ld, px, py, r); return; }
   r -= n_pts;
   if (r < n_grad) { nlp_grad_body(L, w, P, ld, grad, r); return; }
-  nlp_obj_body(L, w, P, ld, f);
 }
 // analytic obstacles (solver.mode casadi): footprint points, union SDF and constraint rows of one knot per block row - its own launch,
 // because the jets of the square obstacles need far more than the 32 registers the light roles of the phase-0 launch are held to
@@ -498,12 +503,12 @@ int nlo_nlp_launch_assembly(nlo_nlp* p, const NlpScratch& sc, const float* w, si
   if (phase == 0) {
     const bool gj = g || jac;
     const bool analytic = L.sdf_mode == NLO_SDF_CIRCLES;
-    const int n_dyn = gj ? L.N : 0, n_copy = gj ? L.n_copy : 0, n_pts = (gj && !analytic && !fused_rows) ? L.N + 1 : 0, n_grad = grad_f ? L.N + 1 : 0, n_obj = f ? 1 : 0;
+    const int n_dyn = gj ? L.N : 0, n_copy = gj ? L.n_copy : 0, n_pts = (gj && !analytic && !fused_rows) ? L.N + 1 : 0, n_grad = grad_f ? L.N + 1 : 0, n_obj = f ? 8 : 0;
     const unsigned rows = (unsigned)(n_dyn + n_copy + n_pts + n_grad + n_obj);
     if (rows) {
       const dim3 grid((unsigned)std::min<size_t>((P + 255) / 256, 4096), rows);
       switch (L.dyn) {
-#define NLO_CASE(D) case D: nlp_phase0_kernel<D><<<grid, 256, 0, st>>>(L, w, P, ld, g, jac, sc.px, sc.py, f, grad_f, n_dyn, n_copy, n_pts, n_grad); break;
+#define NLO_CASE(D) case D: nlp_phase0_kernel<D><<<grid, 256, 0, st>>>(L, w, P, ld, g, jac, sc.px, sc.py, f, grad_f, n_dyn, n_copy, n_pts, n_grad, n_obj); break;
         NLO_CASE(NLO_DYN_POINT_1ST) NLO_CASE(NLO_DYN_POINT_2ND) NLO_CASE(NLO_DYN_UNICYCLE)
         NLO_CASE(NLO_DYN_UNICYCLE_2ND) NLO_CASE(NLO_DYN_ACKERMANN) NLO_CASE(NLO_DYN_ACKERMANN_2ND)
 #undef NLO_CASE
@@ -527,7 +532,7 @@ int nlo_nlp_launch_assembly(nlo_nlp* p, const NlpScratch& sc, const float* w, si
 int nlo_nlp_launch_dynamics(const NlpDev& L, const float* w, size_t P, size_t ld, float* g, float* jac, cudaStream_t st) {
   const dim3 grid((unsigned)std::min<size_t>((P + 255) / 256, 4096), (unsigned)L.N);
   switch (L.dyn) {
-#define NLO_CASE(D) case D: nlp_phase0_kernel<D><<<grid, 256, 0, st>>>(L, w, P, ld, g, jac, nullptr, nullptr, nullptr, nullptr, L.N, 0, 0, 0); break;
+#define NLO_CASE(D) case D: nlp_phase0_kernel<D><<<grid, 256, 0, st>>>(L, w, P, ld, g, jac, nullptr, nullptr, nullptr, nullptr, L.N, 0, 0, 0, 0); break;
     NLO_CASE(NLO_DYN_POINT_1ST) NLO_CASE(NLO_DYN_POINT_2ND) NLO_CASE(NLO_DYN_UNICYCLE)
     NLO_CASE(NLO_DYN_UNICYCLE_2ND) NLO_CASE(NLO_DYN_ACKERMANN) NLO_CASE(NLO_DYN_ACKERMANN_2ND)
 #undef NLO_CASE
