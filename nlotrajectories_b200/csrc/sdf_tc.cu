@@ -598,6 +598,7 @@ struct RrCtx {
   float* part;             // the group's exchange buffer [2][TILE][4]
   float* rows;             // rows mode: the group's row bookkeeping [3][3][TILE]
   float inv_sw, unscale2, max_w0x, max_w0y, max_b0, spx_mul, spy_mul, cb_mul;
+  uint32_t n_tiles, flags;   // copies of what every tile asks (flags: 1 = dynamic tile counter, 2 = timeline, 4 = adjoint seed given)
 };
 
 __device__ __forceinline__ float rr_bound(const RrCtx& c, float px, float py) {
@@ -749,7 +750,7 @@ __device__ __forceinline__ void rr_store_prev(const RrCtx& c, const RrTile& t) {
 template <int HALF, bool JAC, bool ROWS>
 __device__ __forceinline__ void rr_front(const RrCtx& c, RrTile& t) {
   RR_TILE_CONSTS;
-  t.dbg = (tg == RR_ISSUER && c.g->dbg && blockIdx.x == 0 && t.tile >= 32u * 2u * gridDim.x && t.tile < 40u * 2u * gridDim.x)
+  t.dbg = (tg == RR_ISSUER && (c.flags & 2u) && blockIdx.x == 0 && t.tile >= 32u * 2u * gridDim.x && t.tile < 40u * 2u * gridDim.x)
               ? c.g->dbg + ((threadIdx.x / NT) * 8 + (t.tile / (2u * gridDim.x) - 32u)) * 16 : nullptr;
   RR_STAMP(0);
   if (t.dbg) t.dbg[14] = c.g->ret_clock[threadIdx.x / NT];
@@ -769,10 +770,12 @@ __device__ __forceinline__ void rr_front(const RrCtx& c, RrTile& t) {
       uint32_t hi[16], lo[16];
 #pragma unroll
       for (int q = 0; q < 16; ++q) {
-        const uint32_t u0 = d[cc][2 * q], u1 = d[cc][2 * q + 1];
-        const float h0 = __uint_as_float(u0 & 0xFFFFE000u), h1 = __uint_as_float(u1 & 0xFFFFE000u);   // 11 significant bits: exact in fp16
-        hi[q] = pack_relu_f16(h0, h1);
-        lo[q] = pack_relu_f16(__uint_as_float(u0) - h0, __uint_as_float(u1) - h1);
+        const float v0 = __uint_as_float(d[cc][2 * q]), v1 = __uint_as_float(d[cc][2 * q + 1]);
+        // hi = fp16 of max(v, 0) rounded TOWARD ZERO (so that the remainder of a positive v is >= 0), unpacked again on the FMA pipe;
+        // the ALU pipe - the busiest of this kernel - sees two packed conversions per pair instead of two LOP3 and two conversions
+        hi[q] = pack_relu_rz_f16(v0, v1);
+        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi[q]));
+        lo[q] = pack_relu_f16(v0 - hf.x, v1 - hf.y);
       }
       TmemIO<16>::st(c.lane_base + COL_AHI + cc * 16, hi);
       TmemIO<16>::st(c.lane_base + COL_ALO + cc * 16, lo);
@@ -787,17 +790,17 @@ __device__ __forceinline__ void rr_front(const RrCtx& c, RrTile& t) {
   if (tg == RR_ISSUER) {
     rr_issue_gemm(c, true);
     // the tile after the next one: requested here, stored at the end of the tile (the round trip to the one hot counter is long)
-    if (c.g->ctr) t.next_tile_idx = atomicAdd(c.g->ctr, 1u);
+    if (c.flags & 1u) t.next_tile_idx = atomicAdd(c.g->ctr, 1u);
   }
   RR_STAMP(4);
   // ---- in the shadow of GEMM 1 (everything below used to sit between two tiles, behind a group barrier of its own) ----------
   // (the barrier in front of GEMM 1 is what orders these shared-memory reads behind the previous tile's writes)
   if (t.have_prev) {
     // which tile follows the next one: thread 0 stored it at the end of the previous tile
-    t.tile_next = c.g->ctr ? *c.next_slot : t.tile + t.stride;
+    t.tile_next = (c.flags & 1u) ? *c.next_slot : t.tile + t.stride;
     rr_store_prev<HALF, JAC, ROWS>(c, t);                     // the previous tile's results: both halves' partial sums -> global memory
   }
-  const bool has_next = t.tile_next < c.g->n_tiles;
+  const bool has_next = t.tile_next < c.n_tiles;
   // the next tile's coordinates start their way global -> shared memory (consumed in epilogue 2 and by the next tile)
   if (HALF == 0 && has_next) {
     const RrGlobal* g = c.g;
@@ -822,7 +825,7 @@ __device__ __forceinline__ void rr_front(const RrCtx& c, RrTile& t) {
 template <int HALF, bool JAC, bool ROWS>
 __device__ __forceinline__ void rr_back(const RrCtx& c, RrTile& t) {
   RR_TILE_CONSTS;
-  const bool has_next = t.tile_next < c.g->n_tiles;
+  const bool has_next = t.tile_next < c.n_tiles;
   mbar_wait_addr(c.mbar_addr, t.ph); t.ph ^= 1u;
   tc_fence_after();
   RR_STAMP(5);
@@ -917,18 +920,20 @@ __device__ __forceinline__ void rr_back(const RrCtx& c, RrTile& t) {
       tc_wait_ld();
 #pragma unroll
       for (int q = 0; q < 16; ++q) {
+        // select, then two unconditional FFMAs: under a per-thread predicate the constants would arrive one LDC each
+        // instead of four per LDCU.128.  One packed half compare yields both predicates of a pair (hi(h0) >= +0).
+        float gsel[2];
+        asm("{\n\t.reg .pred p, q;\n\tsetp.gt.f16x2 p|q, %2, %3;\n\tselp.f32 %0, %4, 0f00000000, p;\n\tselp.f32 %1, %5, 0f00000000, q;\n\t}"
+            : "=f"(gsel[0]), "=f"(gsel[1]) : "r"(hw[q]), "r"(0u), "f"(__uint_as_float(gz[cc][2 * q])), "f"(__uint_as_float(gz[cc][2 * q + 1])));
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int k = C0 + cc * 32 + 2 * q + e;
-          // select, then two unconditional FFMAs: under a per-thread predicate the constants would arrive one LDC each
-          // instead of four per LDCU.128
-          const float g = (hw[q] & (e == 0 ? 0x00007FFFu : 0x7FFF0000u)) ? __uint_as_float(gz[cc][2 * q + e]) : 0.f;
-          jx = fmaf(g, cst.w0x[k], jx);
-          jy = fmaf(g, cst.w0y[k], jy);
+          jx = fmaf(gsel[e], cst.w0x[k], jx);
+          jy = fmaf(gsel[e], cst.w0y[k], jy);
         }
       }
     }
-    const float unscale2 = ((!ROWS && c.g->sbar) ? cur[2 * TILE] : 1.f) * c.unscale2;
+    const float unscale2 = ((!ROWS && (c.flags & 4u)) ? cur[2 * TILE] : 1.f) * c.unscale2;
     jx *= unscale2; jy *= unscale2;
   }
   RR_STAMP(12);
@@ -938,7 +943,7 @@ __device__ __forceinline__ void rr_back(const RrCtx& c, RrTile& t) {
     float* mine = c.part + (HALF * TILE + pt) * 4;
     mine[0] = s; mine[1] = jx; mine[2] = jy;
   }
-  if (tg == RR_ISSUER && c.g->ctr) *c.next_slot = t.next_tile_idx + c.g->ctr_bias;
+  if (tg == RR_ISSUER && (c.flags & 1u)) *c.next_slot = t.next_tile_idx + c.g->ctr_bias;
   t.prev_tile = t.tile; t.have_prev = 1u;
   RR_STAMP(13);
   t.buf ^= 1u;
@@ -953,14 +958,14 @@ __device__ __noinline__ void sdf_rr_group(RrCtx c, uint32_t tile, uint32_t tile_
   RrTile t;
   t.ph = t.ph2 = t.buf = 0u; t.tile = tile; t.tile_next = tile_next; t.next_tile_idx = 0u; t.inv0 = 1.f; t.dbg = nullptr;
   t.prev_tile = 0u; t.have_prev = 0u; t.stride = stride; t.rb = 0u;
-  if (t.tile >= c.g->n_tiles) return;
+  if (t.tile >= c.n_tiles) return;
   rr_front<HALF, JAC, ROWS>(c, t);
 #pragma unroll 1
   for (;;) {
     rr_back<HALF, JAC, ROWS>(c, t);
-    if (c.g->dbg && threadIdx.x % (2 * TILE) == RR_ISSUER) const_cast<RrGlobal*>(c.g)->ret_clock[threadIdx.x / (2 * TILE)] = clock64();
+    if ((c.flags & 2u) && threadIdx.x % (2 * TILE) == RR_ISSUER) const_cast<RrGlobal*>(c.g)->ret_clock[threadIdx.x / (2 * TILE)] = clock64();
     t.tile = t.tile_next;                 // (its successor is read in the front half, behind the barrier that orders it)
-    if (t.tile >= c.g->n_tiles) break;
+    if (t.tile >= c.n_tiles) break;
     rr_front<HALF, JAC, ROWS>(c, t);
   }
   group_bar<2 * TILE>(c.bar_id);
@@ -1023,6 +1028,7 @@ sdf_tc_rr_kernel(TcParams prm_tc, const __half* __restrict__ bimg, RrGlobal gl) 
   c.inv_sw = prm_tc.inv_sw; c.unscale2 = prm_tc.inv_sv;
   c.max_w0x = prm_tc.max_w0x; c.max_w0y = prm_tc.max_w0y; c.max_b0 = prm_tc.max_b0;
   c.spx_mul = prm_tc.spx_mul; c.spy_mul = prm_tc.spy_mul; c.cb_mul = prm_tc.cb_mul;
+  c.n_tiles = gl.n_tiles; c.flags = (gl.ctr ? 1u : 0u) | (gl.dbg ? 2u : 0u) | (gl.sbar ? 4u : 0u);
   const uint32_t n_tiles = gl.n_tiles;
   const uint32_t stride = gridDim.x * NG;
   uint32_t tile = blockIdx.x * NG + grp;

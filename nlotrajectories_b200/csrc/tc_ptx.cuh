@@ -133,6 +133,13 @@ __device__ __forceinline__ uint32_t pack_relu_f16(float v0, float v1) {
   return d;
 }
 
+// the same with round-toward-zero: the result never exceeds the value, so value - result >= 0 for a positive value
+__device__ __forceinline__ uint32_t pack_relu_rz_f16(float v0, float v1) {
+  uint32_t d;
+  asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(v1), "f"(v0));
+  return d;
+}
+
 // named barrier of one tile group
 template <int NT>
 __device__ __forceinline__ void group_bar(uint32_t id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NT) : "memory"); }
