@@ -88,6 +88,43 @@ def test_batch_matches_oracle_device_and_host_paths(name, netname, shipped_net, 
     assert torch.equal(g2[:, :P], g[:, :P])
 
 
+@pytest.mark.parametrize("P", [1, 5, 130, 1000])
+def test_fused_rows_small_and_ragged_batches(P, library):
+    """benchmark_6 with the ReLU 2-128-128-1 network runs the SDF rows INSIDE the tensor kernel (sdf_tc_rr_kernel, rows form: footprint
+    points formed from the poses, results written straight to g and dg/dw; core/geometry.py:78-83,107-117).  Its tiles are 128 consecutive
+    (row, problem) pairs, so small and odd batches make every tile straddle rows and knots; g-only and Jacobian-only calls take the
+    value-only / full forms of the kernel and must reproduce the full call bit for bit."""
+    import torch
+    net = so.synthetic_mlp(128, 1, seed=0)
+    cfg, model, prob = make_problem("benchmark_6", net)
+    spec = no.NlpSpec.from_yaml_dict(yaml.safe_load(open(bench_yaml("benchmark_6"))))
+    w = prob.multistart_guess(P)
+    rng = np.random.default_rng(P)
+    w[:, prob.n_X:] = rng.normal(0, 0.3, (P, prob.n_w - prob.n_X)).astype(np.float32)
+    w[:, 2:prob.n_X:prob.nx] += rng.normal(0, 0.5, (P, prob.N + 1)).astype(np.float32)      # headings
+    n64 = net.astype(np.float64)
+    g_ref, j_ref = no.eval_g_jac(spec, w.astype(np.float64), lambda Q: so.value_jac(n64, Q))
+    rows, _, _ = no.jac_pattern(spec)
+    n_before = spec.n_g - spec.n_U - (spec.N + 1) * spec.sdf_rows_per_knot
+    tie = sdf_row_ties(spec, net, w, n_before)[:, rows]
+    ld = P + 3
+    wd = torch.zeros((prob.n_w, ld), device="cuda"); wd[:, :P] = torch.from_numpy(w).cuda().T
+    g, jac, f, grad = prob.alloc_outputs(ld)
+    g.zero_(); jac.zero_()
+    prob.eval_device(wd, g, jac, f, grad, P=P)
+    torch.cuda.synchronize()
+    gh, jh = g[:, :P].T.cpu().numpy(), jac[:, :P].T.cpu().numpy()
+    assert not close(gh, g_ref, TOL).any(), np.abs(gh - g_ref).max()
+    assert not (close(jh, j_ref, TOL) & ~tie).any()
+    g2 = torch.zeros_like(g)
+    prob.eval_device(wd, g2, None, None, None, P=P)                 # values only
+    jac2 = torch.zeros_like(jac)
+    prob.eval_device(wd, None, jac2, None, None, P=P)               # Jacobian only
+    torch.cuda.synchronize()
+    assert torch.equal(g2[:, :P], g[:, :P]) and torch.equal(jac2[:, :P], jac[:, :P])
+    assert float(g[:, P:].abs().max()) == 0.0 and float(jac[:, P:].abs().max()) == 0.0      # the padding columns stay untouched
+
+
 def test_all_dynamics_models_and_footprints(library):
     """The three models no shipped YAML uses (point_1st, unicycle, ackermann) and the triangle / hard rows."""
     import torch
